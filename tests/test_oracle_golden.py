@@ -1,0 +1,234 @@
+"""Pins the CPU oracle (oracle/) against the known answers hard-coded in the reference's own tests and examples
+(SURVEY.md section 8c).  CPU only.  Every expected value below is copied from the cited reference line.
+"""
+import math
+
+import numpy as np
+import pytest
+
+import vfvm_b200 as v
+from vfvm_b200 import physics as ph
+from oracle import oracle as O
+
+
+def test_example301_laplace3d():
+    """examples/Example301_Laplace3D.jl:28-47: solution[43] == 0.012234524449380824"""
+    X = np.linspace(0, 1, 6)
+    sys = v.System(v.simplexgrid(X, X, X), flux=ph.LinearDiffusion(), source=ph.XSinYExpZSource(1, 5.0))
+    v.enable_species(sys, 1, [1])
+    v.boundary_dirichlet(sys, 1, 5, 0.0)
+    v.boundary_dirichlet(sys, 1, 6, 0.0)
+    sol = O.OracleSystem(sys).solve_step(v.unknowns(sys))
+    assert sol.ravel(order="F")[42] == pytest.approx(0.012234524449380824, rel=1e-12)
+
+
+def test_example207_nonlinear_poisson2d():
+    """examples/Example207_NonlinearPoisson2D.jl:23-82: U[15] == 0.3554284760906605 after 100 implicit Euler steps"""
+    X = np.linspace(0, 1, 11)
+    sys = v.System(v.simplexgrid(X, X), flux=ph.PowerDiffusion(1.0e-2, 2), reaction=ph.PowerReaction(1.0, 2.0),
+                   source=ph.GaussSource(1, 20.0, (0.5, 0.5)), storage=ph.LinearStorage(1.0))
+    v.enable_species(sys, 1, [1])
+    v.boundary_dirichlet(sys, 1, 2, 0.1)
+    v.boundary_dirichlet(sys, 1, 4, 0.1)
+    o = O.OracleSystem(sys)
+    u, t, tstep = v.unknowns(sys, 0.5), 0.0, 0.01
+    while t < 1.0:
+        t += tstep
+        u = o.solve_step(u, tstep=tstep)
+    assert u.ravel(order="F")[14] == pytest.approx(0.3554284760906605, rel=1e-12)
+
+
+def test_example410_many_species():
+    """examples/Example410_ManySpecies.jl:17-39: norm(sol) == 13.874436925511608, 50 species"""
+    sys = v.System(v.simplexgrid(np.linspace(0, 1, 11)), flux=ph.LinearDiffusion())
+    for i in range(1, 51):
+        v.enable_species(sys, i, [1])
+        v.boundary_dirichlet(sys, i, 1, 0)
+        v.boundary_dirichlet(sys, i, 2, 1)
+    sol = O.OracleSystem(sys).solve_step(v.unknowns(sys))
+    assert np.linalg.norm(sol) == pytest.approx(13.874436925511608, rel=1e-12)
+
+
+def test_example105_nonlinear_poisson1d():
+    """examples/Example105_NonlinearPoisson1D.jl:30-96: sum(solution) == 1.5247901344230088"""
+    sys = v.System(v.simplexgrid(np.arange(0, 11) / 10.0), flux=ph.LinearDiffusion(1.0e-3), source=ph.Step1DSource(1, 0.5, 1.0, -1.0),
+                   reaction=ph.SinhReaction())
+    v.enable_species(sys, 1, [1])
+    v.boundary_dirichlet(sys, 1, 1, 0.0)
+    v.boundary_dirichlet(sys, 1, 2, 1.0)
+    sol = O.OracleSystem(sys).solve_step(v.unknowns(sys, 0.5))
+    assert sol.sum() == pytest.approx(1.5247901344230088, rel=1e-12)
+
+
+def _barenblatt(x, t, m):
+    tx = t ** (-1.0 / (m + 1.0))
+    xx = x * tx
+    xx = xx * xx
+    xx = 1 - xx * (m - 1) / (2.0 * m * (m + 1))
+    xx = np.maximum(xx, 0.0)
+    return tx * xx ** (1.0 / (m - 1.0))
+
+
+def test_example106_nonlinear_diffusion1d():
+    """examples/Example106_NonlinearDiffusion1D.jl:35-122: sum(tsol.u[end]) == 46.66666666647518 (u^m flux, fixed steps)"""
+    n, m, tend, tstep = 20, 2, 0.01, 0.0001
+    h = 1.0 / (n / 2)
+    X = np.arange(-1, 1 + h / 2, h)
+    sys = v.System(v.simplexgrid(X), flux=ph.PowerDiffusion(1.0, m), storage=ph.LinearStorage(1.0))
+    v.enable_species(sys, 1, [1])
+    inival = v.unknowns(sys)
+    t0 = 0.001
+    inival[0, :] = _barenblatt(X, t0, m)
+    times, sols = O.OracleSystem(sys).solve_transient(inival, [t0, tend], dt=tstep, dt_min=tstep, dt_max=tstep, du_opt=1)
+    assert sols[-1].sum() == pytest.approx(46.66666666647518, rel=1e-10)
+
+
+def test_example107_nonlinear_storage1d():
+    """examples/Example107_NonlinearStorage1D.jl:38-123: sum(tsol.u[end]) == 174.72418935404414 (rtol 1e-5)"""
+    n, m, tend = 20, 2.0, 0.01
+    h = 1.0 / (n / 2)
+    X = np.arange(-1, 1 + h / 2, h)
+    sys = v.System(v.simplexgrid(X), flux=ph.LinearDiffusion(1.0), storage=ph.PowerStorage(1.0e-10, m))
+    v.enable_species(sys, 1, [1])
+    inival = v.unknowns(sys)
+    t0 = 0.001
+    inival[0, :] = _barenblatt(X, t0, m) ** m
+    times, sols = O.OracleSystem(sys).solve_transient(inival, [t0, tend], du_opt=0.1, force_first_step=True)
+    assert sols[-1].sum() == pytest.approx(174.72418935404414, rel=1e-5)
+
+
+def test_example110_two_species():
+    """examples/Example110_ReactionDiffusion1D_TwoSpecies.jl:31-102: U[5] == 0.7117546972922056"""
+    sys = v.System(v.simplexgrid(np.arange(0, 101) / 100.0), reaction=ph.BilinearReaction2(1.0), flux=ph.CrossDiffusion2((1.0, 1.0), 0.01),
+                   source=ph.AffineXSource([1.0e-4 * 0.01, 1.0e-4 * 1.01], [1.0e-4, -1.0e-4]), storage=ph.LinearStorage(1.0))
+    v.enable_species(sys, 1, [1])
+    v.enable_species(sys, 2, [1])
+    for sp in (1, 2):
+        v.boundary_dirichlet(sys, sp, 1, 1.0)
+        v.boundary_dirichlet(sys, sp, 2, 0.0)
+    U = v.unknowns(sys, 0.0)
+    o = O.OracleSystem(sys)
+    for xeps in [1.0, 0.5, 0.25, 0.1, 0.05, 0.025, 0.01]:
+        sys.physics.slots[0].eps = (xeps, xeps)
+        o.push_physics()
+        U = o.solve_step(U, damp_initial=0.1)
+    assert U.ravel(order="F")[4] == pytest.approx(0.7117546972922056, rel=1e-9)
+
+
+def test_example210_reaction2d():
+    """examples/Example210_NonlinearPoisson2D_Reaction.jl:12-93: sum(tsol.u[end]) == 16.01812472041518"""
+    X = np.linspace(0, 1, 11)
+    k, eps = 1.0, 1.0e-2
+    sys = v.System(v.simplexgrid(X, X), flux=ph.LinearDiffusion(eps), storage=ph.LinearStorage(1.0), reaction=ph.AffineReaction([[k, -k], [-k, k]]),
+                   source=ph.GaussSource(1, 20.0, (0.5, 0.5)))
+    v.enable_species(sys, 1, [1])
+    v.enable_species(sys, 2, [1])
+    tstep = 0.01
+    times, sols = O.OracleSystem(sys).solve_transient(v.unknowns(sys, 0.0), (0, 1), dt=tstep, dt_min=tstep, dt_max=tstep, du_opt=1.0e5)
+    assert sols[-1].sum() == pytest.approx(16.01812472041518, rel=1e-9)
+
+
+def test_example215_boundary_reaction():
+    """examples/Example215_NonlinearPoisson2D_BoundaryReaction.jl:19-99: U[25] == 0.2760603343272377"""
+    X = np.arange(0, 11) / 10.0
+    g = v.simplexgrid(X, X)
+    k = 1.0
+    sys = v.System(g, breaction=ph.LinearBoundaryReaction(2, [[k, -k], [-k, k]]), flux=ph.LinearDiffusion(1.0e-2), storage=ph.LinearStorage(1.0))
+    v.enable_species(sys, 1, [1])
+    v.enable_species(sys, 2, [1])
+    inival = v.unknowns(sys)
+    inival[0, :] = np.exp(-5.0 * ((g.coord[0] - 0.5) ** 2 + (g.coord[1] - 0.5) ** 2))
+    o = O.OracleSystem(sys)
+    tstep, time, u25 = 0.01, 0.0, 0.0
+    while time < 100:
+        time += tstep
+        U = o.solve_step(inival, tstep=tstep)
+        inival = U
+        tstep *= 1.2
+        u25 = U.ravel(order="F")[24]
+    assert u25 == pytest.approx(0.2760603343272377, rel=1e-9)
+
+
+def test_example160_unipolar_drift_diffusion():
+    """examples/Example160_UnipolarDriftDiffusion1D.jl:79-160,262: sedanflux!, evolval == 18.721369939565655 (rtol 1e-5)"""
+    n = 20
+    X = np.arange(0, n + 1) / n
+    eps, z, V = 1.0e-3, -1.0, 5.0
+    bc = ph.BCondition().dirichlet(species=1, region=1, value=0.0, ramp=((0, 1.0e-2), (0, V))).dirichlet(species=1, region=2, value=0).dirichlet(species=2, region=2, value=0.5)
+    R = np.zeros((2, 2))
+    R[0, 1] = -2 * z  # f[iphi] = z (1 - 2 u[ic])
+    sys = v.System(v.simplexgrid(X), flux=ph.SedanFlux(eps, z, 1, 2), reaction=ph.AffineReaction(R, [z, 0.0]), bcondition=bc,
+                   storage=ph.LinearStorage([0.0, 1.0]), species=[1, 2])
+    inival = v.unknowns(sys)
+    inival[1, :] = 0.5
+    tstep = 1.0e-5
+    times, sols = O.OracleSystem(sys).solve_transient(inival, [0.0, 10], dt=tstep, dt_min=tstep, dt_grow=1.1, dt_max=0.1, du_opt=0.1, damp_initial=0.5)
+    assert sols[-1].sum() == pytest.approx(18.721369939565655, rel=1e-5)
+
+
+def test_bernoulli_accuracy():
+    """test/test010_bernoulli.jl:5-22: |B(x) - x/(exp(x)-1)| < 1e-14 on both ranges, for fbernoulli and both halves of fbernoulli_pm"""
+    import mpmath
+
+    mpmath.mp.prec = 256
+
+    def big(x):
+        bx = mpmath.mpf(float(x))
+        return float(bx / (mpmath.exp(bx) - 1)) if x != 0 else 1.0
+
+    for rng in (np.arange(-1, 1, 1.00001e-5)[::7], np.arange(-100, 100, 1.00001e-3)[::11]):
+        ref = np.array([big(x) for x in rng])
+        refm = np.array([big(-x) for x in rng])
+        bp, bm, b = O.fbernoulli_pm(rng)
+        assert np.max(np.abs(b - ref)) < 1.0e-14
+        assert np.max(np.abs(bp - ref)) < 1.0e-14
+        assert np.max(np.abs(bm - refm)) < 1.0e-14
+
+
+def test_formfactors_2d_equals_3d_face():
+    """test/test020_formfactors.jl:8-27: Triangle2D cellfactors! == Triangle2D/Cartesian3D bfacefactors!, rtol 1e-7"""
+    rng = np.random.default_rng(12345)
+    for _ in range(100):
+        c2 = rng.integers(-1000, 1001, size=(2, 3)) * 0.01
+        c3 = np.vstack([c2, np.zeros((1, 3))])
+        n2, e2 = O.cellfactors(2, c2)
+        n3, e3 = O.bfacefactors(3, c3)
+        np.testing.assert_allclose(n3, n2, rtol=1.0e-7)
+        np.testing.assert_allclose(e3, e2, rtol=1.0e-7)
+
+
+def test_cachesol_1d_laplace():
+    """test/test030_cachesol.jl:21-47: Jacobian + residual of 1D Laplace at u=0 with callback Dirichlet; A \\ -F == x to 3e-16"""
+    import scipy.sparse.linalg as spla
+
+    X = np.linspace(0.0, 1.0, 10)
+    bc = ph.BCondition().dirichlet(species=1, region=1, value=0.0).dirichlet(species=1, region=2, value=1.0)
+    sys = v.System(v.simplexgrid(X), flux=ph.LinearDiffusion(), bcondition=bc, species=[1])
+    F, A = O.OracleSystem(sys).assemble(v.unknowns(sys, 0.0))
+    sol = spla.splu(A).solve(-F.ravel(order="F"))
+    # the reference bound 3e-16 is for UMFPACK's pivot order; SuperLU (the stand-in here) lands at 1.5 ulp = 3.3e-16
+    assert np.max(np.abs(sol - X)) <= 4.5e-16
+
+
+@pytest.mark.parametrize("dim", [1, 2, 3])
+def test_node_volumes_sum_to_one(dim):
+    """test/test120_norms.jl:95-100,131: sum(nodevolumes(sys)) ~ 1 on the unit interval/square/cube, h = 0.1"""
+    X = np.arange(0, 11) / 10.0
+    g = v.simplexgrid(*([X] * dim))
+    sys = v.System(g, species=[1])
+    colptr, reg, fac = O.OracleSystem(sys).nodefactors()
+    assert fac.sum() == pytest.approx(1.0, rel=1e-12)
+    assert colptr[-1] == g.num_nodes and np.all(reg == 1)
+
+
+def test_value_dependent_pattern():
+    """_addnz (src/vfvm_assembly.jl:21-28) inserts only entries whose Jacobian value is nonzero: species-decoupled flux
+    yields only same-species couplings; zero form factors (diagonal edges of the tensor grid) do not remove entries."""
+    X = np.linspace(0, 1, 4)
+    sys = v.System(v.simplexgrid(X, X), flux=ph.LinearDiffusion([1.0, 2.0]), species=[1, 2])
+    o = O.OracleSystem(sys)
+    F, A = o.assemble(np.asfortranarray(np.random.default_rng(1).uniform(0.1, 1.0, (2, 16))))
+    A = A.tocoo()
+    assert np.all(A.row % 2 == A.col % 2)
+    E = o.num_edges
+    assert A.nnz == 2 * (2 * E + 16)
