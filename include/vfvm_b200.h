@@ -222,6 +222,8 @@ int vfvm_timings(vfvm_handle* h, double* ms_out /* VFVM_NUM_TIMES */);
 int vfvm_launch_count(vfvm_handle* h, int64_t* nlaunches); /* kernels launched by this handle so far */
 int vfvm_stream(vfvm_handle* h, void** cuda_stream);       /* the cudaStream_t all work is enqueued on */
 int vfvm_device_bytes(vfvm_handle* h, int64_t* bytes);
+/* stored Jacobian planes: species couplings kept per off-diagonal block (flux mask) / per diagonal block */
+int vfvm_plane_counts(vfvm_handle* h, int* off_planes, int* diag_planes);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,107 @@
+"""CPU-side checks (no GPU): the C-ABI library loads and exports every symbol include/vfvm_b200.h declares; the host
+mirror rejects unregistered callbacks; grid generator invariants; the product package never touches the oracle."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import vfvm_b200 as v
+from vfvm_b200 import physics as ph
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    txt = open(os.path.join(ROOT, "include", "vfvm_b200.h")).read()
+    return sorted(set(re.findall(r"\b(vfvm_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = C.CDLL(v._lib.LIB_PATH)
+    names = _declared_symbols()
+    assert len(names) >= 40
+    for n in names:
+        assert hasattr(lib, n), f"{n} is declared in include/vfvm_b200.h but not exported"
+    # and the ctypes binding covers exactly the same set
+    bound = set(v._lib.SIGNATURES) | set(v._lib.OTHER)
+    assert bound == set(names), (bound ^ set(names))
+
+
+def test_no_cpu_fallback_without_gpu():
+    """creating a device state must fail loudly when there is no CUDA device (this container has none)"""
+    import subprocess, sys
+    code = ("import sys; sys.path.insert(0, %r); import ctypes as C; import vfvm_b200 as v; L = v._lib.lib(); h = C.c_void_p(); "
+            "rc = L.vfvm_create(0, C.byref(h)); print(rc)" % ROOT)
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env)
+    assert out.stdout.strip() == str(v._lib.ERR_CUDA), out
+    X = np.linspace(0, 1, 4)
+    sys_ = v.System(v.simplexgrid(X, X), flux=ph.LinearDiffusion(), species=[1])
+    code2 = ("import sys; sys.path.insert(0, %r); import numpy as np; import vfvm_b200 as v; from vfvm_b200 import physics as ph; X=np.linspace(0,1,4); "
+             "s=v.System(v.simplexgrid(X,X), flux=ph.LinearDiffusion(), species=[1]); v.SystemState(s)" % ROOT)
+    out = subprocess.run([sys.executable, "-c", code2], capture_output=True, text=True, env=env)
+    assert out.returncode != 0 and "no CPU fallback" in out.stderr
+
+
+def test_unregistered_callback_raises():
+    X = np.linspace(0, 1, 4)
+    g = v.simplexgrid(X, X)
+
+    def flux(f, u, edge, data):  # an arbitrary host closure, as a reference user would write it
+        f[0] = u[0, 0] - u[0, 1]
+
+    with pytest.raises(v.UnregisteredPhysicsError):
+        v.System(g, flux=flux)
+    with pytest.raises(v.UnregisteredPhysicsError):
+        v.System(g, flux=ph.LinearStorage())  # registered, but not a flux
+    with pytest.raises(NotImplementedError):
+        v.System(g, flux=ph.LinearDiffusion(), bflux=ph.LinearDiffusion())
+
+
+def test_product_package_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "voronoifvm.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h", ".sh")):
+                txt = open(os.path.join(dirpath, fn)).read()
+                assert "oracle" not in txt.lower().replace("no cpu oracle", ""), f"{fn} mentions the oracle"
+
+
+@pytest.mark.parametrize("dim,nx", [(1, 7), (2, 5), (3, 4)])
+def test_simplexgrid_counts(dim, nx):
+    X = np.linspace(0, 1, nx)
+    g = v.simplexgrid(*([X] * dim))
+    m = nx - 1
+    assert g.num_nodes == nx**dim
+    assert g.num_cells == {1: m, 2: 2 * m * m, 3: 6 * m**3}[dim]
+    assert g.num_bfaces == {1: 2, 2: 4 * m, 3: 12 * m * m}[dim]
+    assert g.num_bfaceregions == 2 * dim
+    # every cell has positive volume and the volumes add up to 1
+    P = g.coord[:, g.cellnodes]  # (dim, dim+1, C)
+    E = P[:, 1:, :] - P[:, :1, :]
+    vol = np.abs(np.linalg.det(np.moveaxis(E, 2, 0))) / {1: 1, 2: 2, 3: 6}[dim]
+    assert vol.min() > 0 and vol.sum() == pytest.approx(1.0)
+    # E = 3m nx^2 + 3 m^2 nx + m^3 in 3D
+    if dim == 3:
+        pairs = set()
+        for a in range(4):
+            for b in range(a + 1, 4):
+                lo = np.minimum(g.cellnodes[a], g.cellnodes[b]).astype(np.int64)
+                hi = np.maximum(g.cellnodes[a], g.cellnodes[b]).astype(np.int64)
+                pairs.update((lo * g.num_nodes + hi).tolist())
+        assert len(pairs) == 3 * m * nx * nx + 3 * m * m * nx + m**3
+
+
+def test_system_mirror_bookkeeping():
+    X = np.linspace(0, 1, 4)
+    s = v.System(v.simplexgrid(X, X), flux=ph.LinearDiffusion())
+    v.enable_species(s, 2, [1])
+    assert s.num_species == 2 and s.region_species[1, 0] == 1 and s.region_species[0, 0] == 0
+    v.boundary_dirichlet(s, 1, 3, 1.0)
+    assert s.boundary_factors[0, 2] == v.DIRICHLET and s.boundary_values[0, 2] == 1.0
+    v.boundary_robin(s, 2, 1, 0.5, 2.0)
+    assert s.boundary_factors[1, 0] == 0.5 and s.has_legacy_bc()
+    u = v.unknowns(s, 0.5)
+    assert u.shape == (2, 16) and u.flags.f_contiguous and v.num_dof(s) == 32

@@ -1,0 +1,335 @@
+"""GPU parity tests (run with `-m gpu` on the B200 box): the CUDA path, called through the C ABI, against the CPU oracle
+on identical seeded inputs.
+
+Bars (north_star): sparsity pattern and edge/node index maps bit-exact; residual and Jacobian entries <= 1e-12 relative;
+Newton solutions <= 1e-10.
+"""
+import math
+
+import numpy as np
+import pytest
+
+import vfvm_b200 as v
+from vfvm_b200 import physics as ph
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+RTOL_ASM = 1.0e-12  # residual / Jacobian entries, relative
+TOL_NEWTON = 1.0e-10  # Newton solutions, absolute (solutions are O(1))
+
+
+def _grid(dim, nx):
+    X = np.linspace(0, 1, nx)
+    return v.simplexgrid(*([X] * dim))
+
+
+def _rand_u(sys, seed=20261017, lo=0.1, hi=1.0):
+    rng = np.random.default_rng(seed)
+    return np.asfortranarray(rng.uniform(lo, hi, (sys.num_species, sys.grid.num_nodes)))
+
+
+def _compare_assembly(sys, U, UOld=None, time=0.0, tstep=math.inf, embed=0.0):
+    st = v.SystemState(sys)
+    try:
+        F = st.eval_res_jac(U, UOld, time=time, tstep=tstep, embed=embed)
+        A = st.matrix("csc")
+    finally:
+        st.close()
+    Fo, Ao = O.OracleSystem(sys).assemble(U, UOld, time=time, tstep=tstep, embed=embed)
+    # pattern: bit-exact
+    assert A.shape == Ao.shape
+    assert np.array_equal(A.indptr, Ao.indptr), "CSC colptr differs"
+    assert np.array_equal(A.indices, Ao.indices), "CSC rowval differs"
+    # values: 1e-12 relative to the entry; entries that are sums with cancellation (diagonal blocks, residuals) are
+    # allowed 1e-12 of the magnitude of the terms that were summed (sum of |non-penalty entries| of the row)
+    coo = Ao.tocoo()
+    mag = np.where(np.abs(coo.data) < 1e29, np.abs(coo.data), 0.0)
+    termscale = np.bincount(coo.row, weights=mag, minlength=Ao.shape[0])
+    err = np.abs(A.data - Ao.data)
+    bound = RTOL_ASM * np.maximum(np.abs(Ao.data), termscale[coo.row])
+    offdiag_block = (coo.row // sys.num_species) != (coo.col // sys.num_species)
+    assert np.all(err[offdiag_block] <= RTOL_ASM * np.abs(Ao.data[offdiag_block])), "off-diagonal Jacobian entries differ"
+    assert np.all(err <= bound), f"Jacobian mismatch: max abs err {err.max():.3e}"
+    f, fo = F.ravel(order="F"), Fo.ravel(order="F")
+    fbound = RTOL_ASM * np.maximum(np.abs(fo), termscale * max(1.0, np.abs(U).max()) + 1e-300)
+    assert np.all(np.abs(f - fo) <= fbound), f"residual mismatch: max abs err {np.abs(f - fo).max():.3e}"
+    return A, F
+
+
+# ---------------------------------------------------------------------------------------------- geometry (K1, K2)
+@pytest.mark.parametrize("dim,nx", [(1, 33), (2, 17), (3, 9)])
+def test_geometry_index_maps_and_factors(dim, nx):
+    sys = v.System(_grid(dim, nx), flux=ph.LinearDiffusion(), species=[1])
+    st = v.SystemState(sys)
+    o = O.OracleSystem(sys)
+    try:
+        assert st.num_edges == o.num_edges
+        assert np.array_equal(st.edgenodes(), o.edgenodes()), "edge->node map differs"
+        assert np.array_equal(st.celledges(), o.celledges()), "cell->edge map differs"
+        for a, b in ((st.nodefactors(), o.nodefactors()), (st.edgefactors(), o.edgefactors())):
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+            np.testing.assert_allclose(a[2], b[2], rtol=1e-13, atol=1e-18)
+        np.testing.assert_allclose(st.bfacefactors(), o.bfacefactors(), rtol=1e-14)
+        # test/test120_norms.jl:95-100: node volumes of the unit cube sum to 1
+        assert st.nodefactors()[2].sum() == pytest.approx(1.0, rel=1e-12)
+    finally:
+        st.close()
+
+
+def test_geometry_random_tets_and_regions():
+    """distorted 3D grid with three cell regions: factors per (region, node/edge), ragged CSC"""
+    g = _grid(3, 7)
+    rng = np.random.default_rng(7)
+    h = 1.0 / 6
+    interior = np.all((g.coord > 1e-9) & (g.coord < 1 - 1e-9), axis=0)
+    g.coord[:, interior] += rng.uniform(-0.2 * h, 0.2 * h, (3, int(interior.sum())))
+    v.cellmask(g, [0, 0, 0.33], [1, 1, 0.67], 2)
+    v.cellmask(g, [0, 0, 0.66], [1, 1, 1.0], 3)
+    sys = v.System(g, flux=ph.LinearDiffusion(), species=[1])
+    st = v.SystemState(sys)
+    o = O.OracleSystem(sys)
+    try:
+        assert np.array_equal(st.edgenodes(), o.edgenodes())
+        for a, b in ((st.nodefactors(), o.nodefactors()), (st.edgefactors(), o.edgefactors())):
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+            np.testing.assert_allclose(a[2], b[2], rtol=1e-12, atol=1e-16)
+    finally:
+        st.close()
+
+
+@pytest.mark.parametrize("coordsys", ["cyl1", "sph1", "cyl2"])
+def test_geometry_curvilinear(coordsys):
+    X = np.linspace(0.1, 1.3, 25)
+    if coordsys == "cyl1":
+        g = v.circular_symmetric(v.simplexgrid(X))
+    elif coordsys == "sph1":
+        g = v.spherical_symmetric(v.simplexgrid(X))
+    else:
+        g = v.circular_symmetric(v.simplexgrid(X, np.linspace(0, 1, 11)))
+    sys = v.System(g, flux=ph.LinearDiffusion(), species=[1])
+    st = v.SystemState(sys)
+    o = O.OracleSystem(sys)
+    try:
+        np.testing.assert_allclose(st.nodefactors()[2], o.nodefactors()[2], rtol=1e-13)
+        np.testing.assert_allclose(st.edgefactors()[2], o.edgefactors()[2], rtol=1e-13, atol=1e-16)
+        np.testing.assert_allclose(st.bfacefactors(), o.bfacefactors(), rtol=1e-13)
+    finally:
+        st.close()
+
+
+# ---------------------------------------------------------------------------------------------- assembly (K3-K6)
+@pytest.mark.parametrize("dim,nx", [(1, 50), (2, 24), (3, 12)])
+def test_assembly_laplace(dim, nx):
+    """Example201 / Example301 physics: linear diffusion, legacy Dirichlet"""
+    sys = v.System(_grid(dim, nx), flux=ph.LinearDiffusion(), source=ph.XSinYExpZSource(1, 5.0) if dim == 3 else None)
+    v.enable_species(sys, 1, [1])
+    v.boundary_dirichlet(sys, 1, 1 if dim < 3 else 5, 0.0)
+    v.boundary_dirichlet(sys, 1, 2 if dim == 1 else (3 if dim == 2 else 6), 1.0)
+    _compare_assembly(sys, _rand_u(sys))
+
+
+def test_assembly_example207_transient():
+    """nonlinear diffusion + reaction + source + storage, implicit Euler step (Example207 physics)"""
+    X = np.linspace(0, 1, 41)
+    sys = v.System(v.simplexgrid(X, X), flux=ph.PowerDiffusion(1.0e-2, 2), reaction=ph.PowerReaction(1.0, 2.0), source=ph.GaussSource(1, 20.0, (0.5, 0.5)),
+                   storage=ph.LinearStorage(1.0))
+    v.enable_species(sys, 1, [1])
+    v.boundary_dirichlet(sys, 1, 2, 0.1)
+    v.boundary_dirichlet(sys, 1, 4, 0.1)
+    U = _rand_u(sys)
+    _compare_assembly(sys, U, _rand_u(sys, seed=5), tstep=0.01)
+    _compare_assembly(sys, U)  # stationary: storage entries are not inserted (value-dependent pattern)
+
+
+def test_assembly_two_species_coupled():
+    """Example110 physics: coupled flux, bilinear reaction, x-dependent source, two species"""
+    sys = v.System(v.simplexgrid(np.linspace(0, 1, 101)), reaction=ph.BilinearReaction2(1.0), flux=ph.CrossDiffusion2((0.25, 0.5), 0.01),
+                   source=ph.AffineXSource([1.0e-4 * 0.01, 1.0e-4 * 1.01], [1.0e-4, -1.0e-4]), storage=ph.LinearStorage(1.0))
+    v.enable_species(sys, 1, [1])
+    v.enable_species(sys, 2, [1])
+    for sp in (1, 2):
+        v.boundary_dirichlet(sys, sp, 1, 1.0)
+        v.boundary_dirichlet(sys, sp, 2, 0.0)
+    _compare_assembly(sys, _rand_u(sys), _rand_u(sys, seed=3), tstep=0.1)
+
+
+def test_assembly_unipolar_sedan_callback_bc():
+    """Example160: sedanflux! with fbernoulli_pm + log1p, affine reaction, callback Dirichlet with ramp"""
+    n = 40
+    X = np.arange(0, n + 1) / n
+    eps, z, V = 1.0e-3, -1.0, 5.0
+    bc = ph.BCondition().dirichlet(species=1, region=1, value=0.0, ramp=((0, 1.0e-2), (0, V))).dirichlet(species=1, region=2, value=0).dirichlet(species=2, region=2, value=0.5)
+    R = np.zeros((2, 2))
+    R[0, 1] = -2 * z
+    for flux in (ph.SedanFlux(eps, z, 1, 2), ph.UnipolarSGFlux(eps, 1, 2)):
+        sys = v.System(v.simplexgrid(X), flux=flux, reaction=ph.AffineReaction(R, [z, 0.0]), bcondition=bc, storage=ph.LinearStorage([0.0, 1.0]), species=[1, 2])
+        U = _rand_u(sys, lo=0.05, hi=0.9)
+        U[0, :] *= 8.0  # potentials large enough to exercise all Bernoulli branches
+        _compare_assembly(sys, U, _rand_u(sys, seed=9, lo=0.05, hi=0.9), time=0.004, tstep=1.0e-3)
+
+
+def test_assembly_bipolar_drift_diffusion_3d():
+    """Example161 physics (3 species, SG flux with exp densities, recombination, doping per cell region) on a 3D grid"""
+    g = _grid(3, 8)
+    v.cellmask(g, [0, 0, 0.3], [1, 1, 0.72], 2)
+    v.cellmask(g, [0, 0, 0.7], [1, 1, 1.0], 3)
+    bc = ph.BCondition()
+    for sp, val in ((1, 0.0), (2, 0.0), (3, 0.5 + math.asinh(10.0 / (2 * math.sqrt(math.exp(-1.0)))))):
+        bc.dirichlet(species=sp, region=5, value=val)
+    for sp, val in ((1, 0.3), (2, 0.3), (3, 0.5 + math.asinh(-10.0 / (2 * math.sqrt(math.exp(-1.0)))) + 0.3)):
+        bc.dirichlet(species=sp, region=6, value=val)
+    sys = v.System(g, flux=ph.BipolarSGFlux(), reaction=ph.BipolarReaction([10.0, 0.0, -10.0]), storage=ph.BipolarStorage(), bcondition=bc, species=[1, 2, 3])
+    U = _rand_u(sys, lo=-0.5, hi=0.5)
+    U[2, :] = np.linspace(3.0, -3.0, g.num_nodes)
+    _compare_assembly(sys, U, _rand_u(sys, seed=2, lo=-0.5, hi=0.5), tstep=1.0e-2)
+    _compare_assembly(sys, U)
+
+
+@pytest.mark.parametrize("ns", [4, 5, 10])
+def test_assembly_many_species_decoupled(ns):
+    """Example410 scaled to 3D: ns decoupled species -> only same-species couplings in the pattern"""
+    sys = v.System(_grid(3, 7), flux=ph.LinearDiffusion(np.arange(1, ns + 1) * 0.5), storage=ph.LinearStorage(1.0))
+    for i in range(1, ns + 1):
+        v.enable_species(sys, i, [1])
+        v.boundary_dirichlet(sys, i, 5, 0)
+        v.boundary_dirichlet(sys, i, 6, 1)
+    A, F = _compare_assembly(sys, _rand_u(sys), _rand_u(sys, seed=4), tstep=0.1)
+    coo = A.tocoo()
+    assert np.all(coo.row % ns == coo.col % ns)
+
+
+def test_assembly_boundary_reaction_and_robin():
+    """Example215 boundary reaction (off-diagonal species coupling only at boundary nodes of region 2) + Robin/Neumann entries"""
+    X = np.arange(0, 11) / 10.0
+    k = 1.0
+    bc = ph.BCondition(ph.LinearBoundaryReaction(2, [[k, -k], [-k, k]])).robin(species=1, region=4, factor=2.0, value=0.5).neumann(species=2, region=3, value=0.25)
+    sys = v.System(v.simplexgrid(X, X), bcondition=bc, flux=ph.LinearDiffusion(1.0e-2), storage=ph.LinearStorage(1.0), species=[1, 2])
+    _compare_assembly(sys, _rand_u(sys), _rand_u(sys, seed=8), tstep=0.01)
+
+
+def test_assembly_nan_is_reported():
+    """src/vfvm_assembly.jl:10-12: a NaN Jacobian value is an error (AssemblyError), not a silent result"""
+    X = np.linspace(0, 1, 9)
+    sys = v.System(v.simplexgrid(X, X), flux=ph.PowerDiffusion(1.0, 0.5), species=[1])  # sqrt of a negative unknown
+    st = v.SystemState(sys)
+    try:
+        U = _rand_u(sys)
+        U[0, 10] = -1.0
+        with pytest.raises(v._lib.VfvmError) as ei:
+            st.eval_res_jac(U)
+        assert ei.value.code == v._lib.ERR_NAN
+        with pytest.raises(O.AssemblyError):
+            O.OracleSystem(sys).assemble(U)
+    finally:
+        st.close()
+
+
+def test_assembly_is_deterministic():
+    sys = v.System(_grid(3, 10), flux=ph.PowerDiffusion(1.0, 2.0), reaction=ph.SinhReaction(0.1), species=[1])
+    st = v.SystemState(sys)
+    try:
+        U = _rand_u(sys)
+        F1 = st.eval_res_jac(U).copy()
+        A1 = st.matrix("csr").data.copy()
+        F2 = st.eval_res_jac(U)
+        A2 = st.matrix("csr").data
+        assert np.array_equal(F1, F2) and np.array_equal(A1, A2)  # no atomics, fixed summation order
+    finally:
+        st.close()
+
+
+# ---------------------------------------------------------------------------------------------- linear algebra (K8-K11)
+def test_spmv_matches_scipy():
+    sys = v.System(_grid(3, 9), flux=ph.CrossDiffusion2((1.0, 2.0), 0.1), reaction=ph.BilinearReaction2(0.5), species=[1, 2])
+    st = v.SystemState(sys)
+    try:
+        st.eval_res_jac(_rand_u(sys))
+        A = st.matrix("csr")
+        x = np.random.default_rng(1).standard_normal(A.shape[1])
+        y = st.spmv(x)
+        np.testing.assert_allclose(y, A @ x, rtol=1e-13, atol=1e-13 * np.abs(A @ x).max())
+    finally:
+        st.close()
+
+
+@pytest.mark.parametrize("method", ["default", "bicgstab_jacobi", "cg_jacobi", "bicgstab_block"])
+def test_newton_example301(method):
+    """Example301: solution[43] known answer, and agreement with the oracle's direct solve"""
+    X = np.linspace(0, 1, 6)
+    sys = v.System(v.simplexgrid(X, X, X), flux=ph.LinearDiffusion(), source=ph.XSinYExpZSource(1, 5.0))
+    v.enable_species(sys, 1, [1])
+    v.boundary_dirichlet(sys, 1, 5, 0.0)
+    v.boundary_dirichlet(sys, 1, 6, 0.0)
+    ml = {"default": None, "bicgstab_jacobi": v.KrylovJL_BICGSTAB(precs=v.JacobiPreconBuilder()), "cg_jacobi": v.KrylovJL_CG(precs=v.JacobiPreconBuilder()),
+          "bicgstab_block": v.KrylovJL_BICGSTAB(precs=v.BlockPreconBuilder())}[method]
+    sol = v.solve(sys, inival=0.0, method_linear=ml, reltol_linear=1e-13, abstol_linear=0.0, maxiters_linear=2000)
+    ref = O.OracleSystem(sys).solve_step(v.unknowns(sys))
+    assert np.max(np.abs(sol - ref)) < TOL_NEWTON
+    assert sol.ravel(order="F")[42] == pytest.approx(0.012234524449380824, rel=1e-9)
+
+
+def test_newton_example207_time_steps():
+    """Example207: 100 implicit Euler steps with a reused device state; U[15] known answer"""
+    X = np.linspace(0, 1, 11)
+    sys = v.System(v.simplexgrid(X, X), flux=ph.PowerDiffusion(1.0e-2, 2), reaction=ph.PowerReaction(1.0, 2.0), source=ph.GaussSource(1, 20.0, (0.5, 0.5)),
+                   storage=ph.LinearStorage(1.0))
+    v.enable_species(sys, 1, [1])
+    v.boundary_dirichlet(sys, 1, 2, 0.1)
+    v.boundary_dirichlet(sys, 1, 4, 0.1)
+    st = v.SystemState(sys)
+    o = O.OracleSystem(sys)
+    try:
+        u = v.unknowns(sys, 0.5)
+        uo = u.copy()
+        t, tstep = 0.0, 0.01
+        while t < 1.0:
+            t += tstep
+            u = v.solve(sys, state=st, inival=u, tstep=tstep)
+            uo = o.solve_step(uo, tstep=tstep)
+        assert np.max(np.abs(u - uo)) < TOL_NEWTON
+        assert u.ravel(order="F")[14] == pytest.approx(0.3554284760906605, rel=1e-9)
+    finally:
+        st.close()
+
+
+def test_transient_example160():
+    """Example160 evolution through the device transient driver: evolval 18.721369939565655 (rtol 1e-5)"""
+    n = 20
+    X = np.arange(0, n + 1) / n
+    eps, z, V = 1.0e-3, -1.0, 5.0
+    bc = ph.BCondition().dirichlet(species=1, region=1, value=0.0, ramp=((0, 1.0e-2), (0, V))).dirichlet(species=1, region=2, value=0).dirichlet(species=2, region=2, value=0.5)
+    R = np.zeros((2, 2))
+    R[0, 1] = -2 * z
+    sys = v.System(v.simplexgrid(X), flux=ph.SedanFlux(eps, z, 1, 2), reaction=ph.AffineReaction(R, [z, 0.0]), bcondition=bc, storage=ph.LinearStorage([0.0, 1.0]),
+                   species=[1, 2])
+    inival = v.unknowns(sys)
+    inival[1, :] = 0.5
+    tstep = 1.0e-5
+    control = v.SolverControl(Δt_min=tstep, Δt=tstep, Δt_grow=1.1, Δt_max=0.1, Δu_opt=0.1, damp_initial=0.5)
+    tsol = v.solve(sys, inival=inival, times=[0.0, 10], control=control)
+    assert tsol.u[-1].sum() == pytest.approx(18.721369939565655, rel=1e-5)
+
+
+def test_newton_many_species_410():
+    """Example410 with 10 species: norm(sol) = sqrt(10 * 3.85)"""
+    sys = v.System(v.simplexgrid(np.linspace(0, 1, 11)), flux=ph.LinearDiffusion())
+    for i in range(1, 11):
+        v.enable_species(sys, i, [1])
+        v.boundary_dirichlet(sys, i, 1, 0)
+        v.boundary_dirichlet(sys, i, 2, 1)
+    sol = v.solve(sys, inival=0.0)
+    assert np.linalg.norm(sol) == pytest.approx(math.sqrt(10 * 3.85), rel=1e-10)
+
+
+def test_unregistered_physics_id_is_an_error():
+    import ctypes as C
+
+    sys = v.System(_grid(2, 5), flux=ph.LinearDiffusion(), species=[1])
+    st = v.SystemState(sys)
+    try:
+        p = np.zeros(1)
+        rc = st.L.vfvm_set_physics(st.h, 0, 99, v._lib.dptr(p), 1)
+        assert rc == v._lib.ERR_UNREGISTERED
+    finally:
+        st.close()

@@ -10,3 +10,8 @@ from .physics import Physics, BCondition, UnregisteredPhysicsError  # noqa: F401
 from .system import (System, enable_species, boundary_dirichlet, boundary_neumann, boundary_robin, unknowns, num_dof,  # noqa: F401
                      DIRICHLET)
 from .system import physics as set_physics  # noqa: F401
+from .state import SystemState  # noqa: F401,E402
+from .solver import (SolverControl, NewtonSolverHistory, TransientSolution, solve, solve_state, solve_step, solve_transient,  # noqa: F401,E402
+                     evaluate_residual_and_jacobian, fixed_timesteps, ConvergenceError, AssemblyError, LinearSolverError, EmbeddingError,
+                     KrylovJL_BICGSTAB, KrylovJL_CG, KrylovJL_GMRES, JacobiPreconBuilder, BlockPreconBuilder, ILUZeroPreconBuilder,
+                     DeviceDirectLike)

@@ -1,0 +1,471 @@
+// K3: sparsity pattern + maps.  Replaces what rawupdateindex!/flush! of ExtendableSparse build implicitly during
+// the first assembly (src/vfvm_assembly.jl:26, src/vfvm_solver.jl:242).
+//
+// Device layout ("DBSR", diagonal + off-diagonal block planes):
+//   rowptr[Nown+1], colidx[nnz_off]   off-diagonal block CSR of the node graph (columns sorted, no diagonal)
+//   offval[cF][nnz_off]               one plane per (i,j) of the flux species-coupling mask
+//   diagval[cD][Nown]                 one plane per (i,j) of the diagonal-block mask
+//   nzfac[nnz_off]                    edge form factor per off-diagonal block (single cell region) -- the row-tile
+//                                     kernel streams (colidx, nzfac) and writes offval fully coalesced, no scatter map
+// The scalar CSR/CSC pattern the reference would hold (value-dependent through _addnz, src/vfvm_assembly.jl:21-28)
+// is derived from the block pattern and the per-physics coupling masks by the getters below.
+#include <algorithm>
+#include <cub/cub.cuh>
+
+#include "vfvm_internal.h"
+
+namespace {
+
+__global__ void k_dir_keys(int64_t E, int64_t Nown, const int32_t* __restrict__ edgenodes, uint64_t* __restrict__ keys, int32_t* __restrict__ vals,
+                           unsigned long long* __restrict__ count) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    const uint64_t hi = (uint32_t)edgenodes[2 * e], lo = (uint32_t)edgenodes[2 * e + 1];
+    int c = 0;
+    if ((int64_t)hi < Nown) {
+        keys[2 * e] = (hi << 32) | lo;
+        c++;
+    } else keys[2 * e] = ~0ull;
+    if ((int64_t)lo < Nown) {
+        keys[2 * e + 1] = (lo << 32) | hi;
+        c++;
+    } else keys[2 * e + 1] = ~0ull;
+    vals[2 * e] = (int32_t)e;
+    vals[2 * e + 1] = (int32_t)e;
+    if (c) atomicAdd(count, (unsigned long long)c);
+}
+
+__global__ void k_rowptr(int64_t nrows, int64_t nkeys, const uint64_t* __restrict__ keys, int32_t* __restrict__ rowptr) {
+    const int64_t K = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (K > nrows) return;
+    int64_t lo = 0, hi = nkeys;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if ((int64_t)(keys[mid] >> 32) < K) lo = mid + 1;
+        else hi = mid;
+    }
+    rowptr[K] = (int32_t)lo;
+}
+
+__global__ void k_cols(int64_t nnz, const uint64_t* __restrict__ keys, const int32_t* __restrict__ vals, const double* __restrict__ ef_fac,
+                       int single_region, int32_t* __restrict__ colidx, int32_t* __restrict__ nz_edge, double* __restrict__ nzfac) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nnz) return;
+    colidx[k] = (int32_t)(keys[k] & 0xffffffffu);
+    nz_edge[k] = vals[k];
+    if (single_region) nzfac[k] = ef_fac[vals[k]];
+}
+
+__global__ void k_upos(int64_t nrows, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, int32_t* __restrict__ upos) {
+    const int64_t K = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (K >= nrows) return;
+    int32_t k = rowptr[K];
+    const int32_t ke = rowptr[K + 1];
+    while (k < ke && colidx[k] < K) k++;
+    upos[K] = k;
+}
+
+}  // namespace
+
+// species-coupling masks of the registered physics; a coefficient that is exactly zero removes the coupling because
+// the reference never inserts Jacobian entries whose value is exactly zero
+int vfvm_physics_masks(vfvm_handle* h) {
+    const int n = h->n;
+    Masks& m = h->masks;
+    memset(&m, 0, sizeof(m));
+    const PhysicsDev& ph = h->phys;
+    auto P = [&](int slot) { return ph.params + ph.slot[slot].off; };
+    auto full = [&](uint64_t* mk) {
+        for (int i = 0; i < n * n; i++) mask_set(mk, i);
+    };
+    {
+        const double* p = P(VFVM_SLOT_FLUX);
+        switch (ph.slot[VFVM_SLOT_FLUX].id) {
+            case VFVM_NONE: break;
+            case VFVM_FLUX_DIFFUSION:
+            case VFVM_FLUX_POWDIFF:
+                for (int i = 0; i < n; i++)
+                    if (p[i] != 0.0) mask_set(m.flux, i * n + i);
+                break;
+            case VFVM_FLUX_CROSSDIFF2: full(m.flux); break;
+            case VFVM_FLUX_SG_UNIPOLAR:
+            case VFVM_FLUX_SEDAN: {
+                const bool sedan = ph.slot[VFVM_SLOT_FLUX].id == VFVM_FLUX_SEDAN;
+                const int iphi = (int)p[sedan ? 2 : 1], ic = (int)p[sedan ? 3 : 2];
+                mask_set(m.flux, iphi * n + iphi);
+                mask_set(m.flux, ic * n + iphi);
+                mask_set(m.flux, ic * n + ic);
+                break;
+            }
+            case VFVM_FLUX_SG_BIPOLAR:
+                mask_set(m.flux, 2 * n + 2);
+                mask_set(m.flux, 0 * n + 0);
+                mask_set(m.flux, 0 * n + 2);
+                mask_set(m.flux, 1 * n + 1);
+                mask_set(m.flux, 1 * n + 2);
+                break;
+            default: return VFVM_ERR_UNREGISTERED;
+        }
+    }
+    {
+        const double* p = P(VFVM_SLOT_REACTION);
+        switch (ph.slot[VFVM_SLOT_REACTION].id) {
+            case VFVM_NONE: break;
+            case VFVM_REACTION_POW:
+            case VFVM_REACTION_SINH:
+                for (int i = 0; i < n; i++)
+                    if (p[i] != 0.0) mask_set(m.reaction, i * n + i);
+                break;
+            case VFVM_REACTION_AFFINE:
+                for (int i = 0; i < n * n; i++)
+                    if (p[i] != 0.0) mask_set(m.reaction, i);
+                break;
+            case VFVM_REACTION_BILINEAR2:
+            case VFVM_REACTION_BIPOLAR: full(m.reaction); break;
+            default: return VFVM_ERR_UNREGISTERED;
+        }
+    }
+    {
+        const double* p = P(VFVM_SLOT_STORAGE);
+        switch (ph.slot[VFVM_SLOT_STORAGE].id) {
+            case VFVM_NONE: break;
+            case VFVM_STORAGE_LINEAR:
+                for (int i = 0; i < n; i++)
+                    if (p[i] != 0.0) mask_set(m.storage, i * n + i);
+                break;
+            case VFVM_STORAGE_POW:
+                for (int i = 0; i < n; i++) mask_set(m.storage, i * n + i);
+                break;
+            case VFVM_STORAGE_BIPOLAR:
+                mask_set(m.storage, 0 * n + 0);
+                mask_set(m.storage, 0 * n + 2);
+                mask_set(m.storage, 1 * n + 1);
+                mask_set(m.storage, 1 * n + 2);
+                break;
+            default: return VFVM_ERR_UNREGISTERED;
+        }
+    }
+    switch (ph.slot[VFVM_SLOT_SOURCE].id) {
+        case VFVM_NONE:
+        case VFVM_SOURCE_CONST:
+        case VFVM_SOURCE_GAUSS:
+        case VFVM_SOURCE_XSINYEXPZ:
+        case VFVM_SOURCE_STEP1D:
+        case VFVM_SOURCE_AFFINE_X:
+        case VFVM_SOURCE_NODAL: break;
+        default: return VFVM_ERR_UNREGISTERED;
+    }
+    switch (ph.slot[VFVM_SLOT_BREACTION].id) {
+        case VFVM_NONE: break;
+        case VFVM_BREACTION_LINEAR: {
+            const double* p = P(VFVM_SLOT_BREACTION);
+            for (int i = 0; i < n * n; i++)
+                if (p[1 + i] != 0.0) mask_set(m.boundary, i);
+            break;
+        }
+        default: return VFVM_ERR_UNREGISTERED;
+    }
+    for (int e = 0; e < ph.nbc; e++) {
+        const vfvm_bc_entry& b = ph.bc[e];
+        if (b.kind == VFVM_BC_DIRICHLET || (b.kind == VFVM_BC_ROBIN && b.factor != 0.0)) mask_set(m.boundary, b.species * n + b.species);
+    }
+    if (ph.has_legacy_bc)
+        for (int r = 0; r < ph.nbregions; r++)
+            for (int i = 0; i < n; i++)
+                if (ph.bfactors[r * n + i] != 0.0) mask_set(m.boundary, i * n + i);
+    return VFVM_OK;
+}
+
+// extra diagonal-block bits a boundary node in boundary region `breg` receives (for the exported scalar pattern)
+static void boundary_bits(const vfvm_handle* h, int breg, uint64_t* out) {
+    const int n = h->n;
+    const PhysicsDev& ph = h->phys;
+    if (ph.slot[VFVM_SLOT_BREACTION].id == VFVM_BREACTION_LINEAR) {
+        const double* p = ph.params + ph.slot[VFVM_SLOT_BREACTION].off;
+        if ((int)p[0] == breg)
+            for (int i = 0; i < n * n; i++)
+                if (p[1 + i] != 0.0) mask_set(out, i);
+    }
+    for (int e = 0; e < ph.nbc; e++) {
+        const vfvm_bc_entry& b = ph.bc[e];
+        if (b.region != 0 && b.region != breg) continue;
+        if (b.kind == VFVM_BC_DIRICHLET || (b.kind == VFVM_BC_ROBIN && b.factor != 0.0)) mask_set(out, b.species * n + b.species);
+    }
+    if (ph.has_legacy_bc && breg >= 1 && breg <= ph.nbregions)
+        for (int i = 0; i < n; i++)
+            if (ph.bfactors[(breg - 1) * n + i] != 0.0) mask_set(out, i * n + i);
+}
+
+int vfvm_pattern_build(vfvm_handle* h) {
+    const int64_t E = h->E, Nown = h->Nown;
+    const int n = h->n;
+    const int B = 256;
+    cudaStream_t s = h->stream;
+    int rc = vfvm_physics_masks(h);
+    if (rc) return vfvm_fail(h, rc, "physics id is not in the registered device library");
+
+    // ---- planes
+    h->cF = h->cD = 0;
+    for (int b = 0; b < n * n; b++) {
+        h->idxF[b] = h->idxD[b] = -1;
+        if (mask_get(h->masks.flux, b)) {
+            h->idxF[b] = h->cF;
+            h->planeF[h->cF++] = b;
+        }
+        const bool diag = (b / n) == (b % n);
+        if (diag || mask_get(h->masks.flux, b) || mask_get(h->masks.reaction, b) || mask_get(h->masks.storage, b) || mask_get(h->masks.boundary, b)) {
+            h->idxD[b] = h->cD;
+            h->planeD[h->cD++] = b;
+        }
+    }
+
+    // ---- directed node graph
+    DevBuf<uint64_t> keys;
+    DevBuf<int32_t> vals;
+    DevBuf<unsigned long long> count;
+    keys.tally = vals.tally = &h->bytes;
+    keys.alloc(2 * E);
+    vals.alloc(2 * E);
+    count.alloc(1);
+    CK(cudaMemsetAsync(count.p, 0, 8, s));
+    k_dir_keys<<<cdiv(E, B), B, 0, s>>>(E, Nown, h->edgenodes.p, keys.p, vals.p, count.p);
+    h->launches++;
+    {
+        DevBuf<uint64_t> keys2;
+        DevBuf<int32_t> vals2;
+        keys2.tally = vals2.tally = &h->bytes;
+        keys2.alloc(2 * E);
+        vals2.alloc(2 * E);
+        cub::DoubleBuffer<uint64_t> dk(keys.p, keys2.p);
+        cub::DoubleBuffer<int32_t> dv(vals.p, vals2.p);
+        size_t tmp = 0;
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, dk, dv, 2 * E, 0, 64, s));
+        DevBuf<char> t;
+        t.alloc(tmp);
+        CK(cub::DeviceRadixSort::SortPairs(t.p, tmp, dk, dv, 2 * E, 0, 64, s));
+        CK(cudaStreamSynchronize(s));
+        if (dk.Current() != keys.p) std::swap(keys.p, keys2.p);
+        if (dv.Current() != vals.p) std::swap(vals.p, vals2.p);
+    }
+    unsigned long long cnt = 0;
+    CK(cudaMemcpy(&cnt, count.p, 8, cudaMemcpyDeviceToHost));
+    h->nnz_off = (int64_t)cnt;
+    if (h->nnz_off >= ((int64_t)1 << 31)) throw std::string("pattern too large for 32-bit block indices");
+    h->rowptr.alloc(Nown + 1);
+    h->colidx.alloc(h->nnz_off);
+    h->nz_edge.alloc(h->nnz_off);
+    if (h->single_region) h->nzfac.alloc(h->nnz_off);
+    k_rowptr<<<cdiv(Nown + 1, B), B, 0, s>>>(Nown, h->nnz_off, keys.p, h->rowptr.p);
+    h->launches++;
+    if (h->nnz_off) {
+        k_cols<<<cdiv(h->nnz_off, B), B, 0, s>>>(h->nnz_off, keys.p, vals.p, h->ef_fac.p, h->single_region ? 1 : 0, h->colidx.p, h->nz_edge.p, h->nzfac.p);
+        h->launches++;
+    }
+    h->upos.alloc(Nown);
+    k_upos<<<cdiv(Nown, B), B, 0, s>>>(Nown, h->rowptr.p, h->colidx.p, h->upos.p);
+    h->launches++;
+    keys.release();
+    vals.release();
+
+    // ---- row tiles for the streaming kernels (host, one-off)
+    std::vector<int32_t> rp = h->rowptr.to_host(s);
+    {
+        const int T = h->tile_nnz, RMAX = 256;
+        std::vector<int32_t> tr;
+        tr.push_back(0);
+        int64_t r = 0;
+        while (r < Nown) {
+            int64_t r1 = r + 1;  // a tile holds at least one row (rows longer than T are handled by the in-kernel loop)
+            while (r1 < Nown && r1 - r < RMAX && rp[r1 + 1] - rp[r] <= T) r1++;
+            tr.push_back((int32_t)r1);
+            r = r1;
+        }
+        h->ntiles = (int)tr.size() - 1;
+        h->tile_row.upload(tr.data(), tr.size(), s);
+    }
+
+    // ---- boundary nodes: node -> (bface, local node) in ascending bface order (the reference's loop order)
+    {
+        std::vector<int32_t> bfn = h->bfacenodes.to_host(s), bfr = h->bfaceregions.to_host(s);
+        const int dim = h->dim;
+        std::vector<std::pair<int32_t, int32_t>> items;
+        items.reserve(bfn.size());
+        for (int64_t i = 0; i < (int64_t)bfn.size(); i++)
+            if (bfn[i] < Nown) items.emplace_back(bfn[i], (int32_t)i);
+        std::stable_sort(items.begin(), items.end(), [](auto& a, auto& b) { return a.first < b.first; });
+        std::vector<int32_t> node, ptr, bface, local;
+        std::vector<uint8_t> bm;
+        for (size_t i = 0; i < items.size(); i++) {
+            if (i == 0 || items[i].first != items[i - 1].first) {
+                node.push_back(items[i].first);
+                ptr.push_back((int32_t)i);
+            }
+            bface.push_back(items[i].second / dim);
+            local.push_back(items[i].second % dim);
+        }
+        ptr.push_back((int32_t)items.size());
+        h->nbnodes = (int64_t)node.size();
+        h->nbitems = (int64_t)items.size();
+        h->bn_node.upload(node.data(), node.size(), s);
+        h->bn_ptr.upload(ptr.data(), ptr.size(), s);
+        h->bn_bface.upload(bface.data(), bface.size(), s);
+        h->bn_local.upload(local.data(), local.size(), s);
+        // per boundary node: diag bits contributed by boundary terms
+        h->bnode_mask_host.assign((size_t)h->nbnodes * 16, 0);
+        for (int64_t b = 0; b < h->nbnodes; b++) {
+            uint64_t bits[2] = {0, 0};
+            for (int32_t q = ptr[b]; q < ptr[b + 1]; q++) boundary_bits(h, bfr[bface[q]], bits);
+            memcpy(&h->bnode_mask_host[(size_t)b * 16], bits, 16);
+        }
+        CK(cudaStreamSynchronize(s));
+    }
+
+    // ---- values + vectors
+    h->offval.alloc((size_t)std::max(1, h->cF) * h->nnz_off);
+    h->diagval.alloc((size_t)h->cD * Nown);
+    for (int v = 0; v < 4; v++) {
+        h->vec[v].alloc((size_t)n * h->N);
+        CK(cudaMemsetAsync(h->vec[v].p, 0, sizeof(double) * n * h->N, s));
+    }
+    CK(cudaMemsetAsync(h->offval.p, 0, sizeof(double) * h->offval.n, s));
+    CK(cudaMemsetAsync(h->diagval.p, 0, sizeof(double) * h->diagval.n, s));
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    h->seen_transient = false;
+    h->precon_valid = false;
+    h->have_pattern = true;
+    return VFVM_OK;
+}
+
+// ---- scalar pattern / value export (host side; parity + interop, not on the hot path) -----------------------------
+struct ScalarPattern {
+    std::vector<int64_t> rowptr, colidx;
+    std::vector<int64_t> src;  // >= 0: offval index (plane*nnz_off + k) ; < 0: -(1 + diag index (plane*Nown + K))
+};
+
+static void build_scalar(vfvm_handle* h, ScalarPattern& sp) {
+    const int n = h->n;
+    const int64_t Nown = h->Nown;
+    std::vector<int32_t> rp = h->rowptr.to_host(h->stream), ci = h->colidx.to_host(h->stream), bn = h->bn_node.to_host(h->stream);
+    std::vector<int64_t> bnode_of(Nown, -1);
+    for (size_t b = 0; b < bn.size(); b++) bnode_of[bn[b]] = (int64_t)b;
+    sp.rowptr.assign((size_t)Nown * n + 1, 0);
+    sp.colidx.clear();
+    sp.src.clear();
+    for (int64_t K = 0; K < Nown; K++) {
+        uint64_t dm[2] = {h->masks.flux[0] | h->masks.reaction[0], h->masks.flux[1] | h->masks.reaction[1]};
+        if (h->seen_transient) {
+            dm[0] |= h->masks.storage[0];
+            dm[1] |= h->masks.storage[1];
+        }
+        if (bnode_of[K] >= 0) {
+            uint64_t bits[2];
+            memcpy(bits, &h->bnode_mask_host[(size_t)bnode_of[K] * 16], 16);
+            dm[0] |= bits[0];
+            dm[1] |= bits[1];
+        }
+        for (int i = 0; i < n; i++) {
+            bool diag_done = false;
+            auto emit_diag = [&]() {
+                for (int j = 0; j < n; j++)
+                    if (mask_get(dm, i * n + j)) {
+                        sp.colidx.push_back(K * n + j);
+                        sp.src.push_back(-(1 + (int64_t)h->idxD[i * n + j] * Nown + K));
+                    }
+                diag_done = true;
+            };
+            for (int32_t k = rp[K]; k < rp[K + 1]; k++) {
+                const int64_t L = ci[k];
+                if (!diag_done && L > K) emit_diag();
+                for (int j = 0; j < n; j++)
+                    if (mask_get(h->masks.flux, i * n + j)) {
+                        sp.colidx.push_back(L * n + j);
+                        sp.src.push_back((int64_t)h->idxF[i * n + j] * h->nnz_off + k);
+                    }
+            }
+            if (!diag_done) emit_diag();
+            sp.rowptr[K * n + i + 1] = (int64_t)sp.colidx.size();
+        }
+    }
+}
+
+static int need_pattern(vfvm_handle* h) {
+    if (!h || !h->have_pattern) return vfvm_fail(h, VFVM_ERR_STATE, "vfvm_build_pattern has not been called");
+    return 0;
+}
+
+extern "C" int vfvm_pattern_size(vfvm_handle* h, int64_t* nrows, int64_t* nnz) {
+    if (int rc = need_pattern(h)) return rc;
+    VFVM_TRY(h, {
+        ScalarPattern sp;
+        build_scalar(h, sp);
+        *nrows = h->Nown * h->n;
+        *nnz = (int64_t)sp.colidx.size();
+    })
+    return VFVM_OK;
+}
+
+extern "C" int vfvm_get_pattern_csr(vfvm_handle* h, int64_t* rowptr, int64_t* colidx) {
+    if (int rc = need_pattern(h)) return rc;
+    VFVM_TRY(h, {
+        ScalarPattern sp;
+        build_scalar(h, sp);
+        std::copy(sp.rowptr.begin(), sp.rowptr.end(), rowptr);
+        std::copy(sp.colidx.begin(), sp.colidx.end(), colidx);
+    })
+    return VFVM_OK;
+}
+
+// CSR -> CSC permutation: perm[c] = CSR position of CSC entry c
+static void csr_to_csc(const ScalarPattern& sp, int64_t ncols, std::vector<int64_t>& colptr, std::vector<int64_t>& rowval, std::vector<int64_t>& perm) {
+    const int64_t nrows = (int64_t)sp.rowptr.size() - 1, nnz = (int64_t)sp.colidx.size();
+    colptr.assign((size_t)ncols + 1, 0);
+    for (int64_t k = 0; k < nnz; k++) colptr[sp.colidx[k] + 1]++;
+    for (int64_t c = 0; c < ncols; c++) colptr[c + 1] += colptr[c];
+    rowval.resize(nnz);
+    perm.resize(nnz);
+    std::vector<int64_t> fill(colptr.begin(), colptr.end() - 1);
+    for (int64_t r = 0; r < nrows; r++)
+        for (int64_t k = sp.rowptr[r]; k < sp.rowptr[r + 1]; k++) {
+            const int64_t o = fill[sp.colidx[k]]++;
+            rowval[o] = r;
+            perm[o] = k;
+        }
+}
+
+extern "C" int vfvm_get_pattern_csc(vfvm_handle* h, int64_t* colptr, int64_t* rowval) {
+    if (int rc = need_pattern(h)) return rc;
+    VFVM_TRY(h, {
+        ScalarPattern sp;
+        build_scalar(h, sp);
+        std::vector<int64_t> cp, rv, perm;
+        csr_to_csc(sp, h->N * h->n, cp, rv, perm);
+        std::copy(cp.begin(), cp.end(), colptr);
+        std::copy(rv.begin(), rv.end(), rowval);
+    })
+    return VFVM_OK;
+}
+
+static int get_nzval(vfvm_handle* h, double* out, int memspace, bool csc) {
+    if (int rc = need_pattern(h)) return rc;
+    VFVM_TRY(h, {
+        ScalarPattern sp;
+        build_scalar(h, sp);
+        std::vector<double> off = h->offval.to_host(h->stream), dg = h->diagval.to_host(h->stream);
+        std::vector<double> v(sp.src.size());
+        for (size_t k = 0; k < sp.src.size(); k++) v[k] = sp.src[k] >= 0 ? off[sp.src[k]] : dg[-(sp.src[k] + 1)];
+        if (csc) {
+            std::vector<int64_t> cp, rv, perm;
+            csr_to_csc(sp, h->N * h->n, cp, rv, perm);
+            std::vector<double> w(v.size());
+            for (size_t c = 0; c < v.size(); c++) w[c] = v[perm[c]];
+            v.swap(w);
+        }
+        if (memspace == VFVM_HOST) std::copy(v.begin(), v.end(), out);
+        else CK(cudaMemcpy(out, v.data(), v.size() * 8, cudaMemcpyHostToDevice));
+    })
+    return VFVM_OK;
+}
+
+extern "C" int vfvm_get_nzval_csr(vfvm_handle* h, double* nzval, int memspace) { return get_nzval(h, nzval, memspace, false); }
+extern "C" int vfvm_get_nzval_csc(vfvm_handle* h, double* nzval, int memspace) { return get_nzval(h, nzval, memspace, true); }

@@ -1,0 +1,271 @@
+// Registered device physics library (north_star item 2): every callback the kernels can evaluate.
+// Each function is generic in the scalar type T (double or Dual<P>), like the Julia callbacks are generic in
+// eltype(u); the reference lines each one restates are cited in include/vfvm_b200.h.
+// FLUX is a template parameter of the row-tile kernel (it dominates register use); the node callbacks are
+// selected by a warp-uniform runtime switch.
+#pragma once
+#include "dual.cuh"
+#include "vfvm_internal.h"
+
+// ---- Bernoulli function, src/vfvm_functions.jl:2-90 ---------------------------------------------
+template <class T>
+__device__ __forceinline__ T bernoulli_horner(const T& x) {
+    const double c1 = 1.0 / 47900160.0, c2 = -1.0 / 1209600.0, c3 = 1.0 / 30240.0, c4 = -1.0 / 720.0, c5 = 1.0 / 12.0, c6 = -0.5;
+    T y = x * c1;
+    y = x * y;
+    y = x * (c2 + y);
+    y = x * y;
+    y = x * (c3 + y);
+    y = x * y;
+    y = x * (c4 + y);
+    y = x * y;
+    y = x * (c5 + y);
+    y = x * (c6 + y);
+    return 1.0 + y;
+}
+
+// (B(x), B(-x)); branches exactly as the reference: |x| < 0.25 Horner, |x| > 50 asymptotes, else x/expm1(x)
+template <class T>
+__device__ __forceinline__ void fbernoulli_pm(const T& x, T& bp, T& bm) {
+    const double xv = dvalue(x);
+    if (xv < -50.0) {
+        bp = -x;
+        bm = T(0.0);
+    } else if (xv > 50.0) {
+        bp = T(0.0);
+        bm = x;
+    } else if (fabs(xv) < 0.25) {
+        T y = bernoulli_horner(x);
+        bp = y;
+        bm = x + y;
+    } else {
+        T y = x / dexpm1(x);
+        bp = y;
+        bm = x + y;
+    }
+}
+
+__device__ __forceinline__ double ramp_fn(double t, double tbegin, double tend, double ubegin, double uend) {
+    if (t < tbegin) return ubegin;
+    if (t < tend) return ubegin + (uend - ubegin) * (t - tbegin) / (tend - tbegin);
+    return uend;
+}
+
+// ---- flux(f,u,edge,data): f must be pre-zeroed ------------------------------------------------------
+template <int FLUX, int NS, class T>
+__device__ __forceinline__ void eval_flux(const double* __restrict__ p, T* f, const T* uK, const T* uL) {
+    if constexpr (FLUX == VFVM_FLUX_DIFFUSION) {
+#pragma unroll
+        for (int i = 0; i < NS; i++) f[i] = p[i] * (uK[i] - uL[i]);
+    } else if constexpr (FLUX == VFVM_FLUX_POWDIFF) {
+        const double m = p[NS];
+#pragma unroll
+        for (int i = 0; i < NS; i++) f[i] = p[i] * (dpowr(uK[i], m) - dpowr(uL[i], m));
+    } else if constexpr (FLUX == VFVM_FLUX_CROSSDIFF2 && NS >= 2) {
+        f[0] = p[0] * (uK[0] - uL[0]) * (p[2] + uK[1] + uL[1]);
+        f[1] = p[1] * (uK[1] - uL[1]) * (p[2] + uK[0] + uL[0]);
+    } else if constexpr (FLUX == VFVM_FLUX_SG_UNIPOLAR && NS == 2) {
+        const double eps = p[0];
+        const bool sw = ((int)p[1]) == 1;  // species order (iphi, ic) = (0,1) or (1,0); resolved without dynamic indexing
+        const T &phiK = sw ? uK[1] : uK[0], &phiL = sw ? uL[1] : uL[0], &cK = sw ? uK[0] : uK[1], &cL = sw ? uL[0] : uL[1];
+        T fphi = eps * (phiK - phiL);
+        T bp, bm;
+        fbernoulli_pm(phiK - phiL, bp, bm);
+        T fc = bm * cK - bp * cL;
+        f[0] = sw ? fc : fphi;
+        f[1] = sw ? fphi : fc;
+    } else if constexpr (FLUX == VFVM_FLUX_SEDAN && NS == 2) {
+        const double eps = p[0], z = p[1], eps_reg = p[4];
+        const bool sw = ((int)p[2]) == 1;
+        const T &phiK = sw ? uK[1] : uK[0], &phiL = sw ? uL[1] : uL[0], &cK = sw ? uK[0] : uK[1], &cL = sw ? uL[0] : uL[1];
+        T fphi = eps * (phiK - phiL);
+        T mu1 = -dlog1p(dmaxr(-1.0 + eps_reg, -cK));
+        T mu2 = -dlog1p(dmaxr(-1.0 + eps_reg, -cL));
+        T bp, bm;
+        fbernoulli_pm(z * 2.0 * (phiK - phiL) + (mu1 - mu2), bp, bm);
+        T fc = bm * cK - bp * cL;
+        f[0] = sw ? fc : fphi;
+        f[1] = sw ? fphi : fc;
+    } else if constexpr (FLUX == VFVM_FLUX_SG_BIPOLAR && NS == 3) {
+        // species order fixed to (iphin, iphip, ipsi) = (0,1,2) on the device (checked at registration)
+        const double lambda = p[0], mun = p[1], mup = p[2], zn = p[3], zp = p[4], En = p[5], Ep = p[6];
+        f[2] = -(lambda * lambda) * (uL[2] - uK[2]);
+        T bp, bm;
+        fbernoulli_pm(-(uL[2] - uK[2]), bp, bm);
+        T nn1 = dexp(zn * (uK[0] - uK[2] + En));
+        T np1 = dexp(zp * (uK[1] - uK[2] + Ep));
+        T nn2 = dexp(zn * (uL[0] - uL[2] + En));
+        T np2 = dexp(zp * (uL[1] - uL[2] + Ep));
+        f[0] = (-zn * mun) * (bm * nn2 - bp * nn1);
+        f[1] = (-zp * mup) * (bp * np2 - bm * np1);
+    }
+}
+
+// which (NS, FLUX) pairs have a device instantiation
+__host__ __device__ constexpr bool flux_supported(int flux, int ns) {
+    return flux == VFVM_NONE || flux == VFVM_FLUX_DIFFUSION || flux == VFVM_FLUX_POWDIFF || (flux == VFVM_FLUX_CROSSDIFF2 && ns == 2) ||
+           (flux == VFVM_FLUX_SG_UNIPOLAR && ns == 2) || (flux == VFVM_FLUX_SEDAN && ns == 2) || (flux == VFVM_FLUX_SG_BIPOLAR && ns == 3);
+}
+
+// ---- reaction(f,u,node,data) -------------------------------------------------------------------------
+template <int NS, class T>
+__device__ __forceinline__ void eval_reaction(int id, const double* __restrict__ p, T* f, const T* u, int region) {
+    switch (id) {
+        case VFVM_REACTION_POW:
+#pragma unroll
+            for (int i = 0; i < NS; i++) f[i] = p[i] * dpowr(u[i], p[NS + i]);
+            break;
+        case VFVM_REACTION_SINH:
+#pragma unroll
+            for (int i = 0; i < NS; i++) f[i] = p[i] * (dexp(u[i]) - dexp(-u[i]));
+            break;
+        case VFVM_REACTION_AFFINE:
+#pragma unroll
+            for (int i = 0; i < NS; i++) {
+                T acc(p[NS * NS + i]);
+#pragma unroll
+                for (int j = 0; j < NS; j++) {
+                    const double r = p[i * NS + j];
+                    if (r != 0.0) acc = acc + r * u[j];
+                }
+                f[i] = acc;
+            }
+            break;
+        case VFVM_REACTION_BILINEAR2:
+            if constexpr (NS == 2) {
+                f[0] = p[0] * (u[0] * u[1]);
+                f[1] = (-p[0]) * (u[0] * u[1]);
+            }
+            break;
+        case VFVM_REACTION_BIPOLAR:
+            if constexpr (NS == 3) {
+                const double zn = p[0], zp = p[1], En = p[2], Ep = p[3], r0 = p[4];
+                const int nreg = (int)p[8];
+                const double C = (region >= 1 && region <= nreg) ? p[9 + region - 1] : 0.0;
+                T nn = dexp(zn * (u[0] - u[2] + En));
+                T np = dexp(zp * (u[1] - u[2] + Ep));
+                f[2] = -(C + zn * nn + zp * np);
+                T recomb = (r0 + 1.0 / (nn + np)) * (nn * np * (1.0 - dexp(u[0] - u[1])));
+                f[0] = zn * recomb;
+                f[1] = zp * recomb;
+            }
+            break;
+        default: break;
+    }
+}
+
+// ---- storage(f,u,node,data) --------------------------------------------------------------------------
+template <int NS, class T>
+__device__ __forceinline__ void eval_storage(int id, const double* __restrict__ p, T* f, const T* u) {
+    switch (id) {
+        case VFVM_STORAGE_LINEAR:
+#pragma unroll
+            for (int i = 0; i < NS; i++) f[i] = p[i] * u[i];
+            break;
+        case VFVM_STORAGE_POW:
+#pragma unroll
+            for (int i = 0; i < NS; i++) f[i] = dpowr(p[i] + u[i], 1.0 / p[NS + i]);
+            break;
+        case VFVM_STORAGE_BIPOLAR:
+            if constexpr (NS == 3) {
+                const double zn = p[0], zp = p[1], En = p[2], Ep = p[3];
+                T nn = dexp(zn * (u[0] - u[2] + En));
+                T np = dexp(zp * (u[1] - u[2] + Ep));
+                f[0] = zn * nn;
+                f[1] = zp * np;
+            }
+            break;
+        default: break;
+    }
+}
+
+// ---- source(f,node,data) -----------------------------------------------------------------------------
+template <int NS>
+__device__ __forceinline__ void eval_source(int id, const double* __restrict__ p, double* f, const double* __restrict__ x, int dim,
+                                            const double* __restrict__ nodal, int64_t K) {
+    switch (id) {
+        case VFVM_SOURCE_CONST:
+#pragma unroll
+            for (int i = 0; i < NS; i++) f[i] = p[i];
+            break;
+        case VFVM_SOURCE_GAUSS: {
+            const int sp = (int)p[0];
+            double r2 = 0.0;
+            for (int d = 0; d < dim; d++) {
+                const double xd = x[d] - p[2 + d];
+                r2 += xd * xd;
+            }
+            const double s = exp(-p[1] * r2);
+#pragma unroll
+            for (int i = 0; i < NS; i++)
+                if (i == sp) f[i] = s;
+            break;
+        }
+        case VFVM_SOURCE_XSINYEXPZ: {
+            const int sp = (int)p[0];
+            const double s = x[0] * sin(p[1] * x[1]) * exp(x[2]);
+#pragma unroll
+            for (int i = 0; i < NS; i++)
+                if (i == sp) f[i] = s;
+            break;
+        }
+        case VFVM_SOURCE_STEP1D: {
+            const int sp = (int)p[0];
+            const double s = (x[0] <= p[1]) ? p[2] : p[3];
+#pragma unroll
+            for (int i = 0; i < NS; i++)
+                if (i == sp) f[i] = s;
+            break;
+        }
+        case VFVM_SOURCE_AFFINE_X:
+#pragma unroll
+            for (int i = 0; i < NS; i++) f[i] = p[i] + p[NS + i] * x[0];
+            break;
+        case VFVM_SOURCE_NODAL:
+#pragma unroll
+            for (int i = 0; i < NS; i++) f[i] = nodal[K * NS + i];
+            break;
+        default: break;
+    }
+}
+
+// ---- breaction(f,u,bnode,data) + boundary_dirichlet!/neumann!/robin! calls --------------------------
+// dirichlet_value (may be null) receives the values set by boundary_dirichlet! (src/vfvm_physics.jl:492)
+template <int NS, class T>
+__device__ __forceinline__ void eval_breaction(const PhysicsDev& ph, T* f, const T* u, int bregion, double time, double Dirichlet,
+                                               double* dirichlet_value) {
+    const PhysSlotDev& s = ph.slot[VFVM_SLOT_BREACTION];
+    const double* p = ph.params + s.off;
+    if (s.id == VFVM_BREACTION_LINEAR) {
+        if (bregion == (int)p[0]) {
+#pragma unroll
+            for (int i = 0; i < NS; i++) {
+                T acc(0.0);
+#pragma unroll
+                for (int j = 0; j < NS; j++) {
+                    const double r = p[1 + i * NS + j];
+                    if (r != 0.0) acc = acc + r * u[j];
+                }
+                f[i] = acc;
+            }
+        }
+    }
+    for (int e = 0; e < ph.nbc; e++) {
+        const vfvm_bc_entry& bc = ph.bc[e];
+        const int ireg = bc.region == 0 ? bregion : bc.region;
+        if (bregion != ireg) continue;
+        const double val = bc.has_ramp ? ramp_fn(time, bc.t0, bc.t1, bc.v0, bc.v1) : bc.value;
+#pragma unroll
+        for (int i = 0; i < NS; i++) {
+            if (i != bc.species) continue;
+            if (bc.kind == VFVM_BC_DIRICHLET) {
+                f[i] = f[i] + Dirichlet * (u[i] - val);
+                if (dirichlet_value) dirichlet_value[i] = val;
+            } else if (bc.kind == VFVM_BC_NEUMANN) {
+                f[i] = f[i] - val;
+            } else if (bc.kind == VFVM_BC_ROBIN) {
+                f[i] = f[i] + (bc.factor * u[i] - val);
+            }
+        }
+    }
+}

@@ -1,0 +1,206 @@
+// Internal declarations of libvfvmb200.so (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/vfvm_b200.h"
+
+#define VFVM_MAX_SPECIES 10
+#define VFVM_MAX_PARAMS 160
+#define VFVM_MAX_BC 32
+#define VFVM_MAX_BREGIONS 16
+
+// ------------------------------------------------------------------------------------------------ device buffers
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    int64_t* tally = nullptr;  // handle-wide byte counter
+    void alloc(size_t count) {
+        if (count == n && p) return;
+        release();
+        n = count;
+        if (count) {
+            cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+            if (e != cudaSuccess) {
+                p = nullptr;
+                n = 0;
+                throw std::string("cudaMalloc of ") + std::to_string(count * sizeof(T)) + " bytes failed: " + cudaGetErrorString(e);
+            }
+            if (tally) *tally += (int64_t)(count * sizeof(T));
+        }
+    }
+    void release() {
+        if (p) {
+            cudaFree(p);
+            if (tally) *tally -= (int64_t)(n * sizeof(T));
+        }
+        p = nullptr;
+        n = 0;
+    }
+    void upload(const T* h, size_t count, cudaStream_t s) {
+        alloc(count);
+        if (count) cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s);
+    }
+    void download(T* h, cudaStream_t s) const {
+        if (n) cudaMemcpyAsync(h, p, n * sizeof(T), cudaMemcpyDeviceToHost, s);
+        cudaStreamSynchronize(s);
+    }
+    std::vector<T> to_host(cudaStream_t s) const {
+        std::vector<T> v(n);
+        download(v.data(), s);
+        return v;
+    }
+    ~DevBuf() { release(); }
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+};
+
+// ------------------------------------------------------------------------------------------------ physics block (kernel argument)
+struct PhysSlotDev {
+    int id;
+    int np;
+    int off;  // offset into params[]
+};
+struct PhysicsDev {
+    PhysSlotDev slot[VFVM_NUM_SLOTS];
+    double params[VFVM_MAX_PARAMS];
+    int nbc;
+    vfvm_bc_entry bc[VFVM_MAX_BC];
+    int has_legacy_bc;
+    int nbregions;
+    double bfactors[VFVM_MAX_SPECIES * VFVM_MAX_BREGIONS];  // n x nbregions, column-major
+    double bvalues[VFVM_MAX_SPECIES * VFVM_MAX_BREGIONS];
+    const double* nodal_source;  // n x N or null
+};
+
+// species-coupling masks: bit (i*n + j) set <=> d f_i / d u_j is not identically zero
+struct Masks {
+    uint64_t flux[2];      // we support n <= 10 -> 100 bits
+    uint64_t reaction[2];
+    uint64_t storage[2];
+    uint64_t boundary[2];  // union over all boundary contributions
+};
+static inline bool mask_get(const uint64_t* m, int bit) { return (m[bit >> 6] >> (bit & 63)) & 1ull; }
+static inline void mask_set(uint64_t* m, int bit) { m[bit >> 6] |= (1ull << (bit & 63)); }
+
+// ------------------------------------------------------------------------------------------------ handle
+struct vfvm_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    std::string err;
+    int64_t bytes = 0;
+    int64_t launches = 0;
+    double times[VFVM_NUM_TIMES] = {0};
+
+    // grid
+    int dim = 0, coordsys = 0;
+    int64_t N = 0, C = 0, NB = 0, Nown = 0;
+    int ncellregions = 0, nbfaceregions = 0;
+    DevBuf<double> coord;
+    DevBuf<int32_t> cellnodes, cellregions, bfacenodes, bfaceregions;
+    bool have_grid = false, have_geometry = false, have_system = false, have_pattern = false;
+
+    // geometry (K1, K2)
+    int64_t E = 0;
+    DevBuf<int32_t> edgenodes, celledges;
+    DevBuf<int64_t> nf_colptr, ef_colptr;
+    DevBuf<int32_t> nf_region, ef_region;
+    DevBuf<double> nf_fac, ef_fac;
+    DevBuf<double> bfacenodefac;
+    bool single_region = true;
+    int the_region = 1;
+
+    // system
+    int n = 0;
+    PhysicsDev phys;
+    DevBuf<PhysicsDev> phys_dev;  // device copy, refreshed by vfvm_sync_physics
+    bool phys_dirty = true;
+    Masks masks;
+    DevBuf<double> nodal_source;
+    std::vector<double> host_params;
+
+    // pattern (K3): off-diagonal block CSR over owned rows + separate diagonal blocks
+    int64_t nnz_off = 0;
+    DevBuf<int32_t> rowptr, colidx;  // rowptr: Nown+1 ; colidx: nnz_off (sorted per row, no diagonal)
+    DevBuf<int32_t> nz_edge;         // nnz -> edge id
+    DevBuf<double> nzfac;            // single-region fast path: edge factor per nnz
+    DevBuf<int32_t> itemptr;         // multi-region: nnz -> [itemptr[k], itemptr[k+1]) into ef_region / ef_fac
+    DevBuf<int32_t> tile_row;        // row tiles of the streaming kernels
+    int ntiles = 0, tile_nnz = 0;
+    // boundary nodes: CSR node -> (bface, local node) in bface order
+    int64_t nbnodes = 0, nbitems = 0;
+    DevBuf<int32_t> bn_node, bn_ptr, bn_bface, bn_local;
+    // plane tables
+    int cF = 0, cD = 0;           // number of stored planes in off-diagonal / diagonal blocks
+    int planeF[100], planeD[100]; // plane -> i*n+j
+    int idxF[100], idxD[100];     // i*n+j -> plane or -1
+    bool seen_transient = false;
+    std::vector<uint8_t> bnode_mask_host;  // per boundary node: extra diag bits (for the exported scalar pattern)
+
+    // values
+    DevBuf<double> offval;   // cF planes x nnz_off
+    DevBuf<double> diagval;  // cD planes x Nown
+    DevBuf<double> vec[4];   // SOLUTION, OLDSOL, RESIDUAL, UPDATE: n x N (N incl. halo)
+    DevBuf<int32_t> flags;   // [0]: NaN seen
+    int32_t* flags_host = nullptr;  // pinned
+
+    // linear solver
+    int krylov = VFVM_KRYLOV_BICGSTAB, precon = VFVM_PRECON_JACOBI, gmres_restart = 30;
+    bool precon_valid = false;
+    DevBuf<double> work[12];
+    DevBuf<double> pc_diag;  // (block-)Jacobi inverse blocks, n*n planes x Nown
+    DevBuf<double> ilu_off, ilu_diag;
+    DevBuf<int32_t> ilu_levelptr_dummy;
+    std::vector<int32_t> ilu_level_ptr;  // host copy of level boundaries
+    DevBuf<int32_t> ilu_level_rows;
+    DevBuf<int32_t> upos;  // first off-diagonal entry with col > row
+    DevBuf<double> red;    // reduction scratch
+    double* red_host = nullptr;  // pinned
+
+    // comm
+    void* nccl = nullptr;  // ncclComm_t
+    int rank = 0, nranks = 1;
+    std::vector<int32_t> nb_ranks;
+    std::vector<int64_t> send_ptr, recv_ptr;
+    DevBuf<int32_t> send_idx;
+    DevBuf<double> send_buf;
+};
+
+#define VFVM_TRY(h, ...)                                        \
+    try {                                                       \
+        __VA_ARGS__                                             \
+    } catch (const std::string& e) {                            \
+        (h)->err = e;                                           \
+        return VFVM_ERR_CUDA;                                   \
+    } catch (const std::exception& e) {                         \
+        (h)->err = e.what();                                    \
+        return VFVM_ERR_CUDA;                                   \
+    }
+
+static inline int vfvm_fail(vfvm_handle* h, int code, const std::string& msg) {
+    if (h) h->err = msg;
+    return code;
+}
+static inline void vfvm_check(cudaError_t e, const char* what) {
+    if (e != cudaSuccess) throw std::string(what) + ": " + cudaGetErrorString(e);
+}
+#define CK(x) vfvm_check((x), #x)
+
+static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// implemented across the .cu files
+int vfvm_geometry_build(vfvm_handle* h);
+int vfvm_pattern_build(vfvm_handle* h);
+int vfvm_assemble_impl(vfvm_handle* h, double time, double tstep, double lambda);
+int vfvm_init_dirichlet_impl(vfvm_handle* h, double time, double lambda);
+int vfvm_physics_masks(vfvm_handle* h);
+void vfvm_spmv_impl(vfvm_handle* h, const double* x, double* y);
+void vfvm_sync_physics(vfvm_handle* h);
+size_t vfvm_asm_smem(const vfvm_handle* h);
