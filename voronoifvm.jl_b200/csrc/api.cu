@@ -326,6 +326,8 @@ void vfvm_sync_physics(vfvm_handle* h) {
     if (!h->phys_dirty && h->phys_dev.p) return;
     h->phys_dev.upload(&h->phys, 1, h->stream);
     CK(cudaStreamSynchronize(h->stream));
+    vfvm_source_cache(h);  // the source callback does not depend on u: tabulate it once per physics change
+    CK(cudaStreamSynchronize(h->stream));
     h->phys_dirty = false;
 }
 

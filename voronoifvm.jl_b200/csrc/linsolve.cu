@@ -9,6 +9,8 @@
 //   * Jacobi / node-block Jacobi preconditioners (ILU0: ilu0.cu).
 // All reductions are two-stage with a fixed order => bitwise reproducible.  With more than one rank the partial sums
 // are combined by ncclAllReduce on the same stream and the SpMV input gets a halo refresh first (comm.cu).
+#include <algorithm>
+
 #include "vfvm_internal.h"
 
 #define LS_THREADS 256
@@ -26,7 +28,6 @@ void vfvm_ilu0_apply(vfvm_handle* h, const double* in, double* out);
 namespace {
 
 struct SpmvArgs {
-    const int32_t* __restrict__ tile_row;
     const int32_t* __restrict__ rowptr;
     const int32_t* __restrict__ colidx;
     const double* __restrict__ offval;
@@ -36,7 +37,7 @@ struct SpmvArgs {
     const double* __restrict__ w;  // optional: fused dots (y,w) and (y,y)
     double* __restrict__ part;     // 2 x gridDim partial sums
     int64_t nnz_off, Nown;
-    int ntiles, tile_nnz;
+    int ngroups, group_maxnnz, warp_smem_bytes;
     signed char idxF[100], idxD[100];
 };
 
@@ -66,44 +67,58 @@ __device__ __forceinline__ double block_max(double v, double* sh) {
     return r;
 }
 
-template <int NS>
+// y = A x on the DBSR planes, warp-autonomous like the assembly kernel: a warp owns R consecutive rows per pass,
+// lane-per-block products into the warp's shared memory, lane-per-row reduction in column order + diagonal block.
+template <int NS, int R, int UNR>
 __global__ void __launch_bounds__(LS_THREADS) k_spmv(const SpmvArgs a) {
-    extern __shared__ double smem[];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double red[32];
-    const int T = a.tile_nnz;
-    double* sP = smem;  // T x NS partial products
-    int32_t* srp = (int32_t*)(sP + (size_t)T * NS);
-    uint8_t* rowof = (uint8_t*)(srp + LS_RMAX + 1);
-    const int tid = threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* sP = (double*)(smem_raw + (size_t)warp * a.warp_smem_bytes);  // M x NS partial products
     double d_yw = 0.0, d_yy = 0.0;
-    for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-        const int r0 = a.tile_row[tile], r1 = a.tile_row[tile + 1], nrows = r1 - r0;
-        for (int t = tid; t <= nrows; t += LS_THREADS) srp[t] = a.rowptr[r0 + t];
-        __syncthreads();
-        const int k0 = srp[0], k1 = srp[nrows];
-        for (int k = k0 + tid; k < k1; k += LS_THREADS) {
-            const int L = a.colidx[k];
-            double xl[NS], acc[NS];
+    const int nwarps = gridDim.x * (LS_THREADS / 32);
+    for (int g = blockIdx.x * (LS_THREADS / 32) + warp; g < a.ngroups; g += nwarps) {
+        const int64_t R0 = (int64_t)g * R;
+        const int nrows = (int)min((int64_t)R, a.Nown - R0);
+        const int myrow = min(lane, nrows - 1);
+        const int64_t r = R0 + myrow;
+        const int rb = a.rowptr[r], re = a.rowptr[r + 1];
+        const int k0 = __shfl_sync(0xffffffffu, rb, 0), k1 = __shfl_sync(0xffffffffu, re, nrows - 1);
+        double xr[NS];
 #pragma unroll
-            for (int j = 0; j < NS; j++) xl[j] = a.x[(int64_t)L * NS + j];
+        for (int j = 0; j < NS; j++) xr[j] = a.x[r * NS + j];
+        for (int kb = k0; kb < k1; kb += 32 * UNR) {
+            int Lc[UNR];
+            bool act[UNR];
 #pragma unroll
-            for (int i = 0; i < NS; i++) {
-                acc[i] = 0.0;
+            for (int u = 0; u < UNR; u++) {
+                const int k = kb + u * 32 + lane;
+                act[u] = k < k1;
+                Lc[u] = act[u] ? a.colidx[k] : 0;
+            }
 #pragma unroll
-                for (int j = 0; j < NS; j++) {
-                    const int p = a.idxF[i * NS + j];
-                    if (p >= 0) acc[i] += a.offval[(int64_t)p * a.nnz_off + k] * xl[j];
+            for (int u = 0; u < UNR; u++) {
+                const int k = kb + u * 32 + lane;
+                double xl[NS];
+#pragma unroll
+                for (int j = 0; j < NS; j++) xl[j] = a.x[(int64_t)Lc[u] * NS + j];
+                if (act[u]) {
+#pragma unroll
+                    for (int i = 0; i < NS; i++) {
+                        double acc = 0.0;
+#pragma unroll
+                        for (int j = 0; j < NS; j++) {
+                            const int p = a.idxF[i * NS + j];
+                            if (p >= 0) acc += a.offval[(int64_t)p * a.nnz_off + k] * xl[j];
+                        }
+                        sP[(k - k0) * NS + i] = acc;
+                    }
                 }
-                sP[(k - k0) * NS + i] = acc[i];
             }
         }
-        __syncthreads();
-        for (int t = tid; t < nrows; t += LS_THREADS) {
-            const int r = r0 + t;
-            const int kb = srp[t] - k0, ke = srp[t + 1] - k0;
-            double xr[NS];
-#pragma unroll
-            for (int j = 0; j < NS; j++) xr[j] = a.x[(int64_t)r * NS + j];
+        __syncwarp();
+        if (lane < nrows) {
+            const int kb = rb - k0, ke = re - k0;
 #pragma unroll
             for (int i = 0; i < NS; i++) {
                 double s = 0.0;
@@ -113,24 +128,23 @@ __global__ void __launch_bounds__(LS_THREADS) k_spmv(const SpmvArgs a) {
                     const int p = a.idxD[i * NS + j];
                     if (p >= 0) s += a.diagval[(int64_t)p * a.Nown + r] * xr[j];
                 }
-                a.y[(int64_t)r * NS + i] = s;
+                a.y[r * NS + i] = s;
                 if (a.w) {
-                    d_yw += s * a.w[(int64_t)r * NS + i];
+                    d_yw += s * a.w[r * NS + i];
                     d_yy += s * s;
                 }
             }
         }
-        __syncthreads();
+        __syncwarp();
     }
     if (a.w) {
         const double s1 = block_sum(d_yw, red);
         const double s2 = block_sum(d_yy, red);
-        if (tid == 0) {
+        if (threadIdx.x == 0) {
             a.part[blockIdx.x] = s1;
             a.part[gridDim.x + blockIdx.x] = s2;
         }
     }
-    (void)rowof;
 }
 
 // sums `nparts` partials for each of `nvals` values into out[0..nvals) in fixed order (single block)
@@ -379,15 +393,15 @@ const int VEC_GRID = 148 * 8;
 SpmvArgs make_spmv_args(vfvm_handle* h) {
     SpmvArgs a;
     memset(&a, 0, sizeof(a));
-    a.tile_row = h->tile_row.p;
     a.rowptr = h->rowptr.p;
     a.colidx = h->colidx.p;
     a.offval = h->offval.p;
     a.diagval = h->diagval.p;
     a.nnz_off = h->nnz_off;
     a.Nown = h->Nown;
-    a.ntiles = h->ntiles;
-    a.tile_nnz = h->tile_nnz;
+    a.ngroups = h->ngroups;
+    a.group_maxnnz = h->group_maxnnz;
+    a.warp_smem_bytes = ((h->group_maxnnz * h->n * 8 + 15) / 16) * 16;
     for (int b = 0; b < 100; b++) {
         a.idxF[b] = (signed char)(b < h->n * h->n ? h->idxF[b] : -1);
         a.idxD[b] = (signed char)(b < h->n * h->n ? h->idxD[b] : -1);
@@ -395,9 +409,40 @@ SpmvArgs make_spmv_args(vfvm_handle* h) {
     return a;
 }
 
-size_t spmv_smem(const vfvm_handle* h) { return (size_t)h->tile_nnz * h->n * sizeof(double) + (LS_RMAX + 1) * sizeof(int32_t) + (size_t)h->tile_nnz; }
+template <int NS> struct SpmvCfg { static constexpr int R = 8, UNR = 2; };
+template <> struct SpmvCfg<1> { static constexpr int R = 32, UNR = 4; };
+template <> struct SpmvCfg<2> { static constexpr int R = 16, UNR = 2; };
+template <> struct SpmvCfg<3> { static constexpr int R = 16, UNR = 2; };
 
-int spmv_grid(const vfvm_handle* h) { return h->ntiles; }
+template <int NS>
+void launch_spmv(vfvm_handle* h, SpmvArgs& a) {
+    constexpr int R = SpmvCfg<NS>::R, UNR = SpmvCfg<NS>::UNR;
+    if (R != h->group_R) throw std::string("row group size mismatch between pattern and SpMV");
+    auto kern = k_spmv<NS, R, UNR>;
+    const size_t smem = (size_t)a.warp_smem_bytes * (LS_THREADS / 32);
+    static int occ = 0;
+    static size_t occ_smem = 0;
+    if (occ == 0 || occ_smem != smem) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, LS_THREADS, smem));
+        occ_smem = smem;
+        if (occ < 1) throw std::string("SpMV kernel does not fit on an SM (shared memory)");
+    }
+    int nsm = 148;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device);
+    const int grid = std::max(1, std::min(cdiv(a.ngroups, LS_THREADS / 32), nsm * occ));
+    if (a.w) {
+        if (h->work[10].n < (size_t)2 * grid) h->work[10].alloc((size_t)2 * grid);
+        a.part = h->work[10].p;
+    }
+    kern<<<grid, LS_THREADS, smem, h->stream>>>(a);
+    h->launches++;
+    if (a.w) {
+        k_finalize<<<1, 1024, 0, h->stream>>>(a.part, grid, 2, h->red.p + S_TMP0);
+        h->launches++;
+    }
+}
 
 // y = A x (+ fused dots (y,w), (y,y) -> sc[S_TMP0], sc[S_TMP1])
 void spmv(vfvm_handle* h, double* x, double* y, const double* w) {
@@ -406,22 +451,8 @@ void spmv(vfvm_handle* h, double* x, double* y, const double* w) {
     a.x = x;
     a.y = y;
     a.w = w;
-    const int grid = spmv_grid(h);
-    if (w) {
-        if (h->work[10].n < (size_t)2 * grid) h->work[10].alloc((size_t)2 * grid);
-        a.part = h->work[10].p;
-    }
-    const size_t smem = spmv_smem(h);
-    NS_DISPATCH(h->n, {
-        CK(cudaFuncSetAttribute(k_spmv<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_spmv<NS><<<grid, LS_THREADS, smem, h->stream>>>(a);
-    });
-    h->launches++;
-    if (w) {
-        k_finalize<<<1, 1024, 0, h->stream>>>(a.part, grid, 2, h->red.p + S_TMP0);
-        h->launches++;
-        vfvm_comm_allreduce_sum(h, h->red.p + S_TMP0, 2);
-    }
+    NS_DISPATCH(h->n, launch_spmv<NS>(h, a));
+    if (w) vfvm_comm_allreduce_sum(h, h->red.p + S_TMP0, 2);
 }
 
 void reduce2_sum(vfvm_handle* h, const double* part, int nparts) {

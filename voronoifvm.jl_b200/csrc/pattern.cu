@@ -16,23 +16,14 @@
 
 namespace {
 
-__global__ void k_dir_keys(int64_t E, int64_t Nown, const int32_t* __restrict__ edgenodes, uint64_t* __restrict__ keys, int32_t* __restrict__ vals,
-                           unsigned long long* __restrict__ count) {
+__global__ void k_dir_keys(int64_t E, int64_t Nown, const int32_t* __restrict__ edgenodes, uint64_t* __restrict__ keys, int32_t* __restrict__ vals) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= E) return;
     const uint64_t hi = (uint32_t)edgenodes[2 * e], lo = (uint32_t)edgenodes[2 * e + 1];
-    int c = 0;
-    if ((int64_t)hi < Nown) {
-        keys[2 * e] = (hi << 32) | lo;
-        c++;
-    } else keys[2 * e] = ~0ull;
-    if ((int64_t)lo < Nown) {
-        keys[2 * e + 1] = (lo << 32) | hi;
-        c++;
-    } else keys[2 * e + 1] = ~0ull;
+    keys[2 * e] = ((int64_t)hi < Nown) ? ((hi << 32) | lo) : ~0ull;      // rows of halo nodes are not stored: sorted to the end
+    keys[2 * e + 1] = ((int64_t)lo < Nown) ? ((lo << 32) | hi) : ~0ull;
     vals[2 * e] = (int32_t)e;
     vals[2 * e + 1] = (int32_t)e;
-    if (c) atomicAdd(count, (unsigned long long)c);
 }
 
 __global__ void k_rowptr(int64_t nrows, int64_t nkeys, const uint64_t* __restrict__ keys, int32_t* __restrict__ rowptr) {
@@ -222,13 +213,10 @@ int vfvm_pattern_build(vfvm_handle* h) {
     // ---- directed node graph
     DevBuf<uint64_t> keys;
     DevBuf<int32_t> vals;
-    DevBuf<unsigned long long> count;
     keys.tally = vals.tally = &h->bytes;
     keys.alloc(2 * E);
     vals.alloc(2 * E);
-    count.alloc(1);
-    CK(cudaMemsetAsync(count.p, 0, 8, s));
-    k_dir_keys<<<cdiv(E, B), B, 0, s>>>(E, Nown, h->edgenodes.p, keys.p, vals.p, count.p);
+    k_dir_keys<<<cdiv(E, B), B, 0, s>>>(E, Nown, h->edgenodes.p, keys.p, vals.p);
     h->launches++;
     {
         DevBuf<uint64_t> keys2;
@@ -247,16 +235,19 @@ int vfvm_pattern_build(vfvm_handle* h) {
         if (dk.Current() != keys.p) std::swap(keys.p, keys2.p);
         if (dv.Current() != vals.p) std::swap(vals.p, vals2.p);
     }
-    unsigned long long cnt = 0;
-    CK(cudaMemcpy(&cnt, count.p, 8, cudaMemcpyDeviceToHost));
-    h->nnz_off = (int64_t)cnt;
-    if (h->nnz_off >= ((int64_t)1 << 31)) throw std::string("pattern too large for 32-bit block indices");
+    if (2 * E >= ((int64_t)1 << 31)) throw std::string("pattern too large for 32-bit block indices");
     h->rowptr.alloc(Nown + 1);
+    k_rowptr<<<cdiv(Nown + 1, B), B, 0, s>>>(Nown, 2 * E, keys.p, h->rowptr.p);  // keys of halo rows sort behind row Nown-1
+    h->launches++;
+    {
+        int32_t last = 0;
+        CK(cudaMemcpyAsync(&last, h->rowptr.p + Nown, 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        h->nnz_off = last;
+    }
     h->colidx.alloc(h->nnz_off);
     h->nz_edge.alloc(h->nnz_off);
     if (h->single_region) h->nzfac.alloc(h->nnz_off);
-    k_rowptr<<<cdiv(Nown + 1, B), B, 0, s>>>(Nown, h->nnz_off, keys.p, h->rowptr.p);
-    h->launches++;
     if (h->nnz_off) {
         k_cols<<<cdiv(h->nnz_off, B), B, 0, s>>>(h->nnz_off, keys.p, vals.p, h->ef_fac.p, h->single_region ? 1 : 0, h->colidx.p, h->nz_edge.p, h->nzfac.p);
         h->launches++;
@@ -267,8 +258,16 @@ int vfvm_pattern_build(vfvm_handle* h) {
     keys.release();
     vals.release();
 
-    // ---- row tiles for the streaming kernels (host, one-off)
+    // ---- warp row groups / row tiles for the streaming kernels (host, one-off)
     std::vector<int32_t> rp = h->rowptr.to_host(s);
+    {
+        const int R = vfvm_rows_per_group(n);
+        h->group_R = R;
+        h->ngroups = (int)((Nown + R - 1) / R);
+        int mx = 1;
+        for (int64_t r0 = 0; r0 < Nown; r0 += R) mx = std::max(mx, rp[std::min<int64_t>(Nown, r0 + R)] - rp[r0]);
+        h->group_maxnnz = mx;
+    }
     {
         const int T = h->tile_nnz, RMAX = 256;
         std::vector<int32_t> tr;

@@ -134,6 +134,8 @@ struct vfvm_handle {
     DevBuf<int32_t> itemptr;         // multi-region: nnz -> [itemptr[k], itemptr[k+1]) into ef_region / ef_fac
     DevBuf<int32_t> tile_row;        // row tiles of the streaming kernels
     int ntiles = 0, tile_nnz = 0;
+    int group_R = 16, ngroups = 0, group_maxnnz = 0;  // warp row groups of the assembly / SpMV kernels
+    DevBuf<double> src_cache;                         // tabulated source callback, n x N
     // boundary nodes: CSR node -> (bface, local node) in bface order
     int64_t nbnodes = 0, nbitems = 0;
     DevBuf<int32_t> bn_node, bn_ptr, bn_bface, bn_local;
@@ -203,4 +205,5 @@ int vfvm_init_dirichlet_impl(vfvm_handle* h, double time, double lambda);
 int vfvm_physics_masks(vfvm_handle* h);
 void vfvm_spmv_impl(vfvm_handle* h, const double* x, double* y);
 void vfvm_sync_physics(vfvm_handle* h);
-size_t vfvm_asm_smem(const vfvm_handle* h);
+void vfvm_source_cache(vfvm_handle* h);
+int vfvm_rows_per_group(int ns);
