@@ -43,7 +43,7 @@ extern "C" int vfvm_create(int device, vfvm_handle** out) {
     for (auto* b : dbl) b->tally = &h->bytes;
     for (auto& w : h->work) w.tally = &h->bytes;
     DevBuf<int32_t>* i32[] = {&h->cellnodes, &h->cellregions, &h->bfacenodes, &h->bfaceregions, &h->edgenodes, &h->celledges, &h->nf_region, &h->ef_region,
-                              &h->rowptr, &h->colidx, &h->nz_edge, &h->tile_row, &h->bn_node, &h->bn_ptr, &h->bn_bface, &h->bn_local, &h->upos, &h->ilu_level_rows, &h->send_idx};
+                              &h->rowptr, &h->colidx, &h->sell_ptr, &h->nz_edge, &h->tile_row, &h->bn_node, &h->bn_ptr, &h->bn_bface, &h->bn_local, &h->upos, &h->ilu_level_rows, &h->send_idx};
     for (auto* b : i32) b->tally = &h->bytes;
     h->nf_colptr.tally = h->ef_colptr.tally = &h->bytes;
     *out = h;
@@ -335,25 +335,8 @@ extern "C" int vfvm_build_pattern(vfvm_handle* h) {
     NEED(h, h->have_geometry && h->have_system, "vfvm_build_geometry and vfvm_set_system must come first");
     VFVM_TRY(h, {
         CK(cudaSetDevice(h->device));
-        // tile size: ~40 KB of shared memory per CTA for the per-block residual / diagonal contributions
-        int rc0 = vfvm_physics_masks(h);
-        if (rc0) return vfvm_fail(h, rc0, "physics id is not in the registered device library");
-        int cF = 0;
-        for (int b = 0; b < h->n * h->n; b++) cF += mask_get(h->masks.flux, b) ? 1 : 0;
-        const int per = (h->n + std::max(1, cF)) * 8 + 1;
-        int T = 40960 / per;
-        T = std::max(256, std::min(2048, (T / 256) * 256));
-        h->tile_nnz = T;
         int rc = vfvm_pattern_build(h);
         if (rc) return rc;
-        // a row longer than a tile would overflow the shared-memory staging
-        std::vector<int32_t> rp = h->rowptr.to_host(h->stream);
-        int maxlen = 0;
-        for (int64_t r = 0; r < h->Nown; r++) maxlen = std::max(maxlen, rp[r + 1] - rp[r]);
-        if (maxlen > h->tile_nnz) {
-            h->have_pattern = false;
-            return vfvm_fail(h, VFVM_ERR_UNSUPPORTED, "a node has more neighbours than one row tile holds");
-        }
         vfvm_sync_physics(h);
     })
     return VFVM_OK;

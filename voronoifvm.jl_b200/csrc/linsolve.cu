@@ -28,7 +28,7 @@ void vfvm_ilu0_apply(vfvm_handle* h, const double* in, double* out);
 namespace {
 
 struct SpmvArgs {
-    const int32_t* __restrict__ rowptr;
+    const int32_t* __restrict__ sell_ptr;
     const int32_t* __restrict__ colidx;
     const double* __restrict__ offval;
     const double* __restrict__ diagval;
@@ -36,8 +36,8 @@ struct SpmvArgs {
     double* __restrict__ y;
     const double* __restrict__ w;  // optional: fused dots (y,w) and (y,y)
     double* __restrict__ part;     // 2 x gridDim partial sums
-    int64_t nnz_off, Nown;
-    int ngroups, group_maxnnz, warp_smem_bytes;
+    int64_t nnz_sell, Nown;
+    int nslices;
     signed char idxF[100], idxD[100];
 };
 
@@ -67,66 +67,62 @@ __device__ __forceinline__ double block_max(double v, double* sh) {
     return r;
 }
 
-// y = A x on the DBSR planes, warp-autonomous like the assembly kernel: a warp owns R consecutive rows per pass,
-// lane-per-block products into the warp's shared memory, lane-per-row reduction in column order + diagonal block.
-template <int NS, int R, int UNR>
+// y = A x on the DBSR planes in SELL-32 order: a warp owns a slice of 32 rows, one lane per row; colidx / value loads are
+// coalesced, x[col] gathers coalesce on structured numberings, the row sum lives in registers (column order, deterministic).
+// Optional fused inner products (y,w) and (y,y) for the Krylov recurrences.
+template <int NS>
 __global__ void __launch_bounds__(LS_THREADS) k_spmv(const SpmvArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ double red[32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double* sP = (double*)(smem_raw + (size_t)warp * a.warp_smem_bytes);  // M x NS partial products
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5, nwarps = gridDim.x * wpb;
+    const int64_t nnz = a.nnz_sell;
     double d_yw = 0.0, d_yy = 0.0;
-    const int nwarps = gridDim.x * (LS_THREADS / 32);
-    for (int g = blockIdx.x * (LS_THREADS / 32) + warp; g < a.ngroups; g += nwarps) {
-        const int64_t R0 = (int64_t)g * R;
-        const int nrows = (int)min((int64_t)R, a.Nown - R0);
-        const int myrow = min(lane, nrows - 1);
-        const int64_t r = R0 + myrow;
-        const int rb = a.rowptr[r], re = a.rowptr[r + 1];
-        const int k0 = __shfl_sync(0xffffffffu, rb, 0), k1 = __shfl_sync(0xffffffffu, re, nrows - 1);
-        double xr[NS];
+    for (int g = blockIdx.x * wpb + (threadIdx.x >> 5); g < a.nslices; g += nwarps) {
+        const int64_t rraw = (int64_t)g * 32 + lane;
+        const bool valid = rraw < a.Nown;
+        const int64_t r = valid ? rraw : a.Nown - 1;
+        const int base = a.sell_ptr[g];
+        const int w = (a.sell_ptr[g + 1] - base) >> 5;
+        double acc[NS];
 #pragma unroll
-        for (int j = 0; j < NS; j++) xr[j] = a.x[r * NS + j];
-        for (int kb = k0; kb < k1; kb += 32 * UNR) {
-            int Lc[UNR];
-            bool act[UNR];
+        for (int i = 0; i < NS; i++) acc[i] = 0.0;
+        constexpr int BATCH = NS == 1 ? 8 : (NS <= 3 ? 4 : 2);
+        for (int j0 = 0; j0 < w; j0 += BATCH) {
+            int Lc[BATCH];
 #pragma unroll
-            for (int u = 0; u < UNR; u++) {
-                const int k = kb + u * 32 + lane;
-                act[u] = k < k1;
-                Lc[u] = act[u] ? a.colidx[k] : 0;
+            for (int b = 0; b < BATCH; b++) {
+                const int64_t e = (int64_t)base + (int64_t)(j0 + b) * 32 + lane;
+                Lc[b] = (j0 + b < w) ? a.colidx[e] : (int)r;
             }
+            double xl[BATCH][NS];
 #pragma unroll
-            for (int u = 0; u < UNR; u++) {
-                const int k = kb + u * 32 + lane;
-                double xl[NS];
+            for (int b = 0; b < BATCH; b++)
 #pragma unroll
-                for (int j = 0; j < NS; j++) xl[j] = a.x[(int64_t)Lc[u] * NS + j];
-                if (act[u]) {
+                for (int jj = 0; jj < NS; jj++) xl[b][jj] = a.x[(int64_t)Lc[b] * NS + jj];
 #pragma unroll
-                    for (int i = 0; i < NS; i++) {
-                        double acc = 0.0;
+            for (int b = 0; b < BATCH; b++) {
+                if (j0 + b >= w) break;
+                const int64_t e = (int64_t)base + (int64_t)(j0 + b) * 32 + lane;
 #pragma unroll
-                        for (int j = 0; j < NS; j++) {
-                            const int p = a.idxF[i * NS + j];
-                            if (p >= 0) acc += a.offval[(int64_t)p * a.nnz_off + k] * xl[j];
-                        }
-                        sP[(k - k0) * NS + i] = acc;
+                for (int i = 0; i < NS; i++)
+#pragma unroll
+                    for (int jj = 0; jj < NS; jj++) {
+                        const int p = a.idxF[i * NS + jj];
+                        if (p >= 0) acc[i] += a.offval[(int64_t)p * nnz + e] * xl[b][jj];
                     }
-                }
             }
         }
-        __syncwarp();
-        if (lane < nrows) {
-            const int kb = rb - k0, ke = re - k0;
+        if (valid) {
+            double xr[NS];
+#pragma unroll
+            for (int jj = 0; jj < NS; jj++) xr[jj] = a.x[r * NS + jj];
 #pragma unroll
             for (int i = 0; i < NS; i++) {
-                double s = 0.0;
-                for (int k = kb; k < ke; k++) s += sP[k * NS + i];
+                double s = acc[i];
 #pragma unroll
-                for (int j = 0; j < NS; j++) {
-                    const int p = a.idxD[i * NS + j];
-                    if (p >= 0) s += a.diagval[(int64_t)p * a.Nown + r] * xr[j];
+                for (int jj = 0; jj < NS; jj++) {
+                    const int p = a.idxD[i * NS + jj];
+                    if (p >= 0) s += a.diagval[(int64_t)p * a.Nown + r] * xr[jj];
                 }
                 a.y[r * NS + i] = s;
                 if (a.w) {
@@ -135,7 +131,6 @@ __global__ void __launch_bounds__(LS_THREADS) k_spmv(const SpmvArgs a) {
                 }
             }
         }
-        __syncwarp();
     }
     if (a.w) {
         const double s1 = block_sum(d_yw, red);
@@ -393,15 +388,13 @@ const int VEC_GRID = 148 * 8;
 SpmvArgs make_spmv_args(vfvm_handle* h) {
     SpmvArgs a;
     memset(&a, 0, sizeof(a));
-    a.rowptr = h->rowptr.p;
+    a.sell_ptr = h->sell_ptr.p;
     a.colidx = h->colidx.p;
     a.offval = h->offval.p;
     a.diagval = h->diagval.p;
-    a.nnz_off = h->nnz_off;
+    a.nnz_sell = h->nnz_sell;
     a.Nown = h->Nown;
-    a.ngroups = h->ngroups;
-    a.group_maxnnz = h->group_maxnnz;
-    a.warp_smem_bytes = ((h->group_maxnnz * h->n * 8 + 15) / 16) * 16;
+    a.nslices = h->ngroups;
     for (int b = 0; b < 100; b++) {
         a.idxF[b] = (signed char)(b < h->n * h->n ? h->idxF[b] : -1);
         a.idxD[b] = (signed char)(b < h->n * h->n ? h->idxD[b] : -1);
@@ -409,34 +402,22 @@ SpmvArgs make_spmv_args(vfvm_handle* h) {
     return a;
 }
 
-template <int NS> struct SpmvCfg { static constexpr int R = 8, UNR = 2; };
-template <> struct SpmvCfg<1> { static constexpr int R = 32, UNR = 4; };
-template <> struct SpmvCfg<2> { static constexpr int R = 16, UNR = 2; };
-template <> struct SpmvCfg<3> { static constexpr int R = 16, UNR = 2; };
-
 template <int NS>
 void launch_spmv(vfvm_handle* h, SpmvArgs& a) {
-    constexpr int R = SpmvCfg<NS>::R, UNR = SpmvCfg<NS>::UNR;
-    if (R != h->group_R) throw std::string("row group size mismatch between pattern and SpMV");
-    auto kern = k_spmv<NS, R, UNR>;
-    const size_t smem = (size_t)a.warp_smem_bytes * (LS_THREADS / 32);
+    auto kern = k_spmv<NS>;
     static int occ = 0;
-    static size_t occ_smem = 0;
-    if (occ == 0 || occ_smem != smem) {
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, LS_THREADS, smem));
-        occ_smem = smem;
-        if (occ < 1) throw std::string("SpMV kernel does not fit on an SM (shared memory)");
+    if (occ == 0) {
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, LS_THREADS, 0));
+        if (occ < 1) throw std::string("SpMV kernel cannot be launched");
     }
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device);
-    const int grid = std::max(1, std::min(cdiv(a.ngroups, LS_THREADS / 32), nsm * occ));
+    const int grid = std::max(1, std::min(cdiv(a.nslices, LS_THREADS / 32), nsm * occ));
     if (a.w) {
         if (h->work[10].n < (size_t)2 * grid) h->work[10].alloc((size_t)2 * grid);
         a.part = h->work[10].p;
     }
-    kern<<<grid, LS_THREADS, smem, h->stream>>>(a);
+    kern<<<grid, LS_THREADS, 0, h->stream>>>(a);
     h->launches++;
     if (a.w) {
         k_finalize<<<1, 1024, 0, h->stream>>>(a.part, grid, 2, h->red.p + S_TMP0);

@@ -1,12 +1,15 @@
 // K3: sparsity pattern + maps.  Replaces what rawupdateindex!/flush! of ExtendableSparse build implicitly during
 // the first assembly (src/vfvm_assembly.jl:26, src/vfvm_solver.jl:242).
 //
-// Device layout ("DBSR", diagonal + off-diagonal block planes):
-//   rowptr[Nown+1], colidx[nnz_off]   off-diagonal block CSR of the node graph (columns sorted, no diagonal)
-//   offval[cF][nnz_off]               one plane per (i,j) of the flux species-coupling mask
+// Device layout ("DBSR": diagonal + off-diagonal block planes, off-diagonal part in sliced ELLPACK order, slice = 32 rows):
+//   rowptr[Nown+1]                    CSR row offsets of the off-diagonal node graph (row lengths; export / ILU0)
+//   sell_ptr[nslices+1]               first entry of each slice; entry j of row r lives at sell_ptr[r/32] + 32*j + r%32, so that
+//                                     a warp working lane-per-row reads colidx / nzfac and writes the Jacobian fully coalesced
+//   colidx[nnz_sell]                  column (neighbour node) per entry, ascending within a row; padding entries point to the
+//                                     row itself and carry a zero form factor (they assemble / multiply to exact zeros)
+//   nzfac[nnz_sell]                   edge form factor per entry (single cell region); nz_edge[nnz_sell]: edge id (-1 = padding)
+//   offval[cF][nnz_sell]              one plane per (i,j) of the flux species-coupling mask
 //   diagval[cD][Nown]                 one plane per (i,j) of the diagonal-block mask
-//   nzfac[nnz_off]                    edge form factor per off-diagonal block (single cell region) -- the row-tile
-//                                     kernel streams (colidx, nzfac) and writes offval fully coalesced, no scatter map
 // The scalar CSR/CSC pattern the reference would hold (value-dependent through _addnz, src/vfvm_assembly.jl:21-28)
 // is derived from the block pattern and the per-physics coupling masks by the getters below.
 #include <algorithm>
@@ -38,22 +41,53 @@ __global__ void k_rowptr(int64_t nrows, int64_t nkeys, const uint64_t* __restric
     rowptr[K] = (int32_t)lo;
 }
 
-__global__ void k_cols(int64_t nnz, const uint64_t* __restrict__ keys, const int32_t* __restrict__ vals, const double* __restrict__ ef_fac,
-                       int single_region, int32_t* __restrict__ colidx, int32_t* __restrict__ nz_edge, double* __restrict__ nzfac) {
-    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= nnz) return;
-    colidx[k] = (int32_t)(keys[k] & 0xffffffffu);
-    nz_edge[k] = vals[k];
-    if (single_region) nzfac[k] = ef_fac[vals[k]];
+// slice width = longest row of the slice
+__global__ void k_slice_width(int nslices, int64_t Nown, const int32_t* __restrict__ rowptr, int64_t* __restrict__ sell_ptr) {
+    const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (g >= nslices) return;
+    const int64_t r = (int64_t)g * 32 + lane;
+    int len = r < Nown ? rowptr[r + 1] - rowptr[r] : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
+    if (lane == 0) {
+        sell_ptr[g + 1] = (int64_t)len * 32;  // exclusive scan follows
+        if (g == 0) sell_ptr[0] = 0;
+    }
 }
 
-__global__ void k_upos(int64_t nrows, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, int32_t* __restrict__ upos) {
-    const int64_t K = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (K >= nrows) return;
-    int32_t k = rowptr[K];
-    const int32_t ke = rowptr[K + 1];
-    while (k < ke && colidx[k] < K) k++;
-    upos[K] = k;
+// CSR (sorted keys) -> SELL-32 entries, one warp per slice, lane per row
+__global__ void k_fill_sell(int nslices, int64_t Nown, const int32_t* __restrict__ rowptr, const int64_t* __restrict__ sell_ptr64,
+                            const uint64_t* __restrict__ keys, const int32_t* __restrict__ vals, const double* __restrict__ ef_fac, int single_region,
+                            int32_t* __restrict__ sell_ptr, int32_t* __restrict__ colidx, int32_t* __restrict__ nz_edge, double* __restrict__ nzfac,
+                            int32_t* __restrict__ lowlen) {
+    const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (g >= nslices) return;
+    const int64_t r = (int64_t)g * 32 + lane;
+    const int64_t base = sell_ptr64[g];
+    const int w = (int)((sell_ptr64[g + 1] - base) >> 5);
+    if (lane == 0) {
+        sell_ptr[g] = (int32_t)base;
+        if (g == nslices - 1) sell_ptr[g + 1] = (int32_t)sell_ptr64[g + 1];
+    }
+    const int rb = r < Nown ? rowptr[r] : 0, len = r < Nown ? rowptr[r + 1] - rb : 0;
+    const int32_t self = (int32_t)min(r, Nown - 1);
+    int nlow = 0;
+    for (int j = 0; j < w; j++) {
+        const int64_t e = base + (int64_t)j * 32 + lane;
+        if (j < len) {
+            const int32_t c = (int32_t)(keys[rb + j] & 0xffffffffu);
+            const int32_t ed = vals[rb + j];
+            colidx[e] = c;
+            nz_edge[e] = ed;
+            if (single_region) nzfac[e] = ef_fac[ed];
+            nlow += (c < r) ? 1 : 0;
+        } else {
+            colidx[e] = self;
+            nz_edge[e] = -1;
+            if (single_region) nzfac[e] = 0.0;
+        }
+    }
+    if (r < Nown) lowlen[r] = nlow;
 }
 
 }  // namespace
@@ -245,43 +279,36 @@ int vfvm_pattern_build(vfvm_handle* h) {
         CK(cudaStreamSynchronize(s));
         h->nnz_off = last;
     }
-    h->colidx.alloc(h->nnz_off);
-    h->nz_edge.alloc(h->nnz_off);
-    if (h->single_region) h->nzfac.alloc(h->nnz_off);
-    if (h->nnz_off) {
-        k_cols<<<cdiv(h->nnz_off, B), B, 0, s>>>(h->nnz_off, keys.p, vals.p, h->ef_fac.p, h->single_region ? 1 : 0, h->colidx.p, h->nz_edge.p, h->nzfac.p);
+    // ---- SELL-32 layout of the off-diagonal blocks
+    const int nslices = (int)((Nown + 31) / 32);
+    h->ngroups = nslices;
+    {
+        DevBuf<int64_t> sp64;
+        sp64.alloc((size_t)nslices + 1);
+        k_slice_width<<<cdiv(nslices, 8), 256, 0, s>>>(nslices, Nown, h->rowptr.p, sp64.p);
         h->launches++;
+        size_t tmp = 0;
+        CK(cub::DeviceScan::InclusiveSum(nullptr, tmp, sp64.p, sp64.p, nslices + 1, s));
+        DevBuf<char> t;
+        t.alloc(tmp);
+        CK(cub::DeviceScan::InclusiveSum(t.p, tmp, sp64.p, sp64.p, nslices + 1, s));
+        int64_t total = 0;
+        CK(cudaMemcpyAsync(&total, sp64.p + nslices, 8, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        if (total >= ((int64_t)1 << 31)) throw std::string("pattern too large for 32-bit block indices");
+        h->nnz_sell = total;
+        h->sell_ptr.alloc((size_t)nslices + 1);
+        h->colidx.alloc(total);
+        h->nz_edge.alloc(total);
+        if (h->single_region) h->nzfac.alloc(total);
+        h->upos.alloc(Nown);
+        k_fill_sell<<<cdiv(nslices, 8), 256, 0, s>>>(nslices, Nown, h->rowptr.p, sp64.p, keys.p, vals.p, h->ef_fac.p, h->single_region ? 1 : 0, h->sell_ptr.p,
+                                                     h->colidx.p, h->nz_edge.p, h->nzfac.p, h->upos.p);
+        h->launches++;
+        CK(cudaStreamSynchronize(s));
     }
-    h->upos.alloc(Nown);
-    k_upos<<<cdiv(Nown, B), B, 0, s>>>(Nown, h->rowptr.p, h->colidx.p, h->upos.p);
-    h->launches++;
     keys.release();
     vals.release();
-
-    // ---- warp row groups / row tiles for the streaming kernels (host, one-off)
-    std::vector<int32_t> rp = h->rowptr.to_host(s);
-    {
-        const int R = vfvm_rows_per_group(n);
-        h->group_R = R;
-        h->ngroups = (int)((Nown + R - 1) / R);
-        int mx = 1;
-        for (int64_t r0 = 0; r0 < Nown; r0 += R) mx = std::max(mx, rp[std::min<int64_t>(Nown, r0 + R)] - rp[r0]);
-        h->group_maxnnz = mx;
-    }
-    {
-        const int T = h->tile_nnz, RMAX = 256;
-        std::vector<int32_t> tr;
-        tr.push_back(0);
-        int64_t r = 0;
-        while (r < Nown) {
-            int64_t r1 = r + 1;  // a tile holds at least one row (rows longer than T are handled by the in-kernel loop)
-            while (r1 < Nown && r1 - r < RMAX && rp[r1 + 1] - rp[r] <= T) r1++;
-            tr.push_back((int32_t)r1);
-            r = r1;
-        }
-        h->ntiles = (int)tr.size() - 1;
-        h->tile_row.upload(tr.data(), tr.size(), s);
-    }
 
     // ---- boundary nodes: node -> (bface, local node) in ascending bface order (the reference's loop order)
     {
@@ -320,7 +347,7 @@ int vfvm_pattern_build(vfvm_handle* h) {
     }
 
     // ---- values + vectors
-    h->offval.alloc((size_t)std::max(1, h->cF) * h->nnz_off);
+    h->offval.alloc((size_t)std::max(1, h->cF) * h->nnz_sell);
     h->diagval.alloc((size_t)h->cD * Nown);
     for (int v = 0; v < 4; v++) {
         h->vec[v].alloc((size_t)n * h->N);
@@ -345,7 +372,8 @@ struct ScalarPattern {
 static void build_scalar(vfvm_handle* h, ScalarPattern& sp) {
     const int n = h->n;
     const int64_t Nown = h->Nown;
-    std::vector<int32_t> rp = h->rowptr.to_host(h->stream), ci = h->colidx.to_host(h->stream), bn = h->bn_node.to_host(h->stream);
+    std::vector<int32_t> rp = h->rowptr.to_host(h->stream), ci = h->colidx.to_host(h->stream), bn = h->bn_node.to_host(h->stream),
+                         sl = h->sell_ptr.to_host(h->stream);
     std::vector<int64_t> bnode_of(Nown, -1);
     for (size_t b = 0; b < bn.size(); b++) bnode_of[bn[b]] = (int64_t)b;
     sp.rowptr.assign((size_t)Nown * n + 1, 0);
@@ -363,6 +391,8 @@ static void build_scalar(vfvm_handle* h, ScalarPattern& sp) {
             dm[0] |= bits[0];
             dm[1] |= bits[1];
         }
+        const int len = rp[K + 1] - rp[K];
+        const int64_t ebase = (int64_t)sl[K >> 5] + (K & 31);
         for (int i = 0; i < n; i++) {
             bool diag_done = false;
             auto emit_diag = [&]() {
@@ -373,13 +403,14 @@ static void build_scalar(vfvm_handle* h, ScalarPattern& sp) {
                     }
                 diag_done = true;
             };
-            for (int32_t k = rp[K]; k < rp[K + 1]; k++) {
-                const int64_t L = ci[k];
+            for (int q = 0; q < len; q++) {
+                const int64_t e = ebase + (int64_t)q * 32;
+                const int64_t L = ci[e];
                 if (!diag_done && L > K) emit_diag();
                 for (int j = 0; j < n; j++)
                     if (mask_get(h->masks.flux, i * n + j)) {
                         sp.colidx.push_back(L * n + j);
-                        sp.src.push_back((int64_t)h->idxF[i * n + j] * h->nnz_off + k);
+                        sp.src.push_back((int64_t)h->idxF[i * n + j] * h->nnz_sell + e);
                     }
             }
             if (!diag_done) emit_diag();

@@ -127,8 +127,9 @@ struct vfvm_handle {
     std::vector<double> host_params;
 
     // pattern (K3): off-diagonal block CSR over owned rows + separate diagonal blocks
-    int64_t nnz_off = 0;
-    DevBuf<int32_t> rowptr, colidx;  // rowptr: Nown+1 ; colidx: nnz_off (sorted per row, no diagonal)
+    int64_t nnz_off = 0, nnz_sell = 0;  // true / padded number of off-diagonal blocks
+    DevBuf<int32_t> rowptr, colidx;  // rowptr: Nown+1 (CSR offsets = row lengths); colidx: nnz_sell in SELL-32 order
+    DevBuf<int32_t> sell_ptr;        // nslices+1: first entry of each 32-row slice
     DevBuf<int32_t> nz_edge;         // nnz -> edge id
     DevBuf<double> nzfac;            // single-region fast path: edge factor per nnz
     DevBuf<int32_t> itemptr;         // multi-region: nnz -> [itemptr[k], itemptr[k+1]) into ef_region / ef_fac
@@ -206,4 +207,4 @@ int vfvm_physics_masks(vfvm_handle* h);
 void vfvm_spmv_impl(vfvm_handle* h, const double* x, double* y);
 void vfvm_sync_physics(vfvm_handle* h);
 void vfvm_source_cache(vfvm_handle* h);
-int vfvm_rows_per_group(int ns);
+
