@@ -224,6 +224,8 @@ int vfvm_stream(vfvm_handle* h, void** cuda_stream);       /* the cudaStream_t a
 int vfvm_device_bytes(vfvm_handle* h, int64_t* bytes);
 /* stored Jacobian planes: species couplings kept per off-diagonal block (flux mask) / per diagonal block */
 int vfvm_plane_counts(vfvm_handle* h, int* off_planes, int* diag_planes);
+/* off-diagonal blocks of the owned rows (= 2 x edges, summed over ranks) and blocks stored incl. SELL-32 padding */
+int vfvm_block_counts(vfvm_handle* h, int64_t* nblocks_off, int64_t* nblocks_stored);
 
 #ifdef __cplusplus
 }

@@ -798,7 +798,7 @@ int vo_set_nodal_source(void* h, const double* table) {
 }
 int vo_set_legacy_bc(void* h, int nbregions, const double* factors, const double* values) {
     System& s = *(System*)h;
-    if (nbregions != s.g.nbfaceregions) return VFVM_ERR_ARG;
+    if (nbregions < s.g.nbfaceregions) return VFVM_ERR_ARG;  // a rank-local grid piece may lack faces of the highest regions
     s.boundary_factors.assign(factors, factors + (size_t)s.n * nbregions);
     s.boundary_values.assign(values, values + (size_t)s.n * nbregions);
     return 0;

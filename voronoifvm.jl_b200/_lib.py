@@ -76,6 +76,7 @@ SIGNATURES = {
     "vfvm_stream": [_H, _p(C.c_void_p)],
     "vfvm_device_bytes": [_H, _I64],
     "vfvm_plane_counts": [_H, _p(C.c_int), _p(C.c_int)],
+    "vfvm_block_counts": [_H, _I64, _I64],
 }
 OTHER = {"vfvm_destroy": ([_H], None), "vfvm_last_error": ([_H], C.c_char_p), "vfvm_abi_version": ([], C.c_int)}
 

@@ -25,6 +25,7 @@ extern "C" int vfvm_create(int device, vfvm_handle** out) {
         CK(cudaEventCreate(&h->ev1));
         CK(cudaEventCreate(&h->ev2));
         CK(cudaEventCreate(&h->ev3));
+        CK(cudaEventCreate(&h->ev4));
         CK(cudaMallocHost((void**)&h->flags_host, 4 * sizeof(int32_t)));
         CK(cudaMallocHost((void**)&h->red_host, 8 * sizeof(double)));
         h->flags.alloc(4);
@@ -51,6 +52,7 @@ extern "C" int vfvm_create(int device, vfvm_handle** out) {
 }
 
 int vfvm_comm_destroy(vfvm_handle* h);
+int vfvm_halo_exchange_ptr(vfvm_handle* h, double* x);
 
 extern "C" void vfvm_destroy(vfvm_handle* h) {
     if (!h) return;
@@ -63,6 +65,7 @@ extern "C" void vfvm_destroy(vfvm_handle* h) {
     cudaEventDestroy(h->ev1);
     cudaEventDestroy(h->ev2);
     cudaEventDestroy(h->ev3);
+    cudaEventDestroy(h->ev4);
     cudaStream_t s = h->stream;
     delete h;
     if (s) cudaStreamDestroy(s);
@@ -285,7 +288,8 @@ extern "C" int vfvm_set_nodal_source(vfvm_handle* h, const double* table) {
 
 extern "C" int vfvm_set_legacy_bc(vfvm_handle* h, int nbregions, const double* factors, const double* values) {
     NEED(h, h->have_system, "vfvm_set_system has not been called");
-    if (nbregions != h->nbfaceregions) return vfvm_fail(h, VFVM_ERR_ARG, "nbregions does not match the grid");
+    // a rank-local grid piece may not contain faces of every boundary region: the table may be larger than the local maximum
+    if (nbregions < h->nbfaceregions || nbregions > VFVM_MAX_BREGIONS) return vfvm_fail(h, VFVM_ERR_ARG, "nbregions does not match the grid (or exceeds 16)");
     PhysicsDev& ph = h->phys;
     bool any = false;
     for (int i = 0; i < h->n * nbregions; i++) {
@@ -376,7 +380,12 @@ extern "C" int vfvm_init_dirichlet(vfvm_handle* h, double time, double lambda) {
     VFVM_TRY(h, {
         CK(cudaSetDevice(h->device));
         vfvm_sync_physics(h);
-        return vfvm_init_dirichlet_impl(h, time, lambda);
+        int rc = vfvm_init_dirichlet_impl(h, time, lambda);
+        if (rc == VFVM_OK && h->nranks > 1) {  // halo copies of Dirichlet nodes follow their owners
+            vfvm_halo_exchange_ptr(h, h->vec[VFVM_VEC_SOLUTION].p);
+            CK(cudaStreamSynchronize(h->stream));
+        }
+        return rc;
     })
 }
 
@@ -433,5 +442,11 @@ extern "C" int vfvm_plane_counts(vfvm_handle* h, int* off_planes, int* diag_plan
     NEED(h, h->have_pattern, "vfvm_build_pattern has not been called");
     *off_planes = h->cF;
     *diag_planes = h->cD;
+    return VFVM_OK;
+}
+extern "C" int vfvm_block_counts(vfvm_handle* h, int64_t* nblocks_off, int64_t* nblocks_stored) {
+    NEED(h, h->have_pattern, "vfvm_build_pattern has not been called");
+    *nblocks_off = h->nnz_off;      // off-diagonal blocks of the owned rows = 2 x edges (summed over ranks)
+    *nblocks_stored = h->nnz_sell;  // including SELL-32 padding
     return VFVM_OK;
 }

@@ -89,10 +89,13 @@ __global__ void __launch_bounds__(LS_THREADS) k_spmv(const SpmvArgs a) {
         constexpr int BATCH = NS == 1 ? 8 : (NS <= 3 ? 4 : 2);
         for (int j0 = 0; j0 < w; j0 += BATCH) {
             int Lc[BATCH];
+            double v1[BATCH];  // NS == 1: the matrix value travels with the index load
 #pragma unroll
             for (int b = 0; b < BATCH; b++) {
+                const bool ok = j0 + b < w;
                 const int64_t e = (int64_t)base + (int64_t)(j0 + b) * 32 + lane;
-                Lc[b] = (j0 + b < w) ? a.colidx[e] : (int)r;
+                Lc[b] = ok ? a.colidx[e] : (int)r;
+                v1[b] = (NS == 1 && ok) ? a.offval[e] : 0.0;
             }
             double xl[BATCH][NS];
 #pragma unroll
@@ -102,14 +105,18 @@ __global__ void __launch_bounds__(LS_THREADS) k_spmv(const SpmvArgs a) {
 #pragma unroll
             for (int b = 0; b < BATCH; b++) {
                 if (j0 + b >= w) break;
-                const int64_t e = (int64_t)base + (int64_t)(j0 + b) * 32 + lane;
+                if constexpr (NS == 1) {
+                    acc[0] += v1[b] * xl[b][0];
+                } else {
+                    const int64_t e = (int64_t)base + (int64_t)(j0 + b) * 32 + lane;
 #pragma unroll
-                for (int i = 0; i < NS; i++)
+                    for (int i = 0; i < NS; i++)
 #pragma unroll
-                    for (int jj = 0; jj < NS; jj++) {
-                        const int p = a.idxF[i * NS + jj];
-                        if (p >= 0) acc[i] += a.offval[(int64_t)p * nnz + e] * xl[b][jj];
-                    }
+                        for (int jj = 0; jj < NS; jj++) {
+                            const int p = a.idxF[i * NS + jj];
+                            if (p >= 0) acc[i] += a.offval[(int64_t)p * nnz + e] * xl[b][jj];
+                        }
+                }
             }
         }
         if (valid) {
@@ -161,61 +168,87 @@ __global__ void k_finalize_max(const double* __restrict__ part, int nparts, doub
     if (threadIdx.x == 0) out[0] = r;
 }
 
-// ---- scalar recurrences on the device (one thread) ----
-enum { OP_BICG_BETA = 0, OP_BICG_ALPHA, OP_BICG_OMEGA, OP_BICG_INIT, OP_CG_ALPHA, OP_CG_BETA, OP_CG_INIT };
-__global__ void k_scalar(int op, double* __restrict__ sc, int32_t* __restrict__ flags) {
+// ---- scalar recurrences on the device; fused with the final reduction when there is a single rank ------------------
+enum { OP_NONE = 0, OP_BICG_INIT, OP_BICG_ALPHA, OP_BICG_OMEGA, OP_BICG_NEXT, OP_CG_INIT, OP_CG_ALPHA, OP_CG_NEXT };
+__device__ void scalar_update(int op, double* __restrict__ sc, int32_t* __restrict__ flags) {
     switch (op) {
-        case OP_BICG_INIT:  // sc[S_RHO] = (rhat, r) = (r,r) was reduced into S_TMP0 / S_TMP1
+        case OP_BICG_INIT:  // TMP0 = (r,r)
             sc[S_RHO] = sc[S_TMP0];
             sc[S_RR] = sc[S_TMP0];
             sc[S_BB] = sc[S_TMP0];
-            sc[S_RHO_OLD] = 1.0;
             sc[S_ALPHA] = 1.0;
             sc[S_OMEGA] = 1.0;
             sc[S_BETA] = 0.0;
             break;
-        case OP_BICG_BETA:  // beta = (rho/rho_old) * (alpha/omega)
-            sc[S_BETA] = (sc[S_RHO] / sc[S_RHO_OLD]) * (sc[S_ALPHA] / sc[S_OMEGA]);
-            break;
-        case OP_BICG_ALPHA:  // (rhat, v) in S_TMP0
+        case OP_BICG_ALPHA:  // TMP0 = (rhat, v)
             sc[S_RV] = sc[S_TMP0];
             sc[S_ALPHA] = sc[S_RHO] / sc[S_RV];
             if (!(fabs(sc[S_RV]) > 0.0) || sc[S_ALPHA] != sc[S_ALPHA]) atomicOr(flags, 2);
             break;
-        case OP_BICG_OMEGA:  // (t,s) in S_TMP0, (t,t) in S_TMP1
-            sc[S_TS] = sc[S_TMP0];
-            sc[S_TT] = sc[S_TMP1];
-            sc[S_OMEGA] = (sc[S_TT] > 0.0) ? sc[S_TS] / sc[S_TT] : 0.0;
+        case OP_BICG_OMEGA:  // TMP0 = (t,s), TMP1 = (t,t)
+            sc[S_OMEGA] = (sc[S_TMP1] > 0.0) ? sc[S_TMP0] / sc[S_TMP1] : 0.0;
             break;
-        case OP_CG_INIT:  // (r,z) in S_TMP0, (r,r) in S_TMP1
+        case OP_BICG_NEXT: {  // TMP0 = (rhat, r_new), TMP1 = (r_new, r_new): beta for the next iteration
+            const double rho_new = sc[S_TMP0];
+            sc[S_BETA] = (rho_new / sc[S_RHO]) * (sc[S_ALPHA] / sc[S_OMEGA]);
+            sc[S_RHO] = rho_new;
+            sc[S_RR] = sc[S_TMP1];
+            break;
+        }
+        case OP_CG_INIT:  // TMP0 = (z,r), TMP1 = (r,r)
             sc[S_RZ] = sc[S_TMP0];
             sc[S_RR] = sc[S_TMP1];
             sc[S_BB] = sc[S_TMP1];
             sc[S_BETA] = 0.0;
             break;
-        case OP_CG_ALPHA:  // (Ap, p) in S_TMP0
-            sc[S_PAP] = sc[S_TMP0];
-            sc[S_ALPHA] = sc[S_RZ] / sc[S_PAP];
-            if (!(fabs(sc[S_PAP]) > 0.0)) atomicOr(flags, 2);
+        case OP_CG_ALPHA:  // TMP0 = (Ap, p)
+            sc[S_ALPHA] = sc[S_RZ] / sc[S_TMP0];
+            if (!(fabs(sc[S_TMP0]) > 0.0)) atomicOr(flags, 2);
             break;
-        case OP_CG_BETA:  // new (r,z) in S_TMP0, (r,r) in S_TMP1
+        case OP_CG_NEXT:  // TMP0 = new (z,r), TMP1 = (r,r)
             sc[S_BETA] = sc[S_TMP0] / sc[S_RZ];
             sc[S_RZ] = sc[S_TMP0];
             sc[S_RR] = sc[S_TMP1];
             break;
+        default: break;
     }
+}
+__global__ void k_scalar(int op, double* __restrict__ sc, int32_t* __restrict__ flags) { scalar_update(op, sc, flags); }
+
+// sums `nparts` partials for each of `nvals` values into sc[S_TMP0 + v] in fixed order (single block), then applies `op`
+__global__ void k_finalize_op(const double* __restrict__ part, int nparts, int nvals, double* __restrict__ sc, int op, int32_t* __restrict__ flags) {
+    __shared__ double red[32];
+    for (int v = 0; v < nvals; v++) {
+        double s = 0.0;
+        for (int i = threadIdx.x; i < nparts; i += blockDim.x) s += part[(int64_t)v * nparts + i];
+        const double r = block_sum(s, red);
+        if (threadIdx.x == 0) sc[S_TMP0 + v] = r;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && op != OP_NONE) scalar_update(op, sc, flags);
 }
 
 // ---- fused vector kernels (grid-stride over n*Nown entries; partial sums per block) -------------------------
-// BiCGStab: p = r + beta (p - omega v)
-__global__ void k_bicg_p(int64_t n, const double* __restrict__ sc, const double* __restrict__ r, const double* __restrict__ v, double* __restrict__ p) {
+// `dinv` = reciprocal point diagonal (Jacobi) or null (identity): the preconditioned vector is produced in the same pass
+// BiCGStab: p = r + beta (p - omega v) ; phat = M^-1 p
+__global__ void k_bicg_p(int64_t n, const double* __restrict__ sc, const double* __restrict__ r, const double* __restrict__ v, double* __restrict__ p,
+                         const double* __restrict__ dinv, double* __restrict__ phat) {
     const double beta = sc[S_BETA], omega = sc[S_OMEGA];
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = r[i] + beta * (p[i] - omega * v[i]);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double pi = r[i] + beta * (p[i] - omega * v[i]);
+        p[i] = pi;
+        if (phat) phat[i] = dinv ? pi * dinv[i] : pi;
+    }
 }
-// s = r - alpha v
-__global__ void k_bicg_s(int64_t n, const double* __restrict__ sc, const double* __restrict__ r, const double* __restrict__ v, double* __restrict__ s) {
+// s = r - alpha v ; shat = M^-1 s
+__global__ void k_bicg_s(int64_t n, const double* __restrict__ sc, const double* __restrict__ r, const double* __restrict__ v, double* __restrict__ s,
+                         const double* __restrict__ dinv, double* __restrict__ shat) {
     const double alpha = sc[S_ALPHA];
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) s[i] = r[i] - alpha * v[i];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double si = r[i] - alpha * v[i];
+        s[i] = si;
+        if (shat) shat[i] = dinv ? si * dinv[i] : si;
+    }
 }
 // x += alpha phat + omega shat ; r = s - omega t ; partial dots (rhat, r), (r, r)
 __global__ void k_bicg_xr(int64_t n, const double* __restrict__ sc, const double* __restrict__ phat, const double* __restrict__ shat,
@@ -253,19 +286,82 @@ __global__ void k_dot2(int64_t n, const double* __restrict__ a, const double* __
         part[gridDim.x + blockIdx.x] = s1;
     }
 }
-// CG: x += alpha p ; r -= alpha q
+// CG: x += alpha p ; r -= alpha q ; z = M^-1 r (if fused) ; partial dots (z,r), (r,r)
 __global__ void k_cg_xr(int64_t n, const double* __restrict__ sc, const double* __restrict__ p, const double* __restrict__ q, double* __restrict__ x,
-                        double* __restrict__ r) {
+                        double* __restrict__ r, const double* __restrict__ dinv, double* __restrict__ z, int fused, double* __restrict__ part) {
+    __shared__ double red[32];
     const double alpha = sc[S_ALPHA];
+    double d0 = 0.0, d1 = 0.0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         x[i] += alpha * p[i];
-        r[i] -= alpha * q[i];
+        const double ri = r[i] - alpha * q[i];
+        r[i] = ri;
+        if (fused) {
+            const double zi = dinv ? ri * dinv[i] : ri;
+            z[i] = zi;
+            d0 += zi * ri;
+            d1 += ri * ri;
+        }
+    }
+    if (fused) {
+        const double s0 = block_sum(d0, red);
+        const double s1 = block_sum(d1, red);
+        if (threadIdx.x == 0) {
+            part[blockIdx.x] = s0;
+            part[gridDim.x + blockIdx.x] = s1;
+        }
     }
 }
 // CG: p = z + beta p
 __global__ void k_cg_p(int64_t n, const double* __restrict__ sc, const double* __restrict__ z, double* __restrict__ p) {
     const double beta = sc[S_BETA];
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = z[i] + beta * p[i];
+}
+// GMRES: partial dots (w, V_i) for i = 0..k-1 plus (w,w) in one pass; V is k vectors of length n, stride ld
+__global__ void k_multidot(int64_t n, int k, const double* __restrict__ V, int64_t ld, const double* __restrict__ w, double* __restrict__ part) {
+    __shared__ double red[32];
+    for (int i0 = 0; i0 <= k; i0 += 4) {
+        double d[4] = {0, 0, 0, 0};
+        for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
+            const double wj = w[j];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int i = i0 + q;
+                if (i < k) d[q] += wj * V[(int64_t)i * ld + j];
+                else if (i == k) d[q] += wj * wj;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const double sres = block_sum(d[q], red);
+            if (threadIdx.x == 0 && i0 + q <= k) part[(int64_t)(i0 + q) * gridDim.x + blockIdx.x] = sres;
+            __syncthreads();
+        }
+    }
+}
+// GMRES: w -= sum_i hcoef[i] V_i
+__global__ void k_multiaxpy(int64_t n, int k, const double* __restrict__ V, int64_t ld, const double* __restrict__ hcoef, double* __restrict__ w) {
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
+        double wj = w[j];
+        for (int i = 0; i < k; i++) wj -= hcoef[i] * V[(int64_t)i * ld + j];
+        w[j] = wj;
+    }
+}
+// y = a * x (+ y if acc)
+__global__ void k_scale(int64_t n, double alpha, const double* __restrict__ x, double* __restrict__ y, int acc) {
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) y[j] = acc ? y[j] + alpha * x[j] : alpha * x[j];
+}
+// z = dinv .* r (or copy if dinv is null)
+__global__ void k_pmul(int64_t n, const double* __restrict__ dinv, const double* __restrict__ r, double* __restrict__ z) {
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) z[j] = dinv ? r[j] * dinv[j] : r[j];
+}
+// reciprocal point diagonal for the fused Jacobi preconditioner
+template <int NS>
+__global__ void k_dinv(int64_t Nown, const double* __restrict__ diagval, double* __restrict__ dinv, const SpmvArgs a) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= Nown) return;
+#pragma unroll
+    for (int i = 0; i < NS; i++) dinv[r * NS + i] = 1.0 / diagval[(int64_t)a.idxD[i * NS + i] * Nown + r];
 }
 
 // ---- preconditioners ----------------------------------------------------------------------------------------
@@ -402,8 +498,25 @@ SpmvArgs make_spmv_args(vfvm_handle* h) {
     return a;
 }
 
+// reduce `nvals` x `nparts` block partials into sc[S_TMP0..] and apply the scalar recurrence `op`; with several ranks the
+// all-reduce sits between the two
+void finalize(vfvm_handle* h, const double* part, int nparts, int nvals, int op) {
+    if (h->nranks <= 1) {
+        k_finalize_op<<<1, 1024, 0, h->stream>>>(part, nparts, nvals, h->red.p, op, h->flags.p);
+        h->launches++;
+    } else {
+        k_finalize_op<<<1, 1024, 0, h->stream>>>(part, nparts, nvals, h->red.p, OP_NONE, h->flags.p);
+        h->launches++;
+        vfvm_comm_allreduce_sum(h, h->red.p + S_TMP0, nvals);
+        if (op != OP_NONE) {
+            k_scalar<<<1, 1, 0, h->stream>>>(op, h->red.p, h->flags.p);
+            h->launches++;
+        }
+    }
+}
+
 template <int NS>
-void launch_spmv(vfvm_handle* h, SpmvArgs& a) {
+void launch_spmv(vfvm_handle* h, SpmvArgs& a, int op) {
     auto kern = k_spmv<NS>;
     static int occ = 0;
     if (occ == 0) {
@@ -419,37 +532,27 @@ void launch_spmv(vfvm_handle* h, SpmvArgs& a) {
     }
     kern<<<grid, LS_THREADS, 0, h->stream>>>(a);
     h->launches++;
-    if (a.w) {
-        k_finalize<<<1, 1024, 0, h->stream>>>(a.part, grid, 2, h->red.p + S_TMP0);
-        h->launches++;
-    }
+    if (a.w) finalize(h, a.part, grid, 2, op);
 }
 
-// y = A x (+ fused dots (y,w), (y,y) -> sc[S_TMP0], sc[S_TMP1])
-void spmv(vfvm_handle* h, double* x, double* y, const double* w) {
+// y = A x (+ fused dots (y,w), (y,y) -> sc[S_TMP0], sc[S_TMP1], then scalar recurrence `op`)
+void spmv(vfvm_handle* h, double* x, double* y, const double* w, int op = OP_NONE) {
     if (h->nranks > 1) vfvm_halo_exchange_ptr(h, x);
     SpmvArgs a = make_spmv_args(h);
     a.x = x;
     a.y = y;
     a.w = w;
-    NS_DISPATCH(h->n, launch_spmv<NS>(h, a));
-    if (w) vfvm_comm_allreduce_sum(h, h->red.p + S_TMP0, 2);
-}
-
-void reduce2_sum(vfvm_handle* h, const double* part, int nparts) {
-    k_finalize<<<1, 1024, 0, h->stream>>>(part, nparts, 2, h->red.p + S_TMP0);
-    h->launches++;
-    vfvm_comm_allreduce_sum(h, h->red.p + S_TMP0, 2);
-}
-
-void scalar_op(vfvm_handle* h, int op) {
-    k_scalar<<<1, 1, 0, h->stream>>>(op, h->red.p, h->flags.p);
-    h->launches++;
+    NS_DISPATCH(h->n, launch_spmv<NS>(h, a, op));
 }
 
 void precond_setup(vfvm_handle* h) {
     const int64_t Nown = h->Nown;
-    if (h->precon == VFVM_PRECON_BLOCKJACOBI) {
+    if (h->precon == VFVM_PRECON_JACOBI) {
+        h->pc_diag.alloc((size_t)h->n * Nown);
+        SpmvArgs a = make_spmv_args(h);
+        NS_DISPATCH(h->n, (k_dinv<NS><<<cdiv(Nown, 256), 256, 0, h->stream>>>(Nown, h->diagval.p, h->pc_diag.p, a)));
+        h->launches++;
+    } else if (h->precon == VFVM_PRECON_BLOCKJACOBI) {
         h->pc_diag.alloc((size_t)h->n * h->n * Nown);
         SpmvArgs a = make_spmv_args(h);
         NS_DISPATCH(h->n, (k_blockjacobi_setup<NS><<<cdiv(Nown, 128), 128, 0, h->stream>>>(Nown, h->diagval.p, h->pc_diag.p, h->flags.p, a)));
@@ -460,17 +563,16 @@ void precond_setup(vfvm_handle* h) {
     h->precon_valid = true;
 }
 
+// preconditioners that are not fused into the vector kernels
 void precond_apply(vfvm_handle* h, const double* in, double* out) {
     const int64_t Nown = h->Nown;
     const int64_t nd = Nown * h->n;
     switch (h->precon) {
         case VFVM_PRECON_NONE: CK(cudaMemcpyAsync(out, in, nd * sizeof(double), cudaMemcpyDeviceToDevice, h->stream)); break;
-        case VFVM_PRECON_JACOBI: {
-            SpmvArgs a = make_spmv_args(h);
-            NS_DISPATCH(h->n, (k_jacobi<NS><<<cdiv(Nown, 256), 256, 0, h->stream>>>(Nown, h->diagval.p, in, out, a)));
+        case VFVM_PRECON_JACOBI:
+            k_pmul<<<VEC_GRID, LS_THREADS, 0, h->stream>>>(nd, h->pc_diag.p, in, out);
             h->launches++;
             break;
-        }
         case VFVM_PRECON_BLOCKJACOBI:
             NS_DISPATCH(h->n, (k_blockjacobi_apply<NS><<<cdiv(Nown, 128), 128, 0, h->stream>>>(Nown, h->pc_diag.p, in, out)));
             h->launches++;
@@ -479,11 +581,34 @@ void precond_apply(vfvm_handle* h, const double* in, double* out) {
     }
 }
 
-double read_scalar(vfvm_handle* h, int slot) {
-    CK(cudaMemcpyAsync(h->red_host, h->red.p + slot, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    return h->red_host[0];
-}
+// stopping test without stalling the stream: the residual norm of iteration k is copied to pinned memory behind an event
+// and inspected after iteration k+1 has been enqueued (at most one extra iteration is performed)
+struct AsyncNorm {
+    vfvm_handle* h;
+    cudaEvent_t ev[2];
+    int pending[2] = {-1, -1};
+    explicit AsyncNorm(vfvm_handle* hh) : h(hh) {
+        ev[0] = hh->ev3;
+        ev[1] = hh->ev4;
+    }
+    void post(int it, int slot_rr) {
+        const int s = it & 1;
+        CK(cudaMemcpyAsync(h->red_host + 2 * s, h->red.p + slot_rr, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(h->flags_host + s, h->flags.p, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaEventRecord(ev[s], h->stream));
+        pending[s] = it;
+    }
+    // returns true and fills rr / flags if iteration `it` has been posted
+    bool fetch(int it, double& rr, int& flags) {
+        const int s = it & 1;
+        if (it < 0 || pending[s] != it) return false;
+        CK(cudaEventSynchronize(ev[s]));
+        rr = h->red_host[2 * s];
+        flags = h->flags_host[s];
+        pending[s] = -1;
+        return true;
+    }
+};
 
 }  // namespace
 
@@ -493,10 +618,9 @@ extern "C" int vfvm_linsolve_setup(vfvm_handle* h, int krylov, int precon, int g
     if (!h) return VFVM_ERR_ARG;
     if (krylov < VFVM_KRYLOV_BICGSTAB || krylov > VFVM_KRYLOV_GMRES) return vfvm_fail(h, VFVM_ERR_ARG, "unknown Krylov method");
     if (precon < VFVM_PRECON_NONE || precon > VFVM_PRECON_ILU0) return vfvm_fail(h, VFVM_ERR_ARG, "unknown preconditioner");
-    if (krylov == VFVM_KRYLOV_GMRES) return vfvm_fail(h, VFVM_ERR_UNSUPPORTED, "GMRES is not built yet; use BiCGStab or CG");
     h->krylov = krylov;
     h->precon = precon;
-    h->gmres_restart = gmres_restart > 0 ? gmres_restart : 30;
+    h->gmres_restart = gmres_restart > 0 ? std::min(gmres_restart, 100) : 30;
     h->precon_valid = false;
     return VFVM_OK;
 }
@@ -505,6 +629,7 @@ extern "C" int vfvm_linsolve_setup(vfvm_handle* h, int krylov, int precon, int g
 extern "C" int vfvm_linsolve(vfvm_handle* h, double abstol, double reltol, int maxiters, int reuse_precs, int* iters, double* resnorm) {
     if (!h || !h->have_pattern) return vfvm_fail(h, VFVM_ERR_STATE, "vfvm_build_pattern has not been called");
     VFVM_TRY(h, {
+        CK(cudaSetDevice(h->device));
         cudaStream_t st = h->stream;
         const int64_t nd = h->Nown * h->n, nall = h->N * h->n;
         double* b = h->vec[VFVM_VEC_RESIDUAL].p;
@@ -514,7 +639,7 @@ extern "C" int vfvm_linsolve(vfvm_handle* h, double abstol, double reltol, int m
                 h->work[i].alloc(nall);
                 CK(cudaMemsetAsync(h->work[i].p, 0, nall * sizeof(double), st));
             }
-        if (h->work[11].n < (size_t)4 * VEC_GRID) h->work[11].alloc((size_t)4 * VEC_GRID);
+        if (h->work[11].n < (size_t)128 * VEC_GRID) h->work[11].alloc((size_t)128 * VEC_GRID);
         double* part = h->work[11].p;
         CK(cudaMemsetAsync(h->flags.p, 0, sizeof(int32_t), st));
 
@@ -522,10 +647,22 @@ extern "C" int vfvm_linsolve(vfvm_handle* h, double abstol, double reltol, int m
         if (!(reuse_precs && h->precon_valid)) precond_setup(h);
         CK(cudaEventRecord(h->ev1, st));
 
+        const bool fusedpc = (h->precon == VFVM_PRECON_NONE || h->precon == VFVM_PRECON_JACOBI);
+        const double* dinv = h->precon == VFVM_PRECON_JACOBI ? h->pc_diag.p : nullptr;
         CK(cudaMemsetAsync(x, 0, nall * sizeof(double), st));
-        int it = 0;
+        int it = 0, done_it = 0;
         double rr = 0.0, bb = 0.0, tol = 0.0;
-        bool converged = false;
+        bool converged = false, breakdown = false;
+        AsyncNorm an(h);
+        auto check = [&](int k) {  // inspects iteration k if posted
+            double v;
+            int fl;
+            if (!an.fetch(k, v, fl)) return;
+            rr = v;
+            done_it = k;
+            if (v != v || (fl & 6)) breakdown = true;
+            else if (sqrt(v) <= tol) converged = true;
+        };
         if (h->krylov == VFVM_KRYLOV_BICGSTAB) {
             double *r = h->work[0].p, *rhat = h->work[1].p, *p = h->work[2].p, *v = h->work[3].p, *s = h->work[4].p, *t = h->work[5].p, *phat = h->work[6].p,
                    *shat = h->work[7].p;
@@ -535,80 +672,167 @@ extern "C" int vfvm_linsolve(vfvm_handle* h, double abstol, double reltol, int m
             CK(cudaMemsetAsync(v, 0, nd * sizeof(double), st));
             k_dot2<<<VEC_GRID, LS_THREADS, 0, st>>>(nd, r, r, part);
             h->launches++;
-            reduce2_sum(h, part, VEC_GRID);
-            scalar_op(h, OP_BICG_INIT);
-            bb = read_scalar(h, S_BB);
+            finalize(h, part, VEC_GRID, 2, OP_BICG_INIT);
+            an.post(0, S_BB);
+            check(0);
+            bb = rr;
             tol = fmax(abstol, reltol * sqrt(bb));
-            rr = bb;
             converged = sqrt(rr) <= tol;
-            while (!converged && it < maxiters) {
+            while (!converged && !breakdown && it < maxiters) {
                 it++;
-                scalar_op(h, OP_BICG_BETA);
-                k_bicg_p<<<VEC_GRID, LS_THREADS, 0, st>>>(nd, h->red.p, r, v, p);
+                k_bicg_p<<<VEC_GRID, LS_THREADS, 0, st>>>(nd, h->red.p, r, v, p, dinv, fusedpc ? phat : nullptr);
                 h->launches++;
-                precond_apply(h, p, phat);
-                spmv(h, phat, v, rhat);  // (v, rhat) -> TMP0
-                scalar_op(h, OP_BICG_ALPHA);
-                k_bicg_s<<<VEC_GRID, LS_THREADS, 0, st>>>(nd, h->red.p, r, v, s);
+                if (!fusedpc) precond_apply(h, p, phat);
+                spmv(h, phat, v, rhat, OP_BICG_ALPHA);  // (v, rhat)
+                k_bicg_s<<<VEC_GRID, LS_THREADS, 0, st>>>(nd, h->red.p, r, v, s, dinv, fusedpc ? shat : nullptr);
                 h->launches++;
-                precond_apply(h, s, shat);
-                spmv(h, shat, t, s);  // (t, s) -> TMP0 ; (t,t) -> TMP1
-                scalar_op(h, OP_BICG_OMEGA);
+                if (!fusedpc) precond_apply(h, s, shat);
+                spmv(h, shat, t, s, OP_BICG_OMEGA);  // (t, s), (t, t)
                 k_bicg_xr<<<VEC_GRID, LS_THREADS, 0, st>>>(nd, h->red.p, phat, shat, s, t, rhat, x, r, part);
                 h->launches++;
-                reduce2_sum(h, part, VEC_GRID);  // (rhat, r) -> TMP0 ; (r,r) -> TMP1
-                // rho_old = rho ; rho = TMP0 ; rr = TMP1  (host reads rr for the stopping test)
-                CK(cudaMemcpyAsync(h->red.p + S_RHO_OLD, h->red.p + S_RHO, sizeof(double), cudaMemcpyDeviceToDevice, st));
-                CK(cudaMemcpyAsync(h->red.p + S_RHO, h->red.p + S_TMP0, sizeof(double), cudaMemcpyDeviceToDevice, st));
-                CK(cudaMemcpyAsync(h->red_host, h->red.p + S_TMP1, sizeof(double), cudaMemcpyDeviceToHost, st));
-                CK(cudaMemcpyAsync(h->flags_host, h->flags.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-                CK(cudaStreamSynchronize(st));
-                rr = h->red_host[0];
-                if (rr != rr || (h->flags_host[0] & 6)) {
-                    *iters = it;
-                    *resnorm = sqrt(rr);
-                    h->err = "BiCGStab breakdown (zero pivot / NaN)";
-                    return VFVM_ERR_LINSOLVE;
-                }
-                converged = sqrt(rr) <= tol;
+                finalize(h, part, VEC_GRID, 2, OP_BICG_NEXT);  // (rhat, r), (r, r)
+                an.post(it, S_RR);
+                check(it - 1);
             }
-        } else {  // preconditioned CG
+            if (!converged && !breakdown) check(it);
+        } else if (h->krylov == VFVM_KRYLOV_CG) {
             double *r = h->work[0].p, *z = h->work[1].p, *p = h->work[2].p, *q = h->work[3].p;
             CK(cudaMemcpyAsync(r, b, nd * sizeof(double), cudaMemcpyDeviceToDevice, st));
-            precond_apply(h, r, z);
+            if (fusedpc) {
+                k_pmul<<<VEC_GRID, LS_THREADS, 0, st>>>(nd, dinv, r, z);
+                h->launches++;
+            } else {
+                precond_apply(h, r, z);
+            }
             CK(cudaMemcpyAsync(p, z, nd * sizeof(double), cudaMemcpyDeviceToDevice, st));
             k_dot2<<<VEC_GRID, LS_THREADS, 0, st>>>(nd, z, r, part);  // (z,r), (r,r)
             h->launches++;
-            reduce2_sum(h, part, VEC_GRID);
-            scalar_op(h, OP_CG_INIT);
-            bb = read_scalar(h, S_BB);
+            finalize(h, part, VEC_GRID, 2, OP_CG_INIT);
+            an.post(0, S_BB);
+            check(0);
+            bb = rr;
             tol = fmax(abstol, reltol * sqrt(bb));
-            rr = bb;
             converged = sqrt(rr) <= tol;
-            while (!converged && it < maxiters) {
+            while (!converged && !breakdown && it < maxiters) {
                 it++;
-                spmv(h, p, q, p);  // (q,p) -> TMP0
-                scalar_op(h, OP_CG_ALPHA);
-                k_cg_xr<<<VEC_GRID, LS_THREADS, 0, st>>>(nd, h->red.p, p, q, x, r);
+                spmv(h, p, q, p, OP_CG_ALPHA);  // (q, p)
+                k_cg_xr<<<VEC_GRID, LS_THREADS, 0, st>>>(nd, h->red.p, p, q, x, r, dinv, z, fusedpc ? 1 : 0, part);
                 h->launches++;
-                precond_apply(h, r, z);
-                k_dot2<<<VEC_GRID, LS_THREADS, 0, st>>>(nd, z, r, part);
-                h->launches++;
-                reduce2_sum(h, part, VEC_GRID);
-                scalar_op(h, OP_CG_BETA);
+                if (!fusedpc) {
+                    precond_apply(h, r, z);
+                    k_dot2<<<VEC_GRID, LS_THREADS, 0, st>>>(nd, z, r, part);
+                    h->launches++;
+                }
+                finalize(h, part, VEC_GRID, 2, OP_CG_NEXT);
                 k_cg_p<<<VEC_GRID, LS_THREADS, 0, st>>>(nd, h->red.p, z, p);
                 h->launches++;
-                CK(cudaMemcpyAsync(h->red_host, h->red.p + S_RR, sizeof(double), cudaMemcpyDeviceToHost, st));
-                CK(cudaMemcpyAsync(h->flags_host, h->flags.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+                an.post(it, S_RR);
+                check(it - 1);
+            }
+            if (!converged && !breakdown) check(it);
+        } else {
+            // restarted GMRES(m), right preconditioned, classical Gram-Schmidt with one fused multi-dot pass (+ one
+            // re-orthogonalisation pass), Givens rotations on the host (m+1 scalars per iteration cross PCIe)
+            const int m = h->gmres_restart;
+            if (h->work[8].n != (size_t)(m + 1) * nall) h->work[8].alloc((size_t)(m + 1) * nall);
+            if (h->work[9].n < (size_t)(m + 2)) h->work[9].alloc((size_t)(m + 2));
+            double* V = h->work[8].p;
+            double* hdev = h->work[9].p;
+            double *w = h->work[0].p, *zv = h->work[1].p, *r = h->work[2].p;
+            std::vector<double> H((size_t)(m + 1) * m, 0.0), cs(m, 0.0), sn(m, 0.0), gvec(m + 1, 0.0), hcol(m + 2, 0.0), y(m, 0.0);
+            auto dots_to_host = [&](int k, const double* wv) {  // hcol[0..k-1] = (w, V_i), hcol[k] = (w,w)
+                k_multidot<<<VEC_GRID, LS_THREADS, 0, st>>>(nd, k, V, nall, wv, part);
+                k_finalize<<<1, 1024, 0, st>>>(part, VEC_GRID, k + 1, hdev);
+                h->launches += 2;
+                vfvm_comm_allreduce_sum(h, hdev, k + 1);
+                CK(cudaMemcpyAsync(hcol.data(), hdev, (k + 1) * sizeof(double), cudaMemcpyDeviceToHost, st));
                 CK(cudaStreamSynchronize(st));
-                rr = h->red_host[0];
-                if (rr != rr || (h->flags_host[0] & 6)) {
-                    *iters = it;
-                    *resnorm = sqrt(rr);
-                    h->err = "CG breakdown (zero curvature / NaN)";
-                    return VFVM_ERR_LINSOLVE;
+            };
+            CK(cudaMemcpyAsync(r, b, nd * sizeof(double), cudaMemcpyDeviceToDevice, st));
+            dots_to_host(0, r);
+            bb = hcol[0];
+            rr = bb;
+            tol = fmax(abstol, reltol * sqrt(bb));
+            converged = sqrt(rr) <= tol;
+            while (!converged && !breakdown && it < maxiters) {
+                const double beta = sqrt(rr);
+                k_scale<<<VEC_GRID, LS_THREADS, 0, st>>>(nd, 1.0 / beta, r, V, 0);
+                h->launches++;
+                std::fill(gvec.begin(), gvec.end(), 0.0);
+                gvec[0] = beta;
+                int k = 0;
+                for (; k < m && it < maxiters && !converged; k++) {
+                    it++;
+                    double* vk = V + (int64_t)k * nall;
+                    if (fusedpc) {
+                        k_pmul<<<VEC_GRID, LS_THREADS, 0, st>>>(nd, dinv, vk, zv);
+                        h->launches++;
+                    } else {
+                        precond_apply(h, vk, zv);
+                    }
+                    spmv(h, zv, w, nullptr);
+                    for (int pass = 0; pass < 2; pass++) {  // CGS2
+                        dots_to_host(k + 1, w);
+                        CK(cudaMemcpyAsync(hdev, hcol.data(), (k + 1) * sizeof(double), cudaMemcpyHostToDevice, st));
+                        k_multiaxpy<<<VEC_GRID, LS_THREADS, 0, st>>>(nd, k + 1, V, nall, hdev, w);
+                        h->launches++;
+                        for (int i = 0; i <= k; i++) H[(size_t)i * m + k] += hcol[i];
+                    }
+                    dots_to_host(0, w);
+                    const double hk1 = sqrt(hcol[0]);
+                    if (hk1 != hk1) {
+                        breakdown = true;
+                        break;
+                    }
+                    H[(size_t)(k + 1) * m + k] = hk1;
+                    if (hk1 > 0.0) {
+                        k_scale<<<VEC_GRID, LS_THREADS, 0, st>>>(nd, 1.0 / hk1, w, V + (int64_t)(k + 1) * nall, 0);
+                        h->launches++;
+                    }
+                    for (int i = 0; i < k; i++) {  // previous rotations
+                        const double t1 = cs[i] * H[(size_t)i * m + k] + sn[i] * H[(size_t)(i + 1) * m + k];
+                        H[(size_t)(i + 1) * m + k] = -sn[i] * H[(size_t)i * m + k] + cs[i] * H[(size_t)(i + 1) * m + k];
+                        H[(size_t)i * m + k] = t1;
+                    }
+                    const double a1 = H[(size_t)k * m + k], a2 = H[(size_t)(k + 1) * m + k], den = hypot(a1, a2);
+                    cs[k] = den > 0 ? a1 / den : 1.0;
+                    sn[k] = den > 0 ? a2 / den : 0.0;
+                    H[(size_t)k * m + k] = den;
+                    H[(size_t)(k + 1) * m + k] = 0.0;
+                    gvec[k + 1] = -sn[k] * gvec[k];
+                    gvec[k] = cs[k] * gvec[k];
+                    rr = gvec[k + 1] * gvec[k + 1];
+                    converged = fabs(gvec[k + 1]) <= tol;
                 }
-                converged = sqrt(rr) <= tol;
+                // x += M^-1 V y with H y = g
+                for (int i = k - 1; i >= 0; i--) {
+                    double sum = gvec[i];
+                    for (int j = i + 1; j < k; j++) sum -= H[(size_t)i * m + j] * y[j];
+                    y[i] = sum / H[(size_t)i * m + i];
+                }
+                CK(cudaMemsetAsync(w, 0, nd * sizeof(double), st));
+                for (int i = 0; i < k; i++) {
+                    k_scale<<<VEC_GRID, LS_THREADS, 0, st>>>(nd, y[i], V + (int64_t)i * nall, w, 1);
+                    h->launches++;
+                }
+                if (fusedpc) {
+                    k_pmul<<<VEC_GRID, LS_THREADS, 0, st>>>(nd, dinv, w, zv);
+                    h->launches++;
+                } else {
+                    precond_apply(h, w, zv);
+                }
+                k_scale<<<VEC_GRID, LS_THREADS, 0, st>>>(nd, 1.0, zv, x, 1);
+                h->launches++;
+                std::fill(H.begin(), H.end(), 0.0);
+                if (!converged && !breakdown && it < maxiters) {  // true residual for the restart
+                    spmv(h, x, w, nullptr);
+                    CK(cudaMemcpyAsync(r, b, nd * sizeof(double), cudaMemcpyDeviceToDevice, st));
+                    k_scale<<<VEC_GRID, LS_THREADS, 0, st>>>(nd, -1.0, w, r, 1);
+                    h->launches++;
+                    dots_to_host(0, r);
+                    rr = hcol[0];
+                    converged = sqrt(rr) <= tol;
+                }
             }
         }
         CK(cudaEventRecord(h->ev2, st));
@@ -621,7 +845,11 @@ extern "C" int vfvm_linsolve(vfvm_handle* h, double abstol, double reltol, int m
         h->times[VFVM_TIME_LINSOLVE_SOLVE] = ms;
         *iters = it;
         *resnorm = sqrt(rr);
-        (void)converged;  // like Krylov.jl under LinearSolve, hitting maxiters is not an error: the Newton loop judges the update
+        if (breakdown) {
+            h->err = "Krylov breakdown (zero pivot / NaN)";
+            return VFVM_ERR_LINSOLVE;
+        }
+        // like Krylov.jl under LinearSolve, hitting maxiters is not an error: the Newton loop judges the update
     })
     return VFVM_OK;
 }

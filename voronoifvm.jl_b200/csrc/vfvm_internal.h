@@ -93,7 +93,7 @@ static inline void mask_set(uint64_t* m, int bit) { m[bit >> 6] |= (1ull << (bit
 struct vfvm_handle {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, ev4 = nullptr;
     std::string err;
     int64_t bytes = 0;
     int64_t launches = 0;

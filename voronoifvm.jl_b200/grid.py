@@ -56,10 +56,14 @@ class Grid:
 
     @property
     def num_cellregions(self) -> int:
+        if getattr(self, "_num_cellregions", None):
+            return self._num_cellregions  # a rank-local piece keeps the region count of the whole grid
         return int(self.cellregions.max()) if self.cellregions.size else 0
 
     @property
     def num_bfaceregions(self) -> int:
+        if getattr(self, "_num_bfaceregions", None):
+            return self._num_bfaceregions
         return int(self.bfaceregions.max()) if self.bfaceregions.size else 0
 
 

@@ -1,0 +1,120 @@
+"""Node-owner partitioning of a grid across ranks (one process per GPU) + halo maps.
+
+The reference only partitions for shared-memory threads (ExtendableGrids `PartitionNodes/PartitionCells`,
+src/vfvm_system.jl:673-682,741-748; coloured loops src/vfvm_assembly.jl:571-612).  Here rank p owns a contiguous range of
+node numbers (z-slabs on x-fastest tensor grids).  Its local grid holds every cell that touches an owned node, so that the
+form factors of all owned nodes and of all edges with an owned end are complete; the local node numbering is
+[owned nodes (ascending global)] + [halo nodes grouped by owner rank, ascending global].  Each rank assembles only its own
+rows -- assembly needs no collective -- and NCCL carries the halo refresh of U / Krylov vectors and the dot-product
+all-reduces (csrc/comm.cu).  Every rank derives all maps from the replicated host grid, without communication.
+"""
+from __future__ import annotations
+
+import dataclasses
+
+import numpy as np
+
+from .grid import Grid
+from .system import System
+
+
+@dataclasses.dataclass
+class PartitionInfo:
+    rank: int
+    nparts: int
+    node_ranges: np.ndarray  # (nparts+1,) global node offsets
+    local_nodes: np.ndarray  # (Nloc,) global index of each local node; first n_owned are owned
+    n_owned: int
+    neighbor_ranks: np.ndarray  # (nn,) int32
+    send_ptr: np.ndarray  # (nn+1,) int64
+    send_idx: np.ndarray  # local (owned) node indices to send, grouped by neighbour
+    recv_ptr: np.ndarray  # (nn+1,) int64 offsets into the halo range
+    num_bfaces: int
+    grid: Grid
+
+    @property
+    def num_halo(self):
+        return self.local_nodes.size - self.n_owned
+
+
+def node_ranges(num_nodes: int, nparts: int) -> np.ndarray:
+    return (np.arange(nparts + 1, dtype=np.int64) * num_nodes) // nparts
+
+
+def partition_grid(grid: Grid, rank: int, nparts: int) -> PartitionInfo:
+    N = grid.num_nodes
+    rng = node_ranges(N, nparts)
+    lo, hi = int(rng[rank]), int(rng[rank + 1])
+    cn = grid.cellnodes
+    owned_mask = (cn >= lo) & (cn < hi)
+    csel = owned_mask.any(axis=0)
+    lcells = cn[:, csel]
+    nodes = np.unique(lcells)
+    is_owned = (nodes >= lo) & (nodes < hi)
+    owned = np.arange(lo, hi, dtype=np.int64)  # every owned node is kept, even if isolated
+    halo = nodes[~is_owned].astype(np.int64)
+    halo_owner = np.searchsorted(rng, halo, side="right") - 1
+    order = np.lexsort((halo, halo_owner))
+    halo, halo_owner = halo[order], halo_owner[order]
+    local_nodes = np.concatenate([owned, halo])
+    # global -> local
+    g2l = np.full(N, -1, dtype=np.int64)
+    g2l[local_nodes] = np.arange(local_nodes.size)
+    lcellnodes = g2l[lcells].astype(np.int32)
+    bsel = ((grid.bfacenodes >= lo) & (grid.bfacenodes < hi)).any(axis=0)
+    lbf = g2l[grid.bfacenodes[:, bsel]]
+    assert (lbf >= 0).all(), "a boundary face with an owned node must belong to a local cell"
+    lgrid = Grid(grid.dim, grid.coord[:, local_nodes], lcellnodes, grid.cellregions[csel], lbf.astype(np.int32), grid.bfaceregions[bsel], grid.coordsys)
+    # the grid-wide region counts must survive on every rank (physics tables are indexed by region label)
+    lgrid._num_cellregions = grid.num_cellregions
+    lgrid._num_bfaceregions = grid.num_bfaceregions
+    # neighbours + exchange lists
+    nbr = np.unique(halo_owner).astype(np.int32)
+    recv_ptr = np.concatenate([[0], np.cumsum([np.count_nonzero(halo_owner == q) for q in nbr])]).astype(np.int64)
+    send_lists = []
+    cell_owner = np.searchsorted(rng, lcells, side="right") - 1  # (nn, Cloc)
+    mine = cell_owner == rank
+    for q in nbr:
+        touches_q = (cell_owner == q).any(axis=0)
+        snodes = np.unique(lcells[:, touches_q][mine[:, touches_q]])
+        send_lists.append(g2l[snodes].astype(np.int32))
+    send_ptr = np.concatenate([[0], np.cumsum([s.size for s in send_lists])]).astype(np.int64)
+    send_idx = np.concatenate(send_lists).astype(np.int32) if send_lists else np.zeros(0, np.int32)
+    return PartitionInfo(rank, nparts, rng, local_nodes, hi - lo, nbr, send_ptr, send_idx, recv_ptr, int(bsel.sum()), lgrid)
+
+
+def local_system(system: System, info: PartitionInfo) -> System:
+    """the same species / physics / legacy boundary tables on the rank's local grid"""
+    ls = System(info.grid, system.physics, is_linear=system.is_linear, assembly=system.assembly_type, unknown_storage=system.unknown_storage)
+    ls._increase_num_species(system.num_species)
+    ls.region_species[:, :] = system.region_species
+    ls.boundary_factors[:, :] = system.boundary_factors
+    ls.boundary_values[:, :] = system.boundary_values
+    ls._version += 1
+    return ls
+
+
+def partitioned_state(system: System, rank: int, world: int, device: int):
+    """device twin of rank `rank`: local grid, owned rows, NCCL communicator (id shared through torch.distributed)"""
+    import ctypes as C
+
+    import torch.distributed as dist
+
+    from . import _lib
+    from .state import SystemState
+
+    info = partition_grid(system.grid, rank, world)
+    ls = local_system(system, info)
+    st = SystemState(ls, device=device, owned_nodes=info.n_owned)
+    L = st.L
+    uid = C.create_string_buffer(128)
+    if rank == 0:
+        _lib.check(st.h, L.vfvm_comm_unique_id(uid))
+    box = [uid.raw]
+    dist.broadcast_object_list(box, src=0)
+    _lib.check(st.h, L.vfvm_comm_init(st.h, rank, world, box[0]))
+    nb = np.ascontiguousarray(info.neighbor_ranks, dtype=np.int32)
+    _lib.check(st.h, L.vfvm_set_halo(st.h, nb.size, _lib.i32ptr(nb), _lib.i64ptr(info.send_ptr), _lib.i32ptr(np.ascontiguousarray(info.send_idx, dtype=np.int32)),
+                                     _lib.i64ptr(info.recv_ptr)))
+    st.partition = info
+    return st, info

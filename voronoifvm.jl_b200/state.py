@@ -196,3 +196,8 @@ class SystemState:
         a, b = C.c_int(), C.c_int()
         check(self.h, self.L.vfvm_plane_counts(self.h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def block_counts(self):
+        a, b = C.c_int64(), C.c_int64()
+        check(self.h, self.L.vfvm_block_counts(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
