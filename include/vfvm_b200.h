@@ -129,7 +129,8 @@ typedef struct vfvm_bc_entry {
 #define VFVM_PRECON_NONE 0
 #define VFVM_PRECON_JACOBI 1      /* JacobiPreconBuilder: point diagonal                         */
 #define VFVM_PRECON_BLOCKJACOBI 2 /* n x n node-block inverse (BlockPreconBuilder with node blocks) */
-#define VFVM_PRECON_ILU0 3        /* ILUZeroPreconBuilder on the block pattern                   */
+#define VFVM_PRECON_ILU0 3        /* ILUZeroPreconBuilder on the node-block pattern, natural order  */
+#define VFVM_PRECON_ILU0_MC 4     /* same factorisation in multicolour elimination order (few levels) */
 
 /* ---- lifecycle -------------------------------------------------------------------------------------- */
 int vfvm_create(int device, vfvm_handle** out);

@@ -252,7 +252,8 @@ def test_spmv_matches_scipy():
         st.close()
 
 
-@pytest.mark.parametrize("method", ["default", "bicgstab_jacobi", "cg_jacobi", "bicgstab_block", "gmres_jacobi", "gmres_block", "cg_none"])
+@pytest.mark.parametrize("method", ["default", "bicgstab_jacobi", "cg_jacobi", "bicgstab_block", "gmres_jacobi", "gmres_block", "cg_none", "bicgstab_ilu0", "cg_ilu0",
+                                    "bicgstab_ilu0mc", "gmres_ilu0mc"])
 def test_newton_example301(method):
     """Example301: solution[43] known answer, and agreement with the oracle's direct solve"""
     X = np.linspace(0, 1, 6)
@@ -262,7 +263,10 @@ def test_newton_example301(method):
     v.boundary_dirichlet(sys, 1, 6, 0.0)
     ml = {"default": None, "bicgstab_jacobi": v.KrylovJL_BICGSTAB(precs=v.JacobiPreconBuilder()), "cg_jacobi": v.KrylovJL_CG(precs=v.JacobiPreconBuilder()),
           "bicgstab_block": v.KrylovJL_BICGSTAB(precs=v.BlockPreconBuilder()), "gmres_jacobi": v.KrylovJL_GMRES(precs=v.JacobiPreconBuilder(), restart=40),
-          "gmres_block": v.KrylovJL_GMRES(precs=v.BlockPreconBuilder(), restart=25), "cg_none": v.KrylovJL_CG()}[method]
+          "gmres_block": v.KrylovJL_GMRES(precs=v.BlockPreconBuilder(), restart=25), "cg_none": v.KrylovJL_CG(),
+          "bicgstab_ilu0": v.KrylovJL_BICGSTAB(precs=v.ILUZeroPreconBuilder()), "cg_ilu0": v.KrylovJL_CG(precs=v.ILUZeroPreconBuilder()),
+          "bicgstab_ilu0mc": v.KrylovJL_BICGSTAB(precs=v.ILUZeroPreconBuilder(multicolor=True)),
+          "gmres_ilu0mc": v.KrylovJL_GMRES(precs=v.ILUZeroPreconBuilder(multicolor=True))}[method]
     if method == "cg_none":  # without a preconditioner the 1e30 Dirichlet penalty makes Krylov hopeless: use Robin-free pure Neumann + reaction instead
         sys = v.System(v.simplexgrid(X, X, X), flux=ph.LinearDiffusion(), source=ph.XSinYExpZSource(1, 5.0), reaction=ph.PowerReaction(1.0, 1.0))
         v.enable_species(sys, 1, [1])
@@ -338,5 +342,81 @@ def test_unregistered_physics_id_is_an_error():
         p = np.zeros(1)
         rc = st.L.vfvm_set_physics(st.h, 0, 99, v._lib.dptr(p), 1)
         assert rc == v._lib.ERR_UNREGISTERED
+    finally:
+        st.close()
+
+
+@pytest.mark.parametrize("ns", [1, 2])
+def test_ilu0_is_exact_on_block_tridiagonal(ns):
+    """on a 1D grid the node-block matrix is block tridiagonal, ILU(0) is the exact LU: the Krylov solver must converge in one step"""
+    import ctypes as C
+
+    X = np.linspace(0, 1, 200)
+    if ns == 1:
+        sys = v.System(v.simplexgrid(X), flux=ph.PowerDiffusion(1.0, 2), reaction=ph.SinhReaction(0.3), species=[1])
+    else:
+        sys = v.System(v.simplexgrid(X), flux=ph.CrossDiffusion2((1.0, 0.5), 0.01), reaction=ph.BilinearReaction2(1.0), storage=ph.LinearStorage(1.0), species=[1, 2])
+    v.boundary_dirichlet(sys, 1, 1, 1.0)
+    v.boundary_dirichlet(sys, ns, 2, 0.5)
+    for precon in (v._lib.PRECON_ILU0, v._lib.PRECON_ILU0_MC):
+        st = v.SystemState(sys)
+        try:
+            U = _rand_u(sys)
+            st.set_vector(v._lib.VEC_SOLUTION, U)
+            st.set_vector(v._lib.VEC_OLDSOL, U)
+            assert st.assemble(tstep=0.1) == 0
+            A = st.matrix("csr")
+            F = st.get_vector(v._lib.VEC_RESIDUAL)
+            v._lib.check(st.h, st.L.vfvm_linsolve_setup(st.h, v._lib.KRYLOV_BICGSTAB, precon, 0))
+            it, rn = C.c_int(), C.c_double()
+            v._lib.check(st.h, st.L.vfvm_linsolve(st.h, 0.0, 1e-12, 50, 0, C.byref(it), C.byref(rn)))
+            x = st.get_vector(v._lib.VEC_UPDATE).ravel(order="F")
+            r = A @ x - F.ravel(order="F")
+            assert np.linalg.norm(r) <= 1e-10 * np.linalg.norm(F)
+            if precon == v._lib.PRECON_ILU0:
+                assert it.value <= 2, f"natural-order ILU(0) of a block tridiagonal matrix is exact, got {it.value} iterations"
+        finally:
+            st.close()
+
+
+def test_newton_example207_cg_ilu0():
+    """examples/Example207_NonlinearPoisson2D.jl:86: KrylovJL_CG(precs = ILUZeroPreconBuilder()) must reproduce U[15]"""
+    X = np.linspace(0, 1, 11)
+    sys = v.System(v.simplexgrid(X, X), flux=ph.PowerDiffusion(1.0e-2, 2), reaction=ph.PowerReaction(1.0, 2.0), source=ph.GaussSource(1, 20.0, (0.5, 0.5)),
+                   storage=ph.LinearStorage(1.0))
+    v.enable_species(sys, 1, [1])
+    v.boundary_dirichlet(sys, 1, 2, 0.1)
+    v.boundary_dirichlet(sys, 1, 4, 0.1)
+    st = v.SystemState(sys)
+    try:
+        control = v.SolverControl(reltol_linear=1.0e-5, method_linear=v.KrylovJL_CG(precs=v.ILUZeroPreconBuilder()))
+        u = v.unknowns(sys, 0.5)
+        t, tstep = 0.0, 0.01
+        while t < 1.0:
+            t += tstep
+            u = v.solve(sys, state=st, inival=u, control=control, tstep=tstep)
+        assert u.ravel(order="F")[14] == pytest.approx(0.3554284760906605, rel=1.5e-8)  # the reference's isapprox default
+    finally:
+        st.close()
+
+
+def test_ilu0_beats_jacobi_in_iterations():
+    import ctypes as C
+
+    sys = v.System(_grid(3, 17), flux=ph.LinearDiffusion(), source=ph.XSinYExpZSource(1, 5.0), species=[1])
+    v.boundary_dirichlet(sys, 1, 5, 0.0)
+    v.boundary_dirichlet(sys, 1, 6, 0.0)
+    st = v.SystemState(sys)
+    try:
+        st.set_vector(v._lib.VEC_SOLUTION, v.unknowns(sys, 0.0))
+        st.set_vector(v._lib.VEC_OLDSOL, v.unknowns(sys, 0.0))
+        assert st.assemble() == 0
+        its = {}
+        for name, pc in (("jacobi", v._lib.PRECON_JACOBI), ("ilu0", v._lib.PRECON_ILU0), ("ilu0mc", v._lib.PRECON_ILU0_MC)):
+            v._lib.check(st.h, st.L.vfvm_linsolve_setup(st.h, v._lib.KRYLOV_CG, pc, 0))
+            it, rn = C.c_int(), C.c_double()
+            v._lib.check(st.h, st.L.vfvm_linsolve(st.h, 0.0, 1e-10, 2000, 0, C.byref(it), C.byref(rn)))
+            its[name] = it.value
+        assert its["ilu0"] < its["ilu0mc"] <= its["jacobi"], its
     finally:
         st.close()

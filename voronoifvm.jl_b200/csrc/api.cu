@@ -44,7 +44,7 @@ extern "C" int vfvm_create(int device, vfvm_handle** out) {
     for (auto* b : dbl) b->tally = &h->bytes;
     for (auto& w : h->work) w.tally = &h->bytes;
     DevBuf<int32_t>* i32[] = {&h->cellnodes, &h->cellregions, &h->bfacenodes, &h->bfaceregions, &h->edgenodes, &h->celledges, &h->nf_region, &h->ef_region,
-                              &h->rowptr, &h->colidx, &h->sell_ptr, &h->nz_edge, &h->tile_row, &h->bn_node, &h->bn_ptr, &h->bn_bface, &h->bn_local, &h->upos, &h->ilu_level_rows, &h->send_idx};
+                              &h->rowptr, &h->colidx, &h->sell_ptr, &h->nz_edge, &h->tile_row, &h->bn_node, &h->bn_ptr, &h->bn_bface, &h->bn_local, &h->upos, &h->ilu_rank, &h->ilu_lrows, &h->ilu_urows, &h->send_idx};
     for (auto* b : i32) b->tally = &h->bytes;
     h->nf_colptr.tally = h->ef_colptr.tally = &h->bytes;
     *out = h;

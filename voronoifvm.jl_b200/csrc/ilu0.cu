@@ -1,5 +1,414 @@
-// K10: ILU(0) preconditioner -- placeholder until the level-scheduled kernels land.
+// K10: ILU(0) preconditioner on the DBSR / SELL-32 pattern (node blocks of NS x NS), replacing ILUZero.jl behind
+// `ILUZeroPreconBuilder` (examples/Example207_NonlinearPoisson2D.jl:86, examples/DevEx003_Solvers.jl:100-147; third party,
+// not under /root/reference -- the published algorithm is the standard IKJ incomplete factorisation without fill).
+//
+// Two elimination orders:
+//   VFVM_PRECON_ILU0     natural node order: the same factors a CPU ILU(0) on the block matrix produces; dependency levels
+//                        follow the mesh wavefronts (3 nx levels on an nx^3 tensor grid) -- level-scheduled launches
+//   VFVM_PRECON_ILU0_MC  multicolour order (greedy colouring of the node graph): a handful of levels, every triangular sweep
+//                        is as parallel as an SpMV -- the GPU-native variant, slightly weaker per iteration
+// With several ranks the factorisation is local to each rank (columns of halo nodes are dropped): additive Schwarz without
+// overlap, no communication inside the preconditioner.
+// Factor storage: full NS x NS blocks (the product of two masked blocks may fill inside a block), same SELL-32 positions as
+// A for the off-diagonal blocks; the diagonal block is stored inverted.
+#include <algorithm>
+#include <cub/cub.cuh>
+
 #include "vfvm_internal.h"
 
-void vfvm_ilu0_setup(vfvm_handle* h) { throw std::string("ILU0 preconditioner is not built yet; use Jacobi or block-Jacobi"); }
-void vfvm_ilu0_apply(vfvm_handle* h, const double* in, double* out) { throw std::string("ILU0 preconditioner is not built yet"); }
+namespace {
+
+struct IluArgs {
+    const int32_t* __restrict__ sell_ptr;
+    const int32_t* __restrict__ rowptr;
+    const int32_t* __restrict__ colidx;
+    const int32_t* __restrict__ rank;  // elimination order of each node
+    const int32_t* __restrict__ rows;  // rows of the current level
+    double* __restrict__ off;          // NS*NS planes x nnz_sell
+    double* __restrict__ dinv;         // NS*NS planes x Nown
+    const double* __restrict__ in;
+    double* __restrict__ out;
+    int32_t* flags;
+    int64_t nnz_sell, Nown;
+    int nrows;
+};
+
+// A planes (masked) -> full blocks
+template <int NS>
+__global__ void k_ilu_copy(int64_t nnz_sell, int64_t Nown, const double* __restrict__ offval, const double* __restrict__ diagval, double* __restrict__ off,
+                           double* __restrict__ dg, const signed char* __restrict__ idx) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nnz_sell) {
+#pragma unroll
+        for (int b = 0; b < NS * NS; b++) {
+            const int p = idx[b];
+            off[(int64_t)b * nnz_sell + i] = p >= 0 ? offval[(int64_t)p * nnz_sell + i] : 0.0;
+        }
+    }
+    if (i < Nown) {
+#pragma unroll
+        for (int b = 0; b < NS * NS; b++) {
+            const int p = idx[100 + b];
+            dg[(int64_t)b * Nown + i] = p >= 0 ? diagval[(int64_t)p * Nown + i] : 0.0;
+        }
+    }
+}
+
+template <int NS>
+__device__ __forceinline__ void blk_load(const double* __restrict__ base, int64_t stride, int64_t pos, double* B) {
+#pragma unroll
+    for (int b = 0; b < NS * NS; b++) B[b] = base[(int64_t)b * stride + pos];
+}
+template <int NS>
+__device__ __forceinline__ void blk_store(double* __restrict__ base, int64_t stride, int64_t pos, const double* B) {
+#pragma unroll
+    for (int b = 0; b < NS * NS; b++) base[(int64_t)b * stride + pos] = B[b];
+}
+// C = A * B
+template <int NS>
+__device__ __forceinline__ void blk_mul(const double* A, const double* B, double* C) {
+#pragma unroll
+    for (int i = 0; i < NS; i++)
+#pragma unroll
+        for (int j = 0; j < NS; j++) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < NS; k++) s += A[i * NS + k] * B[k * NS + j];
+            C[i * NS + j] = s;
+        }
+}
+// in-place inverse by Gauss-Jordan without pivoting; returns false on a zero pivot
+template <int NS>
+__device__ __forceinline__ bool blk_inv(double* A) {
+    double B[NS * NS];
+#pragma unroll
+    for (int i = 0; i < NS * NS; i++) B[i] = ((i / NS) == (i % NS)) ? 1.0 : 0.0;
+    bool ok = true;
+#pragma unroll
+    for (int c = 0; c < NS; c++) {
+        const double piv = A[c * NS + c];
+        ok &= fabs(piv) > 0.0;
+        const double ip = 1.0 / piv;
+#pragma unroll
+        for (int j = 0; j < NS; j++) {
+            A[c * NS + j] *= ip;
+            B[c * NS + j] *= ip;
+        }
+#pragma unroll
+        for (int i = 0; i < NS; i++) {
+            if (i == c) continue;
+            const double f = A[i * NS + c];
+#pragma unroll
+            for (int j = 0; j < NS; j++) {
+                A[i * NS + j] -= f * A[c * NS + j];
+                B[i * NS + j] -= f * B[c * NS + j];
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NS * NS; i++) A[i] = B[i];
+    return ok;
+}
+
+// one level of the IKJ factorisation: thread per row
+template <int NS>
+__global__ void k_ilu_factor(const IluArgs a) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.nrows) return;
+    const int K = a.rows[t];
+    const int64_t e0 = (int64_t)a.sell_ptr[K >> 5] + (K & 31);
+    const int len = a.rowptr[K + 1] - a.rowptr[K];
+    const int rk = a.rank[K];
+    double D[NS * NS];
+    blk_load<NS>(a.dinv, a.Nown, K, D);
+    int last = -1;  // rank of the lower neighbour processed last: neighbours are taken in ascending elimination order
+    for (;;) {
+        int jbest = -1, rbest = 0x7fffffff;
+        for (int j = 0; j < len; j++) {
+            const int L = a.colidx[e0 + 32 * (int64_t)j];
+            if (L >= a.Nown) continue;  // halo column: dropped (rank-local factorisation)
+            const int rl = a.rank[L];
+            if (rl < rk && rl > last && rl < rbest) {
+                rbest = rl;
+                jbest = j;
+            }
+        }
+        if (jbest < 0) break;
+        last = rbest;
+        const int64_t eKL = e0 + 32 * (int64_t)jbest;
+        const int L = a.colidx[eKL];
+        double B[NS * NS], T[NS * NS], W[NS * NS];
+        blk_load<NS>(a.off, a.nnz_sell, eKL, T);
+        blk_load<NS>(a.dinv, a.Nown, L, W);
+        blk_mul<NS>(T, W, B);  // L_KL = A_KL * inv(U_LL)
+        blk_store<NS>(a.off, a.nnz_sell, eKL, B);
+        const int64_t f0 = (int64_t)a.sell_ptr[L >> 5] + (L & 31);
+        const int lenL = a.rowptr[L + 1] - a.rowptr[L];
+        for (int q = 0; q < lenL; q++) {
+            const int64_t eLM = f0 + 32 * (int64_t)q;
+            const int M = a.colidx[eLM];
+            if (M >= a.Nown || a.rank[M] <= rbest) continue;  // only the U part of row L
+            blk_load<NS>(a.off, a.nnz_sell, eLM, W);
+            blk_mul<NS>(B, W, T);
+            if (M == K) {
+#pragma unroll
+                for (int b = 0; b < NS * NS; b++) D[b] -= T[b];
+            } else {
+                for (int j2 = 0; j2 < len; j2++) {
+                    const int64_t eKM = e0 + 32 * (int64_t)j2;
+                    if (a.colidx[eKM] == M) {
+#pragma unroll
+                        for (int b = 0; b < NS * NS; b++) a.off[(int64_t)b * a.nnz_sell + eKM] -= T[b];
+                        break;
+                    }
+                }
+            }
+        }
+    }
+    if (!blk_inv<NS>(D)) atomicOr(a.flags, 4);
+    blk_store<NS>(a.dinv, a.Nown, K, D);
+}
+
+// forward sweep level: y_K = r_K - sum_{rank L < rank K} L_KL y_L      (out holds y)
+template <int NS>
+__global__ void k_ilu_fwd(const IluArgs a) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.nrows) return;
+    const int K = a.rows[t];
+    const int64_t e0 = (int64_t)a.sell_ptr[K >> 5] + (K & 31);
+    const int len = a.rowptr[K + 1] - a.rowptr[K];
+    const int rk = a.rank[K];
+    double y[NS];
+#pragma unroll
+    for (int i = 0; i < NS; i++) y[i] = a.in[(int64_t)K * NS + i];
+    for (int j = 0; j < len; j++) {
+        const int64_t e = e0 + 32 * (int64_t)j;
+        const int L = a.colidx[e];
+        if (L >= a.Nown || a.rank[L] >= rk) continue;
+#pragma unroll
+        for (int i = 0; i < NS; i++)
+#pragma unroll
+            for (int k = 0; k < NS; k++) y[i] -= a.off[(int64_t)(i * NS + k) * a.nnz_sell + e] * a.out[(int64_t)L * NS + k];
+    }
+#pragma unroll
+    for (int i = 0; i < NS; i++) a.out[(int64_t)K * NS + i] = y[i];
+}
+
+// backward sweep level: z_K = inv(U_KK) (y_K - sum_{rank M > rank K} U_KM z_M)      (in place on out)
+template <int NS>
+__global__ void k_ilu_bwd(const IluArgs a) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.nrows) return;
+    const int K = a.rows[t];
+    const int64_t e0 = (int64_t)a.sell_ptr[K >> 5] + (K & 31);
+    const int len = a.rowptr[K + 1] - a.rowptr[K];
+    const int rk = a.rank[K];
+    double y[NS], z[NS];
+#pragma unroll
+    for (int i = 0; i < NS; i++) y[i] = a.out[(int64_t)K * NS + i];
+    for (int j = 0; j < len; j++) {
+        const int64_t e = e0 + 32 * (int64_t)j;
+        const int M = a.colidx[e];
+        if (M >= a.Nown || a.rank[M] <= rk) continue;
+#pragma unroll
+        for (int i = 0; i < NS; i++)
+#pragma unroll
+            for (int k = 0; k < NS; k++) y[i] -= a.off[(int64_t)(i * NS + k) * a.nnz_sell + e] * a.out[(int64_t)M * NS + k];
+    }
+#pragma unroll
+    for (int i = 0; i < NS; i++) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < NS; k++) s += a.dinv[(int64_t)(i * NS + k) * a.Nown + K] * y[k];
+        z[i] = s;
+    }
+#pragma unroll
+    for (int i = 0; i < NS; i++) a.out[(int64_t)K * NS + i] = z[i];
+}
+
+// dependency levels by fixed-point sweeps: lev[K] = 1 + max lev[L] over neighbours eliminated before (upper = 0) / after (upper = 1) K
+__global__ void k_level_sweep(int64_t Nown, int upper, const int32_t* __restrict__ sell_ptr, const int32_t* __restrict__ rowptr,
+                              const int32_t* __restrict__ colidx, const int32_t* __restrict__ rank, int32_t* __restrict__ lev, int32_t* __restrict__ changed) {
+    const int64_t K = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (K >= Nown) return;
+    const int64_t e0 = (int64_t)sell_ptr[K >> 5] + (K & 31);
+    const int len = rowptr[K + 1] - rowptr[K];
+    const int rk = rank[K];
+    int m = 0;
+    for (int j = 0; j < len; j++) {
+        const int L = colidx[e0 + 32 * (int64_t)j];
+        if (L >= Nown) continue;
+        const int rl = rank[L];
+        if (upper ? (rl > rk) : (rl < rk)) m = max(m, lev[L] + 1);
+    }
+    if (m != lev[K]) {
+        lev[K] = m;
+        *changed = 1;
+    }
+}
+__global__ void k_iota(int64_t n, int32_t* p) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = (int32_t)i;
+}
+
+#define NS_DISPATCH(n, ...)                                          \
+    switch (n) {                                                     \
+        case 1: { constexpr int NS = 1; __VA_ARGS__; } break;        \
+        case 2: { constexpr int NS = 2; __VA_ARGS__; } break;        \
+        case 3: { constexpr int NS = 3; __VA_ARGS__; } break;        \
+        case 4: { constexpr int NS = 4; __VA_ARGS__; } break;        \
+        case 5: { constexpr int NS = 5; __VA_ARGS__; } break;        \
+        case 10: { constexpr int NS = 10; __VA_ARGS__; } break;      \
+        default: throw std::string("number of species without device instantiation (supported: 1,2,3,4,5,10)"); \
+    }
+
+// rows sorted by level + level boundaries
+void build_levels(vfvm_handle* h, int upper, DevBuf<int32_t>& rows, std::vector<int32_t>& ptr) {
+    const int64_t Nown = h->Nown;
+    cudaStream_t s = h->stream;
+    DevBuf<int32_t> lev, lev2, rows2, changed;
+    lev.alloc(Nown);
+    changed.alloc(1);
+    CK(cudaMemsetAsync(lev.p, 0, Nown * 4, s));
+    for (int sweep = 0; sweep < 1 << 20; sweep++) {
+        CK(cudaMemsetAsync(changed.p, 0, 4, s));
+        k_level_sweep<<<cdiv(Nown, 256), 256, 0, s>>>(Nown, upper, h->sell_ptr.p, h->rowptr.p, h->colidx.p, h->ilu_rank.p, lev.p, changed.p);
+        h->launches++;
+        int32_t c = 0;
+        CK(cudaMemcpyAsync(&c, changed.p, 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        if (!c) break;
+    }
+    rows.alloc(Nown);
+    rows2.alloc(Nown);
+    lev2.alloc(Nown);
+    k_iota<<<cdiv(Nown, 256), 256, 0, s>>>(Nown, rows2.p);
+    size_t tmp = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, lev.p, lev2.p, rows2.p, rows.p, (int)Nown, 0, 32, s));
+    DevBuf<char> t;
+    t.alloc(tmp);
+    CK(cub::DeviceRadixSort::SortPairs(t.p, tmp, lev.p, lev2.p, rows2.p, rows.p, (int)Nown, 0, 32, s));
+    std::vector<int32_t> sl = lev2.to_host(s);
+    ptr.clear();
+    ptr.push_back(0);
+    for (int64_t i = 1; i < Nown; i++)
+        if (sl[i] != sl[i - 1]) ptr.push_back((int32_t)i);
+    ptr.push_back((int32_t)Nown);
+}
+
+// greedy multicolouring of the node graph (host, one-off per pattern); rank = position in (colour, index) order
+void multicolor_rank(vfvm_handle* h, std::vector<int32_t>& rank) {
+    const int64_t Nown = h->Nown;
+    std::vector<int32_t> rp = h->rowptr.to_host(h->stream), ci = h->colidx.to_host(h->stream), sp = h->sell_ptr.to_host(h->stream);
+    std::vector<int32_t> color(Nown, -1);
+    int ncolors = 0;
+    std::vector<int64_t> count;
+    for (int64_t K = 0; K < Nown; K++) {
+        uint64_t used = 0;
+        const int64_t e0 = (int64_t)sp[K >> 5] + (K & 31);
+        for (int j = 0; j < rp[K + 1] - rp[K]; j++) {
+            const int L = ci[e0 + 32 * (int64_t)j];
+            if (L < Nown && color[L] >= 0 && color[L] < 64) used |= (1ull << color[L]);
+        }
+        int c = 0;
+        while (c < 63 && ((used >> c) & 1ull)) c++;
+        color[K] = c;
+        if (c + 1 > ncolors) {
+            ncolors = c + 1;
+            count.resize(ncolors, 0);
+        }
+        count[c]++;
+    }
+    std::vector<int64_t> start(ncolors + 1, 0);
+    for (int c = 0; c < ncolors; c++) start[c + 1] = start[c] + count[c];
+    rank.resize(Nown);
+    for (int64_t K = 0; K < Nown; K++) rank[K] = (int32_t)start[color[K]]++;
+}
+
+}  // namespace
+
+void vfvm_ilu0_setup(vfvm_handle* h) {
+    const int64_t Nown = h->Nown;
+    const int n = h->n;
+    cudaStream_t s = h->stream;
+    const int order = h->precon == VFVM_PRECON_ILU0_MC ? 1 : 0;
+    if (!h->ilu_struct_valid || h->ilu_order != order) {
+        h->ilu_rank.alloc(Nown);
+        if (order == 0) {
+            k_iota<<<cdiv(Nown, 256), 256, 0, s>>>(Nown, h->ilu_rank.p);
+            h->launches++;
+        } else {
+            std::vector<int32_t> rank;
+            multicolor_rank(h, rank);
+            h->ilu_rank.upload(rank.data(), rank.size(), s);
+        }
+        build_levels(h, 0, h->ilu_lrows, h->ilu_lptr);
+        build_levels(h, 1, h->ilu_urows, h->ilu_uptr);
+        std::vector<int32_t> rp = h->rowptr.to_host(s);
+        h->ilu_struct_valid = true;
+        h->ilu_order = order;
+    }
+    h->ilu_off.alloc((size_t)n * n * h->nnz_sell);
+    h->ilu_diag.alloc((size_t)n * n * Nown);
+    // plane tables for the expansion kernel
+    signed char idx[200];
+    for (int b = 0; b < 100; b++) {
+        idx[b] = (signed char)(b < n * n ? h->idxF[b] : -1);
+        idx[100 + b] = (signed char)(b < n * n ? h->idxD[b] : -1);
+    }
+    DevBuf<signed char> didx;
+    didx.upload(idx, 200, s);
+    const int64_t m = std::max<int64_t>(h->nnz_sell, Nown);
+    NS_DISPATCH(n, (k_ilu_copy<NS><<<cdiv(m, 256), 256, 0, s>>>(h->nnz_sell, Nown, h->offval.p, h->diagval.p, h->ilu_off.p, h->ilu_diag.p, didx.p)));
+    h->launches++;
+    IluArgs a;
+    a.sell_ptr = h->sell_ptr.p;
+    a.rowptr = h->rowptr.p;
+    a.colidx = h->colidx.p;
+    a.rank = h->ilu_rank.p;
+    a.off = h->ilu_off.p;
+    a.dinv = h->ilu_diag.p;
+    a.in = nullptr;
+    a.out = nullptr;
+    a.flags = h->flags.p;
+    a.nnz_sell = h->nnz_sell;
+    a.Nown = Nown;
+    const int nlev = (int)h->ilu_lptr.size() - 1;
+    for (int l = 0; l < nlev; l++) {
+        a.rows = h->ilu_lrows.p + h->ilu_lptr[l];
+        a.nrows = h->ilu_lptr[l + 1] - h->ilu_lptr[l];
+        NS_DISPATCH(n, (k_ilu_factor<NS><<<cdiv(a.nrows, 128), 128, 0, s>>>(a)));
+        h->launches++;
+    }
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+}
+
+void vfvm_ilu0_apply(vfvm_handle* h, const double* in, double* out) {
+    const int n = h->n;
+    cudaStream_t s = h->stream;
+    IluArgs a;
+    a.sell_ptr = h->sell_ptr.p;
+    a.rowptr = h->rowptr.p;
+    a.colidx = h->colidx.p;
+    a.rank = h->ilu_rank.p;
+    a.off = h->ilu_off.p;
+    a.dinv = h->ilu_diag.p;
+    a.in = in;
+    a.out = out;
+    a.flags = h->flags.p;
+    a.nnz_sell = h->nnz_sell;
+    a.Nown = h->Nown;
+    const int nl = (int)h->ilu_lptr.size() - 1, nu = (int)h->ilu_uptr.size() - 1;
+    for (int l = 0; l < nl; l++) {
+        a.rows = h->ilu_lrows.p + h->ilu_lptr[l];
+        a.nrows = h->ilu_lptr[l + 1] - h->ilu_lptr[l];
+        NS_DISPATCH(n, (k_ilu_fwd<NS><<<cdiv(a.nrows, 128), 128, 0, s>>>(a)));
+    }
+    for (int l = 0; l < nu; l++) {  // upper level 0 = rows without later neighbours: solved first
+        a.rows = h->ilu_urows.p + h->ilu_uptr[l];
+        a.nrows = h->ilu_uptr[l + 1] - h->ilu_uptr[l];
+        NS_DISPATCH(n, (k_ilu_bwd<NS><<<cdiv(a.nrows, 128), 128, 0, s>>>(a)));
+    }
+    h->launches += nl + nu;
+}

@@ -557,7 +557,7 @@ void precond_setup(vfvm_handle* h) {
         SpmvArgs a = make_spmv_args(h);
         NS_DISPATCH(h->n, (k_blockjacobi_setup<NS><<<cdiv(Nown, 128), 128, 0, h->stream>>>(Nown, h->diagval.p, h->pc_diag.p, h->flags.p, a)));
         h->launches++;
-    } else if (h->precon == VFVM_PRECON_ILU0) {
+    } else if (h->precon == VFVM_PRECON_ILU0 || h->precon == VFVM_PRECON_ILU0_MC) {
         vfvm_ilu0_setup(h);
     }
     h->precon_valid = true;
@@ -577,7 +577,8 @@ void precond_apply(vfvm_handle* h, const double* in, double* out) {
             NS_DISPATCH(h->n, (k_blockjacobi_apply<NS><<<cdiv(Nown, 128), 128, 0, h->stream>>>(Nown, h->pc_diag.p, in, out)));
             h->launches++;
             break;
-        case VFVM_PRECON_ILU0: vfvm_ilu0_apply(h, in, out); break;
+        case VFVM_PRECON_ILU0:
+        case VFVM_PRECON_ILU0_MC: vfvm_ilu0_apply(h, in, out); break;
     }
 }
 
@@ -617,7 +618,7 @@ void vfvm_spmv_impl(vfvm_handle* h, const double* x, double* y) { spmv(h, const_
 extern "C" int vfvm_linsolve_setup(vfvm_handle* h, int krylov, int precon, int gmres_restart) {
     if (!h) return VFVM_ERR_ARG;
     if (krylov < VFVM_KRYLOV_BICGSTAB || krylov > VFVM_KRYLOV_GMRES) return vfvm_fail(h, VFVM_ERR_ARG, "unknown Krylov method");
-    if (precon < VFVM_PRECON_NONE || precon > VFVM_PRECON_ILU0) return vfvm_fail(h, VFVM_ERR_ARG, "unknown preconditioner");
+    if (precon < VFVM_PRECON_NONE || precon > VFVM_PRECON_ILU0_MC) return vfvm_fail(h, VFVM_ERR_ARG, "unknown preconditioner");
     h->krylov = krylov;
     h->precon = precon;
     h->gmres_restart = gmres_restart > 0 ? std::min(gmres_restart, 100) : 30;

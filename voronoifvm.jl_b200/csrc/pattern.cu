@@ -359,6 +359,7 @@ int vfvm_pattern_build(vfvm_handle* h) {
     CK(cudaGetLastError());
     h->seen_transient = false;
     h->precon_valid = false;
+    h->ilu_struct_valid = false;
     h->have_pattern = true;
     return VFVM_OK;
 }

@@ -160,9 +160,10 @@ struct vfvm_handle {
     DevBuf<double> work[12];
     DevBuf<double> pc_diag;  // (block-)Jacobi inverse blocks, n*n planes x Nown
     DevBuf<double> ilu_off, ilu_diag;
-    DevBuf<int32_t> ilu_levelptr_dummy;
-    std::vector<int32_t> ilu_level_ptr;  // host copy of level boundaries
-    DevBuf<int32_t> ilu_level_rows;
+    DevBuf<int32_t> ilu_rank, ilu_lrows, ilu_urows;  // elimination order; rows sorted by lower / upper dependency level
+    std::vector<int32_t> ilu_lptr, ilu_uptr;         // level boundaries (host)
+    bool ilu_struct_valid = false;
+    int ilu_order = 0;
     DevBuf<int32_t> upos;  // first off-diagonal entry with col > row
     DevBuf<double> red;    // reduction scratch
     double* red_host = nullptr;  // pinned

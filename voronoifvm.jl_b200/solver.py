@@ -51,7 +51,10 @@ class BlockPreconBuilder:
 
 
 class ILUZeroPreconBuilder:
-    precon = _lib.PRECON_ILU0
+    """ILU(0) on the node-block pattern; `multicolor=True` eliminates in multicolour order (few, wide levels)"""
+
+    def __init__(self, multicolor: bool = False):
+        self.precon = _lib.PRECON_ILU0_MC if multicolor else _lib.PRECON_ILU0
 
 
 class _Krylov:
