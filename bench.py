@@ -365,7 +365,12 @@ def _newton_step(st, system, U, tstep, world):
     st.set_vector(v._lib.VEC_OLDSOL, U)
     L.vfvm_copy_vector(h, v._lib.VEC_SOLUTION, v._lib.VEC_OLDSOL)
     L.vfvm_init_dirichlet(h, 0.0, 0.0)
-    v._lib.check(h, L.vfvm_linsolve_setup(h, v._lib.KRYLOV_BICGSTAB, v._lib.PRECON_JACOBI if system.num_species == 1 else v._lib.PRECON_BLOCKJACOBI, 0))
+    # symmetric positive definite Jacobians (pure linear diffusion) take CG, everything else BiCGStab; node-block Jacobi for systems
+    fid = system.physics.flux.id if system.physics.flux is not None else 0
+    spd = fid == ph.FLUX_DIFFUSION and system.physics.reaction is None
+    krylov = v._lib.KRYLOV_CG if spd else v._lib.KRYLOV_BICGSTAB
+    precon = v._lib.PRECON_JACOBI if system.num_species == 1 or spd else v._lib.PRECON_BLOCKJACOBI
+    v._lib.check(h, L.vfvm_linsolve_setup(h, krylov, precon, 0))
     iters, resn = C.c_int(), C.c_double()
     assert L.vfvm_assemble(h, 0.0, tstep, 0.0) == 0
     L.vfvm_linsolve(h, 0.0, 1.0e-10, 3, 0, C.byref(iters), C.byref(resn))  # warm-up: work vectors, NCCL channels
@@ -377,7 +382,7 @@ def _newton_step(st, system, U, tstep, world):
     L.vfvm_newton_update(h, 1.0, C.byref(ninf), C.byref(n1))
     dt = time.perf_counter() - t0
     t = st.timings()
-    return {"ms": dt * 1e3, "assemble_ms": float(t[0]), "linsolve_ms": float(t[1] + t[2]), "krylov": "BiCGStab+(block)Jacobi", "reltol": 1e-10, "iters": iters.value,
+    return {"ms": dt * 1e3, "assemble_ms": float(t[0]), "linsolve_ms": float(t[1] + t[2]), "krylov": ("CG" if spd else "BiCGStab") + ("+Jacobi" if precon == v._lib.PRECON_JACOBI else "+block-Jacobi"), "reltol": 1e-10, "iters": iters.value,
             "resnorm": resn.value, "update_norm_inf": ninf.value, "rc": rc}
 
 
