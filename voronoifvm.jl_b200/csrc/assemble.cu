@@ -49,18 +49,30 @@ struct AsmArgs {
     signed char idxF[100], idxD[100];
 };
 
-__host__ __device__ constexpr bool flux_separable(int flux) { return flux == VFVM_NONE || flux == VFVM_FLUX_DIFFUSION || flux == VFVM_FLUX_POWDIFF; }
+// internal flux id: power-law diffusion with exponent exactly 2 (Example207): u*u, no pow() code in the kernel
+#define FLUX_POWDIFF_SQ 100
+__host__ __device__ constexpr bool flux_separable(int flux) {
+    return flux == VFVM_NONE || flux == VFVM_FLUX_DIFFUSION || flux == VFVM_FLUX_POWDIFF || flux == FLUX_POWDIFF_SQ;
+}
 
 // species-separable, antisymmetric fluxes f_i = D_i (g(u_i,K) - g(u_i,L)): 2 partials instead of 2n.  fac*f and its
 // derivatives are bitwise the same for either edge orientation, so no orientation handling is needed for them.
 template <int FLUX>
-__device__ __forceinline__ Dual<2> eval_flux_sep(const double* __restrict__ p, int i, int ns, const Dual<2>& a, const Dual<2>& b) {
-    if constexpr (FLUX == VFVM_FLUX_DIFFUSION) return p[i] * (a - b);
-    else if constexpr (FLUX == VFVM_FLUX_POWDIFF) return p[i] * (dpowr(a, p[ns]) - dpowr(b, p[ns]));
+__device__ __forceinline__ Dual<2> eval_flux_sep(double Di, double m, const Dual<2>& a, const Dual<2>& b) {
+    if constexpr (FLUX == VFVM_FLUX_DIFFUSION) return Di * (a - b);
+    else if constexpr (FLUX == VFVM_FLUX_POWDIFF) return Di * (dpowr(a, m) - dpowr(b, m));
+    else if constexpr (FLUX == FLUX_POWDIFF_SQ) return Di * (a * a - b * b);
     else return Dual<2>(0.0);
 }
-template <class T>
+// LIGHT: node physics without transcendental code paths (power reactions with exponent 1 or 2, affine, linear storage):
+// keeps pow()/exp() out of the streaming kernels of cfg1/2/3/5 (register pressure)
+template <bool LIGHT, class T>
 __device__ __forceinline__ T reaction_sep(int id, const double* __restrict__ p, int i, int ns, const T& u) {
+    if constexpr (LIGHT) {
+        if (id == VFVM_REACTION_POW) return (p[ns + i] == 2.0) ? p[i] * (u * u) : p[i] * u;
+        if (id == VFVM_REACTION_AFFINE) return p[1] + p[0] * u;
+        return T(0.0);
+    }
     switch (id) {
         case VFVM_REACTION_POW: return p[i] * dpowr(u, p[ns + i]);
         case VFVM_REACTION_SINH: return p[i] * (dexp(u) - dexp(-u));
@@ -68,8 +80,9 @@ __device__ __forceinline__ T reaction_sep(int id, const double* __restrict__ p, 
         default: return T(0.0);
     }
 }
-template <class T>
+template <bool LIGHT, class T>
 __device__ __forceinline__ T storage_sep(int id, const double* __restrict__ p, int i, int ns, const T& u) {
+    if constexpr (LIGHT) return id == VFVM_STORAGE_LINEAR ? p[i] * u : T(0.0);
     switch (id) {
         case VFVM_STORAGE_LINEAR: return p[i] * u;
         case VFVM_STORAGE_POW: return dpowr(p[i] + u, 1.0 / p[ns + i]);
@@ -79,8 +92,8 @@ __device__ __forceinline__ T storage_sep(int id, const double* __restrict__ p, i
 
 // SEP: every coupling mask is exactly the species diagonal (plane i <-> (i,i)) and flux / reaction / storage are species-
 // separable: the fast path of cfg1/2/3/5.  Otherwise the general path with Dual<2 NS> and the runtime plane tables.
-template <int NS, int FLUX, bool MULTIREG, bool SEP>
-__global__ void __launch_bounds__(ASM_THREADS) k_assemble_rows(const AsmArgs a) {
+template <int NS, int FLUX, bool MULTIREG, bool SEP, bool LIGHT>
+__global__ void __launch_bounds__(ASM_THREADS, (SEP && LIGHT && NS == 1) ? 4 : 1) k_assemble_rows(const AsmArgs a) {
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5, nwarps = gridDim.x * wpb;
     const PhysicsDev& ph = *a.ph;
@@ -91,6 +104,10 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble_rows(const AsmArgs a) 
     const bool has_storage = sid != VFVM_NONE;
     const int64_t nnz = a.nnz_sell;
     bool nan_seen = false;
+    double Dcoef[NS], mexp = 0.0;  // separable fluxes: coefficients live in registers
+#pragma unroll
+    for (int i = 0; i < NS; i++) Dcoef[i] = flux_separable(FLUX) && FLUX != VFVM_NONE ? pf[i] : 0.0;
+    if constexpr (FLUX == VFVM_FLUX_POWDIFF) mexp = pf[NS];
 
     for (int g = blockIdx.x * wpb + (threadIdx.x >> 5); g < a.nslices; g += nwarps) {
         const int64_t rraw = (int64_t)g * 32 + lane;
@@ -103,6 +120,14 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble_rows(const AsmArgs a) 
         for (int i = 0; i < NS; i++) {
             u_r[i] = a.U[r * NS + i];
             Fr[i] = 0.0;
+        }
+        // node data of this lane's row, loaded now so that the latency overlaps the neighbour loop
+        double nfac0 = 0.0, uo_r[NS], src_r[NS];
+        if constexpr (!MULTIREG) nfac0 = a.nf_fac[r];
+#pragma unroll
+        for (int i = 0; i < NS; i++) {
+            uo_r[i] = has_storage ? a.UOld[r * NS + i] : 0.0;
+            src_r[i] = a.src ? a.src[r * NS + i] : 0.0;
         }
         constexpr int ND = SEP ? NS : NS * NS;
         double Dr[ND];
@@ -119,7 +144,7 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble_rows(const AsmArgs a) 
                 const bool ok = j0 + b < w;  // warp-uniform
                 const int64_t e = (int64_t)base + (int64_t)(j0 + b) * 32 + lane;
                 Lc[b] = ok ? a.colidx[e] : (int)r;
-                fc[b] = (!MULTIREG && ok) ? a.nzfac[e] : 0.0;
+                fc[b] = ok ? a.nzfac[e] : 0.0;
             }
             double ucb[BATCH][NS];
 #pragma unroll
@@ -132,29 +157,16 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble_rows(const AsmArgs a) 
                 const int64_t e = (int64_t)base + (int64_t)(j0 + b) * 32 + lane;
                 const int L = Lc[b];
                 const double* uc = ucb[b];
-                int64_t it0 = 0, it1 = 1;
-                const double fac0 = fc[b];
-                if constexpr (MULTIREG) {
-                    const int ed = a.nz_edge[e];
-                    it0 = ed >= 0 ? a.ef_colptr[ed] : 0;
-                    it1 = ed >= 0 ? a.ef_colptr[ed + 1] : 0;
-                    if (ed < 0) {  // padding entry: exact zeros
-#pragma unroll
-                        for (int q = 0; q < NS * NS; q++)
-                            if (a.idxF[q] >= 0) a.offval[(int64_t)a.idxF[q] * nnz + e] = 0.0;
-                    }
-                }
-                for (int64_t it = it0; it < it1; it++) {
-                    const bool first = (it == it0);
-                    double fac = fac0;
-                    if constexpr (MULTIREG) fac = a.ef_fac[it];
+                const double fac = fc[b];
+                {
+                    constexpr bool first = true;
                     if constexpr (flux_separable(FLUX)) {
 #pragma unroll
                         for (int i = 0; i < NS; i++) {
                             Dual<2> x(u_r[i]), y(uc[i]);
                             x.d[0] = 1.0;
                             y.d[1] = 1.0;
-                            const Dual<2> f = eval_flux_sep<FLUX>(pf, i, NS, x, y);
+                            const Dual<2> f = eval_flux_sep<FLUX>(Dcoef[i], mexp, x, y);
                             nan_seen |= (f.d[0] != f.d[0]) | (f.d[1] != f.d[1]);
                             Fr[i] += fac * f.v;
                             if constexpr (SEP) {
@@ -206,19 +218,19 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble_rows(const AsmArgs a) 
         // ---------------- node terms (K4) + write-out
         if (valid) {
             if constexpr (SEP) {
-                const double nfac = a.nf_fac[r];
+                const double nfac = nfac0;
 #pragma unroll
                 for (int i = 0; i < NS; i++) {
                     Dual<1> u(u_r[i]);
                     u.d[0] = 1.0;
-                    const Dual<1> rea = reaction_sep(rid, pr, i, NS, u);
+                    const Dual<1> rea = reaction_sep<LIGHT>(rid, pr, i, NS, u);
                     Dual<1> stor(0.0);
                     double ostor = 0.0;
                     if (has_storage) {
-                        stor = storage_sep(sid, ps, i, NS, u);
-                        ostor = storage_sep(sid, ps, i, NS, a.UOld[r * NS + i]);
+                        stor = storage_sep<LIGHT>(sid, ps, i, NS, u);
+                        ostor = storage_sep<LIGHT>(sid, ps, i, NS, uo_r[i]);
                     }
-                    const double srcv = a.src ? a.src[r * NS + i] : 0.0;
+                    const double srcv = src_r[i];
                     const double jv = rea.d[0] + stor.d[0] * a.tstepinv;
                     nan_seen |= (jv != jv);
                     a.F[r * NS + i] = Fr[i] + nfac * (rea.v - srcv + (stor.v - ostor) * a.tstepinv);
@@ -232,16 +244,15 @@ __global__ void __launch_bounds__(ASM_THREADS) k_assemble_rows(const AsmArgs a) 
                 }
                 typedef Dual<NS> DN;
                 DN u[NS];
-                double uo[NS], srcv[NS];
+                const double* uo = uo_r;
+                const double* srcv = src_r;
 #pragma unroll
                 for (int i = 0; i < NS; i++) {
                     u[i] = DN(u_r[i]);
                     u[i].d[i] = 1.0;
-                    uo[i] = has_storage ? a.UOld[r * NS + i] : 0.0;
-                    srcv[i] = a.src ? a.src[r * NS + i] : 0.0;
                 }
                 for (int64_t q = q0; q < q1; q++) {
-                    const double fac = a.nf_fac[q];
+                    const double fac = MULTIREG ? a.nf_fac[q] : nfac0;
                     const int region = MULTIREG ? a.nf_region[q] : a.the_region;
                     double ostor[NS];
                     DN rea[NS], stor[NS];
@@ -403,17 +414,29 @@ __global__ void k_init_dirichlet(const BNodeArgs a) {
     for (int i = 0; i < NS; i++) a.U[(int64_t)K * NS + i] = u[i];
 }
 
-// persistent grid: one wave of blocks (SMs x resident blocks), warps stride over the slices
+// persistent grid: one wave of blocks (SMs x resident blocks), warps stride over the slices.  The block size is the one
+// that keeps the most warps resident for the kernel's register footprint (heavy dual-number kernels prefer small blocks).
 template <class Kern>
-static void launch_slices(vfvm_handle* h, Kern kern, int& occ, const AsmArgs& a) {
-    if (occ == 0) {
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, ASM_THREADS, 0));
-        if (occ < 1) throw std::string("assembly kernel cannot be launched (registers)");
+static void launch_slices(vfvm_handle* h, Kern kern, int& plan, const AsmArgs& a) {
+    if (plan == 0) {
+        int best_t = 0, best_w = 0, best_b = 0;
+        for (int t = ASM_THREADS; t >= 64; t /= 2) {
+            int b = 0;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, t, 0));
+            if (b * t > best_w) {
+                best_w = b * t;
+                best_t = t;
+                best_b = b;
+            }
+        }
+        if (best_t == 0) throw std::string("assembly kernel cannot be launched (registers)");
+        plan = best_t * 1024 + best_b;
     }
+    const int threads = plan / 1024, occ = plan % 1024;
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device);
-    const int grid = std::max(1, std::min(cdiv(a.nslices, ASM_WARPS), nsm * occ));
-    kern<<<grid, ASM_THREADS, 0, h->stream>>>(a);
+    const int grid = std::max(1, std::min(cdiv(a.nslices, threads / 32), nsm * occ));
+    kern<<<grid, threads, 0, h->stream>>>(a);
     h->launches++;
 }
 
@@ -430,19 +453,43 @@ static bool fast_path_ok(const vfvm_handle* h) {
     return getenv("VFVM_NO_FAST_PATH") == nullptr;
 }
 
+// node physics without transcendental functions?
+static bool light_node_physics(const vfvm_handle* h) {
+    const PhysicsDev& ph = h->phys;
+    const int n = h->n, rid = ph.slot[VFVM_SLOT_REACTION].id, sid = ph.slot[VFVM_SLOT_STORAGE].id;
+    if (!(sid == VFVM_NONE || sid == VFVM_STORAGE_LINEAR)) return false;
+    if (rid == VFVM_NONE || (rid == VFVM_REACTION_AFFINE && n == 1)) return true;
+    if (rid == VFVM_REACTION_POW) {
+        const double* p = ph.params + ph.slot[VFVM_SLOT_REACTION].off;
+        for (int i = 0; i < n; i++)
+            if (!(p[n + i] == 1.0 || p[n + i] == 2.0)) return false;
+        return true;
+    }
+    return false;
+}
+
 template <int NS, int FLUX>
 static void launch_rows(vfvm_handle* h, const AsmArgs& a) {
     if constexpr (FLUX == VFVM_FLUX_DIFFUSION || FLUX == VFVM_FLUX_POWDIFF) {
         if (fast_path_ok(h)) {
-            static int occ = 0;
-            launch_slices(h, k_assemble_rows<NS, FLUX, false, true>, occ, a);
+            static int occ[3] = {0, 0, 0};
+            const bool light = light_node_physics(h);
+            if constexpr (FLUX == VFVM_FLUX_POWDIFF) {
+                const double m = h->phys.params[h->phys.slot[VFVM_SLOT_FLUX].off + NS];
+                if (m == 2.0 && light) {
+                    launch_slices(h, k_assemble_rows<NS, FLUX_POWDIFF_SQ, false, true, true>, occ[2], a);
+                    return;
+                }
+            }
+            if (light && FLUX == VFVM_FLUX_DIFFUSION) launch_slices(h, k_assemble_rows<NS, FLUX, false, true, true>, occ[1], a);
+            else launch_slices(h, k_assemble_rows<NS, FLUX, false, true, false>, occ[0], a);
             return;
         }
     }
     if constexpr (flux_supported(FLUX, NS)) {
         static int occ0 = 0, occ1 = 0;
-        if (h->single_region) launch_slices(h, k_assemble_rows<NS, FLUX, false, false>, occ0, a);
-        else launch_slices(h, k_assemble_rows<NS, FLUX, true, false>, occ1, a);
+        if (h->single_region) launch_slices(h, k_assemble_rows<NS, FLUX, false, false, false>, occ0, a);
+        else launch_slices(h, k_assemble_rows<NS, FLUX, true, false, false>, occ1, a);
     } else {
         throw std::string("flux id ") + std::to_string(FLUX) + " has no device instantiation for " + std::to_string(NS) + " species";
     }

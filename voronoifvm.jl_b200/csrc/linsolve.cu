@@ -70,7 +70,7 @@ __device__ __forceinline__ double block_max(double v, double* sh) {
 // y = A x on the DBSR planes in SELL-32 order: a warp owns a slice of 32 rows, one lane per row; colidx / value loads are
 // coalesced, x[col] gathers coalesce on structured numberings, the row sum lives in registers (column order, deterministic).
 // Optional fused inner products (y,w) and (y,y) for the Krylov recurrences.
-template <int NS>
+template <int NS, bool DIAGMASK>
 __global__ void __launch_bounds__(LS_THREADS) k_spmv(const SpmvArgs a) {
     __shared__ double red[32];
     const int lane = threadIdx.x & 31;
@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(LS_THREADS) k_spmv(const SpmvArgs a) {
                 const bool ok = j0 + b < w;
                 const int64_t e = (int64_t)base + (int64_t)(j0 + b) * 32 + lane;
                 Lc[b] = ok ? a.colidx[e] : (int)r;
-                v1[b] = (NS == 1 && ok) ? a.offval[e] : 0.0;
+                v1[b] = (NS == 1 && DIAGMASK && ok) ? a.offval[e] : 0.0;
             }
             double xl[BATCH][NS];
 #pragma unroll
@@ -105,8 +105,12 @@ __global__ void __launch_bounds__(LS_THREADS) k_spmv(const SpmvArgs a) {
 #pragma unroll
             for (int b = 0; b < BATCH; b++) {
                 if (j0 + b >= w) break;
-                if constexpr (NS == 1) {
+                if constexpr (NS == 1 && DIAGMASK) {
                     acc[0] += v1[b] * xl[b][0];
+                } else if constexpr (DIAGMASK) {  // species-decoupled planes: plane i <-> (i,i)
+                    const int64_t e = (int64_t)base + (int64_t)(j0 + b) * 32 + lane;
+#pragma unroll
+                    for (int i = 0; i < NS; i++) acc[i] += a.offval[(int64_t)i * nnz + e] * xl[b][i];
                 } else {
                     const int64_t e = (int64_t)base + (int64_t)(j0 + b) * 32 + lane;
 #pragma unroll
@@ -126,10 +130,14 @@ __global__ void __launch_bounds__(LS_THREADS) k_spmv(const SpmvArgs a) {
 #pragma unroll
             for (int i = 0; i < NS; i++) {
                 double s = acc[i];
+                if constexpr (DIAGMASK) {
+                    s += a.diagval[(int64_t)i * a.Nown + r] * xr[i];
+                } else {
 #pragma unroll
-                for (int jj = 0; jj < NS; jj++) {
-                    const int p = a.idxD[i * NS + jj];
-                    if (p >= 0) s += a.diagval[(int64_t)p * a.Nown + r] * xr[jj];
+                    for (int jj = 0; jj < NS; jj++) {
+                        const int p = a.idxD[i * NS + jj];
+                        if (p >= 0) s += a.diagval[(int64_t)p * a.Nown + r] * xr[jj];
+                    }
                 }
                 a.y[r * NS + i] = s;
                 if (a.w) {
@@ -515,9 +523,9 @@ void finalize(vfvm_handle* h, const double* part, int nparts, int nvals, int op)
     }
 }
 
-template <int NS>
-void launch_spmv(vfvm_handle* h, SpmvArgs& a, int op) {
-    auto kern = k_spmv<NS>;
+template <int NS, bool DIAGMASK>
+void launch_spmv_k(vfvm_handle* h, SpmvArgs& a, int op) {
+    auto kern = k_spmv<NS, DIAGMASK>;
     static int occ = 0;
     if (occ == 0) {
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, LS_THREADS, 0));
@@ -533,6 +541,14 @@ void launch_spmv(vfvm_handle* h, SpmvArgs& a, int op) {
     kern<<<grid, LS_THREADS, 0, h->stream>>>(a);
     h->launches++;
     if (a.w) finalize(h, a.part, grid, 2, op);
+}
+
+template <int NS>
+void launch_spmv(vfvm_handle* h, SpmvArgs& a, int op) {
+    bool diagmask = (h->cF == NS && h->cD == NS);
+    for (int i = 0; i < NS && diagmask; i++) diagmask = (h->idxF[i * NS + i] == i && h->idxD[i * NS + i] == i);
+    if (diagmask) launch_spmv_k<NS, true>(h, a, op);
+    else launch_spmv_k<NS, false>(h, a, op);
 }
 
 // y = A x (+ fused dots (y,w), (y,y) -> sc[S_TMP0], sc[S_TMP1], then scalar recurrence `op`)

@@ -7,7 +7,7 @@
 //                                     a warp working lane-per-row reads colidx / nzfac and writes the Jacobian fully coalesced
 //   colidx[nnz_sell]                  column (neighbour node) per entry, ascending within a row; padding entries point to the
 //                                     row itself and carry a zero form factor (they assemble / multiply to exact zeros)
-//   nzfac[nnz_sell]                   edge form factor per entry (single cell region); nz_edge[nnz_sell]: edge id (-1 = padding)
+//   nzfac[nnz_sell]                   edge form factor per entry (summed over the cell regions of the edge); nz_edge: edge id (-1 = padding)
 //   offval[cF][nnz_sell]              one plane per (i,j) of the flux species-coupling mask
 //   diagval[cD][Nown]                 one plane per (i,j) of the diagonal-block mask
 // The scalar CSR/CSC pattern the reference would hold (value-dependent through _addnz, src/vfvm_assembly.jl:21-28)
@@ -57,7 +57,8 @@ __global__ void k_slice_width(int nslices, int64_t Nown, const int32_t* __restri
 
 // CSR (sorted keys) -> SELL-32 entries, one warp per slice, lane per row
 __global__ void k_fill_sell(int nslices, int64_t Nown, const int32_t* __restrict__ rowptr, const int64_t* __restrict__ sell_ptr64,
-                            const uint64_t* __restrict__ keys, const int32_t* __restrict__ vals, const double* __restrict__ ef_fac, int single_region,
+                            const uint64_t* __restrict__ keys, const int32_t* __restrict__ vals, const int64_t* __restrict__ ef_colptr,
+                            const double* __restrict__ ef_fac,
                             int32_t* __restrict__ sell_ptr, int32_t* __restrict__ colidx, int32_t* __restrict__ nz_edge, double* __restrict__ nzfac,
                             int32_t* __restrict__ lowlen) {
     const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
@@ -79,12 +80,16 @@ __global__ void k_fill_sell(int nslices, int64_t Nown, const int32_t* __restrict
             const int32_t ed = vals[rb + j];
             colidx[e] = c;
             nz_edge[e] = ed;
-            if (single_region) nzfac[e] = ef_fac[ed];
+            // an edge on a region interface carries one factor per adjacent cell region; no registered flux depends on the
+            // region, so the factors are summed here (in region order) and the flux is evaluated once per edge end
+            double fsum = 0.0;
+            for (int64_t q = ef_colptr[ed]; q < ef_colptr[ed + 1]; q++) fsum += ef_fac[q];
+            nzfac[e] = fsum;
             nlow += (c < r) ? 1 : 0;
         } else {
             colidx[e] = self;
             nz_edge[e] = -1;
-            if (single_region) nzfac[e] = 0.0;
+            nzfac[e] = 0.0;
         }
     }
     if (r < Nown) lowlen[r] = nlow;
@@ -300,9 +305,9 @@ int vfvm_pattern_build(vfvm_handle* h) {
         h->sell_ptr.alloc((size_t)nslices + 1);
         h->colidx.alloc(total);
         h->nz_edge.alloc(total);
-        if (h->single_region) h->nzfac.alloc(total);
+        h->nzfac.alloc(total);
         h->upos.alloc(Nown);
-        k_fill_sell<<<cdiv(nslices, 8), 256, 0, s>>>(nslices, Nown, h->rowptr.p, sp64.p, keys.p, vals.p, h->ef_fac.p, h->single_region ? 1 : 0, h->sell_ptr.p,
+        k_fill_sell<<<cdiv(nslices, 8), 256, 0, s>>>(nslices, Nown, h->rowptr.p, sp64.p, keys.p, vals.p, h->ef_colptr.p, h->ef_fac.p, h->sell_ptr.p,
                                                      h->colidx.p, h->nz_edge.p, h->nzfac.p, h->upos.p);
         h->launches++;
         CK(cudaStreamSynchronize(s));
