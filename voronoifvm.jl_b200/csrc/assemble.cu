@@ -93,7 +93,7 @@ __device__ __forceinline__ T storage_sep(int id, const double* __restrict__ p, i
 // SEP: every coupling mask is exactly the species diagonal (plane i <-> (i,i)) and flux / reaction / storage are species-
 // separable: the fast path of cfg1/2/3/5.  Otherwise the general path with Dual<2 NS> and the runtime plane tables.
 template <int NS, int FLUX, bool MULTIREG, bool SEP, bool LIGHT>
-__global__ void __launch_bounds__(ASM_THREADS, (SEP && LIGHT && NS == 1) ? 4 : 1) k_assemble_rows(const AsmArgs a) {
+__global__ void __launch_bounds__(ASM_THREADS, (SEP && LIGHT && NS == 1) ? 4 : ((!SEP && NS <= 3) ? 2 : 1)) k_assemble_rows(const AsmArgs a) {
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5, nwarps = gridDim.x * wpb;
     const PhysicsDev& ph = *a.ph;
