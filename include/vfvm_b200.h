@@ -228,6 +228,10 @@ int vfvm_plane_counts(vfvm_handle* h, int* off_planes, int* diag_planes);
 /* off-diagonal blocks of the owned rows (= 2 x edges, summed over ranks) and blocks stored incl. SELL-32 padding */
 int vfvm_block_counts(vfvm_handle* h, int64_t* nblocks_off, int64_t* nblocks_stored);
 
+/* parity probe for test/test010_bernoulli.jl: evaluates the device fbernoulli_pm (src/vfvm_functions.jl:78-90) and its
+ * dual-number derivative at n host points: bp = B(x), bm = B(-x), dbp = B'(x) */
+int vfvm_probe_bernoulli(vfvm_handle* h, int n, const double* x, double* bp, double* bm, double* dbp);
+
 #ifdef __cplusplus
 }
 #endif

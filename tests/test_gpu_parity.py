@@ -420,3 +420,123 @@ def test_ilu0_beats_jacobi_in_iterations():
         assert its["ilu0"] < its["ilu0mc"] <= its["jacobi"], its
     finally:
         st.close()
+
+
+# ---------------------------------------------------------------------------------------------- reference known answers on the device
+def test_device_bernoulli_accuracy():
+    """test/test010_bernoulli.jl:5-22 on the device function: |B(x) - x/(exp(x)-1)| < 1e-14 on both ranges, both halves of fbernoulli_pm"""
+    import ctypes as C
+
+    import mpmath
+
+    mpmath.mp.prec = 256
+
+    def big(x):
+        bx = mpmath.mpf(float(x))
+        return float(bx / (mpmath.exp(bx) - 1)) if x != 0 else 1.0
+
+    h = C.c_void_p()
+    L = v._lib.lib()
+    assert L.vfvm_create(0, C.byref(h)) == 0
+    try:
+        for rng in (np.arange(-1, 1, 1.00001e-5)[::7], np.arange(-100, 100, 1.00001e-3)[::11]):
+            x = np.ascontiguousarray(rng)
+            bp, bm, dbp = np.zeros_like(x), np.zeros_like(x), np.zeros_like(x)
+            v._lib.check(h, L.vfvm_probe_bernoulli(h, x.size, v._lib.dptr(x), v._lib.dptr(bp), v._lib.dptr(bm), v._lib.dptr(dbp)))
+            ref = np.array([big(t) for t in x])
+            refm = np.array([big(-t) for t in x])
+            assert np.max(np.abs(bp - ref)) < 1.0e-14
+            assert np.max(np.abs(bm - refm)) < 1.0e-14
+            obp, odbp, obm, odbm = O.fbernoulli_dual(x)
+            np.testing.assert_allclose(dbp, odbp, rtol=1e-13, atol=1e-15)  # derivative through the dual-number path vs the oracle's
+    finally:
+        L.vfvm_destroy(h)
+
+
+def test_example105_device():
+    """examples/Example105_NonlinearPoisson1D.jl: sum(solution) == 1.5247901344230088"""
+    sys = v.System(v.simplexgrid(np.arange(0, 11) / 10.0), flux=ph.LinearDiffusion(1.0e-3), source=ph.Step1DSource(1, 0.5, 1.0, -1.0), reaction=ph.SinhReaction())
+    v.enable_species(sys, 1, [1])
+    v.boundary_dirichlet(sys, 1, 1, 0.0)
+    v.boundary_dirichlet(sys, 1, 2, 1.0)
+    sol = v.solve(sys, inival=0.5)
+    assert sol.sum() == pytest.approx(1.5247901344230088, rel=1e-10)
+
+
+def test_example106_device_transient():
+    """examples/Example106_NonlinearDiffusion1D.jl: fixed-step implicit Euler, sum(tsol.u[end]) == 46.66666666647518"""
+    n, m, tend, tstep = 20, 2, 0.01, 0.0001
+    h = 1.0 / (n / 2)
+    X = np.arange(-1, 1 + h / 2, h)
+    sys = v.System(v.simplexgrid(X), flux=ph.PowerDiffusion(1.0, m), storage=ph.LinearStorage(1.0))
+    v.enable_species(sys, 1, [1])
+    inival = v.unknowns(sys)
+    t0 = 0.001
+    tx = t0 ** (-1.0 / (m + 1.0))
+    xx = np.maximum(1 - (X * tx) ** 2 * (m - 1) / (2.0 * m * (m + 1)), 0.0)
+    inival[0, :] = tx * xx ** (1.0 / (m - 1.0))
+    control = v.SolverControl(Δt_min=tstep, Δt_max=tstep, Δt=tstep, Δu_opt=1)
+    tsol = v.solve(sys, inival=inival, times=[t0, tend], control=control)
+    assert tsol.u[-1].sum() == pytest.approx(46.66666666647518, rel=1e-9)
+
+
+def test_example110_device_parameter_continuation():
+    """examples/Example110: seven solves with changing diffusion coefficients on ONE device state (parameters are re-uploaded,
+    the pattern is kept); U[5] == 0.7117546972922056"""
+    sys = v.System(v.simplexgrid(np.arange(0, 101) / 100.0), reaction=ph.BilinearReaction2(1.0), flux=ph.CrossDiffusion2((1.0, 1.0), 0.01),
+                   source=ph.AffineXSource([1.0e-4 * 0.01, 1.0e-4 * 1.01], [1.0e-4, -1.0e-4]), storage=ph.LinearStorage(1.0))
+    v.enable_species(sys, 1, [1])
+    v.enable_species(sys, 2, [1])
+    for sp in (1, 2):
+        v.boundary_dirichlet(sys, sp, 1, 1.0)
+        v.boundary_dirichlet(sys, sp, 2, 0.0)
+    st = v.SystemState(sys)
+    try:
+        U = v.unknowns(sys, 0.0)
+        control = v.SolverControl(damp_initial=0.1)
+        for xeps in [1.0, 0.5, 0.25, 0.1, 0.05, 0.025, 0.01]:
+            sys.physics.slots[0].eps = (xeps, xeps)
+            sys._version += 1
+            U = v.solve(sys, state=st, inival=U, control=control)
+        assert U.ravel(order="F")[4] == pytest.approx(0.7117546972922056, rel=1e-8)
+    finally:
+        st.close()
+
+
+def test_example210_device_transient_two_species():
+    """examples/Example210_NonlinearPoisson2D_Reaction.jl: sum(tsol.u[end]) == 16.01812472041518"""
+    X = np.linspace(0, 1, 11)
+    k, eps = 1.0, 1.0e-2
+    sys = v.System(v.simplexgrid(X, X), flux=ph.LinearDiffusion(eps), storage=ph.LinearStorage(1.0), reaction=ph.AffineReaction([[k, -k], [-k, k]]),
+                   source=ph.GaussSource(1, 20.0, (0.5, 0.5)))
+    v.enable_species(sys, 1, [1])
+    v.enable_species(sys, 2, [1])
+    tstep = 0.01
+    control = v.SolverControl(Δt=tstep, Δt_min=tstep, Δt_max=tstep, Δu_opt=1.0e5, method_linear=v.KrylovJL_BICGSTAB(precs=v.ILUZeroPreconBuilder()),
+                              reltol_linear=1e-12, abstol_linear=0.0, maxiters_linear=500, factorize_every_timestep=2)
+    tsol = v.solve(sys, inival=v.unknowns(sys, 0.0), times=(0, 1), control=control)
+    assert tsol.u[-1].sum() == pytest.approx(16.01812472041518, rel=1e-8)
+
+
+def test_example215_device_boundary_reaction():
+    """examples/Example215_NonlinearPoisson2D_BoundaryReaction.jl: U[25] == 0.2760603343272377"""
+    X = np.arange(0, 11) / 10.0
+    g = v.simplexgrid(X, X)
+    k = 1.0
+    sys = v.System(g, breaction=ph.LinearBoundaryReaction(2, [[k, -k], [-k, k]]), flux=ph.LinearDiffusion(1.0e-2), storage=ph.LinearStorage(1.0))
+    v.enable_species(sys, 1, [1])
+    v.enable_species(sys, 2, [1])
+    inival = v.unknowns(sys)
+    inival[0, :] = np.exp(-5.0 * ((g.coord[0] - 0.5) ** 2 + (g.coord[1] - 0.5) ** 2))
+    st = v.SystemState(sys)
+    try:
+        tstep, time, u25 = 0.01, 0.0, 0.0
+        while time < 100:
+            time += tstep
+            U = v.solve(sys, state=st, inival=inival, tstep=tstep)
+            inival = U
+            tstep *= 1.2
+            u25 = U.ravel(order="F")[24]
+        assert u25 == pytest.approx(0.2760603343272377, rel=1e-8)
+    finally:
+        st.close()

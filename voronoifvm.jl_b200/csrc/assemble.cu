@@ -755,3 +755,34 @@ int vfvm_init_dirichlet_impl(vfvm_handle* h, double time, double lambda) {
     CK(cudaGetLastError());
     return VFVM_OK;
 }
+
+// ---- parity probe of the device Bernoulli function ------------------------------------------------------------------
+__global__ void k_probe_bernoulli(int n, const double* __restrict__ x, double* __restrict__ bp, double* __restrict__ bm, double* __restrict__ dbp) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Dual<1> xx(x[i]), p, m;
+    xx.d[0] = 1.0;
+    fbernoulli_pm(xx, p, m);
+    bp[i] = p.v;
+    bm[i] = m.v;
+    dbp[i] = p.d[0];
+}
+
+extern "C" int vfvm_probe_bernoulli(vfvm_handle* h, int n, const double* x, double* bp, double* bm, double* dbp) {
+    if (!h || n < 0) return VFVM_ERR_ARG;
+    VFVM_TRY(h, {
+        CK(cudaSetDevice(h->device));
+        DevBuf<double> dx, d1, d2, d3;
+        dx.upload(x, n, h->stream);
+        d1.alloc(n);
+        d2.alloc(n);
+        d3.alloc(n);
+        if (n) k_probe_bernoulli<<<cdiv(n, 256), 256, 0, h->stream>>>(n, dx.p, d1.p, d2.p, d3.p);
+        h->launches++;
+        d1.download(bp, h->stream);
+        d2.download(bm, h->stream);
+        d3.download(dbp, h->stream);
+        CK(cudaGetLastError());
+    })
+    return VFVM_OK;
+}
