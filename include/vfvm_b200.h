@@ -183,6 +183,10 @@ int vfvm_init_dirichlet(vfvm_handle* h, double time, double lambda);
 /* ---- K4-K6: eval_and_assemble (src/vfvm_assembly.jl:520-643) ---------------------------------------- */
 /* assembles residual + Jacobian at the resident SOLUTION / OLDSOL vectors; tstep = Inf for stationary */
 int vfvm_assemble(vfvm_handle* h, double time, double tstep, double lambda);
+/* same, but only enqueued on the handle's stream (SURVEY 8b "unless flags & VFVM_ASYNC"): a NaN is reported by the next
+ * vfvm_sync; the following vfvm_linsolve / vfvm_newton_update run on the same stream and need no host round trip */
+int vfvm_assemble_async(vfvm_handle* h, double time, double tstep, double lambda);
+int vfvm_sync(vfvm_handle* h);
 /* convenience = evaluate_residual_and_jacobian! (src/vfvm_solver.jl:224-243): upload U (and UOld, may be
  * NULL = U), assemble, download residual; the Jacobian stays on the device for the linear solve */
 int vfvm_eval_res_jac(vfvm_handle* h, const double* U, const double* UOld, double* F, int memspace,

@@ -1,0 +1,127 @@
+"""GPU parity at BASELINE.json's full sizes (cfg3: 193^3 nodes, 49.9 M edges; cfg2: 2583^2 nodes, 20.0 M edges).
+
+At these sizes the CUDA path is checked (a) entry by entry against the CPU oracle for the residual and the Jacobian of cfg3,
+and (b) through size-independent properties of the discretisation: partition of unity of the node volumes, constants in
+the kernel of the flux Jacobian, symmetry of the diffusion operator, consistency of residual and Jacobian for a linear
+problem (F(u) - F(0) = A u), discrete conservation (fluxes cancel in the sum over all control volumes), determinism.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+
+import vfvm_b200 as v
+from vfvm_b200 import physics as ph
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cfg3():
+    X = np.linspace(0, 1, 193)
+    s = v.System(v.simplexgrid(X, X, X), flux=ph.LinearDiffusion(), source=ph.XSinYExpZSource(1, 5.0))
+    v.enable_species(s, 1, [1])
+    v.boundary_dirichlet(s, 1, 5, 0.0)
+    v.boundary_dirichlet(s, 1, 6, 0.0)
+    st = v.SystemState(s)
+    yield s, st
+    st.close()
+
+
+def _smooth(g, k=3.0):
+    return np.asfortranarray((0.5 + 0.25 * np.sin(k * g.coord[0]) * np.cos(2.0 * g.coord[-1] + 0.3))[None, :])
+
+
+def test_cfg3_counts_and_partition_of_unity(cfg3):
+    s, st = cfg3
+    m, nx = 192, 193
+    assert st.num_edges == 3 * m * nx * nx + 3 * m * m * nx + m**3 == 49877568
+    colptr, reg, fac = st.nodefactors()
+    assert colptr[-1] == s.grid.num_nodes
+    assert fac.sum() == pytest.approx(1.0, rel=1e-11)  # test/test120_norms.jl:95-100
+    assert st.bfacefactors().sum() == pytest.approx(6.0, rel=1e-11)  # surface of the unit cube
+    off, stored = st.block_counts()
+    assert off == 2 * st.num_edges and stored < 1.01 * off  # SELL-32 padding below 1 %
+
+
+def test_cfg3_operator_properties(cfg3):
+    s, st = cfg3
+    g = s.grid
+    N = g.num_nodes
+    U = _smooth(g)
+    F = st.eval_res_jac(U).ravel(order="F")
+    F0 = st.eval_res_jac(np.zeros_like(U)).ravel(order="F")
+    # linear problem: F(u) - F(0) = A u   (residual and Jacobian are assembled by the same kernel, applied by the SpMV kernel)
+    Au = st.spmv(U.ravel(order="F"))
+    dirichlet = np.zeros(N, bool)
+    dirichlet[np.unique(g.bfacenodes[:, (g.bfaceregions == 5) | (g.bfaceregions == 6)])] = True
+    err = np.abs((F - F0) - Au)
+    assert err[~dirichlet].max() <= 1e-12 * np.abs(Au[~dirichlet]).max()
+    assert np.all(err[dirichlet] <= 1e-12 * np.abs(Au[dirichlet]))  # penalty rows: relative
+    # constants are in the kernel of the flux Jacobian: (A 1)_K = penalty_K
+    A1 = st.spmv(np.ones(N))
+    assert np.abs(A1[~dirichlet]).max() <= 1e-12 * 16.0
+    assert np.all(A1[dirichlet] >= 1e30)
+    # symmetry of the diffusion operator
+    rng = np.random.default_rng(5)
+    x, y = rng.standard_normal(N), rng.standard_normal(N)
+    x[dirichlet] = 0
+    y[dirichlet] = 0
+    a, b = float(y @ st.spmv(x)), float(x @ st.spmv(y))
+    assert abs(a - b) <= 1e-11 * max(abs(a), abs(b))
+    # determinism at full size
+    F2 = st.eval_res_jac(U).ravel(order="F")
+    assert np.array_equal(F, F2)
+
+
+def test_cfg3_full_size_against_oracle(cfg3):
+    """every residual entry and every Jacobian entry of the 193^3 problem against the CPU oracle (pattern bit-exact, values 1e-12)"""
+    s, st = cfg3
+    U = _smooth(s.grid)
+    F = st.eval_res_jac(U)
+    A = st.matrix("csc")
+    o = O.OracleSystem(s)
+    assert np.array_equal(st.edgenodes(), o.edgenodes())
+    Fo, Ao = o.assemble(U, U, nthreads=O.lib().vo_max_threads())
+    assert np.array_equal(A.indptr, Ao.indptr) and np.array_equal(A.indices, Ao.indices)
+    rowscale = 0.1  # bound on the magnitude of the summed terms (form factors are O(h) = 5e-3); penalty entries use the relative term
+    err = np.abs(A.data - Ao.data)
+    assert np.all(err <= 1e-12 * np.abs(Ao.data) + 8 * np.finfo(float).eps * rowscale)
+    f, fo = F.ravel(order="F"), Fo.ravel(order="F")
+    assert np.all(np.abs(f - fo) <= 1e-12 * np.abs(fo) + 8 * np.finfo(float).eps * rowscale)
+
+
+def test_cfg2_conservation_full_size():
+    """cfg2 (Example207 physics, 2583^2): the fluxes cancel in the sum over all control volumes, so
+    sum_K F_K = sum_K omega_K (r(u_K) - s_K + (u_K - uold_K)/dt) once the Dirichlet values are initialised (penalty terms vanish)"""
+    nx = 2583
+    X = np.linspace(0, 1, nx)
+    g = v.simplexgrid(X, X)
+    s = v.System(g, flux=ph.PowerDiffusion(1.0e-2, 2), reaction=ph.PowerReaction(1.0, 2.0), source=ph.GaussSource(1, 20.0, (0.5, 0.5)), storage=ph.LinearStorage(1.0))
+    v.enable_species(s, 1, [1])
+    v.boundary_dirichlet(s, 1, 2, 0.1)
+    v.boundary_dirichlet(s, 1, 4, 0.1)
+    st = v.SystemState(s)
+    try:
+        assert st.num_edges == 20005336
+        U = _smooth(g)
+        dnodes = np.unique(g.bfacenodes[:, (g.bfaceregions == 2) | (g.bfaceregions == 4)])
+        U[0, dnodes] = 0.1
+        Uold = _smooth(g, k=2.0)
+        tstep = 0.01
+        F = st.eval_res_jac(U, Uold, tstep=tstep).ravel(order="F")
+        omega = st.nodefactors()[2]
+        src = np.exp(-20.0 * ((g.coord[0] - 0.5) ** 2 + (g.coord[1] - 0.5) ** 2))
+        rhs = omega * (U[0] ** 2 - src + (U[0] - Uold[0]) / tstep)
+        assert math.fsum(F) == pytest.approx(math.fsum(rhs), rel=1e-9, abs=1e-12 * np.abs(rhs).sum())
+        # a Newton step on the full-size problem reduces the residual quadratically (Jacobian consistent with the residual)
+        sol = v.solve(s, state=st, inival=Uold, tstep=tstep, method_linear=v.KrylovJL_BICGSTAB(precs=v.JacobiPreconBuilder()), reltol_linear=1e-12,
+                      abstol_linear=0.0, maxiters_linear=3000)
+        Fs = st.eval_res_jac(sol, Uold, tstep=tstep).ravel(order="F")
+        free = np.ones(g.num_nodes, bool)
+        free[dnodes] = False
+        assert np.abs(Fs[free]).max() <= 1e-9 * np.abs(omega).max() * 100
+    finally:
+        st.close()

@@ -58,6 +58,8 @@ SIGNATURES = {
     "vfvm_copy_vector": [_H, C.c_int, C.c_int],
     "vfvm_init_dirichlet": [_H, C.c_double, C.c_double],
     "vfvm_assemble": [_H, C.c_double, C.c_double, C.c_double],
+    "vfvm_assemble_async": [_H, C.c_double, C.c_double, C.c_double],
+    "vfvm_sync": [_H],
     "vfvm_eval_res_jac": [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double],
     "vfvm_get_nzval_csr": [_H, C.c_void_p, C.c_int],
     "vfvm_get_nzval_csc": [_H, C.c_void_p, C.c_int],

@@ -398,6 +398,23 @@ extern "C" int vfvm_assemble(vfvm_handle* h, double time, double tstep, double l
     })
 }
 
+extern "C" int vfvm_assemble_async(vfvm_handle* h, double time, double tstep, double lambda) {
+    NEED(h, h->have_pattern, "vfvm_build_pattern has not been called (or physics structure changed since)");
+    VFVM_TRY(h, {
+        CK(cudaSetDevice(h->device));
+        vfvm_sync_physics(h);
+        return vfvm_assemble_impl(h, time, tstep, lambda, true);
+    })
+}
+
+extern "C" int vfvm_sync(vfvm_handle* h) {
+    if (!h) return VFVM_ERR_ARG;
+    VFVM_TRY(h, {
+        CK(cudaSetDevice(h->device));
+        return vfvm_assemble_finish(h);
+    })
+}
+
 extern "C" int vfvm_eval_res_jac(vfvm_handle* h, const double* U, const double* UOld, double* F, int memspace, double time, double tstep, double lambda) {
     NEED(h, h->have_pattern, "vfvm_build_pattern has not been called (or physics structure changed since)");
     if (!U || !F) return vfvm_fail(h, VFVM_ERR_ARG, "null vector");

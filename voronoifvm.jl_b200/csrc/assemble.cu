@@ -656,7 +656,7 @@ void vfvm_source_cache(vfvm_handle* h) {
     h->launches++;
 }
 
-int vfvm_assemble_impl(vfvm_handle* h, double time, double tstep, double lambda) {
+int vfvm_assemble_impl(vfvm_handle* h, double time, double tstep, double lambda, bool async) {
     cudaStream_t s = h->stream;
     const double tstepinv = 1.0 / tstep;  // src/vfvm_assembly.jl:554 (1/Inf == 0)
     if (tstepinv != 0.0) h->seen_transient = true;
@@ -678,7 +678,7 @@ int vfvm_assemble_impl(vfvm_handle* h, double time, double tstep, double lambda)
     a.offval = h->offval.p;
     a.diagval = h->diagval.p;
     a.ph = h->phys_dev.p;
-    a.flags = h->flags.p;
+    a.flags = h->flags.p + 1;  // word 1: NaN seen during assembly (word 0 belongs to the linear solver)
     a.nnz_sell = h->nnz_sell;
     a.Nown = h->Nown;
     a.nslices = h->ngroups;
@@ -692,7 +692,7 @@ int vfvm_assemble_impl(vfvm_handle* h, double time, double tstep, double lambda)
         a.idxF[b] = (signed char)(b < h->n * h->n ? h->idxF[b] : -1);
         a.idxD[b] = (signed char)(b < h->n * h->n ? h->idxD[b] : -1);
     }
-    CK(cudaMemsetAsync(h->flags.p, 0, sizeof(int32_t), s));
+    if (!async) CK(cudaMemsetAsync(h->flags.p + 1, 0, sizeof(int32_t), s));  // async: the flag stays sticky until vfvm_sync
     CK(cudaEventRecord(h->ev0, s));
     NS_DISPATCH(h->n, (launch_rows_ns<NS>(h, a)));
     CK(cudaEventRecord(h->ev1, s));
@@ -708,7 +708,7 @@ int vfvm_assemble_impl(vfvm_handle* h, double time, double tstep, double lambda)
         b.F = h->vec[VFVM_VEC_RESIDUAL].p;
         b.diagval = h->diagval.p;
         b.ph = a.ph;
-        b.flags = h->flags.p;
+        b.flags = h->flags.p + 1;
         b.nbnodes = h->nbnodes;
         b.Nown = h->Nown;
         b.dim = h->dim;
@@ -719,16 +719,29 @@ int vfvm_assemble_impl(vfvm_handle* h, double time, double tstep, double lambda)
         h->launches++;
     }
     CK(cudaEventRecord(h->ev2, s));
-    CK(cudaMemcpyAsync(h->flags_host, h->flags.p, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    h->precon_valid = false;
+    h->asm_pending = true;
+    if (async) return VFVM_OK;
+    return vfvm_assemble_finish(h);
+}
+
+// waits for the stream, reads the timing events of the last assembly and the (sticky) NaN flag
+int vfvm_assemble_finish(vfvm_handle* h) {
+    cudaStream_t s = h->stream;
+    CK(cudaMemcpyAsync(h->flags_host + 2, h->flags.p + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     CK(cudaGetLastError());
+    if (!h->asm_pending) return VFVM_OK;
+    h->asm_pending = false;
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, h->ev0, h->ev2));
     h->times[VFVM_TIME_ASSEMBLE] = ms;
     CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     h->times[VFVM_TIME_EDGE_KERNEL] = ms;
-    h->precon_valid = false;
-    if (h->flags_host[0] & 1) return vfvm_fail(h, VFVM_ERR_NAN, "trying to assemble NaN");
+    if (h->flags_host[2] & 1) {
+        CK(cudaMemsetAsync(h->flags.p + 1, 0, sizeof(int32_t), s));
+        return vfvm_fail(h, VFVM_ERR_NAN, "trying to assemble NaN");
+    }
     return VFVM_OK;
 }
 

@@ -122,6 +122,7 @@ struct vfvm_handle {
     PhysicsDev phys;
     DevBuf<PhysicsDev> phys_dev;  // device copy, refreshed by vfvm_sync_physics
     bool phys_dirty = true;
+    bool asm_pending = false;  // an assembly was enqueued whose status / timings have not been collected yet
     Masks masks;
     DevBuf<double> nodal_source;
     std::vector<double> host_params;
@@ -202,7 +203,8 @@ static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 // implemented across the .cu files
 int vfvm_geometry_build(vfvm_handle* h);
 int vfvm_pattern_build(vfvm_handle* h);
-int vfvm_assemble_impl(vfvm_handle* h, double time, double tstep, double lambda);
+int vfvm_assemble_impl(vfvm_handle* h, double time, double tstep, double lambda, bool async = false);
+int vfvm_assemble_finish(vfvm_handle* h);
 int vfvm_init_dirichlet_impl(vfvm_handle* h, double time, double lambda);
 int vfvm_physics_masks(vfvm_handle* h);
 void vfvm_spmv_impl(vfvm_handle* h, const double* x, double* y);
