@@ -40,7 +40,7 @@ extern "C" int vfvm_create(int device, vfvm_handle** out) {
     }
     // byte accounting for the long-lived buffers
     DevBuf<double>* dbl[] = {&h->coord, &h->nf_fac, &h->ef_fac, &h->bfacenodefac, &h->nzfac, &h->offval, &h->diagval, &h->vec[0], &h->vec[1], &h->vec[2], &h->vec[3],
-                             &h->pc_diag, &h->ilu_off, &h->ilu_diag, &h->nodal_source, &h->send_buf};
+                             &h->pc_diag, &h->ilu_off, &h->ilu_diag, &h->nodal_source, &h->send_buf, &h->node_q};
     for (auto* b : dbl) b->tally = &h->bytes;
     for (auto& w : h->work) w.tally = &h->bytes;
     DevBuf<int32_t>* i32[] = {&h->cellnodes, &h->cellregions, &h->bfacenodes, &h->bfaceregions, &h->edgenodes, &h->celledges, &h->nf_region, &h->ef_region,

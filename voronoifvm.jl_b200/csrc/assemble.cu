@@ -38,12 +38,13 @@ struct AsmArgs {
     const double* __restrict__ U;
     const double* __restrict__ UOld;
     const double* __restrict__ src;  // cached source term n x N (u-independent callback), or null
+    const double* __restrict__ Q;    // node-transformed unknowns q(u), n planes of N, for fluxes that are functions of q (flux_node_transform); else = U
     double* __restrict__ F;
     double* __restrict__ offval;
     double* __restrict__ diagval;
     const PhysicsDev* __restrict__ ph;
     int32_t* flags;
-    int64_t nnz_sell, Nown;
+    int64_t nnz_sell, Nown, Ntot;
     int nslices, cF, cD, the_region;
     double time, tstepinv, lambda;
     signed char idxF[100], idxD[100];
@@ -53,6 +54,26 @@ struct AsmArgs {
 #define FLUX_POWDIFF_SQ 100
 __host__ __device__ constexpr bool flux_separable(int flux) {
     return flux == VFVM_NONE || flux == VFVM_FLUX_DIFFUSION || flux == VFVM_FLUX_POWDIFF || flux == FLUX_POWDIFF_SQ;
+}
+
+// Fluxes of the form g(q(u_K), q(u_L)) with an expensive node map q: q is tabulated once per assembly by k_node_transform
+// (2 exp per NODE instead of 4 Dual<6> exp per (row, neighbour) pair) and the neighbour loop gathers q_L instead of u_L.
+// Bipolar Scharfetter-Gummel (examples/Example161_BipolarDriftDiffusionCurrent.jl:134-150): q = (n_n, n_p, psi) with
+// n_n = exp(z_n (phi_n - psi + E_n)), n_p = exp(z_p (phi_p - psi + E_p)).
+__host__ __device__ constexpr bool flux_node_transform(int flux) { return flux == VFVM_FLUX_SG_BIPOLAR; }
+
+template <int FLUX, int NS>
+__global__ void k_node_transform(int64_t N, const double* __restrict__ U, const PhysicsDev* __restrict__ ph, double* __restrict__ Q) {
+    const int64_t K = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (K >= N) return;
+    const double* __restrict__ p = ph->params + ph->slot[VFVM_SLOT_FLUX].off;
+    if constexpr (FLUX == VFVM_FLUX_SG_BIPOLAR && NS == 3) {
+        const double zn = p[3], zp = p[4], En = p[5], Ep = p[6];
+        const double phin = U[K * 3], phip = U[K * 3 + 1], psi = U[K * 3 + 2];
+        Q[K] = exp(zn * (phin - psi + En));  // one plane per component: the row kernel's gathers are unit-stride across lanes
+        Q[N + K] = exp(zp * (phip - psi + Ep));
+        Q[2 * N + K] = psi;
+    }
 }
 
 // species-separable, antisymmetric fluxes f_i = D_i (g(u_i,K) - g(u_i,L)): 2 partials instead of 2n.  fac*f and its
@@ -385,6 +406,238 @@ __global__ void __launch_bounds__(ASM_THREADS, (LIGHT && CH == 1) ? 4 : (CH <= 5
     if (nan_seen) atomicOr(a.flags, 1);
 }
 
+// ---- bipolar Scharfetter-Gummel drift-diffusion (cfg4; examples/Example161_BipolarDriftDiffusionCurrent.jl:134-150) ----------
+// One edge of g(q_K, q_L), q = (n_n, n_p, psi) tabulated by k_node_transform, with the chain rule through q written out.
+// The only dual-number evaluation left is the Bernoulli pair in its single argument x = psi_K - psi_L (B(-x) = x + B(x),
+// so bm' = 1 + bp').  POS: the row node is edge.node[1] = K (the larger index); the reference's orientation is kept because
+// x + B(x) is not an antisymmetric floating-point expression.  The five flux couplings (n,n) (n,psi) (p,p) (p,psi) (psi,psi)
+// are the fixed mask of this flux (pattern.cu), so their planes are plain pointers.
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+struct BipolarCoef {
+    double cn, cp, zn, zp, lam2;
+};
+
+// B(x) and B'(x) for a batch of independent arguments, branches as src/vfvm_functions.jl:78-90.  The two expensive
+// branches are guarded by warp votes and evaluated for the whole batch (instruction-level parallelism across the batch,
+// no divergence); the per-lane choice is a select.  |x| >= 0.25: x / expm1(x) with expm1(x) = exp(x) - 1, whose relative
+// error there is below 5e-16 (exp(x) - 1 >= 0.22 exp(x)), and d expm1 = exp(x) as ForwardDiff has it.
+template <int B>
+__device__ __forceinline__ void bernoulli_batch(const double (&x)[B], double (&bp)[B], double (&dbp)[B]) {
+    bool small[B], any_small = false, any_big = false;
+#pragma unroll
+    for (int b = 0; b < B; b++) {
+        small[b] = fabs(x[b]) < 0.25;
+        any_small |= small[b];
+        any_big |= !small[b];
+    }
+    double hv[B], hd[B], ev[B], ed[B];
+#pragma unroll
+    for (int b = 0; b < B; b++) hv[b] = hd[b] = ev[b] = ed[b] = 0.0;
+    if (__any_sync(0xffffffffu, any_small)) {
+#pragma unroll
+        for (int b = 0; b < B; b++) {
+            Dual<1> X(x[b]);
+            X.d[0] = 1.0;
+            const Dual<1> Y = bernoulli_horner(X);
+            hv[b] = Y.v;
+            hd[b] = Y.d[0];
+        }
+    }
+    if (__any_sync(0xffffffffu, any_big)) {
+#pragma unroll
+        for (int b = 0; b < B; b++) {
+            const double e = exp(x[b]), ib = 1.0 / (e - 1.0), y = x[b] * ib;
+            ev[b] = y;
+            ed[b] = (1.0 - y * e) * ib;
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < B; b++) {
+        double v = small[b] ? hv[b] : ev[b], d = small[b] ? hd[b] : ed[b];
+        if (x[b] < -50.0) {
+            v = -x[b];
+            d = -1.0;
+        }
+        if (x[b] > 50.0) v = d = 0.0;
+        bp[b] = v;
+        dbp[b] = d;
+    }
+}
+
+template <bool MULTIREG, int BATCH, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) k_assemble_rows_bipolar(const AsmArgs a) {
+    constexpr int NS = 3;
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5, nwarps = gridDim.x * wpb;
+    const PhysicsDev& ph = *a.ph;
+    const double* __restrict__ pf = ph.params + ph.slot[VFVM_SLOT_FLUX].off;
+    const int rid = ph.slot[VFVM_SLOT_REACTION].id, sid = ph.slot[VFVM_SLOT_STORAGE].id;
+    const double* __restrict__ pr = ph.params + ph.slot[VFVM_SLOT_REACTION].off;
+    const double* __restrict__ ps = ph.params + ph.slot[VFVM_SLOT_STORAGE].off;
+    const bool has_storage = sid != VFVM_NONE;
+    const int64_t nnz = a.nnz_sell;
+    const BipolarCoef c = {-pf[3] * pf[1], -pf[4] * pf[2], pf[3], pf[4], pf[0] * pf[0]};
+    double* __restrict__ o0 = a.offval + (int64_t)a.idxF[0] * nnz;  // (n,n)
+    double* __restrict__ o1 = a.offval + (int64_t)a.idxF[2] * nnz;  // (n,psi)
+    double* __restrict__ o2 = a.offval + (int64_t)a.idxF[4] * nnz;  // (p,p)
+    double* __restrict__ o3 = a.offval + (int64_t)a.idxF[5] * nnz;  // (p,psi)
+    double* __restrict__ o4 = a.offval + (int64_t)a.idxF[8] * nnz;  // (psi,psi)
+    bool nan_seen = false;
+
+    for (int g = blockIdx.x * wpb + (threadIdx.x >> 5); g < a.nslices; g += nwarps) {
+        const int64_t rraw = (int64_t)g * 32 + lane;
+        const bool valid = rraw < a.Nown;
+        const int64_t r = valid ? rraw : a.Nown - 1;
+        const int base = a.sell_ptr[g];
+        const int w = (a.sell_ptr[g + 1] - base) >> 5;
+        double Fr[3] = {0.0, 0.0, 0.0}, Df[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+        const double* __restrict__ Q0 = a.Q;
+        const double* __restrict__ Q1 = a.Q + a.Ntot;
+        const double* __restrict__ Q2 = a.Q + 2 * a.Ntot;
+        const double nn_r = Q0[r], np_r = Q1[r], ps_r = Q2[r];
+        // the node terms' inputs are only needed after the neighbour loop: pull them towards L2 now, without holding registers
+        prefetch_l2(a.U + r * 3);
+        if (has_storage) prefetch_l2(a.UOld + r * 3);
+        if (a.src) prefetch_l2(a.src + r * 3);
+        int nq0 = (int)r, nq1 = (int)r + 1;
+        if constexpr (MULTIREG) {
+            nq0 = (int)a.nf_colptr[r];
+            nq1 = (int)a.nf_colptr[r + 1];
+        }
+        const int gnext = g + nwarps < a.nslices ? g + nwarps : g;  // the slice this warp handles next
+        const int base_next = a.sell_ptr[gnext];
+        const double zr = c.zn * nn_r, yr = c.zp * np_r;
+
+        // Software pipeline over batches of BATCH entries, three batches in flight: while batch k is computed, the gathers
+        // of q_c and the factors of batch k+1 and the indices of batch k+2 are outstanding.  (q, fac, pos) ping-pong
+        // between two register sets (A, B), so nothing waits on a load before its batch is due.
+        int L[BATCH];
+        double fA[BATCH], fB[BATCH], qA[BATCH][3], qB[BATCH][3];
+        bool posA[BATCH], posB[BATCH];
+        auto load_idx = [&](int jb) {
+#pragma unroll
+            for (int b = 0; b < BATCH; b++) L[b] = (jb + b < w) ? a.colidx[base + (jb + b) * 32 + lane] : (int)r;  // warp-uniform guard
+        };
+        auto gather = [&](double (&q)[BATCH][3], double (&f)[BATCH], bool (&pos)[BATCH], int jb) {
+#pragma unroll
+            for (int b = 0; b < BATCH; b++) {
+                q[b][0] = Q0[L[b]];
+                q[b][1] = Q1[L[b]];
+                q[b][2] = Q2[L[b]];
+                pos[b] = r > L[b];  // row node is edge.node[1] = K (the larger index)
+                f[b] = (jb + b < w) ? a.nzfac[base + (jb + b) * 32 + lane] : 0.0;
+            }
+        };
+        auto compute = [&](const double (&q)[BATCH][3], const double (&f)[BATCH], const bool (&pos)[BATCH], int jb) {
+            double x[BATCH], bp[BATCH], dbp[BATCH];
+#pragma unroll
+            for (int b = 0; b < BATCH; b++) x[b] = pos[b] ? ps_r - q[b][2] : q[b][2] - ps_r;  // psi_K - psi_L
+            bernoulli_batch<BATCH>(x, bp, dbp);
+#pragma unroll
+            for (int b = 0; b < BATCH; b++) {
+                if (jb + b >= w) break;
+                const int e = base + (jb + b) * 32 + lane;
+                // Row contribution of edge {r,c} in either orientation (K = larger index; the reference's flux is
+                // c_n (bm n_L - bp n_K), c_p (bp p_L - bm p_K) with bp = B(x), bm = B(-x) = x + B(x), x = psi_K - psi_L):
+                //   R_n = fac c_n (bc n_c - br n_r),  R_p = fac c_p (br p_c - bc p_r),  (bc, br) = pos ? (bm, bp) : (bp, bm)
+                // -- bitwise the reference's value, because negating a difference is exact.
+                const double bm = x[b] + bp[b], dbm = 1.0 + dbp[b];
+                const double bc = pos[b] ? bm : bp[b], br = pos[b] ? bp[b] : bm;
+                const double dc = pos[b] ? dbm : -dbp[b], dr = pos[b] ? dbp[b] : -dbm;  // d/d psi_r of bc, br
+                const double nn_c = q[b][0], np_c = q[b][1];
+                const double sn = f[b] * c.cn, sp = f[b] * c.cp, sl = f[b] * c.lam2;
+                const double zc = c.zn * nn_c, yc = c.zp * np_c;
+                const double dn = dc * nn_c - dr * nn_r, dp = dr * np_c - dc * np_r;
+                Fr[0] += sn * (bc * nn_c - br * nn_r);
+                Fr[1] += sp * (br * np_c - bc * np_r);
+                Fr[2] += sl * (ps_r - q[b][2]);
+                Df[0] -= sn * (br * zr);
+                Df[1] += sn * (dn + br * zr);
+                Df[2] -= sp * (bc * yr);
+                Df[3] += sp * (dp + bc * yr);
+                Df[4] += sl;
+                const double v0 = sn * (bc * zc), v1 = -(sn * (dn + bc * zc)), v2 = sp * (br * yc), v3 = -(sp * (dp + br * yc));
+                nan_seen |= (v0 != v0) | (v1 != v1) | (v2 != v2) | (v3 != v3);
+                o0[e] = v0;
+                o1[e] = v1;
+                o2[e] = v2;
+                o3[e] = v3;
+                o4[e] = -sl;
+            }
+        };
+        load_idx(0);
+        gather(qA, fA, posA, 0);
+        load_idx(BATCH);
+        for (int j0 = 0; j0 < w; j0 += 2 * BATCH) {
+            gather(qB, fB, posB, j0 + BATCH);
+            load_idx(j0 + 2 * BATCH);
+            compute(qA, fA, posA, j0);
+            gather(qA, fA, posA, j0 + 2 * BATCH);
+            load_idx(j0 + 3 * BATCH);
+            compute(qB, fB, posB, j0 + BATCH);
+        }
+        if (gnext != g) {  // head of the next slice's streams -> L2 while the node terms are evaluated
+            prefetch_l2(a.colidx + base_next + lane);
+            prefetch_l2(a.nzfac + base_next + lane);
+            prefetch_l2(a.nzfac + base_next + 32 + lane);
+        }
+        nan_seen |= (Df[0] != Df[0]) | (Df[1] != Df[1]) | (Df[2] != Df[2]) | (Df[3] != Df[3]);
+
+        // ---------------- node terms (K4) + write-out
+        if (valid) {
+            double Dr[9] = {Df[0], 0.0, Df[1], 0.0, Df[2], Df[3], 0.0, 0.0, Df[4]};
+            typedef Dual<NS> DN;
+            DN u[NS];
+            double uo[NS], srcv[NS];
+#pragma unroll
+            for (int i = 0; i < NS; i++) {
+                u[i] = DN(a.U[r * NS + i]);
+                u[i].d[i] = 1.0;
+                uo[i] = has_storage ? a.UOld[r * NS + i] : 0.0;
+                srcv[i] = a.src ? a.src[r * NS + i] : 0.0;
+            }
+            for (int q = nq0; q < nq1; q++) {
+                const double fac = a.nf_fac[q];
+                const int region = MULTIREG ? a.nf_region[q] : a.the_region;
+                double ostor[NS];
+                DN rea[NS], stor[NS];
+#pragma unroll
+                for (int i = 0; i < NS; i++) {
+                    ostor[i] = 0.0;
+                    rea[i] = DN(0.0);
+                    stor[i] = DN(0.0);
+                }
+                eval_reaction<NS>(rid, pr, rea, u, region);
+                if (has_storage) {
+                    eval_storage<NS>(sid, ps, stor, u);
+                    eval_storage<NS>(sid, ps, ostor, uo);
+                }
+#pragma unroll
+                for (int i = 0; i < NS; i++) {
+                    Fr[i] += fac * (rea[i].v - srcv[i] + (stor[i].v - ostor[i]) * a.tstepinv);
+#pragma unroll
+                    for (int jj = 0; jj < NS; jj++) {
+                        const double jv = rea[i].d[jj] + stor[i].d[jj] * a.tstepinv;
+                        nan_seen |= (jv != jv);
+                        Dr[i * NS + jj] += jv * fac;
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < NS; i++) {
+                a.F[r * NS + i] = Fr[i];
+#pragma unroll
+                for (int jj = 0; jj < NS; jj++) {
+                    const int pD = a.idxD[i * NS + jj];
+                    if (pD >= 0) a.diagval[(int64_t)pD * a.Nown + r] = Dr[i * NS + jj];
+                }
+            }
+        }
+    }
+    if (nan_seen) atomicOr(a.flags, 1);
+}
+
 // tabulates the (u-independent) source callback once per physics change: src[i,K] = source(f, node)[i]
 template <int NS>
 __global__ void k_source_cache(int64_t N, int dim, const double* __restrict__ coord, const PhysicsDev* __restrict__ ph, double* __restrict__ out) {
@@ -509,10 +762,10 @@ __global__ void k_init_dirichlet(const BNodeArgs a) {
 // persistent grid: one wave of blocks (SMs x resident blocks), warps stride over the slices.  The block size is the one
 // that keeps the most warps resident for the kernel's register footprint (heavy dual-number kernels prefer small blocks).
 template <class Kern>
-static void launch_slices(vfvm_handle* h, Kern kern, int& plan, const AsmArgs& a) {
+static void launch_slices(vfvm_handle* h, Kern kern, int& plan, const AsmArgs& a, int max_threads = ASM_THREADS) {
     if (plan == 0) {
         int best_t = 0, best_w = 0, best_b = 0;
-        for (int t = ASM_THREADS; t >= 64; t /= 2) {
+        for (int t = max_threads; t >= 64; t /= 2) {
             int b = 0;
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kern, t, 0));
             if (b * t > best_w) {
@@ -611,6 +864,15 @@ static void launch_rows(vfvm_handle* h, const AsmArgs& a) {
             return;
         }
     }
+    if constexpr (FLUX == VFVM_FLUX_SG_BIPOLAR && NS == 3) {
+        if (a.Q != a.U) {
+            // 128-thread blocks x 3 per SM (168 registers, no spills in the neighbour loop) measured 5-8 % faster than 256 x 2
+            static int ps = 0, pb = 0;
+            if (h->single_region) launch_slices(h, k_assemble_rows_bipolar<false, 2, 128, 3>, ps, a, 128);
+            else launch_slices(h, k_assemble_rows_bipolar<true, 2, 128, 3>, pb, a, 128);
+            return;
+        }
+    }
     if constexpr (flux_supported(FLUX, NS)) {
         static int occ0 = 0, occ1 = 0;
         if (h->single_region) launch_slices(h, k_assemble_rows<NS, FLUX, false, false, false>, occ0, a);
@@ -674,6 +936,7 @@ int vfvm_assemble_impl(vfvm_handle* h, double time, double tstep, double lambda,
     a.U = h->vec[VFVM_VEC_SOLUTION].p;
     a.UOld = h->vec[VFVM_VEC_OLDSOL].p;
     a.src = h->src_cache.p;
+    a.Q = a.U;
     a.F = h->vec[VFVM_VEC_RESIDUAL].p;
     a.offval = h->offval.p;
     a.diagval = h->diagval.p;
@@ -681,6 +944,7 @@ int vfvm_assemble_impl(vfvm_handle* h, double time, double tstep, double lambda,
     a.flags = h->flags.p + 1;  // word 1: NaN seen during assembly (word 0 belongs to the linear solver)
     a.nnz_sell = h->nnz_sell;
     a.Nown = h->Nown;
+    a.Ntot = h->N;
     a.nslices = h->ngroups;
     a.cF = h->cF;
     a.cD = h->cD;
@@ -694,6 +958,12 @@ int vfvm_assemble_impl(vfvm_handle* h, double time, double tstep, double lambda,
     }
     if (!async) CK(cudaMemsetAsync(h->flags.p + 1, 0, sizeof(int32_t), s));  // async: the flag stays sticky until vfvm_sync
     CK(cudaEventRecord(h->ev0, s));
+    if (flux_node_transform(h->phys.slot[VFVM_SLOT_FLUX].id) && !getenv("VFVM_GENERIC_DUAL_FLUX")) {  // env: parity probe of the generic Dual<2n> path
+        h->node_q.alloc((size_t)h->n * h->N);
+        a.Q = h->node_q.p;
+        if (h->n == 3) k_node_transform<VFVM_FLUX_SG_BIPOLAR, 3><<<cdiv(h->N, 256), 256, 0, s>>>(h->N, a.U, a.ph, h->node_q.p);
+        h->launches++;
+    }
     NS_DISPATCH(h->n, (launch_rows_ns<NS>(h, a)));
     CK(cudaEventRecord(h->ev1, s));
     if (h->nbnodes) {

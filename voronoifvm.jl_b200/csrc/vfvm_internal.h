@@ -138,6 +138,7 @@ struct vfvm_handle {
     int ntiles = 0, tile_nnz = 0;
     int group_R = 16, ngroups = 0, group_maxnnz = 0;  // warp row groups of the assembly / SpMV kernels
     DevBuf<double> src_cache;                         // tabulated source callback, n x N
+    DevBuf<double> node_q;                            // node-transformed unknowns q(u) of flux_node_transform fluxes, n x N
     // boundary nodes: CSR node -> (bface, local node) in bface order
     int64_t nbnodes = 0, nbitems = 0;
     DevBuf<int32_t> bn_node, bn_ptr, bn_bface, bn_local;
