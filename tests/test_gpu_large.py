@@ -125,3 +125,46 @@ def test_cfg2_conservation_full_size():
         assert np.abs(Fs[free]).max() <= 1e-9 * np.abs(omega).max() * 100
     finally:
         st.close()
+
+
+def test_pipelined_host_assembly_is_bitwise_the_plain_one(cfg3, monkeypatch):
+    """vfvm_eval_res_jac with host vectors overlaps the upload of U, the row chunks and the download of F; the result must be
+    bit-identical to upload -> assemble -> download (same kernels, same per-row order)."""
+    s, st = cfg3
+    U = _smooth(s.grid, k=4.0)
+    F1 = st.eval_res_jac(U).copy()
+    A1 = st.matrix("csr").data.copy()
+    monkeypatch.setenv("VFVM_NO_PIPELINE", "1")
+    F2 = st.eval_res_jac(U).copy()
+    A2 = st.matrix("csr").data.copy()
+    assert np.array_equal(F1, F2) and np.array_equal(A1, A2)
+
+
+@pytest.mark.parametrize("chunks", [2, 5, 16])
+def test_pipelined_bipolar_chunks(chunks, monkeypatch):
+    """pipelined path with the node transform of the bipolar flux (q(u) is tabulated piece by piece) and three cell regions"""
+    X = np.linspace(0, 1, 41)
+    g = v.simplexgrid(X, X, X)
+    v.cellmask(g, [0, 0, 0.3], [1, 1, 0.72], 2)
+    v.cellmask(g, [0, 0, 0.7], [1, 1, 1.0], 3)
+    bc = ph.BCondition()
+    for sp in (1, 2, 3):
+        bc.dirichlet(species=sp, region=5, value=0.1 * sp)
+        bc.dirichlet(species=sp, region=6, value=-0.1 * sp)
+    s = v.System(g, flux=ph.BipolarSGFlux(), reaction=ph.BipolarReaction([10.0, 0.0, -10.0]), storage=ph.BipolarStorage(), bcondition=bc, species=[1, 2, 3])
+    st = v.SystemState(s)
+    try:
+        rng = np.random.default_rng(7)
+        U = np.asfortranarray(rng.uniform(-0.5, 0.5, (3, g.num_nodes)))
+        Uo = np.asfortranarray(rng.uniform(-0.5, 0.5, (3, g.num_nodes)))
+        monkeypatch.setenv("VFVM_NO_PIPELINE", "1")
+        F0 = st.eval_res_jac(U, Uo, tstep=0.1).copy()
+        A0 = st.matrix("csr").data.copy()
+        monkeypatch.delenv("VFVM_NO_PIPELINE")
+        monkeypatch.setenv("VFVM_PIPE_MIN_BYTES", "1")
+        monkeypatch.setenv("VFVM_PIPE_CHUNKS", str(chunks))
+        F1 = st.eval_res_jac(U, Uo, tstep=0.1).copy()
+        A1 = st.matrix("csr").data.copy()
+        assert np.array_equal(F0, F1) and np.array_equal(A0, A1)
+    finally:
+        st.close()

@@ -61,6 +61,9 @@ extern "C" void vfvm_destroy(vfvm_handle* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->flags_host) cudaFreeHost(h->flags_host);
     if (h->red_host) cudaFreeHost(h->red_host);
+    for (cudaEvent_t e : h->pipe_ev) cudaEventDestroy(e);
+    if (h->stream_in) cudaStreamDestroy(h->stream_in);
+    if (h->stream_out) cudaStreamDestroy(h->stream_out);
     cudaEventDestroy(h->ev0);
     cudaEventDestroy(h->ev1);
     cudaEventDestroy(h->ev2);
@@ -420,6 +423,10 @@ extern "C" int vfvm_eval_res_jac(vfvm_handle* h, const double* U, const double* 
     if (!U || !F) return vfvm_fail(h, VFVM_ERR_ARG, "null vector");
     VFVM_TRY(h, {
         CK(cudaSetDevice(h->device));
+        if (memspace == VFVM_HOST && vfvm_pipeline_applies(h)) {
+            vfvm_sync_physics(h);
+            return vfvm_eval_res_jac_pipelined(h, U, UOld, F, time, tstep, lambda);
+        }
         const size_t bytes = sizeof(double) * h->n * h->N;
         const cudaMemcpyKind in = memspace == VFVM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
         const cudaMemcpyKind out = memspace == VFVM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;

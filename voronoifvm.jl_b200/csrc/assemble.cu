@@ -45,7 +45,7 @@ struct AsmArgs {
     const PhysicsDev* __restrict__ ph;
     int32_t* flags;
     int64_t nnz_sell, Nown, Ntot;
-    int nslices, cF, cD, the_region;
+    int slice0, nslices, cF, cD, the_region;  // this launch handles the slices [slice0, nslices)
     double time, tstepinv, lambda;
     signed char idxF[100], idxD[100];
 };
@@ -63,9 +63,9 @@ __host__ __device__ constexpr bool flux_separable(int flux) {
 __host__ __device__ constexpr bool flux_node_transform(int flux) { return flux == VFVM_FLUX_SG_BIPOLAR; }
 
 template <int FLUX, int NS>
-__global__ void k_node_transform(int64_t N, const double* __restrict__ U, const PhysicsDev* __restrict__ ph, double* __restrict__ Q) {
-    const int64_t K = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (K >= N) return;
+__global__ void k_node_transform(int64_t K0, int64_t K1, int64_t N, const double* __restrict__ U, const PhysicsDev* __restrict__ ph, double* __restrict__ Q) {
+    const int64_t K = K0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (K >= K1) return;
     const double* __restrict__ p = ph->params + ph->slot[VFVM_SLOT_FLUX].off;
     if constexpr (FLUX == VFVM_FLUX_SG_BIPOLAR && NS == 3) {
         const double zn = p[3], zp = p[4], En = p[5], Ep = p[6];
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(ASM_THREADS, (SEP && LIGHT && NS == 1) ? 4 : (
     for (int i = 0; i < NS; i++) Dcoef[i] = flux_separable(FLUX) && FLUX != VFVM_NONE ? pf[i] : 0.0;
     if constexpr (FLUX == VFVM_FLUX_POWDIFF) mexp = pf[NS];
 
-    for (int g = blockIdx.x * wpb + (threadIdx.x >> 5); g < a.nslices; g += nwarps) {
+    for (int g = a.slice0 + blockIdx.x * wpb + (threadIdx.x >> 5); g < a.nslices; g += nwarps) {
         const int64_t rraw = (int64_t)g * 32 + lane;
         const bool valid = rraw < a.Nown;
         const int64_t r = valid ? rraw : a.Nown - 1;
@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(ASM_THREADS, (LIGHT && CH == 1) ? 4 : (CH <= 5
     for (int i = 0; i < CH; i++) Dcoef[i] = pf[c0 + i];
     if constexpr (FLUX == VFVM_FLUX_POWDIFF) mexp = pf[NS];
 
-    for (int g = blockIdx.x * wpb + (threadIdx.x >> 5); g < a.nslices; g += nwarps) {
+    for (int g = a.slice0 + blockIdx.x * wpb + (threadIdx.x >> 5); g < a.nslices; g += nwarps) {
         const int64_t rraw = (int64_t)g * 32 + lane;
         const bool valid = rraw < a.Nown;
         const int64_t r = valid ? rraw : a.Nown - 1;
@@ -485,7 +485,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assemble_rows_bipolar(const A
     double* __restrict__ o4 = a.offval + (int64_t)a.idxF[8] * nnz;  // (psi,psi)
     bool nan_seen = false;
 
-    for (int g = blockIdx.x * wpb + (threadIdx.x >> 5); g < a.nslices; g += nwarps) {
+    for (int g = a.slice0 + blockIdx.x * wpb + (threadIdx.x >> 5); g < a.nslices; g += nwarps) {
         const int64_t rraw = (int64_t)g * 32 + lane;
         const bool valid = rraw < a.Nown;
         const int64_t r = valid ? rraw : a.Nown - 1;
@@ -664,7 +664,7 @@ struct BNodeArgs {
     double* __restrict__ diagval;
     const PhysicsDev* __restrict__ ph;
     int32_t* flags;
-    int64_t nbnodes, Nown;
+    int64_t b0, nbnodes, Nown;  // this launch handles the boundary nodes [b0, nbnodes)
     int dim;
     double time, lambda;
     signed char idxD[100];
@@ -672,7 +672,7 @@ struct BNodeArgs {
 
 template <int NS>
 __global__ void k_assemble_bnodes(const BNodeArgs a) {
-    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t b = a.b0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= a.nbnodes) return;
     const PhysicsDev& ph = *a.ph;
     const int K = a.bn_node[b];
@@ -780,7 +780,7 @@ static void launch_slices(vfvm_handle* h, Kern kern, int& plan, const AsmArgs& a
     const int threads = plan / 1024, occ = plan % 1024;
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device);
-    const int grid = std::max(1, std::min(cdiv(a.nslices, threads / 32), nsm * occ));
+    const int grid = std::max(1, std::min(cdiv(a.nslices - a.slice0, threads / 32), nsm * occ * h->grid_pct / 100));
     kern<<<grid, threads, 0, h->stream>>>(a);
     h->launches++;
 }
@@ -804,7 +804,7 @@ static void launch_slices_sep(vfvm_handle* h, Kern kern, int& plan, const AsmArg
     const int threads = plan / 1024, occ = plan % 1024;
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device);
-    const int gx = std::max(1, std::min(cdiv(a.nslices, threads / 32), std::max(1, nsm * occ / nchunks)));
+    const int gx = std::max(1, std::min(cdiv(a.nslices - a.slice0, threads / 32), std::max(1, nsm * occ * h->grid_pct / 100 / nchunks)));
     kern<<<dim3(gx, nchunks), threads, 0, h->stream>>>(a);
     h->launches++;
 }
@@ -918,11 +918,7 @@ void vfvm_source_cache(vfvm_handle* h) {
     h->launches++;
 }
 
-int vfvm_assemble_impl(vfvm_handle* h, double time, double tstep, double lambda, bool async) {
-    cudaStream_t s = h->stream;
-    const double tstepinv = 1.0 / tstep;  // src/vfvm_assembly.jl:554 (1/Inf == 0)
-    if (tstepinv != 0.0) h->seen_transient = true;
-    AsmArgs a;
+static void fill_asm_args(vfvm_handle* h, AsmArgs& a, double time, double tstepinv, double lambda) {
     a.sell_ptr = h->sell_ptr.p;
     a.colidx = h->colidx.p;
     a.nzfac = h->nzfac.p;
@@ -945,6 +941,7 @@ int vfvm_assemble_impl(vfvm_handle* h, double time, double tstep, double lambda,
     a.nnz_sell = h->nnz_sell;
     a.Nown = h->Nown;
     a.Ntot = h->N;
+    a.slice0 = 0;
     a.nslices = h->ngroups;
     a.cF = h->cF;
     a.cD = h->cD;
@@ -956,42 +953,211 @@ int vfvm_assemble_impl(vfvm_handle* h, double time, double tstep, double lambda,
         a.idxF[b] = (signed char)(b < h->n * h->n ? h->idxF[b] : -1);
         a.idxD[b] = (signed char)(b < h->n * h->n ? h->idxD[b] : -1);
     }
-    if (!async) CK(cudaMemsetAsync(h->flags.p + 1, 0, sizeof(int32_t), s));  // async: the flag stays sticky until vfvm_sync
-    CK(cudaEventRecord(h->ev0, s));
     if (flux_node_transform(h->phys.slot[VFVM_SLOT_FLUX].id) && !getenv("VFVM_GENERIC_DUAL_FLUX")) {  // env: parity probe of the generic Dual<2n> path
         h->node_q.alloc((size_t)h->n * h->N);
         a.Q = h->node_q.p;
-        if (h->n == 3) k_node_transform<VFVM_FLUX_SG_BIPOLAR, 3><<<cdiv(h->N, 256), 256, 0, s>>>(h->N, a.U, a.ph, h->node_q.p);
-        h->launches++;
     }
+}
+
+static void fill_bnode_args(vfvm_handle* h, BNodeArgs& b, const AsmArgs& a, double time, double lambda) {
+    b.bn_node = h->bn_node.p;
+    b.bn_ptr = h->bn_ptr.p;
+    b.bn_bface = h->bn_bface.p;
+    b.bn_local = h->bn_local.p;
+    b.bfaceregions = h->bfaceregions.p;
+    b.bfnf = h->bfacenodefac.p;
+    b.U = h->vec[VFVM_VEC_SOLUTION].p;
+    b.F = h->vec[VFVM_VEC_RESIDUAL].p;
+    b.diagval = h->diagval.p;
+    b.ph = a.ph;
+    b.flags = h->flags.p + 1;
+    b.b0 = 0;
+    b.nbnodes = h->nbnodes;
+    b.Nown = h->Nown;
+    b.dim = h->dim;
+    b.time = time;
+    b.lambda = lambda;
+    memcpy(b.idxD, a.idxD, sizeof(b.idxD));
+}
+
+// q(u) of the nodes [K0, K1) (only for flux_node_transform fluxes)
+static void launch_node_transform(vfvm_handle* h, const AsmArgs& a, int64_t K0, int64_t K1) {
+    if (a.Q == a.U || K1 <= K0) return;
+    if (h->n == 3) k_node_transform<VFVM_FLUX_SG_BIPOLAR, 3><<<cdiv(K1 - K0, 256), 256, 0, h->stream>>>(K0, K1, h->N, a.U, a.ph, h->node_q.p);
+    h->launches++;
+}
+static void launch_rows_range(vfvm_handle* h, AsmArgs a, int s0, int s1) {
+    if (s1 <= s0) return;
+    a.slice0 = s0;
+    a.nslices = s1;
     NS_DISPATCH(h->n, (launch_rows_ns<NS>(h, a)));
+}
+static void launch_bnodes_range(vfvm_handle* h, BNodeArgs b, int64_t b0, int64_t b1) {
+    if (b1 <= b0) return;
+    b.b0 = b0;
+    b.nbnodes = b1;
+    NS_DISPATCH(h->n, (k_assemble_bnodes<NS><<<cdiv(b1 - b0, 128), 128, 0, h->stream>>>(b)));
+    h->launches++;
+}
+
+int vfvm_assemble_impl(vfvm_handle* h, double time, double tstep, double lambda, bool async) {
+    cudaStream_t s = h->stream;
+    const double tstepinv = 1.0 / tstep;  // src/vfvm_assembly.jl:554 (1/Inf == 0)
+    if (tstepinv != 0.0) h->seen_transient = true;
+    AsmArgs a;
+    fill_asm_args(h, a, time, tstepinv, lambda);
+    if (!async) CK(cudaMemsetAsync(h->flags.p + 1, 0, sizeof(int32_t), s));  // async: the flag stays sticky until vfvm_sync
+    CK(cudaEventRecord(h->ev0, s));
+    launch_node_transform(h, a, 0, h->N);
+    launch_rows_range(h, a, 0, h->ngroups);
     CK(cudaEventRecord(h->ev1, s));
     if (h->nbnodes) {
         BNodeArgs b;
-        b.bn_node = h->bn_node.p;
-        b.bn_ptr = h->bn_ptr.p;
-        b.bn_bface = h->bn_bface.p;
-        b.bn_local = h->bn_local.p;
-        b.bfaceregions = h->bfaceregions.p;
-        b.bfnf = h->bfacenodefac.p;
-        b.U = h->vec[VFVM_VEC_SOLUTION].p;
-        b.F = h->vec[VFVM_VEC_RESIDUAL].p;
-        b.diagval = h->diagval.p;
-        b.ph = a.ph;
-        b.flags = h->flags.p + 1;
-        b.nbnodes = h->nbnodes;
-        b.Nown = h->Nown;
-        b.dim = h->dim;
-        b.time = time;
-        b.lambda = lambda;
-        memcpy(b.idxD, a.idxD, sizeof(b.idxD));
-        NS_DISPATCH(h->n, (k_assemble_bnodes<NS><<<cdiv(h->nbnodes, 128), 128, 0, s>>>(b)));
-        h->launches++;
+        fill_bnode_args(h, b, a, time, lambda);
+        launch_bnodes_range(h, b, 0, h->nbnodes);
     }
     CK(cudaEventRecord(h->ev2, s));
     h->precon_valid = false;
     h->asm_pending = true;
     if (async) return VFVM_OK;
+    return vfvm_assemble_finish(h);
+}
+
+// ---- evaluate_residual_and_jacobian with HOST vectors, pipelined (src/vfvm_solver.jl:224-243) ---------------------------
+// The rows are cut into chunks of whole slices.  U travels host -> device chunk by chunk on a copy stream; the rows of chunk c
+// are assembled as soon as the last piece of U their columns reach has arrived (for a banded numbering: piece c+1), and
+// the residual of chunk c returns to the host on a second copy stream while later chunks are still being uploaded and
+// assembled.  PCIe is full duplex, so the call approaches max(H2D, D2H) instead of H2D + assembly + D2H.
+__global__ void k_slice_colmax(int nslices, const int32_t* __restrict__ sell_ptr, const int32_t* __restrict__ colidx, int32_t* __restrict__ out) {
+    const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (g >= nslices) return;
+    int m = g * 32 + lane;  // the row itself
+    for (int e = sell_ptr[g] + lane; e < sell_ptr[g + 1]; e += 32) m = max(m, colidx[e]);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) out[g] = m;
+}
+
+static int pipe_chunks(const vfvm_handle* h) {  // pieces of >= 4 MB keep the copies at full PCIe rate
+    const int64_t bytes = (int64_t)sizeof(double) * h->n * h->N;
+    const char* env = getenv("VFVM_PIPE_CHUNKS");
+    const int K = env ? atoi(env) : (int)std::min<int64_t>(16, bytes / (7 << 19));  // measured on cfg3 (57.5 MB each way): 16-24 chunks of >= 3.5 MB are best
+    return std::max(1, std::min(K, h->ngroups));
+}
+
+static void build_pipe_plan(vfvm_handle* h) {
+    PipePlan& P = h->pipe;
+    const int K = pipe_chunks(h);
+    P.K = K;
+    P.slice_begin.assign(K + 1, 0);
+    for (int c = 0; c <= K; c++) P.slice_begin[c] = (int)((int64_t)h->ngroups * c / K);
+    DevBuf<int32_t> cm;
+    cm.alloc(h->ngroups);
+    k_slice_colmax<<<cdiv(h->ngroups, 8), 256, 0, h->stream>>>(h->ngroups, h->sell_ptr.p, h->colidx.p, cm.p);
+    h->launches++;
+    std::vector<int32_t> colmax = cm.to_host(h->stream);
+    P.piece_hi.assign(K, 0);
+    P.bn_begin.assign(K + 1, 0);
+    for (int c = 0; c < K; c++) {
+        int32_t m = 0;
+        for (int g = P.slice_begin[c]; g < P.slice_begin[c + 1]; g++) m = std::max(m, colmax[g]);
+        int p = c;
+        while (p + 1 < K && (int64_t)P.slice_begin[p + 1] * 32 <= m) p++;
+        P.piece_hi[c] = p;
+        P.bn_begin[c + 1] = std::lower_bound(h->bn_node_host.begin(), h->bn_node_host.end(), (int32_t)std::min<int64_t>((int64_t)P.slice_begin[c + 1] * 32, h->Nown)) - h->bn_node_host.begin();
+    }
+    P.bn_begin[K] = h->nbnodes;
+    if (!h->stream_in) {
+        CK(cudaStreamCreateWithFlags(&h->stream_in, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&h->stream_out, cudaStreamNonBlocking));
+    }
+    while ((int)h->pipe_ev.size() < 2 * K + 1) {
+        cudaEvent_t e;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        h->pipe_ev.push_back(e);
+    }
+    P.valid = true;
+}
+
+bool vfvm_pipeline_applies(vfvm_handle* h) {
+    if (h->nranks > 1 || getenv("VFVM_NO_PIPELINE")) return false;
+    const char* env = getenv("VFVM_PIPE_MIN_BYTES");  // below this vector size one copy each way is as fast
+    return (int64_t)sizeof(double) * h->n * h->N >= (env ? atoll(env) : (8ll << 20));
+}
+
+int vfvm_eval_res_jac_pipelined(vfvm_handle* h, const double* U, const double* UOld, double* F, double time, double tstep, double lambda) {
+    if (!h->pipe.valid || h->pipe.K != pipe_chunks(h)) build_pipe_plan(h);
+    const PipePlan& P = h->pipe;
+    cudaStream_t s = h->stream, sin = h->stream_in, sout = h->stream_out;
+    const double tstepinv = 1.0 / tstep;
+    if (tstepinv != 0.0) h->seen_transient = true;
+    AsmArgs a;
+    fill_asm_args(h, a, time, tstepinv, lambda);
+    BNodeArgs bn;
+    fill_bnode_args(h, bn, a, time, lambda);
+    const int n = h->n, K = P.K;
+    // UOld == NULL means UOld = U: the kernels read U in its place; the resident OLDSOL vector is refreshed by one device copy
+    // after the last chunk (a device copy per piece on the copy-in stream would compete with the copy engines)
+    const bool have_old = UOld && UOld != U;
+    if (!have_old) a.UOld = a.U;
+    auto node_begin = [&](int c) { return c >= K ? h->N : (int64_t)P.slice_begin[c] * 32; };  // the last piece carries the tail
+    CK(cudaMemsetAsync(h->flags.p + 1, 0, sizeof(int32_t), s));
+    CK(cudaEventRecord(h->ev0, s));
+    CK(cudaEventRecord(h->pipe_ev[2 * K], s));  // the copy-in stream must not overwrite U before earlier work on the main stream is done
+    CK(cudaStreamWaitEvent(sin, h->pipe_ev[2 * K], 0));
+    double* dU = h->vec[VFVM_VEC_SOLUTION].p;
+    double* dO = h->vec[VFVM_VEC_OLDSOL].p;
+    double* dF = h->vec[VFVM_VEC_RESIDUAL].p;
+    for (int p = 0; p < K; p++) {
+        const int64_t o = node_begin(p) * n, cnt = (node_begin(p + 1) - node_begin(p)) * n;
+        CK(cudaMemcpyAsync(dU + o, U + o, cnt * sizeof(double), cudaMemcpyHostToDevice, sin));
+        if (have_old) CK(cudaMemcpyAsync(dO + o, UOld + o, cnt * sizeof(double), cudaMemcpyHostToDevice, sin));
+        CK(cudaEventRecord(h->pipe_ev[p], sin));
+    }
+    // A row kernel on the full persistent grid saturates HBM and starves the copy engines (measured: the upload stalls for
+    // exactly the kernels' run time).  On 30 % of the grid the chunk kernels still keep up with PCIe and the copies run at
+    // full rate beside them (cfg3: 2.51 ms unpipelined, 1.76 ms pipelined on the full grid, 1.5 ms on 30 %).
+    const char* gp = getenv("VFVM_PIPE_GRID_PCT");
+    h->grid_pct = gp ? std::max(1, std::min(100, atoi(gp))) : 30;
+    int arrived = -1;  // last piece the main stream has waited for
+    for (int c = 0; c < K; c++) {
+        if (P.piece_hi[c] > arrived) {
+            CK(cudaStreamWaitEvent(s, h->pipe_ev[P.piece_hi[c]], 0));
+            launch_node_transform(h, a, node_begin(arrived + 1), node_begin(P.piece_hi[c] + 1));
+            arrived = P.piece_hi[c];
+        }
+        launch_rows_range(h, a, P.slice_begin[c], P.slice_begin[c + 1]);
+        launch_bnodes_range(h, bn, P.bn_begin[c], P.bn_begin[c + 1]);
+        CK(cudaEventRecord(h->pipe_ev[K + c], s));
+        CK(cudaStreamWaitEvent(sout, h->pipe_ev[K + c], 0));
+        const int64_t r0 = (int64_t)P.slice_begin[c] * 32, r1 = std::min<int64_t>((int64_t)P.slice_begin[c + 1] * 32, h->Nown);
+        CK(cudaMemcpyAsync(F + r0 * n, dF + r0 * n, (r1 - r0) * n * sizeof(double), cudaMemcpyDeviceToHost, sout));
+    }
+    h->grid_pct = 100;
+    CK(cudaEventRecord(h->ev1, s));
+    CK(cudaEventRecord(h->ev2, s));
+    if (!have_old) CK(cudaMemcpyAsync(dO, dU, sizeof(double) * n * h->N, cudaMemcpyDeviceToDevice, s));
+    h->precon_valid = false;
+    h->asm_pending = true;
+    static const bool trace = getenv("VFVM_PIPE_TRACE") != nullptr;  // diagnostic: when each stream finished, relative to the start
+    cudaEvent_t t_in = nullptr, t_out = nullptr;
+    if (trace) {
+        CK(cudaEventCreate(&t_in));
+        CK(cudaEventCreate(&t_out));
+        CK(cudaEventRecord(t_in, sin));
+        CK(cudaEventRecord(t_out, sout));
+    }
+    CK(cudaStreamSynchronize(sout));
+    if (trace) {
+        CK(cudaStreamSynchronize(s));
+        float a_in = 0, a_cmp = 0, a_out = 0;
+        cudaEventElapsedTime(&a_in, h->ev0, t_in);
+        cudaEventElapsedTime(&a_cmp, h->ev0, h->ev2);
+        cudaEventElapsedTime(&a_out, h->ev0, t_out);
+        fprintf(stderr, "[vfvm pipe] K=%d  copy-in done %.3f ms, last chunk assembled %.3f ms, copy-out done %.3f ms\n", K, a_in, a_cmp, a_out);
+        cudaEventDestroy(t_in);
+        cudaEventDestroy(t_out);
+    }
     return vfvm_assemble_finish(h);
 }
 

@@ -337,6 +337,8 @@ int vfvm_pattern_build(vfvm_handle* h) {
         ptr.push_back((int32_t)items.size());
         h->nbnodes = (int64_t)node.size();
         h->nbitems = (int64_t)items.size();
+        h->bn_node_host = node;
+        h->pipe.valid = false;
         h->bn_node.upload(node.data(), node.size(), s);
         h->bn_ptr.upload(ptr.data(), ptr.size(), s);
         h->bn_bface.upload(bface.data(), bface.size(), s);

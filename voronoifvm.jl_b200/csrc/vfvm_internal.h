@@ -89,10 +89,23 @@ struct Masks {
 static inline bool mask_get(const uint64_t* m, int bit) { return (m[bit >> 6] >> (bit & 63)) & 1ull; }
 static inline void mask_set(uint64_t* m, int bit) { m[bit >> 6] |= (1ull << (bit & 63)); }
 
+// chunking of the pipelined host-vector assembly (vfvm_eval_res_jac with VFVM_HOST)
+struct PipePlan {
+    bool valid = false;
+    int K = 0;
+    std::vector<int> slice_begin;   // K+1: chunk c = slices [slice_begin[c], slice_begin[c+1])
+    std::vector<int> piece_hi;      // K: last piece of U the columns of chunk c reach
+    std::vector<int64_t> bn_begin;  // K+1: boundary nodes of chunk c
+};
+
 // ------------------------------------------------------------------------------------------------ handle
 struct vfvm_handle {
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, stream_in = nullptr, stream_out = nullptr;  // main stream; copy streams of the pipelined host path
+    std::vector<cudaEvent_t> pipe_ev;
+    PipePlan pipe;
+    int grid_pct = 100;  // share of the persistent grid the row kernels may use (pipelined host path: leaves HBM slots to the copy engines)
+    std::vector<int32_t> bn_node_host;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, ev4 = nullptr;
     std::string err;
     int64_t bytes = 0;
@@ -206,6 +219,8 @@ int vfvm_geometry_build(vfvm_handle* h);
 int vfvm_pattern_build(vfvm_handle* h);
 int vfvm_assemble_impl(vfvm_handle* h, double time, double tstep, double lambda, bool async = false);
 int vfvm_assemble_finish(vfvm_handle* h);
+bool vfvm_pipeline_applies(vfvm_handle* h);
+int vfvm_eval_res_jac_pipelined(vfvm_handle* h, const double* U, const double* UOld, double* F, double time, double tstep, double lambda);
 int vfvm_init_dirichlet_impl(vfvm_handle* h, double time, double lambda);
 int vfvm_physics_masks(vfvm_handle* h);
 void vfvm_spmv_impl(vfvm_handle* h, const double* x, double* y);
