@@ -216,6 +216,13 @@ int vfvm_comm_init(vfvm_handle* h, int rank, int nranks, const char id[128]);
 int vfvm_set_halo(vfvm_handle* h, int nneighbors, const int32_t* neighbor_ranks, const int64_t* send_ptr,
                   const int32_t* send_idx, const int64_t* recv_ptr);
 int vfvm_halo_exchange(vfvm_handle* h, int which);
+/* Peer-memory transport (CUDA IPC mailboxes over NVLink, csrc/peer.cuh): after vfvm_set_halo and vfvm_set_system every rank
+ * exports its mailbox (64-byte IPC handle), the host gathers the handles of all ranks (rank order) and every rank connects.
+ * From then on the halo exchange is part of the SpMV kernel and the Krylov reductions are part of their finalize kernel;
+ * NCCL stays the transport if vfvm_peer_connect fails (returns VFVM_ERR_COMM) or VFVM_NO_PEER is set. */
+int vfvm_peer_export(vfvm_handle* h, char handle_out[64]);
+int vfvm_peer_connect(vfvm_handle* h, const char* handles /* nranks x 64 bytes */);
+int vfvm_peer_active(vfvm_handle* h);
 
 /* ---- instrumentation --------------------------------------------------------------------------------- */
 #define VFVM_TIME_ASSEMBLE 0       /* last vfvm_assemble, ms, CUDA events on the handle's stream (tasm)      */

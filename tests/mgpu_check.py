@@ -51,7 +51,7 @@ def main():
         ref = o.solve_step(Ug, tstep=0.05)
         ef = np.max(np.abs(Fg - Fo) / np.maximum(np.abs(Fo), 1e-3))
         eu = np.max(np.abs(solg - ref))
-        print(f"mgpu_check world={world}: residual rel err {ef:.2e}, Newton solution err {eu:.2e}")
+        print(f"mgpu_check world={world} transport={'peer mailboxes' if st.peer else 'NCCL'}: residual rel err {ef:.2e}, Newton solution err {eu:.2e}")
         assert ef < 1e-11 and eu < 1e-10
         print("MGPU_OK")
     st.close()

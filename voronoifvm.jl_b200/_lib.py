@@ -58,6 +58,9 @@ SIGNATURES = {
     "vfvm_copy_vector": [_H, C.c_int, C.c_int],
     "vfvm_init_dirichlet": [_H, C.c_double, C.c_double],
     "vfvm_assemble": [_H, C.c_double, C.c_double, C.c_double],
+    "vfvm_peer_export": [_H, C.c_char_p],
+    "vfvm_peer_connect": [_H, C.c_char_p],
+    "vfvm_peer_active": [_H],
     "vfvm_assemble_async": [_H, C.c_double, C.c_double, C.c_double],
     "vfvm_sync": [_H],
     "vfvm_eval_res_jac": [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double],

@@ -10,7 +10,7 @@ mkdir -p build
 pids=()
 compile() { # src extra-flags
   local src=$1; shift
-  if [ ! -f build/${src%.cu}.o ] || [ $src -nt build/${src%.cu}.o ] || [ vfvm_internal.h -nt build/${src%.cu}.o ] || [ physics.cuh -nt build/${src%.cu}.o ] || [ dual.cuh -nt build/${src%.cu}.o ] || [ ../../include/vfvm_b200.h -nt build/${src%.cu}.o ]; then
+  if [ ! -f build/${src%.cu}.o ] || [ $src -nt build/${src%.cu}.o ] || [ vfvm_internal.h -nt build/${src%.cu}.o ] || [ physics.cuh -nt build/${src%.cu}.o ] || [ dual.cuh -nt build/${src%.cu}.o ] || [ peer.cuh -nt build/${src%.cu}.o ] || [ ../../include/vfvm_b200.h -nt build/${src%.cu}.o ]; then
     $NVCC $COMMON "$@" -c $src -o build/${src%.cu}.o &
     pids+=($!)
   fi

@@ -6,6 +6,7 @@
 // The host shares the ncclUniqueId through its own rendezvous (torch.distributed in bench.py / the tests).
 #include <dlfcn.h>
 
+#include <algorithm>
 #include <cstring>
 
 #include "vfvm_internal.h"
@@ -74,7 +75,182 @@ __global__ void k_pack(int64_t cnt, int ns, const int32_t* __restrict__ idx, con
     buf[i] = x[(int64_t)idx[q] * ns + s];
 }
 
+// ---- peer mailboxes (peer.cuh) ---------------------------------------------------------------------------------------
+struct BoxLayout {
+    size_t dir, hflag, rflag, red, halo;
+};
+inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+// the header part depends on the number of ranks only, so every rank can address every other rank's mailbox
+BoxLayout box_layout(int R) {
+    BoxLayout b;
+    b.dir = 0;  // int64 recv_off[R], slot[R], halo_doubles
+    b.hflag = align256(b.dir + sizeof(int64_t) * (2 * R + 1));             // u64 [2][R]
+    b.rflag = b.hflag + sizeof(uint64_t) * 2 * R;                           // u64 [2][R]
+    b.red = align256(b.rflag + sizeof(uint64_t) * 2 * R);                   // double [2][R][VFVM_PEER_RED_W]
+    b.halo = align256(b.red + sizeof(double) * 2 * R * VFVM_PEER_RED_W);    // double [2][halo_doubles]
+    return b;
+}
+
+// generic halo refresh of a vector through the mailboxes, one kernel: push, raise flags, wait for the neighbours, unpack
+template <int NS>
+__global__ void k_peer_halo(const PeerArgs P, double* __restrict__ x) {
+    peer_push<NS>(P, x);
+    if (threadIdx.x < P.nn) peer_wait(P.hflag_local + threadIdx.x, P.seq, P.err);
+    __syncthreads();
+    const int64_t total = P.nhalo * NS;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) x[P.Nown * NS + i] = peer_ld_data(P.halo_local + i);
+}
+
+// in-place all-reduce (sum or max) of `count` <= VFVM_PEER_RED_W device values: store my values into every rank's box, wait
+// for every rank's values in mine, combine in rank order
+__global__ void k_peer_allreduce(const PeerArgs P, double* __restrict__ vals, int count, int ismax) {
+    const int t = threadIdx.x;
+    if (t < P.nranks) {
+        for (int v = 0; v < count; v++) P.red_dst[t][v] = vals[v];
+        __threadfence_system();
+        peer_st_flag(P.rflag_dst[t], P.seq);
+        peer_wait(P.rflag_local + t, P.seq, P.err);
+    }
+    __syncthreads();
+    if (t < count) {
+        double acc = peer_ld_data(P.red_local + t);
+        for (int q = 1; q < P.nranks; q++) {
+            const double v = peer_ld_data(P.red_local + (size_t)q * VFVM_PEER_RED_W + t);
+            acc = ismax ? fmax(acc, v) : acc + v;
+        }
+        vals[t] = acc;
+    }
+}
+
 }  // namespace
+
+static void fill_peer_common(vfvm_handle* h, PeerArgs& P) {
+    memset(&P, 0, sizeof(P));
+    P.nn = (int)h->nb_ranks.size();
+    P.nranks = h->nranks;
+    P.rank = h->rank;
+    P.ns = h->n;
+    for (int r = 0; r <= P.nn; r++) P.send_ptr[r] = h->send_ptr[r];
+    P.send_idx = h->send_idx.p;
+    P.Nown = h->Nown;
+    P.nhalo = h->N - h->Nown;
+    P.push_count = h->peer_counter.p;
+    P.err = h->flags.p;
+}
+
+PeerArgs vfvm_peer_args_halo(vfvm_handle* h) {
+    PeerArgs P;
+    fill_peer_common(h, P);
+    P.seq = ++h->halo_seq;
+    const int par = (int)(P.seq & 1), R = h->nranks;
+    const BoxLayout b = box_layout(R);
+    for (int r = 0; r < P.nn; r++) {
+        char* base = h->peer_base[h->nb_ranks[r]];
+        P.halo_dst[r] = (double*)(base + b.halo) + (size_t)par * h->peer_halo_doubles[r] + (size_t)h->peer_recv_off[r] * h->n;
+        P.hflag_dst[r] = (unsigned long long*)(base + b.hflag) + (size_t)par * R + h->peer_slot[r];
+    }
+    P.halo_local = (const double*)(h->peer_box + b.halo) + (size_t)par * (size_t)P.nhalo * h->n;
+    P.hflag_local = (const unsigned long long*)(h->peer_box + b.hflag) + (size_t)par * R;
+    return P;
+}
+
+PeerArgs vfvm_peer_args_reduce(vfvm_handle* h) {
+    PeerArgs P;
+    fill_peer_common(h, P);
+    P.seq = ++h->red_seq;
+    const int par = (int)(P.seq & 1), R = h->nranks;
+    const BoxLayout b = box_layout(R);
+    for (int q = 0; q < R; q++) {
+        char* base = h->peer_base[q];
+        P.red_dst[q] = (double*)(base + b.red) + ((size_t)par * R + h->rank) * VFVM_PEER_RED_W;
+        P.rflag_dst[q] = (unsigned long long*)(base + b.rflag) + (size_t)par * R + h->rank;
+    }
+    P.red_local = (const double*)(h->peer_box + b.red) + (size_t)par * R * VFVM_PEER_RED_W;
+    P.rflag_local = (const unsigned long long*)(h->peer_box + b.rflag) + (size_t)par * R;
+    return P;
+}
+
+// Allocates this rank's mailbox (after vfvm_set_halo and vfvm_set_system), writes its directory (where each neighbour's values
+// land) and returns the CUDA IPC handle the host passes to the other ranks (64 bytes).
+extern "C" int vfvm_peer_export(vfvm_handle* h, char handle_out[64]) {
+    if (!h || !handle_out) return VFVM_ERR_ARG;
+    if (h->nranks <= 1 || h->nranks > VFVM_PEER_MAX || h->n <= 0) return vfvm_fail(h, VFVM_ERR_STATE, "peer mailboxes need 2..8 ranks, a halo description and a system");
+    if ((int)h->nb_ranks.size() > VFVM_PEER_MAX) return vfvm_fail(h, VFVM_ERR_STATE, "too many neighbours");
+    VFVM_TRY(h, {
+        CK(cudaSetDevice(h->device));
+        const int R = h->nranks;
+        const BoxLayout b = box_layout(R);
+        const int64_t halo_doubles = (h->N - h->Nown) * h->n;
+        const size_t bytes = b.halo + sizeof(double) * 2 * (size_t)std::max<int64_t>(1, halo_doubles);
+        if (h->peer_box) CK(cudaFree(h->peer_box));
+        CK(cudaMalloc((void**)&h->peer_box, bytes));
+        CK(cudaMemset(h->peer_box, 0, bytes));
+        std::vector<int64_t> dir(2 * R + 1, -1);
+        for (size_t r = 0; r < h->nb_ranks.size(); r++) {
+            dir[h->nb_ranks[r]] = h->recv_ptr[r];
+            dir[R + h->nb_ranks[r]] = (int64_t)r;
+        }
+        dir[2 * R] = halo_doubles;
+        CK(cudaMemcpy(h->peer_box + b.dir, dir.data(), dir.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
+        h->peer_counter.alloc(1);
+        CK(cudaMemset(h->peer_counter.p, 0, sizeof(unsigned int)));
+        cudaIpcMemHandle_t ih;
+        CK(cudaIpcGetMemHandle(&ih, h->peer_box));
+        static_assert(sizeof(ih) == 64, "CUDA IPC handle size");
+        memcpy(handle_out, &ih, 64);
+        h->peer_ok = false;
+    })
+    return VFVM_OK;
+}
+
+// Maps the mailboxes of all ranks (handles = nranks x 64 bytes, gathered by the host after every rank exported) and looks up
+// this rank's place in each neighbour's mailbox.  On failure the NCCL transport stays in use.
+extern "C" int vfvm_peer_connect(vfvm_handle* h, const char* handles) {
+    if (!h || !handles || !h->peer_box) return vfvm_fail(h, VFVM_ERR_STATE, "vfvm_peer_export first");
+    if (getenv("VFVM_NO_PEER")) {
+        h->peer_ok = false;
+        return vfvm_fail(h, VFVM_ERR_COMM, "peer mailboxes disabled by VFVM_NO_PEER");
+    }
+    VFVM_TRY(h, {
+        CK(cudaSetDevice(h->device));
+        const int R = h->nranks;
+        const BoxLayout b = box_layout(R);
+        h->peer_base.assign(R, nullptr);
+        h->peer_base[h->rank] = h->peer_box;
+        for (int q = 0; q < R; q++) {
+            if (q == h->rank) continue;
+            cudaIpcMemHandle_t ih;
+            memcpy(&ih, handles + (size_t)q * 64, 64);
+            void* p = nullptr;
+            cudaError_t e = cudaIpcOpenMemHandle(&p, ih, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                for (int k = 0; k < q; k++)
+                    if (k != h->rank && h->peer_base[k]) cudaIpcCloseMemHandle(h->peer_base[k]);
+                h->peer_base.clear();
+                return vfvm_fail(h, VFVM_ERR_COMM, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+            }
+            h->peer_base[q] = (char*)p;
+        }
+        const size_t nn = h->nb_ranks.size();
+        h->peer_recv_off.assign(nn, 0);
+        h->peer_slot.assign(nn, 0);
+        h->peer_halo_doubles.assign(nn, 0);
+        for (size_t r = 0; r < nn; r++) {
+            std::vector<int64_t> dir(2 * R + 1);
+            CK(cudaMemcpy(dir.data(), h->peer_base[h->nb_ranks[r]] + b.dir, dir.size() * sizeof(int64_t), cudaMemcpyDeviceToHost));
+            if (dir[h->rank] < 0 || dir[R + h->rank] < 0) return vfvm_fail(h, VFVM_ERR_COMM, "halo description is not symmetric between neighbours");
+            h->peer_recv_off[r] = dir[h->rank];
+            h->peer_slot[r] = dir[R + h->rank];
+            h->peer_halo_doubles[r] = dir[2 * R];
+        }
+        h->halo_seq = h->red_seq = 0;
+        h->peer_ok = true;
+    })
+    return VFVM_OK;
+}
+
+extern "C" int vfvm_peer_active(vfvm_handle* h) { return h && h->peer_ok ? 1 : 0; }
 
 extern "C" int vfvm_comm_unique_id(char id_out[128]) {
     std::string err;
@@ -106,6 +282,14 @@ extern "C" int vfvm_comm_init(vfvm_handle* h, int rank, int nranks, const char i
 }
 
 int vfvm_comm_destroy(vfvm_handle* h) {
+    if (h->peer_box) {
+        cudaStreamSynchronize(h->stream);
+        for (size_t q = 0; q < h->peer_base.size(); q++)
+            if ((int)q != h->rank && h->peer_base[q]) cudaIpcCloseMemHandle(h->peer_base[q]);
+        cudaFree(h->peer_box);
+        h->peer_box = nullptr;
+        h->peer_ok = false;
+    }
     if (h->nccl && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)h->nccl);
     h->nccl = nullptr;
     return VFVM_OK;
@@ -128,6 +312,22 @@ extern "C" int vfvm_set_halo(vfvm_handle* h, int nneighbors, const int32_t* neig
 // refresh x[Nown*n .. N*n) from the owners; x is an n x N device vector
 int vfvm_halo_exchange_ptr(vfvm_handle* h, double* x) {
     if (h->nranks <= 1 || h->nb_ranks.empty()) return VFVM_OK;
+    if (h->peer_ok) {
+        const PeerArgs P = vfvm_peer_args_halo(h);
+        const int64_t work = std::max<int64_t>(h->send_ptr[P.nn], P.nhalo) * h->n;
+        const int grid = std::max(1, std::min(cdiv(work, 256), 148));  // every block must be resident: the last one raises the flags
+        switch (h->n) {
+            case 1: k_peer_halo<1><<<grid, 256, 0, h->stream>>>(P, x); break;
+            case 2: k_peer_halo<2><<<grid, 256, 0, h->stream>>>(P, x); break;
+            case 3: k_peer_halo<3><<<grid, 256, 0, h->stream>>>(P, x); break;
+            case 4: k_peer_halo<4><<<grid, 256, 0, h->stream>>>(P, x); break;
+            case 5: k_peer_halo<5><<<grid, 256, 0, h->stream>>>(P, x); break;
+            case 10: k_peer_halo<10><<<grid, 256, 0, h->stream>>>(P, x); break;
+            default: throw std::string("number of species without device instantiation");
+        }
+        h->launches++;
+        return VFVM_OK;
+    }
     const int ns = h->n;
     const int nn = (int)h->nb_ranks.size();
     const int64_t nsend = h->send_ptr[nn];
@@ -159,12 +359,22 @@ extern "C" int vfvm_halo_exchange(vfvm_handle* h, int which) {
 
 int vfvm_comm_allreduce_sum(vfvm_handle* h, double* dev, int count) {
     if (h->nranks <= 1) return VFVM_OK;
+    if (h->peer_ok && count <= VFVM_PEER_RED_W) {
+        k_peer_allreduce<<<1, 32, 0, h->stream>>>(vfvm_peer_args_reduce(h), dev, count, 0);
+        h->launches++;
+        return VFVM_OK;
+    }
     int rc = g_nccl.AllReduce(dev, dev, (size_t)count, ncclFloat64, ncclSum, (ncclComm_t)h->nccl, h->stream);
     if (rc != ncclSuccess) throw std::string("ncclAllReduce: ") + g_nccl.GetErrorString(rc);
     return VFVM_OK;
 }
 int vfvm_comm_allreduce_max(vfvm_handle* h, double* dev, int count) {
     if (h->nranks <= 1) return VFVM_OK;
+    if (h->peer_ok && count <= VFVM_PEER_RED_W) {
+        k_peer_allreduce<<<1, 32, 0, h->stream>>>(vfvm_peer_args_reduce(h), dev, count, 1);
+        h->launches++;
+        return VFVM_OK;
+    }
     int rc = g_nccl.AllReduce(dev, dev, (size_t)count, ncclFloat64, ncclMax, (ncclComm_t)h->nccl, h->stream);
     if (rc != ncclSuccess) throw std::string("ncclAllReduce: ") + g_nccl.GetErrorString(rc);
     return VFVM_OK;

@@ -70,13 +70,18 @@ __device__ __forceinline__ double block_max(double v, double* sh) {
 // y = A x on the DBSR planes in SELL-32 order: a warp owns a slice of 32 rows, one lane per row; colidx / value loads are
 // coalesced, x[col] gathers coalesce on structured numberings, the row sum lives in registers (column order, deterministic).
 // Optional fused inner products (y,w) and (y,y) for the Krylov recurrences.
-template <int NS, bool DIAGMASK>
-__global__ void __launch_bounds__(LS_THREADS) k_spmv(const SpmvArgs a) {
+// PEER (several ranks, peer.cuh): the kernel first pushes this rank's boundary values of x into the neighbours' mailboxes and
+// raises its flag there; columns >= Nown are read from the local mailbox, and only a warp that reaches such a column waits
+// for the neighbours' flags -- halo exchange and SpMV are one kernel, the transfer hides behind the interior rows.
+template <int NS, bool DIAGMASK, bool PEER>
+__global__ void __launch_bounds__(LS_THREADS) k_spmv(const SpmvArgs a, const PeerArgs P) {
     __shared__ double red[32];
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5, nwarps = gridDim.x * wpb;
     const int64_t nnz = a.nnz_sell;
     double d_yw = 0.0, d_yy = 0.0;
+    bool halo_ready = false;  // warp-uniform
+    if constexpr (PEER) peer_push<NS>(P, a.x);
     for (int g = blockIdx.x * wpb + (threadIdx.x >> 5); g < a.nslices; g += nwarps) {
         const int64_t rraw = (int64_t)g * 32 + lane;
         const bool valid = rraw < a.Nown;
@@ -98,10 +103,26 @@ __global__ void __launch_bounds__(LS_THREADS) k_spmv(const SpmvArgs a) {
                 v1[b] = (NS == 1 && DIAGMASK && ok) ? a.offval[e] : 0.0;
             }
             double xl[BATCH][NS];
+            if constexpr (PEER) {
+                bool need = false;
 #pragma unroll
-            for (int b = 0; b < BATCH; b++)
+                for (int b = 0; b < BATCH; b++) need |= Lc[b] >= a.Nown;
+                if (!halo_ready && __any_sync(0xffffffffu, need)) {
+                    if (lane < P.nn) peer_wait(P.hflag_local + lane, P.seq, P.err);
+                    __syncwarp();
+                    halo_ready = true;
+                }
 #pragma unroll
-                for (int jj = 0; jj < NS; jj++) xl[b][jj] = a.x[(int64_t)Lc[b] * NS + jj];
+                for (int b = 0; b < BATCH; b++)
+#pragma unroll
+                    for (int jj = 0; jj < NS; jj++)
+                        xl[b][jj] = Lc[b] >= a.Nown ? peer_ld_data(P.halo_local + (int64_t)(Lc[b] - a.Nown) * NS + jj) : a.x[(int64_t)Lc[b] * NS + jj];
+            } else {
+#pragma unroll
+                for (int b = 0; b < BATCH; b++)
+#pragma unroll
+                    for (int jj = 0; jj < NS; jj++) xl[b][jj] = a.x[(int64_t)Lc[b] * NS + jj];
+            }
 #pragma unroll
             for (int b = 0; b < BATCH; b++) {
                 if (j0 + b >= w) break;
@@ -234,6 +255,36 @@ __global__ void k_finalize_op(const double* __restrict__ part, int nparts, int n
         __syncthreads();
     }
     if (threadIdx.x == 0 && op != OP_NONE) scalar_update(op, sc, flags);
+}
+
+// several ranks with peer mailboxes: local sums -> every rank's reduction box -> wait -> sum over ranks in rank order -> `op`,
+// all in this one single-block kernel (no ncclAllReduce, no separate scalar kernel)
+__global__ void k_finalize_op_peer(const double* __restrict__ part, int nparts, int nvals, double* __restrict__ sc, int op, int32_t* __restrict__ flags,
+                                   const PeerArgs P) {
+    __shared__ double red[32];
+    __shared__ double mine[VFVM_PEER_RED_W];
+    for (int v = 0; v < nvals; v++) {
+        double s = 0.0;
+        for (int i = threadIdx.x; i < nparts; i += blockDim.x) s += part[(int64_t)v * nparts + i];
+        const double r = block_sum(s, red);
+        if (threadIdx.x == 0) mine[v] = r;
+        __syncthreads();
+    }
+    const int t = threadIdx.x;
+    if (t < P.nranks) {
+        for (int v = 0; v < nvals; v++) P.red_dst[t][v] = mine[v];
+        __threadfence_system();
+        peer_st_flag(P.rflag_dst[t], P.seq);
+        peer_wait(P.rflag_local + t, P.seq, P.err);
+    }
+    __syncthreads();
+    if (t < nvals) {
+        double acc = peer_ld_data(P.red_local + t);
+        for (int q = 1; q < P.nranks; q++) acc += peer_ld_data(P.red_local + (size_t)q * VFVM_PEER_RED_W + t);
+        sc[S_TMP0 + t] = acc;
+    }
+    __syncthreads();
+    if (t == 0 && op != OP_NONE) scalar_update(op, sc, flags);
 }
 
 // ---- fused vector kernels (grid-stride over n*Nown entries; partial sums per block) -------------------------
@@ -512,6 +563,9 @@ void finalize(vfvm_handle* h, const double* part, int nparts, int nvals, int op)
     if (h->nranks <= 1) {
         k_finalize_op<<<1, 1024, 0, h->stream>>>(part, nparts, nvals, h->red.p, op, h->flags.p);
         h->launches++;
+    } else if (h->peer_ok && nvals <= VFVM_PEER_RED_W) {
+        k_finalize_op_peer<<<1, 1024, 0, h->stream>>>(part, nparts, nvals, h->red.p, op, h->flags.p, vfvm_peer_args_reduce(h));
+        h->launches++;
     } else {
         k_finalize_op<<<1, 1024, 0, h->stream>>>(part, nparts, nvals, h->red.p, OP_NONE, h->flags.p);
         h->launches++;
@@ -523,9 +577,9 @@ void finalize(vfvm_handle* h, const double* part, int nparts, int nvals, int op)
     }
 }
 
-template <int NS, bool DIAGMASK>
+template <int NS, bool DIAGMASK, bool PEER>
 void launch_spmv_k(vfvm_handle* h, SpmvArgs& a, int op) {
-    auto kern = k_spmv<NS, DIAGMASK>;
+    auto kern = k_spmv<NS, DIAGMASK, PEER>;
     static int occ = 0;
     if (occ == 0) {
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, LS_THREADS, 0));
@@ -538,7 +592,10 @@ void launch_spmv_k(vfvm_handle* h, SpmvArgs& a, int op) {
         if (h->work[10].n < (size_t)2 * grid) h->work[10].alloc((size_t)2 * grid);
         a.part = h->work[10].p;
     }
-    kern<<<grid, LS_THREADS, 0, h->stream>>>(a);
+    PeerArgs P;
+    if constexpr (PEER) P = vfvm_peer_args_halo(h);  // the grid is one resident wave, so the block that finishes the push last can raise the flags
+    else memset(&P, 0, sizeof(P));
+    kern<<<grid, LS_THREADS, 0, h->stream>>>(a, P);
     h->launches++;
     if (a.w) finalize(h, a.part, grid, 2, op);
 }
@@ -547,13 +604,19 @@ template <int NS>
 void launch_spmv(vfvm_handle* h, SpmvArgs& a, int op) {
     bool diagmask = (h->cF == NS && h->cD == NS);
     for (int i = 0; i < NS && diagmask; i++) diagmask = (h->idxF[i * NS + i] == i && h->idxD[i * NS + i] == i);
-    if (diagmask) launch_spmv_k<NS, true>(h, a, op);
-    else launch_spmv_k<NS, false>(h, a, op);
+    const bool peer = h->nranks > 1 && h->peer_ok && !h->nb_ranks.empty();
+    if (diagmask) {
+        if (peer) launch_spmv_k<NS, true, true>(h, a, op);
+        else launch_spmv_k<NS, true, false>(h, a, op);
+    } else {
+        if (peer) launch_spmv_k<NS, false, true>(h, a, op);
+        else launch_spmv_k<NS, false, false>(h, a, op);
+    }
 }
 
 // y = A x (+ fused dots (y,w), (y,y) -> sc[S_TMP0], sc[S_TMP1], then scalar recurrence `op`)
 void spmv(vfvm_handle* h, double* x, double* y, const double* w, int op = OP_NONE) {
-    if (h->nranks > 1) vfvm_halo_exchange_ptr(h, x);
+    if (h->nranks > 1 && !h->peer_ok) vfvm_halo_exchange_ptr(h, x);  // NCCL transport; with peer mailboxes the exchange is part of the SpMV kernel
     SpmvArgs a = make_spmv_args(h);
     a.x = x;
     a.y = y;
@@ -677,6 +740,7 @@ extern "C" int vfvm_linsolve(vfvm_handle* h, double abstol, double reltol, int m
             if (!an.fetch(k, v, fl)) return;
             rr = v;
             done_it = k;
+            if (fl & 256) throw std::string("peer exchange timed out: a neighbouring rank did not deliver its halo / partial sums");
             if (v != v || (fl & 6)) breakdown = true;
             else if (sqrt(v) <= tol) converged = true;
         };

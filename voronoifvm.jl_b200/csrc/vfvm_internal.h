@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "../../include/vfvm_b200.h"
+#include "peer.cuh"
 
 #define VFVM_MAX_SPECIES 10
 #define VFVM_MAX_PARAMS 160
@@ -190,6 +191,13 @@ struct vfvm_handle {
     std::vector<int64_t> send_ptr, recv_ptr;
     DevBuf<int32_t> send_idx;
     DevBuf<double> send_buf;
+    // peer memory (CUDA IPC mailboxes, peer.cuh)
+    bool peer_ok = false;
+    char* peer_box = nullptr;                 // my mailbox
+    std::vector<char*> peer_base;             // every rank's mailbox as mapped here ([rank] = peer_box)
+    std::vector<int64_t> peer_recv_off, peer_slot, peer_halo_doubles;  // per neighbour slot: my place in that neighbour's mailbox
+    unsigned long long halo_seq = 0, red_seq = 0;
+    DevBuf<unsigned int> peer_counter;
 };
 
 #define VFVM_TRY(h, ...)                                        \
@@ -226,4 +234,6 @@ int vfvm_physics_masks(vfvm_handle* h);
 void vfvm_spmv_impl(vfvm_handle* h, const double* x, double* y);
 void vfvm_sync_physics(vfvm_handle* h);
 void vfvm_source_cache(vfvm_handle* h);
+PeerArgs vfvm_peer_args_halo(vfvm_handle* h);    // starts a new halo exchange (advances the sequence number)
+PeerArgs vfvm_peer_args_reduce(vfvm_handle* h);  // starts a new reduction
 

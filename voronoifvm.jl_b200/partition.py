@@ -11,6 +11,7 @@ all-reduces (csrc/comm.cu).  Every rank derives all maps from the replicated hos
 from __future__ import annotations
 
 import dataclasses
+import os
 
 import numpy as np
 
@@ -116,5 +117,20 @@ def partitioned_state(system: System, rank: int, world: int, device: int):
     nb = np.ascontiguousarray(info.neighbor_ranks, dtype=np.int32)
     _lib.check(st.h, L.vfvm_set_halo(st.h, nb.size, _lib.i32ptr(nb), _lib.i64ptr(info.send_ptr), _lib.i32ptr(np.ascontiguousarray(info.send_idx, dtype=np.int32)),
                                      _lib.i64ptr(info.recv_ptr)))
+    # peer mailboxes: halo exchange fused into the SpMV kernel, reductions into their finalize kernel (csrc/peer.cuh)
+    st.peer = False
+    if world <= 8 and not os.environ.get("VFVM_NO_PEER"):
+        hbuf = C.create_string_buffer(64)
+        _lib.check(st.h, L.vfvm_peer_export(st.h, hbuf))
+        handles = [None] * world
+        dist.all_gather_object(handles, hbuf.raw)
+        rc = L.vfvm_peer_connect(st.h, b"".join(handles))
+        oks = [None] * world
+        dist.all_gather_object(oks, rc == 0)  # all ranks or none: the transports must match
+        if not all(oks):
+            os.environ["VFVM_NO_PEER"] = "1"
+            if rc == 0:
+                L.vfvm_peer_connect(st.h, b"".join(handles))  # with VFVM_NO_PEER set this switches the transport back to NCCL
+        st.peer = bool(L.vfvm_peer_active(st.h))
     st.partition = info
     return st, info
