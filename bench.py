@@ -397,6 +397,8 @@ def _newton_step(st, system, U, tstep, world):
     spd = fid == ph.FLUX_DIFFUSION and system.physics.reaction is None
     krylov = v._lib.KRYLOV_CG if spd else v._lib.KRYLOV_BICGSTAB
     precon = v._lib.PRECON_JACOBI if system.num_species == 1 or spd else v._lib.PRECON_BLOCKJACOBI
+    if os.environ.get("VFVM_BENCH_PRECON", "amg") == "amg":
+        precon = v._lib.PRECON_AMG  # aggregation AMG (csrc/amg.cu); VFVM_BENCH_PRECON=jacobi gives the one-level baseline
     v._lib.check(h, L.vfvm_linsolve_setup(h, krylov, precon, 0))
     iters, resn = C.c_int(), C.c_double()
     assert L.vfvm_assemble(h, 0.0, tstep, 0.0) == 0
@@ -409,7 +411,7 @@ def _newton_step(st, system, U, tstep, world):
     L.vfvm_newton_update(h, 1.0, C.byref(ninf), C.byref(n1))
     dt = time.perf_counter() - t0
     t = st.timings()
-    return {"ms": dt * 1e3, "assemble_ms": float(t[0]), "linsolve_ms": float(t[1] + t[2]), "krylov": ("CG" if spd else "BiCGStab") + ("+Jacobi" if precon == v._lib.PRECON_JACOBI else "+block-Jacobi"), "reltol": 1e-10, "iters": iters.value,
+    return {"ms": dt * 1e3, "assemble_ms": float(t[0]), "linsolve_ms": float(t[1] + t[2]), "krylov": ("CG" if spd else "BiCGStab") + {v._lib.PRECON_JACOBI: "+Jacobi", v._lib.PRECON_BLOCKJACOBI: "+block-Jacobi", v._lib.PRECON_AMG: "+aggregation-AMG"}[precon], "reltol": 1e-10, "iters": iters.value,
             "resnorm": resn.value, "update_norm_inf": ninf.value, "rc": rc}
 
 

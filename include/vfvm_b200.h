@@ -131,6 +131,7 @@ typedef struct vfvm_bc_entry {
 #define VFVM_PRECON_BLOCKJACOBI 2 /* n x n node-block inverse (BlockPreconBuilder with node blocks) */
 #define VFVM_PRECON_ILU0 3        /* ILUZeroPreconBuilder on the node-block pattern, natural order  */
 #define VFVM_PRECON_ILU0_MC 4     /* same factorisation in multicolour elimination order (few levels) */
+#define VFVM_PRECON_AMG 5         /* AMGPreconBuilder: aggregation AMG V-cycle on the node-block matrix (csrc/amg.cu)  */
 
 /* ---- lifecycle -------------------------------------------------------------------------------------- */
 int vfvm_create(int device, vfvm_handle** out);

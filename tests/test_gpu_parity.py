@@ -253,7 +253,7 @@ def test_spmv_matches_scipy():
 
 
 @pytest.mark.parametrize("method", ["default", "bicgstab_jacobi", "cg_jacobi", "bicgstab_block", "gmres_jacobi", "gmres_block", "cg_none", "bicgstab_ilu0", "cg_ilu0",
-                                    "bicgstab_ilu0mc", "gmres_ilu0mc"])
+                                    "bicgstab_ilu0mc", "gmres_ilu0mc", "cg_amg", "bicgstab_amg", "gmres_amg"])
 def test_newton_example301(method):
     """Example301: solution[43] known answer, and agreement with the oracle's direct solve"""
     X = np.linspace(0, 1, 6)
@@ -266,7 +266,8 @@ def test_newton_example301(method):
           "gmres_block": v.KrylovJL_GMRES(precs=v.BlockPreconBuilder(), restart=25), "cg_none": v.KrylovJL_CG(),
           "bicgstab_ilu0": v.KrylovJL_BICGSTAB(precs=v.ILUZeroPreconBuilder()), "cg_ilu0": v.KrylovJL_CG(precs=v.ILUZeroPreconBuilder()),
           "bicgstab_ilu0mc": v.KrylovJL_BICGSTAB(precs=v.ILUZeroPreconBuilder(multicolor=True)),
-          "gmres_ilu0mc": v.KrylovJL_GMRES(precs=v.ILUZeroPreconBuilder(multicolor=True))}[method]
+          "gmres_ilu0mc": v.KrylovJL_GMRES(precs=v.ILUZeroPreconBuilder(multicolor=True)), "cg_amg": v.KrylovJL_CG(precs=v.AMGPreconBuilder()),
+          "bicgstab_amg": v.KrylovJL_BICGSTAB(precs=v.AMGPreconBuilder()), "gmres_amg": v.KrylovJL_GMRES(precs=v.SmoothedAggregationPreconBuilder())}[method]
     if method == "cg_none":  # without a preconditioner the 1e30 Dirichlet penalty makes Krylov hopeless: use Robin-free pure Neumann + reaction instead
         sys = v.System(v.simplexgrid(X, X, X), flux=ph.LinearDiffusion(), source=ph.XSinYExpZSource(1, 5.0), reaction=ph.PowerReaction(1.0, 1.0))
         v.enable_species(sys, 1, [1])
@@ -540,3 +541,40 @@ def test_example215_device_boundary_reaction():
         assert u25 == pytest.approx(0.2760603343272377, rel=1e-8)
     finally:
         st.close()
+
+
+def test_amg_multilevel_matches_direct_solve_and_beats_jacobi():
+    """aggregation AMG (csrc/amg.cu) on a problem with several coarse levels: Newton solution = oracle's direct solve to 1e-10,
+    and far fewer Krylov iterations than point Jacobi"""
+    X = np.linspace(0, 1, 33)
+    sys = v.System(v.simplexgrid(X, X, X), flux=ph.LinearDiffusion(), source=ph.XSinYExpZSource(1, 5.0))
+    v.enable_species(sys, 1, [1])
+    v.boundary_dirichlet(sys, 1, 5, 0.0)
+    v.boundary_dirichlet(sys, 1, 6, 0.0)
+    ref = O.OracleSystem(sys).solve_step(v.unknowns(sys))
+    its = {}
+    for name, pc in (("jacobi", v.JacobiPreconBuilder()), ("amg", v.AMGPreconBuilder())):
+        st = v.SystemState(sys)
+        try:
+            sol = v.solve(sys, state=st, inival=0.0, method_linear=v.KrylovJL_CG(precs=pc), reltol_linear=1e-13, abstol_linear=0.0, maxiters_linear=3000)
+            its[name] = st.history.nlin
+        finally:
+            st.close()
+        assert np.max(np.abs(sol - ref)) < TOL_NEWTON, name
+    assert 0 < its["amg"] * 3 < its["jacobi"], its
+
+
+def test_amg_block_system_bipolar_newton():
+    """AMG on a 3-species block system with non-symmetric coupled blocks (bipolar drift-diffusion, BiCGStab): same Newton
+    iterates as BiCGStab + block-Jacobi"""
+    g = _grid(3, 14)
+    bc = ph.BCondition()
+    for sp, val in ((1, 0.0), (2, 0.0), (3, 0.5)):
+        bc.dirichlet(species=sp, region=5, value=val)
+    for sp, val in ((1, 0.1), (2, 0.1), (3, 0.2)):
+        bc.dirichlet(species=sp, region=6, value=val)
+    sys = v.System(g, flux=ph.BipolarSGFlux(), reaction=ph.BipolarReaction([1.0]), storage=ph.BipolarStorage(), bcondition=bc, species=[1, 2, 3])
+    sols = []
+    for pc in (v.BlockPreconBuilder(), v.AMGPreconBuilder()):
+        sols.append(v.solve(sys, inival=0.1, tstep=1.0e-2, method_linear=v.KrylovJL_BICGSTAB(precs=pc), reltol_linear=1e-13, abstol_linear=0.0, maxiters_linear=3000))
+    assert np.max(np.abs(sols[0] - sols[1])) < TOL_NEWTON

@@ -13,5 +13,5 @@ from .system import physics as set_physics  # noqa: F401
 from .state import SystemState  # noqa: F401,E402
 from .solver import (SolverControl, NewtonSolverHistory, TransientSolution, solve, solve_state, solve_step, solve_transient,  # noqa: F401,E402
                      evaluate_residual_and_jacobian, fixed_timesteps, ConvergenceError, AssemblyError, LinearSolverError, EmbeddingError,
-                     KrylovJL_BICGSTAB, KrylovJL_CG, KrylovJL_GMRES, JacobiPreconBuilder, BlockPreconBuilder, ILUZeroPreconBuilder,
+                     KrylovJL_BICGSTAB, KrylovJL_CG, KrylovJL_GMRES, JacobiPreconBuilder, BlockPreconBuilder, ILUZeroPreconBuilder, AMGPreconBuilder, SmoothedAggregationPreconBuilder,
                      DeviceDirectLike)

@@ -17,7 +17,7 @@ ERR_ARG, ERR_STATE, ERR_CUDA, ERR_NAN, ERR_LINSOLVE, ERR_UNREGISTERED, ERR_COMM,
 HOST, DEVICE = 0, 1
 VEC_SOLUTION, VEC_OLDSOL, VEC_RESIDUAL, VEC_UPDATE = 0, 1, 2, 3
 KRYLOV_BICGSTAB, KRYLOV_CG, KRYLOV_GMRES = 0, 1, 2
-PRECON_NONE, PRECON_JACOBI, PRECON_BLOCKJACOBI, PRECON_ILU0, PRECON_ILU0_MC = 0, 1, 2, 3, 4
+PRECON_NONE, PRECON_JACOBI, PRECON_BLOCKJACOBI, PRECON_ILU0, PRECON_ILU0_MC, PRECON_AMG = 0, 1, 2, 3, 4, 5
 TIME_ASSEMBLE, TIME_LINSOLVE_SETUP, TIME_LINSOLVE_SOLVE, TIME_EDGE_KERNEL = 0, 1, 2, 3
 NUM_TIMES = 8
 

@@ -1,0 +1,681 @@
+// Aggregation algebraic multigrid preconditioner (VFVM_PRECON_AMG).
+//
+// The reference reaches multigrid through `precs = AMGPreconBuilder()` / `SmoothedAggregationPreconBuilder()` of
+// AMGCLWrap / AlgebraicMultigrid (examples/DevEx003_Solvers.jl:149-169, examples/DevEx004_EquationBlock3D.jl:225-251);
+// this is the device twin: a V-cycle of plain (piecewise constant) aggregation on the NODE graph, species kept as n x n
+// blocks, so that every level is again a matrix in the DBSR / SELL-32 layout and reuses the SpMV kernel.
+//
+//   hierarchy (once per sparsity pattern, independent of the matrix values):
+//     strength graph = the Voronoi edge factors sigma/h (nzfac) -- symmetric and value independent; on coarse levels their
+//     Galerkin sums.  Aggregates = root + strong neighbours, roots chosen in rounds as the maxima of a fixed hash priority
+//     among the still eligible nodes within distance two (no two roots share a neighbour => conflict-free, deterministic);
+//     left-over nodes join the neighbouring aggregate they are most strongly tied to.  Nodes whose whole diagonal block is a
+//     Dirichlet penalty (1e30) stay out of the coarse problem.
+//     coarse pattern: sort the fine entries by (aggregate of row, aggregate of column) -- one CUB radix sort -- and
+//     run-length encode; the sorted entry list is kept as the gather map of the numeric Galerkin product.
+//   numeric phase (every new Jacobian): A_c(I,J) = sum of the fine blocks (K,L), K in I, L in J, plane by plane, as a GATHER
+//     in the fixed sorted order (no atomics => bitwise reproducible); block inverses of the diagonal for the smoother.
+//   cycle: damped block-Jacobi pre-/post-smoothing (symmetric, so CG stays applicable), residual fused into the restriction,
+//     over-weighted coarse correction (plain aggregation under-estimates smooth corrections), a few sweeps on the coarsest level.
+// With several ranks the hierarchy is built on the rank's own diagonal block (halo columns dropped): block-Jacobi across
+// ranks with AMG inside, no communication inside the preconditioner.
+#include <algorithm>
+#include <cub/cub.cuh>
+
+#include "vfvm_internal.h"
+
+namespace {
+
+struct Level {
+    int64_t N = 0;     // nodes of this level (level 0: the owned nodes)
+    int64_t Nvec = 0;  // nodes a vector of this level holds (level 0: including the halo, whose entries stay zero here)
+    int nslices = 0;
+    int64_t nnz_sell = 0;
+    // matrix in DBSR / SELL-32 layout; level 0 aliases the handle's Jacobian
+    const int32_t* sell_ptr = nullptr;
+    const int32_t* colidx = nullptr;
+    const double* offval = nullptr;
+    const double* diagval = nullptr;
+    const double* w = nullptr;  // symmetric edge weights in SELL order (strength graph)
+    DevBuf<int32_t> sell_ptr_b, colidx_b;
+    DevBuf<double> offval_b, diagval_b, w_b;
+    DevBuf<double> binv;  // n*n planes x N: inverse diagonal blocks
+    // transfer to the next coarser level
+    int64_t Nc = 0;
+    DevBuf<int32_t> agg;                 // N: aggregate of each node, -1 = not represented on the coarse level
+    DevBuf<int32_t> agg_ptr, agg_nodes;  // Nc+1 / nodes sorted by aggregate
+    int64_t nuniq = 0;
+    DevBuf<int32_t> gal_ptr, gal_src, gal_dst;  // coarse entry u <- fine entries gal_src[gal_ptr[u] .. gal_ptr[u+1]); dst >= 0: SELL position, < 0: diagonal of node -dst-1
+    // work vectors (n x Nvec)
+    DevBuf<double> x, b, t;
+};
+
+struct Amg {
+    std::vector<Level*> L;
+    bool struct_valid = false;
+    int64_t pattern_nnz = -1, pattern_N = -1;
+    double omega = 0.8, alpha = 1.75, theta = 0.08;  // alpha: measured on cfg3 (CG iterations 153 / 101 / 79 / 71 / 69 for alpha = 1 / 1.25 / 1.5 / 1.75 / 2)
+    int coarse_sweeps = 8, max_levels = 20, sweeps = 1;  // sweeps: pre- and post-smoothing steps per level
+    ~Amg() {
+        for (Level* l : L) delete l;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------ aggregation kernels
+// All of them use the SpMV mapping: a warp owns a slice of 32 rows, one lane per row, entries e = base + 32 j + lane.
+__device__ __forceinline__ bool strong(double w, double dK, double dL, double theta2) { return w > 0.0 && w * w >= theta2 * dK * dL; }
+__device__ __forceinline__ unsigned long long prio_of(int K) {
+    unsigned int x = (unsigned int)K * 2654435761u;
+    x ^= x >> 15;
+    x *= 2246822519u;
+    x ^= x >> 13;
+    return ((unsigned long long)x << 32) | (unsigned int)(K + 1);
+}
+
+#define ROW_LOOP_BEGIN(N_, nsl_)                                                                  \
+    const int lane = threadIdx.x & 31;                                                            \
+    const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);                            \
+    if (g >= (nsl_)) return;                                                                      \
+    const int K = g * 32 + lane;                                                                  \
+    const bool valid = K < (N_);                                                                  \
+    const int base = sell_ptr[g];                                                                 \
+    const int wd = (sell_ptr[g + 1] - base) >> 5;
+
+// node weight d_K = sum of the edge weights of the row (owned columns only); fixed nodes (whole diagonal block is a Dirichlet
+// penalty) get d = inf, which makes every connection to them weak
+template <int NS>
+__global__ void k_node_weight(int64_t N, int nsl, const int32_t* __restrict__ sell_ptr, const int32_t* __restrict__ colidx, const double* __restrict__ w,
+                              const double* __restrict__ diagval, SpmvArgs a, int check_fixed, double* __restrict__ d) {
+    ROW_LOOP_BEGIN(N, nsl)
+    double s = 0.0;
+    for (int j = 0; j < wd; j++) {
+        const int e = base + 32 * j + lane;
+        const int L = colidx[e];
+        if (valid && L != K && L < N) s += w[e];
+    }
+    if (!valid) return;
+    if (check_fixed) {
+        bool all_fixed = true;
+#pragma unroll
+        for (int i = 0; i < NS; i++) all_fixed &= fabs(diagval[(int64_t)a.idxD[i * NS + i] * N + K]) >= 1.0e29;
+        if (all_fixed) s = INFINITY;
+    }
+    d[K] = s;
+}
+
+// -1 undecided, -2 out (fixed or without strong neighbour)
+__global__ void k_agg_init(int64_t N, int nsl, const int32_t* __restrict__ sell_ptr, const int32_t* __restrict__ colidx, const double* __restrict__ w,
+                           const double* __restrict__ d, double theta2, int32_t* __restrict__ agg) {
+    ROW_LOOP_BEGIN(N, nsl)
+    const double dK = valid ? d[K] : INFINITY;
+    bool any = false;
+    for (int j = 0; j < wd; j++) {
+        const int e = base + 32 * j + lane;
+        const int L = colidx[e];
+        if (valid && L != K && L < N) any |= strong(w[e], dK, d[L], theta2);
+    }
+    if (valid) agg[K] = any ? -1 : -2;
+}
+
+// eligible = undecided and every strong neighbour undecided; ep = priority of eligible nodes, else 0
+__global__ void k_agg_elig(int64_t N, int nsl, const int32_t* __restrict__ sell_ptr, const int32_t* __restrict__ colidx, const double* __restrict__ w,
+                           const double* __restrict__ d, double theta2, const int32_t* __restrict__ agg, unsigned long long* __restrict__ ep) {
+    ROW_LOOP_BEGIN(N, nsl)
+    const double dK = valid ? d[K] : INFINITY;
+    bool ok = valid && agg[K] == -1;
+    for (int j = 0; j < wd; j++) {
+        const int e = base + 32 * j + lane;
+        const int L = colidx[e];
+        if (ok && L != K && L < N && strong(w[e], dK, d[L], theta2)) ok = agg[L] == -1;
+    }
+    if (valid) ep[K] = ok ? prio_of(K) : 0ull;
+}
+
+// out[K] = max(in[K], in[L] over strong neighbours L)
+__global__ void k_agg_max(int64_t N, int nsl, const int32_t* __restrict__ sell_ptr, const int32_t* __restrict__ colidx, const double* __restrict__ w,
+                          const double* __restrict__ d, double theta2, const unsigned long long* __restrict__ in, unsigned long long* __restrict__ out) {
+    ROW_LOOP_BEGIN(N, nsl)
+    const double dK = valid ? d[K] : INFINITY;
+    unsigned long long m = valid ? in[K] : 0ull;
+    for (int j = 0; j < wd; j++) {
+        const int e = base + 32 * j + lane;
+        const int L = colidx[e];
+        if (valid && L != K && L < N && strong(w[e], dK, d[L], theta2)) m = max(m, in[L]);
+    }
+    if (valid) out[K] = m;
+}
+
+// an eligible node whose priority is the maximum within distance two becomes a root and takes its strong neighbours
+__global__ void k_agg_root(int64_t N, int nsl, const int32_t* __restrict__ sell_ptr, const int32_t* __restrict__ colidx, const double* __restrict__ w,
+                           const double* __restrict__ d, double theta2, const unsigned long long* __restrict__ ep, const unsigned long long* __restrict__ m1,
+                           int32_t* __restrict__ agg, int32_t* __restrict__ nroots) {
+    ROW_LOOP_BEGIN(N, nsl)
+    const double dK = valid ? d[K] : INFINITY;
+    const unsigned long long mine = valid ? ep[K] : 0ull;
+    unsigned long long m = valid ? m1[K] : 0ull;
+    for (int j = 0; j < wd; j++) {
+        const int e = base + 32 * j + lane;
+        const int L = colidx[e];
+        if (mine && L != K && L < N && strong(w[e], dK, d[L], theta2)) m = max(m, m1[L]);
+    }
+    const bool root = mine != 0ull && m == mine;
+    if (root) {
+        agg[K] = K;
+        atomicAdd(nroots, 1);
+    }
+    for (int j = 0; j < wd; j++) {
+        const int e = base + 32 * j + lane;
+        const int L = colidx[e];
+        if (root && L != K && L < N && strong(w[e], dK, d[L], theta2)) agg[L] = K;  // no other root reaches L
+    }
+}
+
+// undecided nodes join the aggregate of the neighbour they are most strongly tied to (reads `agg`, writes `out`)
+__global__ void k_agg_join(int64_t N, int nsl, const int32_t* __restrict__ sell_ptr, const int32_t* __restrict__ colidx, const double* __restrict__ w,
+                           const double* __restrict__ d, double theta2, const int32_t* __restrict__ agg, int32_t* __restrict__ out) {
+    ROW_LOOP_BEGIN(N, nsl)
+    const double dK = valid ? d[K] : INFINITY;
+    const int mine = valid ? agg[K] : -2;
+    double best = 0.0;
+    int target = -1;
+    for (int j = 0; j < wd; j++) {
+        const int e = base + 32 * j + lane;
+        const int L = colidx[e];
+        if (mine == -1 && L != K && L < N) {
+            const double we = w[e];
+            if (strong(we, dK, d[L], theta2) && we > best) {  // columns ascend: ties go to the lower node number
+                const int aL = agg[L];
+                if (aL >= 0) {
+                    best = we;
+                    target = aL;
+                }
+            }
+        }
+    }
+    if (valid) out[K] = mine == -1 ? target : mine;  // target -1: still undecided
+}
+
+__global__ void k_agg_rest(int64_t N, int32_t* __restrict__ agg, int32_t* __restrict__ isroot) {
+    const int64_t K = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (K >= N) return;
+    if (agg[K] == -1) agg[K] = (int)K;  // nobody to join: an aggregate of its own
+    isroot[K] = agg[K] == (int)K ? 1 : 0;
+}
+__global__ void k_agg_renumber(int64_t N, const int32_t* __restrict__ newid, int32_t* __restrict__ agg, int32_t* __restrict__ keys, int32_t* __restrict__ vals, int Nc) {
+    const int64_t K = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (K >= N) return;
+    const int a = agg[K];
+    const int id = a >= 0 ? newid[a] : -1;
+    agg[K] = id;
+    keys[K] = id >= 0 ? id : Nc;  // nodes outside the coarse problem sort to the end
+    vals[K] = (int)K;
+}
+__global__ void k_lower_bounds32(int n, const int32_t* __restrict__ sorted, int64_t len, int32_t* __restrict__ out) {  // out[i] = first position with key >= i
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int64_t lo = 0, hi = len;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (sorted[mid] < i) lo = mid + 1;
+        else hi = mid;
+    }
+    out[i] = (int32_t)lo;
+}
+
+// ------------------------------------------------------------------------------------------------ coarse pattern kernels
+#define KEY_SENTINEL 0xffffffffffffffffull
+__global__ void k_pair_keys(int64_t N, int nsl, const int32_t* __restrict__ sell_ptr, const int32_t* __restrict__ colidx, const int32_t* __restrict__ agg, int64_t Nc,
+                            unsigned long long* __restrict__ keys, int32_t* __restrict__ vals) {
+    ROW_LOOP_BEGIN(N, nsl)
+    const int I = valid ? agg[K] : -1;
+    for (int j = 0; j < wd; j++) {
+        const int e = base + 32 * j + lane;
+        const int L = colidx[e];
+        unsigned long long key = KEY_SENTINEL;
+        if (valid && I >= 0 && L != K && L < N) {
+            const int J = agg[L];
+            if (J >= 0) key = (unsigned long long)I * (unsigned long long)Nc + (unsigned long long)J;
+        }
+        keys[e] = key;
+        vals[e] = e;
+    }
+}
+__global__ void k_flag_heads(int64_t n, const unsigned long long* __restrict__ keys, int32_t* __restrict__ flag) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    flag[k] = (keys[k] != KEY_SENTINEL && (k == 0 || keys[k] != keys[k - 1])) ? 1 : 0;
+}
+__global__ void k_collect_uniques(int64_t n, const unsigned long long* __restrict__ keys, const int32_t* __restrict__ flag, const int32_t* __restrict__ uid,
+                                  unsigned long long* __restrict__ ukey, int32_t* __restrict__ gal_ptr) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    if (flag[k]) {
+        ukey[uid[k]] = keys[k];
+        gal_ptr[uid[k]] = (int32_t)k;
+    }
+}
+__device__ __forceinline__ int64_t lb64(const unsigned long long* __restrict__ a, int64_t n, unsigned long long v) {
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (a[mid] < v) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+__global__ void k_first_sentinel(const unsigned long long* __restrict__ a, int64_t n, int32_t* __restrict__ out) { *out = (int32_t)lb64(a, n, KEY_SENTINEL); }
+// off-diagonal row lengths of the coarse matrix from the sorted unique (I,J) keys
+__global__ void k_coarse_rowlen(int64_t Nc, const unsigned long long* __restrict__ ukey, int64_t nuniq, int32_t* __restrict__ rowlen) {
+    const int64_t I = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (I >= Nc) return;
+    const int64_t f = lb64(ukey, nuniq, (unsigned long long)I * Nc), g = lb64(ukey, nuniq, (unsigned long long)(I + 1) * Nc);
+    const unsigned long long dk = (unsigned long long)I * Nc + I;
+    const int64_t dpos = lb64(ukey, nuniq, dk);
+    const bool hasdiag = dpos < nuniq && ukey[dpos] == dk;
+    rowlen[I] = (int32_t)(g - f - (hasdiag ? 1 : 0));
+}
+__global__ void k_slice_width(int nslc, int64_t Nc, const int32_t* __restrict__ rowlen, int32_t* __restrict__ width32) {
+    const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (g >= nslc) return;
+    const int64_t I = (int64_t)g * 32 + lane;
+    int m = I < Nc ? rowlen[I] : 0;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) width32[g] = 32 * m;
+}
+__global__ void k_fill_rowid(int nslc, const int32_t* __restrict__ sell_ptr, int32_t* __restrict__ colidx) {  // padding entries point to their own row
+    const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (g >= nslc) return;
+    for (int e = sell_ptr[g] + lane; e < sell_ptr[g + 1]; e += 32) colidx[e] = g * 32 + lane;
+}
+__global__ void k_place_uniques(int64_t nuniq, int64_t Nc, const unsigned long long* __restrict__ ukey, const int32_t* __restrict__ sell_ptr, int32_t* __restrict__ colidx,
+                                int32_t* __restrict__ gal_dst) {
+    const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= nuniq) return;
+    const unsigned long long key = ukey[u];
+    const int64_t I = (int64_t)(key / (unsigned long long)Nc), J = (int64_t)(key - (unsigned long long)I * Nc);
+    if (I == J) {
+        gal_dst[u] = -(int32_t)I - 1;
+        return;
+    }
+    const int64_t f = lb64(ukey, nuniq, (unsigned long long)I * Nc);
+    int64_t j = u - f;
+    if (J > I) {
+        const unsigned long long dk = (unsigned long long)I * Nc + I;
+        const int64_t dpos = lb64(ukey, nuniq, dk);
+        if (dpos < nuniq && ukey[dpos] == dk) j--;
+    }
+    const int pos = sell_ptr[I >> 5] + 32 * (int)j + (int)(I & 31);
+    colidx[pos] = (int32_t)J;
+    gal_dst[u] = pos;
+}
+
+// ------------------------------------------------------------------------------------------------ numeric Galerkin product
+// diagonal blocks: sum of the fine diagonal blocks of the aggregate (node list in ascending order)
+__global__ void k_gal_diag(int64_t Nc, int cD, const int32_t* __restrict__ agg_ptr, const int32_t* __restrict__ agg_nodes, const double* __restrict__ fdiag, int64_t Nf,
+                           double* __restrict__ cdiag) {
+    const int64_t I = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (I >= Nc) return;
+    const int q0 = agg_ptr[I], q1 = agg_ptr[I + 1];
+    for (int p = 0; p < cD; p++) {
+        double s = 0.0;
+        for (int q = q0; q < q1; q++) s += fdiag[(int64_t)p * Nf + agg_nodes[q]];
+        cdiag[(int64_t)p * Nc + I] = s;
+    }
+}
+// off-diagonal blocks (and the aggregate-internal fine blocks, which go to the coarse diagonal): gather in sorted order.
+// planeD[p] = diagonal plane that holds the coupling of off-diagonal plane p.  One unique (I,I) per aggregate => single writer.
+struct PlaneMap {
+    int cF;
+    int toD[100];
+};
+__global__ void k_gal_off(int64_t nuniq, PlaneMap pm, const int32_t* __restrict__ gal_ptr, const int32_t* __restrict__ gal_src, const int32_t* __restrict__ gal_dst,
+                          const double* __restrict__ foff, int64_t fnnz, double* __restrict__ coff, int64_t cnnz, double* __restrict__ cdiag, int64_t Nc) {
+    const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= nuniq) return;
+    const int k0 = gal_ptr[u], k1 = gal_ptr[u + 1], dst = gal_dst[u];
+    for (int p = 0; p < pm.cF; p++) {
+        double s = 0.0;
+        for (int k = k0; k < k1; k++) s += foff[(int64_t)p * fnnz + gal_src[k]];
+        if (dst >= 0) coff[(int64_t)p * cnnz + dst] = s;
+        else cdiag[(int64_t)pm.toD[p] * Nc + (-dst - 1)] += s;
+    }
+}
+__global__ void k_gal_weight(int64_t nuniq, const int32_t* __restrict__ gal_ptr, const int32_t* __restrict__ gal_src, const int32_t* __restrict__ gal_dst,
+                             const double* __restrict__ fw, double* __restrict__ cw) {
+    const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= nuniq) return;
+    const int dst = gal_dst[u];
+    if (dst < 0) return;
+    double s = 0.0;
+    for (int k = gal_ptr[u]; k < gal_ptr[u + 1]; k++) s += fw[gal_src[k]];
+    cw[dst] = s;
+}
+
+// ------------------------------------------------------------------------------------------------ cycle kernels
+// x = omega B^-1 b  (first sweep from a zero guess)    or    x += omega B^-1 (b - t), t = A x; optionally mirrored to `out`
+template <int NS>
+__global__ void k_smooth(int64_t N, double omega, const double* __restrict__ binv, const double* __restrict__ b, const double* __restrict__ t, double* __restrict__ x,
+                         double* __restrict__ out) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= N) return;
+    double res[NS];
+#pragma unroll
+    for (int j = 0; j < NS; j++) res[j] = t ? b[r * NS + j] - t[r * NS + j] : b[r * NS + j];
+#pragma unroll
+    for (int i = 0; i < NS; i++) {
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < NS; j++) s += binv[(int64_t)(i * NS + j) * N + r] * res[j];
+        const double v = (t ? x[r * NS + i] : 0.0) + omega * s;
+        x[r * NS + i] = v;
+        if (out) out[r * NS + i] = v;
+    }
+}
+// coarse right-hand side: b_c[I] = sum over the aggregate of (b - t), t = A x  (residual fused into the restriction)
+template <int NS>
+__global__ void k_restrict(int64_t Nc, const int32_t* __restrict__ agg_ptr, const int32_t* __restrict__ agg_nodes, const double* __restrict__ b, const double* __restrict__ t,
+                           double* __restrict__ bc) {
+    const int64_t I = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (I >= Nc) return;
+    double s[NS];
+#pragma unroll
+    for (int i = 0; i < NS; i++) s[i] = 0.0;
+    for (int q = agg_ptr[I]; q < agg_ptr[I + 1]; q++) {
+        const int64_t K = agg_nodes[q];
+#pragma unroll
+        for (int i = 0; i < NS; i++) s[i] += b[K * NS + i] - t[K * NS + i];
+    }
+#pragma unroll
+    for (int i = 0; i < NS; i++) bc[I * NS + i] = s[i];
+}
+template <int NS>
+__global__ void k_prolong(int64_t N, double alpha, const int32_t* __restrict__ agg, const double* __restrict__ xc, double* __restrict__ x) {
+    const int64_t K = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (K >= N) return;
+    const int I = agg[K];
+    if (I < 0) return;
+#pragma unroll
+    for (int i = 0; i < NS; i++) x[K * NS + i] += alpha * xc[(int64_t)I * NS + i];
+}
+
+#define NS_SWITCH(n, ...)                                                                  \
+    switch (n) {                                                                           \
+        case 1: { constexpr int NS = 1; __VA_ARGS__; } break;                              \
+        case 2: { constexpr int NS = 2; __VA_ARGS__; } break;                              \
+        case 3: { constexpr int NS = 3; __VA_ARGS__; } break;                              \
+        case 4: { constexpr int NS = 4; __VA_ARGS__; } break;                              \
+        case 5: { constexpr int NS = 5; __VA_ARGS__; } break;                              \
+        case 10: { constexpr int NS = 10; __VA_ARGS__; } break;                            \
+        default: throw std::string("number of species without device instantiation");      \
+    }
+
+SpmvArgs level_args(vfvm_handle* h, const Level& l) {
+    SpmvArgs a = vfvm_spmv_args(h);  // plane tables
+    a.sell_ptr = l.sell_ptr;
+    a.colidx = l.colidx;
+    a.offval = l.offval;
+    a.diagval = l.diagval;
+    a.nnz_sell = l.nnz_sell;
+    a.Nown = l.N;
+    a.nslices = l.nslices;
+    return a;
+}
+
+template <class T>
+T fetch(const T* dev, cudaStream_t s) {
+    T v;
+    CK(cudaMemcpyAsync(&v, dev, sizeof(T), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return v;
+}
+
+// aggregates of level l; returns the number of aggregates
+int64_t aggregate(vfvm_handle* h, Amg& A, Level& l, bool level0) {
+    cudaStream_t s = h->stream;
+    const int64_t N = l.N;
+    const int nsl = l.nslices, gridw = cdiv(nsl, 8);
+    const double th2 = A.theta * A.theta;
+    DevBuf<double> d;
+    d.alloc(N);
+    SpmvArgs a = level_args(h, l);
+    NS_SWITCH(h->n, (k_node_weight<NS><<<gridw, 256, 0, s>>>(N, nsl, l.sell_ptr, l.colidx, l.w, l.diagval, a, level0 ? 1 : 0, d.p)));
+    l.agg.alloc(N);
+    k_agg_init<<<gridw, 256, 0, s>>>(N, nsl, l.sell_ptr, l.colidx, l.w, d.p, th2, l.agg.p);
+    DevBuf<unsigned long long> ep, m1;
+    ep.alloc(N);
+    m1.alloc(N);
+    DevBuf<int32_t> cnt, agg2, isroot, newid;
+    cnt.alloc(1);
+    h->launches += 2;
+    for (int round = 0; round < 64; round++) {
+        CK(cudaMemsetAsync(cnt.p, 0, sizeof(int32_t), s));
+        k_agg_elig<<<gridw, 256, 0, s>>>(N, nsl, l.sell_ptr, l.colidx, l.w, d.p, th2, l.agg.p, ep.p);
+        k_agg_max<<<gridw, 256, 0, s>>>(N, nsl, l.sell_ptr, l.colidx, l.w, d.p, th2, ep.p, m1.p);
+        k_agg_root<<<gridw, 256, 0, s>>>(N, nsl, l.sell_ptr, l.colidx, l.w, d.p, th2, ep.p, m1.p, l.agg.p, cnt.p);
+        h->launches += 3;
+        if (fetch(cnt.p, s) == 0) break;
+    }
+    agg2.alloc(N);
+    for (int pass = 0; pass < 2; pass++) {  // left-overs join a neighbouring aggregate; the second pass serves nodes whose neighbours joined in the first
+        k_agg_join<<<gridw, 256, 0, s>>>(N, nsl, l.sell_ptr, l.colidx, l.w, d.p, th2, l.agg.p, agg2.p);
+        CK(cudaMemcpyAsync(l.agg.p, agg2.p, N * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
+        h->launches++;
+    }
+    isroot.alloc(N);
+    newid.alloc(N);
+    k_agg_rest<<<cdiv(N, 256), 256, 0, s>>>(N, l.agg.p, isroot.p);
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, isroot.p, newid.p, (int)N, s);
+    DevBuf<char> tmp;
+    tmp.alloc(tb + 16);
+    cub::DeviceScan::ExclusiveSum(tmp.p, tb, isroot.p, newid.p, (int)N, s);
+    const int64_t Nc = (int64_t)fetch(newid.p + (N - 1), s) + fetch(isroot.p + (N - 1), s);
+    // node lists of the aggregates
+    DevBuf<int32_t> keys, vals, keys_s;
+    keys.alloc(N);
+    vals.alloc(N);
+    keys_s.alloc(N);
+    l.agg_nodes.alloc(N);
+    k_agg_renumber<<<cdiv(N, 256), 256, 0, s>>>(N, newid.p, l.agg.p, keys.p, vals.p, (int)Nc);
+    int bits = 1;
+    while ((1ll << bits) <= Nc) bits++;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, keys.p, keys_s.p, vals.p, l.agg_nodes.p, (int)N, 0, bits, s);
+    tmp.alloc(tb + 16);
+    cub::DeviceRadixSort::SortPairs(tmp.p, tb, keys.p, keys_s.p, vals.p, l.agg_nodes.p, (int)N, 0, bits, s);
+    l.agg_ptr.alloc(Nc + 1);
+    k_lower_bounds32<<<cdiv(Nc + 1, 256), 256, 0, s>>>((int)Nc + 1, keys_s.p, N, l.agg_ptr.p);
+    h->launches += 6;
+    CK(cudaStreamSynchronize(s));
+    l.Nc = Nc;
+    return Nc;
+}
+
+// pattern of the next level + gather maps of the Galerkin product
+void coarsen_pattern(vfvm_handle* h, Level& f, Level& c) {
+    cudaStream_t s = h->stream;
+    const int64_t Nc = f.Nc, nnz = f.nnz_sell;
+    c.N = c.Nvec = Nc;
+    c.nslices = cdiv(Nc, 32);
+    DevBuf<unsigned long long> keys, keys_s, ukey;
+    DevBuf<int32_t> vals, flag, uid;
+    keys.alloc(nnz);
+    keys_s.alloc(nnz);
+    vals.alloc(nnz);
+    f.gal_src.alloc(nnz);
+    k_pair_keys<<<cdiv(f.nslices, 8), 256, 0, s>>>(f.N, f.nslices, f.sell_ptr, f.colidx, f.agg.p, Nc, keys.p, vals.p);
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, keys.p, keys_s.p, vals.p, f.gal_src.p, (int)nnz, 0, 64, s);
+    DevBuf<char> tmp;
+    tmp.alloc(tb + 16);
+    cub::DeviceRadixSort::SortPairs(tmp.p, tb, keys.p, keys_s.p, vals.p, f.gal_src.p, (int)nnz, 0, 64, s);
+    keys.release();
+    vals.release();
+    flag.alloc(nnz);
+    uid.alloc(nnz);
+    k_flag_heads<<<cdiv(nnz, 256), 256, 0, s>>>(nnz, keys_s.p, flag.p);
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, flag.p, uid.p, (int)nnz, s);
+    tmp.alloc(tb + 16);
+    cub::DeviceScan::ExclusiveSum(tmp.p, tb, flag.p, uid.p, (int)nnz, s);
+    const int64_t nuniq = (int64_t)fetch(uid.p + (nnz - 1), s) + fetch(flag.p + (nnz - 1), s);
+    f.nuniq = nuniq;
+    ukey.alloc(std::max<int64_t>(1, nuniq));
+    f.gal_ptr.alloc(nuniq + 1);
+    f.gal_dst.alloc(std::max<int64_t>(1, nuniq));
+    k_collect_uniques<<<cdiv(nnz, 256), 256, 0, s>>>(nnz, keys_s.p, flag.p, uid.p, ukey.p, f.gal_ptr.p);
+    // number of valid (non-sentinel) sorted entries = end of the last segment
+    {
+        DevBuf<int32_t> nv;
+        nv.alloc(1);
+        k_first_sentinel<<<1, 1, 0, s>>>(keys_s.p, nnz, nv.p);
+        CK(cudaMemcpyAsync(f.gal_ptr.p + nuniq, nv.p, sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
+        CK(cudaStreamSynchronize(s));
+    }
+    DevBuf<int32_t> rowlen, width32;
+    rowlen.alloc(Nc);
+    width32.alloc(c.nslices + 1);
+    CK(cudaMemsetAsync(width32.p, 0, (c.nslices + 1) * sizeof(int32_t), s));
+    k_coarse_rowlen<<<cdiv(Nc, 256), 256, 0, s>>>(Nc, ukey.p, nuniq, rowlen.p);
+    k_slice_width<<<cdiv(c.nslices, 8), 256, 0, s>>>(c.nslices, Nc, rowlen.p, width32.p);
+    c.sell_ptr_b.alloc(c.nslices + 1);
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, width32.p, c.sell_ptr_b.p, c.nslices + 1, s);
+    tmp.alloc(tb + 16);
+    cub::DeviceScan::ExclusiveSum(tmp.p, tb, width32.p, c.sell_ptr_b.p, c.nslices + 1, s);
+    c.nnz_sell = fetch(c.sell_ptr_b.p + c.nslices, s);
+    c.colidx_b.alloc(std::max<int64_t>(1, c.nnz_sell));
+    c.w_b.alloc(std::max<int64_t>(1, c.nnz_sell));
+    CK(cudaMemsetAsync(c.w_b.p, 0, std::max<int64_t>(1, c.nnz_sell) * sizeof(double), s));
+    k_fill_rowid<<<cdiv(c.nslices, 8), 256, 0, s>>>(c.nslices, c.sell_ptr_b.p, c.colidx_b.p);
+    if (nuniq) {
+        k_place_uniques<<<cdiv(nuniq, 256), 256, 0, s>>>(nuniq, Nc, ukey.p, c.sell_ptr_b.p, c.colidx_b.p, f.gal_dst.p);
+        k_gal_weight<<<cdiv(nuniq, 256), 256, 0, s>>>(nuniq, f.gal_ptr.p, f.gal_src.p, f.gal_dst.p, f.w, c.w_b.p);
+    }
+    h->launches += 10;
+    c.offval_b.alloc((size_t)std::max(1, h->cF) * std::max<int64_t>(1, c.nnz_sell));
+    CK(cudaMemsetAsync(c.offval_b.p, 0, c.offval_b.n * sizeof(double), s));  // padding entries stay exact zeros
+    c.diagval_b.alloc((size_t)std::max(1, h->cD) * Nc);
+    c.sell_ptr = c.sell_ptr_b.p;
+    c.colidx = c.colidx_b.p;
+    c.offval = c.offval_b.p;
+    c.diagval = c.diagval_b.p;
+    c.w = c.w_b.p;
+    CK(cudaStreamSynchronize(s));
+}
+
+void build_hierarchy(vfvm_handle* h, Amg& A) {
+    for (Level* l : A.L) delete l;
+    A.L.clear();
+    Level* l0 = new Level();
+    l0->N = h->Nown;
+    l0->Nvec = h->N;
+    l0->nslices = h->ngroups;
+    l0->nnz_sell = h->nnz_sell;
+    l0->sell_ptr = h->sell_ptr.p;
+    l0->colidx = h->colidx.p;
+    l0->offval = h->offval.p;
+    l0->diagval = h->diagval.p;
+    l0->w = h->nzfac.p;
+    A.L.push_back(l0);
+    while ((int)A.L.size() < A.max_levels) {
+        Level& f = *A.L.back();
+        if (f.N <= 64) break;
+        const int64_t Nc = aggregate(h, A, f, A.L.size() == 1);
+        if (Nc < 1 || Nc > (int64_t)(0.8 * f.N)) {  // no real coarsening any more: this level is the coarsest
+            f.Nc = 0;
+            break;
+        }
+        Level* c = new Level();
+        coarsen_pattern(h, f, *c);
+        A.L.push_back(c);
+    }
+    A.L.back()->Nc = 0;
+    const int n = h->n;
+    for (size_t i = 0; i < A.L.size(); i++) {
+        Level& l = *A.L[i];
+        l.binv.alloc((size_t)n * n * l.N);
+        l.x.alloc((size_t)n * l.Nvec);
+        l.t.alloc((size_t)n * l.Nvec);
+        CK(cudaMemsetAsync(l.x.p, 0, l.x.n * sizeof(double), h->stream));
+        if (i > 0) l.b.alloc((size_t)n * l.Nvec);
+    }
+    A.struct_valid = true;
+    A.pattern_nnz = h->nnz_sell;
+    A.pattern_N = h->Nown;
+    if (getenv("VFVM_AMG_VERBOSE")) {
+        fprintf(stderr, "[vfvm amg] levels:");
+        for (Level* l : A.L) fprintf(stderr, " %lld(%lld)", (long long)l->N, (long long)l->nnz_sell);
+        fprintf(stderr, "\n");
+    }
+}
+
+void numeric_setup(vfvm_handle* h, Amg& A) {
+    cudaStream_t s = h->stream;
+    PlaneMap pm;
+    pm.cF = h->cF;
+    for (int p = 0; p < 100; p++) pm.toD[p] = p < h->cF ? h->idxD[h->planeF[p]] : 0;
+    A.L[0]->offval = h->offval.p;  // (the handle may have reallocated its planes)
+    A.L[0]->diagval = h->diagval.p;
+    for (size_t i = 0; i + 1 < A.L.size(); i++) {
+        Level &f = *A.L[i], &c = *A.L[i + 1];
+        k_gal_diag<<<cdiv(c.N, 128), 128, 0, s>>>(c.N, h->cD, f.agg_ptr.p, f.agg_nodes.p, f.diagval, f.N, c.diagval_b.p);
+        if (f.nuniq)
+            k_gal_off<<<cdiv(f.nuniq, 128), 128, 0, s>>>(f.nuniq, pm, f.gal_ptr.p, f.gal_src.p, f.gal_dst.p, f.offval, f.nnz_sell, c.offval_b.p, c.nnz_sell, c.diagval_b.p, c.N);
+        h->launches += 2;
+    }
+    for (Level* l : A.L) vfvm_blockinv_level(h, level_args(h, *l), l->N, l->diagval, l->binv.p);
+}
+
+void smooth(vfvm_handle* h, Amg& A, Level& l, const double* b, bool first, double* out) {
+    cudaStream_t s = h->stream;
+    if (!first) vfvm_spmv_level(h, level_args(h, l), l.x.p, l.t.p);
+    NS_SWITCH(h->n, (k_smooth<NS><<<cdiv(l.N, 128), 128, 0, s>>>(l.N, A.omega, l.binv.p, b, first ? nullptr : l.t.p, l.x.p, out)));
+    h->launches++;
+}
+
+void cycle(vfvm_handle* h, Amg& A, size_t i, const double* b, double* out) {
+    cudaStream_t s = h->stream;
+    Level& l = *A.L[i];
+    if (i + 1 == A.L.size()) {  // coarsest level: a few sweeps
+        for (int k = 0; k < A.coarse_sweeps; k++) smooth(h, A, l, b, k == 0, k + 1 == A.coarse_sweeps ? out : nullptr);
+        return;
+    }
+    Level& c = *A.L[i + 1];
+    smooth(h, A, l, b, true, nullptr);
+    for (int k = 1; k < A.sweeps; k++) smooth(h, A, l, b, false, nullptr);
+    vfvm_spmv_level(h, level_args(h, l), l.x.p, l.t.p);
+    NS_SWITCH(h->n, (k_restrict<NS><<<cdiv(c.N, 128), 128, 0, s>>>(c.N, l.agg_ptr.p, l.agg_nodes.p, b, l.t.p, c.b.p)));
+    cycle(h, A, i + 1, c.b.p, nullptr);
+    NS_SWITCH(h->n, (k_prolong<NS><<<cdiv(l.N, 256), 256, 0, s>>>(l.N, A.alpha, l.agg.p, c.x.p, l.x.p)));
+    h->launches += 2;
+    for (int k = 1; k < A.sweeps; k++) smooth(h, A, l, b, false, nullptr);
+    smooth(h, A, l, b, false, out);
+}
+
+}  // namespace
+
+void vfvm_amg_setup(vfvm_handle* h) {
+    if (!h->nzfac.p) throw std::string("AMG needs the edge-factor plane of the pattern");
+    if (!h->amg) h->amg = new Amg();
+    Amg& A = *(Amg*)h->amg;
+    {  // tuning knobs (read at every setup so that a probe can sweep them)
+        const double theta_old = A.theta;
+        if (const char* e = getenv("VFVM_AMG_OMEGA")) A.omega = atof(e);
+        if (const char* e = getenv("VFVM_AMG_ALPHA")) A.alpha = atof(e);
+        if (const char* e = getenv("VFVM_AMG_THETA")) A.theta = atof(e);
+        if (const char* e = getenv("VFVM_AMG_COARSE_SWEEPS")) A.coarse_sweeps = std::max(1, atoi(e));
+        if (const char* e = getenv("VFVM_AMG_SWEEPS")) A.sweeps = std::max(1, atoi(e));
+        if (A.theta != theta_old) A.struct_valid = false;
+    }
+    if (!A.struct_valid || A.pattern_nnz != h->nnz_sell || A.pattern_N != h->Nown || A.L.empty() || A.L[0]->sell_ptr != h->sell_ptr.p) build_hierarchy(h, A);
+    numeric_setup(h, A);
+}
+
+void vfvm_amg_apply(vfvm_handle* h, const double* in, double* out) {
+    Amg& A = *(Amg*)h->amg;
+    cycle(h, A, 0, in, out);
+}
+
+void vfvm_amg_free(vfvm_handle* h) {
+    if (h->amg) delete (Amg*)h->amg;
+    h->amg = nullptr;
+}

@@ -59,6 +59,7 @@ extern "C" void vfvm_destroy(vfvm_handle* h) {
     cudaSetDevice(h->device);
     vfvm_comm_destroy(h);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    vfvm_amg_free(h);
     if (h->flags_host) cudaFreeHost(h->flags_host);
     if (h->red_host) cudaFreeHost(h->red_host);
     for (cudaEvent_t e : h->pipe_ev) cudaEventDestroy(e);

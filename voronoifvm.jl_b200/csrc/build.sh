@@ -22,7 +22,8 @@ compile assemble.cu ${VFVM_PTXAS_V:+-Xptxas -v}
 compile linsolve.cu
 compile ilu0.cu
 compile comm.cu
+compile amg.cu
 compile api.cu
 for p in "${pids[@]}"; do wait $p; done
-$NVCC $ARCH -shared -cudart static -o $OUT build/geometry.o build/pattern.o build/assemble.o build/linsolve.o build/ilu0.o build/comm.o build/api.o -ldl
+$NVCC $ARCH -shared -cudart static -o $OUT build/geometry.o build/pattern.o build/assemble.o build/linsolve.o build/ilu0.o build/comm.o build/amg.o build/api.o -ldl
 echo "built $(realpath $OUT)"

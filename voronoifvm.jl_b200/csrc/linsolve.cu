@@ -27,19 +27,6 @@ void vfvm_ilu0_apply(vfvm_handle* h, const double* in, double* out);
 
 namespace {
 
-struct SpmvArgs {
-    const int32_t* __restrict__ sell_ptr;
-    const int32_t* __restrict__ colidx;
-    const double* __restrict__ offval;
-    const double* __restrict__ diagval;
-    const double* __restrict__ x;
-    double* __restrict__ y;
-    const double* __restrict__ w;  // optional: fused dots (y,w) and (y,y)
-    double* __restrict__ part;     // 2 x gridDim partial sums
-    int64_t nnz_sell, Nown;
-    int nslices;
-    signed char idxF[100], idxD[100];
-};
 
 __device__ __forceinline__ double block_sum(double v, double* sh) {
     // fixed-order tree reduction over LS_THREADS threads
@@ -638,6 +625,8 @@ void precond_setup(vfvm_handle* h) {
         h->launches++;
     } else if (h->precon == VFVM_PRECON_ILU0 || h->precon == VFVM_PRECON_ILU0_MC) {
         vfvm_ilu0_setup(h);
+    } else if (h->precon == VFVM_PRECON_AMG) {
+        vfvm_amg_setup(h);
     }
     h->precon_valid = true;
 }
@@ -658,6 +647,7 @@ void precond_apply(vfvm_handle* h, const double* in, double* out) {
             break;
         case VFVM_PRECON_ILU0:
         case VFVM_PRECON_ILU0_MC: vfvm_ilu0_apply(h, in, out); break;
+        case VFVM_PRECON_AMG: vfvm_amg_apply(h, in, out); break;
     }
 }
 
@@ -694,10 +684,30 @@ struct AsyncNorm {
 
 void vfvm_spmv_impl(vfvm_handle* h, const double* x, double* y) { spmv(h, const_cast<double*>(x), y, nullptr); }
 
+// y = A x for any matrix in the DBSR / SELL-32 layout described by `a` (AMG levels): rank-local, no halo exchange, no dots
+void vfvm_spmv_level(vfvm_handle* h, SpmvArgs a, const double* x, double* y) {
+    a.x = x;
+    a.y = y;
+    a.w = nullptr;
+    bool diagmask = (h->cF == h->n && h->cD == h->n);
+    for (int i = 0; i < h->n && diagmask; i++) diagmask = (h->idxF[i * h->n + i] == i && h->idxD[i * h->n + i] == i);
+    if (diagmask) {
+        NS_DISPATCH(h->n, (launch_spmv_k<NS, true, false>(h, a, OP_NONE)));
+    } else {
+        NS_DISPATCH(h->n, (launch_spmv_k<NS, false, false>(h, a, OP_NONE)));
+    }
+}
+SpmvArgs vfvm_spmv_args(vfvm_handle* h) { return make_spmv_args(h); }
+// explicit inverses of the n x n diagonal blocks of a level (planes i*n+j of N entries)
+void vfvm_blockinv_level(vfvm_handle* h, const SpmvArgs& a, int64_t N, const double* diagval, double* inv) {
+    NS_DISPATCH(h->n, (k_blockjacobi_setup<NS><<<cdiv(N, 128), 128, 0, h->stream>>>(N, diagval, inv, h->flags.p, a)));
+    h->launches++;
+}
+
 extern "C" int vfvm_linsolve_setup(vfvm_handle* h, int krylov, int precon, int gmres_restart) {
     if (!h) return VFVM_ERR_ARG;
     if (krylov < VFVM_KRYLOV_BICGSTAB || krylov > VFVM_KRYLOV_GMRES) return vfvm_fail(h, VFVM_ERR_ARG, "unknown Krylov method");
-    if (precon < VFVM_PRECON_NONE || precon > VFVM_PRECON_ILU0_MC) return vfvm_fail(h, VFVM_ERR_ARG, "unknown preconditioner");
+    if (precon < VFVM_PRECON_NONE || precon > VFVM_PRECON_AMG) return vfvm_fail(h, VFVM_ERR_ARG, "unknown preconditioner");
     h->krylov = krylov;
     h->precon = precon;
     h->gmres_restart = gmres_restart > 0 ? std::min(gmres_restart, 100) : 30;

@@ -198,6 +198,7 @@ struct vfvm_handle {
     std::vector<int64_t> peer_recv_off, peer_slot, peer_halo_doubles;  // per neighbour slot: my place in that neighbour's mailbox
     unsigned long long halo_seq = 0, red_seq = 0;
     DevBuf<unsigned int> peer_counter;
+    void* amg = nullptr;  // aggregation AMG hierarchy (amg.cu)
 };
 
 #define VFVM_TRY(h, ...)                                        \
@@ -222,6 +223,21 @@ static inline void vfvm_check(cudaError_t e, const char* what) {
 
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// one matrix in the DBSR / SELL-32 layout + the vectors of one SpMV (kernel argument)
+struct SpmvArgs {
+    const int32_t* __restrict__ sell_ptr;
+    const int32_t* __restrict__ colidx;
+    const double* __restrict__ offval;
+    const double* __restrict__ diagval;
+    const double* __restrict__ x;
+    double* __restrict__ y;
+    const double* __restrict__ w;  // optional: fused dots (y,w) and (y,y)
+    double* __restrict__ part;     // 2 x gridDim partial sums
+    int64_t nnz_sell, Nown;
+    int nslices;
+    signed char idxF[100], idxD[100];
+};
+
 // implemented across the .cu files
 int vfvm_geometry_build(vfvm_handle* h);
 int vfvm_pattern_build(vfvm_handle* h);
@@ -234,6 +250,12 @@ int vfvm_physics_masks(vfvm_handle* h);
 void vfvm_spmv_impl(vfvm_handle* h, const double* x, double* y);
 void vfvm_sync_physics(vfvm_handle* h);
 void vfvm_source_cache(vfvm_handle* h);
+SpmvArgs vfvm_spmv_args(vfvm_handle* h);
+void vfvm_spmv_level(vfvm_handle* h, SpmvArgs a, const double* x, double* y);
+void vfvm_blockinv_level(vfvm_handle* h, const SpmvArgs& a, int64_t N, const double* diagval, double* inv);
+void vfvm_amg_setup(vfvm_handle* h);
+void vfvm_amg_apply(vfvm_handle* h, const double* in, double* out);
+void vfvm_amg_free(vfvm_handle* h);
 PeerArgs vfvm_peer_args_halo(vfvm_handle* h);    // starts a new halo exchange (advances the sequence number)
 PeerArgs vfvm_peer_args_reduce(vfvm_handle* h);  // starts a new reduction
 

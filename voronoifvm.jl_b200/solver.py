@@ -50,6 +50,16 @@ class BlockPreconBuilder:
     precon = _lib.PRECON_BLOCKJACOBI
 
 
+class AMGPreconBuilder:
+    """aggregation AMG V-cycle on the node-block matrix (csrc/amg.cu); the reference reaches AMG through
+    `precs = AMGPreconBuilder()` (AMGCLWrap) or `SmoothedAggregationPreconBuilder()` (AlgebraicMultigrid),
+    examples/DevEx003_Solvers.jl:149-169, examples/DevEx004_EquationBlock3D.jl:225-251"""
+    precon = _lib.PRECON_AMG
+
+
+SmoothedAggregationPreconBuilder = AMGPreconBuilder  # same entry point; the device hierarchy uses plain aggregation with an over-weighted correction
+
+
 class ILUZeroPreconBuilder:
     """ILU(0) on the node-block pattern; `multicolor=True` eliminates in multicolour order (few, wide levels)"""
 
