@@ -36,7 +36,12 @@ def main():
     F = st.eval_res_jac(Ug[:, info.local_nodes], tstep=0.05)
     # ---- one implicit Euler step (Newton to convergence) with BiCGStab + Jacobi across ranks
     sol = v.solve_state(st, inival=np.asfortranarray(Ug[:, info.local_nodes]), tstep=0.05)
+    # the same step with rank-local aggregation AMG inside BiCGStab (block-Jacobi across ranks, no communication in the preconditioner)
+    sol_amg = v.solve_state(st, inival=np.asfortranarray(Ug[:, info.local_nodes]), tstep=0.05, method_linear=v.KrylovJL_BICGSTAB(precs=v.AMGPreconBuilder()),
+                            reltol_linear=1e-13, abstol_linear=0.0, maxiters_linear=2000)
     own = slice(0, info.n_owned)
+    assert np.max(np.abs(sol_amg[:, own] - sol[:, own])) < 1e-10, "AMG-preconditioned solve differs"
+
     gathered = [None] * world
     dist.all_gather_object(gathered, (info.local_nodes[own], F[:, own], sol[:, own]))
     if rank == 0:
