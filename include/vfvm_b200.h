@@ -209,6 +209,14 @@ int vfvm_vector_norms(vfvm_handle* h, int which, double* norm_inf, double* norm1
 /* ||a - b||_inf: SolverControl.delta (src/vfvm_solvercontrol.jl:257) */
 int vfvm_vector_diffnorm(vfvm_handle* h, int which_a, int which_b, double* norm_inf);
 
+/* ---- post-processing integrals of a resident vector (src/vfvm_postprocess.jl:18-67, :109-146) -------------
+ * out: n x ncellregions (column-major) on the host.  vfvm_integrate: slot = VFVM_SLOT_REACTION or VFVM_SLOT_STORAGE selects the
+ * evaluator of a registered node function, id = VFVM_NONE integrates the vector itself (integrate(system, U)).
+ * vfvm_edgeintegrate: id = a registered flux id, or -1 = the W^{1,p} seminorm integrand dim ((u_K - u_L) / h)^p, p = params[0]
+ * (w1pseminorm, :300-312), -2 = the edge average (u_K + u_L) / 2 (test/test120_norms.jl:35-38).  Collective with several ranks. */
+int vfvm_integrate(vfvm_handle* h, int slot, int id, const double* params, int np, int which, double* out);
+int vfvm_edgeintegrate(vfvm_handle* h, int id, const double* params, int np, int which, double* out);
+
 /* ---- multi-GPU (one process per GPU; the host shares the NCCL id through its own rendezvous) ------- */
 int vfvm_comm_unique_id(char id_out[128]);
 int vfvm_comm_init(vfvm_handle* h, int rank, int nranks, const char id[128]);

@@ -165,6 +165,22 @@ class OracleSystem:
         self.L.vo_get_matrix_csc(self.h, _p(colptr, C.c_int64), _p(rowval, C.c_int64), _p(nzval, C.c_double))
         return sp.csc_matrix((nzval, rowval, colptr), shape=(ndof, ndof))
 
+    def integrate(self, U, slot=1, pid=0, params=()):
+        """integrate(system, F, U) src/vfvm_postprocess.jl:18-67 for a registered node function (pid 0: the identity) -> n x ncellregions"""
+        u = np.ascontiguousarray(np.asarray(U, dtype=np.float64).T).ravel()
+        prm = np.ascontiguousarray(params, dtype=np.float64)
+        out = np.zeros(self.n * self.g.num_cellregions)
+        assert self.L.vo_integrate(self.h, slot, pid, _p(prm, C.c_double), prm.size, _p(u, C.c_double), _p(out, C.c_double)) == 0
+        return out.reshape((self.n, self.g.num_cellregions), order="F")
+
+    def edgeintegrate(self, U, pid, params=()):
+        """edgeintegrate(system, F, U) src/vfvm_postprocess.jl:109-146 for a registered flux (pid -1: the W^{1,p} integrand)"""
+        u = np.ascontiguousarray(np.asarray(U, dtype=np.float64).T).ravel()
+        prm = np.ascontiguousarray(params, dtype=np.float64)
+        out = np.zeros(self.n * self.g.num_cellregions)
+        assert self.L.vo_edgeintegrate(self.h, pid, _p(prm, C.c_double), prm.size, _p(u, C.c_double), _p(out, C.c_double)) == 0
+        return out.reshape((self.n, self.g.num_cellregions), order="F")
+
     def initialize(self, U, time=0.0, embed=0.0):
         u = np.asfortranarray(U, dtype=np.float64).ravel(order="F").copy()
         self.L.vo_initialize(self.h, _p(u, C.c_double), C.c_double(time), C.c_double(embed))

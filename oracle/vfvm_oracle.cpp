@@ -834,6 +834,83 @@ void vo_get_matrix_values(void* h, double* nzval) {
 }
 
 // unit-test probes (test/test010_bernoulli.jl, test/test020_formfactors.jl)
+// ---- post-processing integrals, src/vfvm_postprocess.jl:18-67 (integrate) and :109-146 (edgeintegrate) ----------------------
+// slot: VFVM_SLOT_REACTION / VFVM_SLOT_STORAGE select the evaluator of a registered node function; id 0 = the identity
+// (integrate(system, U), :94-98).  out: n x ncellregions, column-major.
+int vo_integrate(void* h, int slot, int id, const double* params, int np, const double* U, double* out) {
+    System& s = *(System*)h;
+    const Grid& g = s.g;
+    const int n = s.n;
+    PhysSlot ps;
+    ps.id = id;
+    ps.p.assign(params, params + np);
+    std::fill(out, out + (size_t)n * g.ncellregions, 0.0);
+    NodeCtx node;
+    node.dim = g.dim;
+    std::vector<double> res(n), u(n);
+    for (int K = 0; K < g.N; K++)
+        for (int64_t k = s.nodefactors.colptr[K]; k < s.nodefactors.colptr[K + 1]; k++) {
+            node.index = K;
+            node.region = s.nodefactors.region[k];
+            node.fac = s.nodefactors.fac[k];
+            node.x = &g.coord[(size_t)K * g.dim];
+            for (int i = 0; i < n; i++) {
+                u[i] = U[(size_t)K * n + i];
+                res[i] = 0.0;
+            }
+            if (id == 0) res = u;
+            else if (slot == VFVM_SLOT_STORAGE) eval_storage(ps, n, res.data(), u.data(), node);
+            else eval_reaction(ps, n, res.data(), u.data(), node);
+            const uint8_t* rs = &s.region_species[(size_t)(node.region - 1) * n];
+            for (int i = 0; i < n; i++)
+                if (rs[i]) out[(size_t)(node.region - 1) * n + i] += node.fac * res[i];  // :60
+        }
+    return 0;
+}
+// id: a registered flux id, or -1 = the W^{1,p} seminorm integrand dim ((u_K - u_L) / h)^p with p = params[0] (:300-312)
+int vo_edgeintegrate(void* h, int id, const double* params, int np, const double* U, double* out) {
+    System& s = *(System*)h;
+    const Grid& g = s.g;
+    const int n = s.n;
+    PhysSlot ps;
+    ps.id = id;
+    ps.p.assign(params, params + np);
+    std::fill(out, out + (size_t)n * g.ncellregions, 0.0);
+    EdgeCtx edge;
+    edge.dim = g.dim;
+    std::vector<double> res(n), uK(n), uL(n);
+    for (int ie = 0; ie < g.E; ie++)
+        for (int64_t k = s.edgefactors.colptr[ie]; k < s.edgefactors.colptr[ie + 1]; k++) {
+            const int K = g.edgenodes[2 * (size_t)ie], L = g.edgenodes[2 * (size_t)ie + 1];
+            edge.index = ie;
+            edge.nodeK = K;
+            edge.nodeL = L;
+            edge.region = s.edgefactors.region[k];
+            edge.fac = s.edgefactors.fac[k];
+            edge.xK = &g.coord[(size_t)K * g.dim];
+            edge.xL = &g.coord[(size_t)L * g.dim];
+            double h2 = 0.0;  // meas(edge)^2, src/vfvm_geometryitems.jl (distance of the two edge nodes)
+            for (int d = 0; d < g.dim; d++) h2 += (edge.xK[d] - edge.xL[d]) * (edge.xK[d] - edge.xL[d]);
+            const double hh = std::sqrt(h2);
+            for (int i = 0; i < n; i++) {
+                uK[i] = U[(size_t)K * n + i];
+                uL[i] = U[(size_t)L * n + i];
+                res[i] = 0.0;
+            }
+            if (id == -1) {
+                for (int i = 0; i < n; i++) res[i] = g.dim * std::pow((uK[i] - uL[i]) / hh, params[0]);
+            } else if (id == -2) {  // edge average, test/test120_norms.jl:35-38
+                for (int i = 0; i < n; i++) res[i] = 0.5 * (uK[i] + uL[i]);
+            } else {
+                eval_flux(ps, n, res.data(), uK.data(), uL.data(), edge);
+            }
+            const uint8_t* rs = &s.region_species[(size_t)(edge.region - 1) * n];
+            for (int i = 0; i < n; i++)
+                if (rs[i]) out[(size_t)(edge.region - 1) * n + i] += hh * hh * edge.fac * res[i] / g.dim;  // :138
+        }
+    return 0;
+}
+
 void vo_fbernoulli_pm(int n, const double* x, double* bp, double* bm, double* b) {
     for (int i = 0; i < n; i++) {
         fbernoulli_pm<double>(x[i], bp[i], bm[i]);

@@ -1,0 +1,68 @@
+"""Post-processing integrals on the device: the reference's known answers of test/test120_norms.jl
+and entry-by-entry agreement with the CPU oracle's restatement of integrate / edgeintegrate."""
+import math
+
+import numpy as np
+import pytest
+
+import vfvm_b200 as v
+from vfvm_b200 import physics as ph
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _grid(dim, h=0.1):
+    X = np.linspace(0, 1, int(round(1 / h)) + 1)
+    return v.simplexgrid(*([X] * dim))
+
+
+@pytest.mark.parametrize("dim", [1, 2, 3])
+@pytest.mark.parametrize("c", [0.5, 1.0, 2.0])
+def test_norms_known_answers(dim, c):
+    """test/test120_norms.jl:103-133: int c = c, edge integral of c = c, l2norm(c) = c, h1seminorm(c) = 0, h1seminorm(c sum(x)/sqrt(dim)) = c,
+    sum of the node volumes = 1"""
+    g = _grid(dim)
+    sys = v.System(g, species=[1])
+    st = v.SystemState(sys)
+    try:
+        F = np.full((1, g.num_nodes), c)
+        assert v.integrate(sys, F, state=st)[0, 0] == pytest.approx(c, rel=1e-12)                               # test_solint
+        assert v.edgeintegrate(sys, v.postprocess.EdgeAverage(), F, state=st)[0, 0] == pytest.approx(c, rel=1e-12)  # test_edgeint: f = (u_K + u_L) / 2
+        assert v.l2norm(sys, F, state=st) == pytest.approx(c, rel=1e-12)
+        assert v.h1seminorm(sys, F, state=st) == pytest.approx(0.0, abs=1e-12)
+        lin = (c * g.coord.sum(axis=0) / math.sqrt(dim))[None, :]
+        assert v.h1seminorm(sys, lin, state=st) == pytest.approx(c, rel=1e-10)
+        assert v.nodevolumes(sys, state=st).sum() == pytest.approx(1.0, rel=1e-12)
+    finally:
+        st.close()
+
+
+def test_integrals_match_the_oracle_multiregion_multispecies():
+    X = np.linspace(0, 1, 13)
+    g = v.simplexgrid(X, X, X)
+    v.cellmask(g, [0, 0, 0.3], [1, 1, 0.72], 2)
+    v.cellmask(g, [0, 0, 0.7], [1, 1, 1.0], 3)
+    sys = v.System(g, flux=ph.BipolarSGFlux(), reaction=ph.BipolarReaction([10.0, 0.0, -10.0]), storage=ph.BipolarStorage(), species=[1, 2, 3])
+    rng = np.random.default_rng(3)
+    U = np.asfortranarray(rng.uniform(-0.5, 0.5, (3, g.num_nodes)))
+    o = O.OracleSystem(sys)
+    st = v.SystemState(sys)
+    try:
+        for F in (None, sys.physics.reaction, sys.physics.storage, ph.PowerReaction(1.0, 2.0)):
+            dev = v.integrate(sys, U, state=st) if F is None else v.integrate(sys, F, U, state=st)
+            ref = o.integrate(U) if F is None else o.integrate(U, F.slot, F.id, F.params(3))
+            assert dev.shape == (3, 3)
+            assert np.all(np.abs(dev - ref) <= 1e-12 * np.abs(ref) + 1e-14), (F, dev, ref)
+        for F in (sys.physics.flux, ph.LinearDiffusion([1.0, 2.0, 3.0]), v.postprocess.W1pIntegrand(2.0), v.postprocess.EdgeAverage()):
+            dev = v.edgeintegrate(sys, F, U, state=st)
+            ref = o.edgeintegrate(U, F.id, F.params(3))
+            assert np.all(np.abs(dev - ref) <= 1e-12 * np.abs(ref) + 1e-13), (F, dev, ref)
+    finally:
+        st.close()
+
+
+def test_integrate_rejects_unregistered_functions():
+    sys = v.System(_grid(2), species=[1])
+    with pytest.raises(v.UnregisteredPhysicsError):
+        v.integrate(sys, lambda y, u, node, data=None: None, np.zeros((1, sys.grid.num_nodes)))

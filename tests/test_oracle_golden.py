@@ -232,3 +232,22 @@ def test_value_dependent_pattern():
     assert np.all(A.row % 2 == A.col % 2)
     E = o.num_edges
     assert A.nnz == 2 * (2 * E + 16)
+
+
+@pytest.mark.parametrize("dim", [1, 2, 3])
+@pytest.mark.parametrize("c", [0.5, 1.0, 2.0])
+def test_norm_integrals_known_answers(dim, c):
+    """test/test120_norms.jl:103-118: integrate(c) = c, edgeintegrate(edge average of c) = c, l2norm(c) = c, h1seminorm(c) = 0,
+    h1seminorm(c sum(x) / sqrt(dim)) = c on the unit interval / square / cube (oracle restatement of src/vfvm_postprocess.jl:18-146)"""
+    import vfvm_b200 as v
+
+    X = np.linspace(0, 1, 11)
+    g = v.simplexgrid(*([X] * dim))
+    o = O.OracleSystem(v.System(g, species=[1]))
+    F = np.full((1, g.num_nodes), c)
+    lin = (c * g.coord.sum(axis=0) / math.sqrt(dim))[None, :]
+    assert o.integrate(F)[0, 0] == pytest.approx(c, rel=1e-12)
+    assert o.edgeintegrate(F, -2)[0, 0] == pytest.approx(c, rel=1e-12)
+    assert math.sqrt(o.integrate(F, 1, 1, [1.0, 2.0])[0, 0]) == pytest.approx(c, rel=1e-12)
+    assert math.sqrt(abs(o.edgeintegrate(F, -1, [2.0])[0, 0])) == pytest.approx(0.0, abs=1e-12)
+    assert math.sqrt(o.edgeintegrate(lin, -1, [2.0])[0, 0]) == pytest.approx(c, rel=1e-12)

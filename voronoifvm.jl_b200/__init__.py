@@ -15,3 +15,5 @@ from .solver import (SolverControl, NewtonSolverHistory, TransientSolution, solv
                      evaluate_residual_and_jacobian, fixed_timesteps, ConvergenceError, AssemblyError, LinearSolverError, EmbeddingError,
                      KrylovJL_BICGSTAB, KrylovJL_CG, KrylovJL_GMRES, JacobiPreconBuilder, BlockPreconBuilder, ILUZeroPreconBuilder, AMGPreconBuilder, SmoothedAggregationPreconBuilder,
                      DeviceDirectLike)
+from . import postprocess  # noqa: F401,E402
+from .postprocess import (integrate, edgeintegrate, lpnorm, l2norm, w1pseminorm, h1seminorm, w1pnorm, h1norm, nodevolumes)  # noqa: F401,E402

@@ -23,7 +23,8 @@ compile linsolve.cu
 compile ilu0.cu
 compile comm.cu
 compile amg.cu
+compile postprocess.cu
 compile api.cu
 for p in "${pids[@]}"; do wait $p; done
-$NVCC $ARCH -shared -cudart static -o $OUT build/geometry.o build/pattern.o build/assemble.o build/linsolve.o build/ilu0.o build/comm.o build/amg.o build/api.o -ldl
+$NVCC $ARCH -shared -cudart static -o $OUT build/geometry.o build/pattern.o build/assemble.o build/linsolve.o build/ilu0.o build/comm.o build/amg.o build/postprocess.o build/api.o -ldl
 echo "built $(realpath $OUT)"

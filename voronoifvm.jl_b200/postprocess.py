@@ -1,0 +1,129 @@
+"""Post-processing on the device twin: `integrate`, `edgeintegrate`, the discrete norms and `nodevolumes`
+(src/vfvm_postprocess.jl:18-67, 94-98, 109-146, 278-343, 397-411).
+
+`F` must be a registered physics object (the reference takes any callback with the reaction / flux signature): node functions
+are the registered reaction and storage objects, edge functions the registered fluxes.  Everything runs on the resident
+device vectors; only the n x ncellregions result comes back.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import check
+from .physics import RegisteredPhysics, UnregisteredPhysicsError, SLOT_FLUX, SLOT_REACTION, SLOT_STORAGE
+from .state import SystemState
+from .system import System
+
+
+def _with_state(system, state):
+    if state is not None:
+        return state, False
+    return SystemState(system), True
+
+
+def _call(state: SystemState, U, fn):
+    state.sync()
+    state.set_vector(_lib.VEC_UPDATE, np.asfortranarray(np.asarray(U, dtype=np.float64)))  # scratch vector of the Newton loop
+    out = np.zeros(state.n * state.system.grid.num_cellregions)
+    check(state.h, fn(out))
+    return out.reshape((state.n, state.system.grid.num_cellregions), order="F")
+
+
+def integrate(system: System, F, U=None, state: SystemState | None = None, boundary=False):
+    """`integrate(system, F, U)`: region-wise integrals of a node function -> (nspecies, ncellregions);
+    `integrate(system, U)` integrates the solution itself (src/vfvm_postprocess.jl:94-98)"""
+    if U is None:
+        F, U = None, F
+    if boundary:
+        raise NotImplementedError("boundary integrals are not on the device path yet")
+    if F is not None and not (isinstance(F, RegisteredPhysics) and F.slot in (SLOT_REACTION, SLOT_STORAGE)):
+        raise UnregisteredPhysicsError("integrate: F must be a registered reaction or storage object")
+    st, own = _with_state(system, state)
+    try:
+        n = system.num_species
+        if F is None:
+            slot, pid, prm = SLOT_REACTION, 0, np.zeros(0)
+        else:
+            slot, pid, prm = F.slot, F.id, np.ascontiguousarray(F.params(n), dtype=np.float64)
+        return _call(st, U, lambda out: st.L.vfvm_integrate(st.h, slot, pid, prm.ctypes.data if prm.size else None, prm.size, _lib.VEC_UPDATE, out.ctypes.data))
+    finally:
+        if own:
+            st.close()
+
+
+class W1pIntegrand:
+    """edge function of `w1pseminorm`: y_i = dim ((u_iK - u_iL) / h)^p (src/vfvm_postprocess.jl:304-310)"""
+
+    slot, id = SLOT_FLUX, -1
+
+    def __init__(self, p=2.0):
+        self.p = float(p)
+
+    def params(self, n):
+        return np.array([self.p])
+
+
+class EdgeAverage:
+    """edge function y_i = (u_iK + u_iL) / 2 (test/test120_norms.jl:35-38)"""
+
+    slot, id = SLOT_FLUX, -2
+
+    def params(self, n):
+        return np.zeros(0)
+
+
+def edgeintegrate(system: System, F, U, state: SystemState | None = None):
+    """`edgeintegrate(system, F, U)`: region-wise integrals of an edge function (diamond volumes h^2 sigma/h / dim)"""
+    if not ((isinstance(F, RegisteredPhysics) and F.slot == SLOT_FLUX) or isinstance(F, (W1pIntegrand, EdgeAverage))):
+        raise UnregisteredPhysicsError("edgeintegrate: F must be a registered flux object")
+    st, own = _with_state(system, state)
+    try:
+        prm = np.ascontiguousarray(F.params(system.num_species), dtype=np.float64)
+        return _call(st, U, lambda out: st.L.vfvm_edgeintegrate(st.h, F.id, prm.ctypes.data if prm.size else None, prm.size, _lib.VEC_UPDATE, out.ctypes.data))
+    finally:
+        if own:
+            st.close()
+
+
+def lpnorm(system, u, p, species_weights=None, state=None):
+    from .physics import PowerReaction
+
+    w = np.ones(system.num_species) if species_weights is None else np.asarray(species_weights, dtype=float)
+    II = integrate(system, PowerReaction(1.0, float(p)), u, state=state)
+    return float((II.sum(axis=1) * w).sum() ** (1.0 / p))
+
+
+def l2norm(system, u, species_weights=None, state=None):
+    return lpnorm(system, u, 2, species_weights, state)
+
+
+def w1pseminorm(system, u, p, species_weights=None, state=None):
+    w = np.ones(system.num_species) if species_weights is None else np.asarray(species_weights, dtype=float)
+    II = edgeintegrate(system, W1pIntegrand(p), u, state=state)
+    return float((II.sum(axis=1) * w).sum() ** (1.0 / p))
+
+
+def h1seminorm(system, u, species_weights=None, state=None):
+    return w1pseminorm(system, u, 2, species_weights, state)
+
+
+def w1pnorm(system, u, p, species_weights=None, state=None):
+    return lpnorm(system, u, p, species_weights, state) + w1pseminorm(system, u, p, species_weights, state)
+
+
+def h1norm(system, u, species_weights=None, state=None):
+    return w1pnorm(system, u, 2, species_weights, state)
+
+
+def nodevolumes(system: System, state: SystemState | None = None):
+    """volumes of the Voronoi cells (src/vfvm_postprocess.jl:397-411): node factors summed over the cell regions"""
+    st, own = _with_state(system, state)
+    try:
+        colptr, _, fac = st.nodefactors()
+        return np.add.reduceat(fac, colptr[:-1])
+    finally:
+        if own:
+            st.close()
