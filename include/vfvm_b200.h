@@ -82,6 +82,7 @@ typedef struct vfvm_handle vfvm_handle;
 #define VFVM_REACTION_SINH 2      /* f_i = k_i (exp(u_i) - exp(-u_i))       params: k[n]         (Example105:55-58)                  */
 #define VFVM_REACTION_AFFINE 3    /* f = R u + r0                           params: R[n*n] row-major, r0[n] (Example210:27-31, 160:60-66) */
 #define VFVM_REACTION_BILINEAR2 4 /* n=2: f_1 = k u1 u2, f_2 = -k u1 u2     params: k            (Example110:38-42)                  */
+#define VFVM_REACTION_REGION_AFFINE 6 /* f = R_r u + r0_r in cell region r  params: nreg, then per region R[n*n] row-major, r0[n] (Example221:54-66) */
 #define VFVM_REACTION_BIPOLAR 5   /* Example161 reaction! :109-132          params: zn, zp, En, Ep, r0, iphin, iphip, ipsi, nreg, C[nreg] */
 
 /* storage(f,u,node,data) */

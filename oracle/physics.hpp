@@ -184,6 +184,19 @@ inline bool eval_reaction(const PhysSlot& s, int n, T* f, const T* u, const Node
                 f[i] = acc;
             }
             return true;
+        case VFVM_REACTION_REGION_AFFINE: {  // Example221 reaction: one affine map per cell region
+            const int nreg = (int)p[0];
+            if (node.region >= 1 && node.region <= nreg) {
+                const double* q = p + 1 + (node.region - 1) * (n * n + n);
+                for (int i = 0; i < n; i++) {
+                    T acc(q[n * n + i]);
+                    for (int j = 0; j < n; j++)
+                        if (q[i * n + j] != 0.0) acc = acc + q[i * n + j] * u[j];
+                    f[i] = acc;
+                }
+            }
+            return true;
+        }
         case VFVM_REACTION_BILINEAR2:
             f[0] = p[0] * (u[0] * u[1]);
             f[1] = (-p[0]) * (u[0] * u[1]);

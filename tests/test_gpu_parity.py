@@ -578,3 +578,40 @@ def test_amg_block_system_bipolar_newton():
     for pc in (v.BlockPreconBuilder(), v.AMGPreconBuilder()):
         sols.append(v.solve(sys, inival=0.1, tstep=1.0e-2, method_linear=v.KrylovJL_BICGSTAB(precs=pc), reltol_linear=1e-13, abstol_linear=0.0, maxiters_linear=3000))
     assert np.max(np.abs(sols[0] - sols[1])) < TOL_NEWTON
+
+
+# ---- species enabled per cell region (enable_species!(sys, i, regions)), inactive dofs ---------------------------------------
+@pytest.mark.parametrize("dim", [1, 2, 3])
+def test_example221_species_per_region_device(dim):
+    """examples/Example221_EquationBlockPrecon.jl: species 1 in region 1, species 2 everywhere, species 3 in region 3.
+    Pattern bit-exact and values 1e-12 against the oracle (which reproduces the reference's known answers), Newton solution 1e-10,
+    inactive dofs identically zero"""
+    from test_oracle_golden import example221_system
+
+    s = example221_system(dim)
+    U = _rand_u(s)
+    U[~s.node_dof()] = 0.0
+    _compare_assembly(s, U)
+    _compare_assembly(s, U, _rand_u(s, seed=4) * s.node_dof(), tstep=0.1)
+    ref = O.OracleSystem(s).solve_step(v.unknowns(s, inival=0.0))
+    for ml in (None, v.KrylovJL_BICGSTAB(precs=v.BlockPreconBuilder()), v.KrylovJL_BICGSTAB(precs=v.AMGPreconBuilder())):
+        sol = v.solve(s, inival=0.0, method_linear=ml, reltol_linear=1e-13, abstol_linear=0.0, maxiters_linear=5000)
+        assert np.max(np.abs(sol - ref)) < TOL_NEWTON
+        assert np.all(sol[~s.node_dof()] == 0.0)
+    expected = {1: 0.014101758266210086, 2: 0.12691582439590407, 3: 1.1422561017685693}[dim]
+    assert sol[1].sum() == pytest.approx(expected, rel=1e-9 if dim < 3 else 5e-5)
+
+
+def test_masked_coupled_flux_two_species():
+    """cross-diffusion flux (full 2x2 coupling) with species 2 restricted to one of two cell regions: couplings exist only where
+    both species share a region"""
+    g = _grid(2, 13)
+    v.cellmask(g, [0.0, 0.0], [0.5, 1.0], 2)
+    s = v.System(g, flux=ph.CrossDiffusion2([1.0, 0.5], 0.1), reaction=ph.BilinearReaction2(0.3), storage=ph.LinearStorage([1.0, 2.0]))
+    v.enable_species(s, 1, [1, 2])
+    v.enable_species(s, 2, [2])
+    v.boundary_dirichlet(s, 1, 2, 1.0)
+    v.boundary_dirichlet(s, 2, 4, 0.5)
+    U = _rand_u(s)
+    U[~s.node_dof()] = 0.0
+    _compare_assembly(s, U, _rand_u(s, seed=11) * s.node_dof(), tstep=0.05)

@@ -180,10 +180,15 @@ extern "C" int vfvm_set_system(vfvm_handle* h, int nspecies, const uint8_t* regi
     NEED(h, h->have_grid, "vfvm_set_grid has not been called");
     if (nspecies < 1 || nspecies > VFVM_MAX_SPECIES) return vfvm_fail(h, VFVM_ERR_UNSUPPORTED, "number of species out of range (1..10)");
     if (!(nspecies <= 5 || nspecies == 10)) return vfvm_fail(h, VFVM_ERR_UNSUPPORTED, "species counts with a device instantiation: 1,2,3,4,5,10");
+    if (h->ncellregions > VFVM_MAX_CREGIONS) return vfvm_fail(h, VFVM_ERR_UNSUPPORTED, "more than 32 cell regions");
+    // region_species (n x ncellregions, column-major): species enabled per cell region, enable_species! src/vfvm_system.jl:433-480
+    h->region_species.assign((size_t)nspecies * h->ncellregions, 1);
+    h->masked = false;
     if (region_species)
-        for (int i = 0; i < nspecies * h->ncellregions; i++)
-            if (!region_species[i])
-                return vfvm_fail(h, VFVM_ERR_UNSUPPORTED, "species that are not enabled in every cell region are a 'next' row (SURVEY.md section 8f rank 3)");
+        for (int i = 0; i < nspecies * h->ncellregions; i++) {
+            h->region_species[i] = region_species[i] ? 1 : 0;
+            if (!region_species[i]) h->masked = true;
+        }
     if (h->nbfaceregions > VFVM_MAX_BREGIONS) return vfvm_fail(h, VFVM_ERR_UNSUPPORTED, "more than 16 boundary regions");
     h->n = nspecies;
     PhysicsDev& ph = h->phys;
@@ -211,7 +216,7 @@ static int min_species(int slot, int id) {
 extern "C" int vfvm_set_physics(vfvm_handle* h, int slot, int id, const double* params, int np) {
     NEED(h, h->have_system, "vfvm_set_system has not been called");
     if (slot < 0 || slot >= VFVM_NUM_SLOTS || np < 0 || (np > 0 && !params)) return vfvm_fail(h, VFVM_ERR_ARG, "bad slot / params");
-    static const int maxid[VFVM_NUM_SLOTS] = {VFVM_FLUX_SG_BIPOLAR, VFVM_REACTION_BIPOLAR, VFVM_STORAGE_BIPOLAR, VFVM_SOURCE_NODAL, VFVM_BREACTION_LINEAR};
+    static const int maxid[VFVM_NUM_SLOTS] = {VFVM_FLUX_SG_BIPOLAR, VFVM_REACTION_REGION_AFFINE, VFVM_STORAGE_BIPOLAR, VFVM_SOURCE_NODAL, VFVM_BREACTION_LINEAR};
     if (id < 0 || id > maxid[slot])
         return vfvm_fail(h, VFVM_ERR_UNREGISTERED, "physics id is not in the registered device library; arbitrary host callbacks are not evaluated (no CPU fallback)");
     const int n = h->n;
@@ -230,6 +235,10 @@ extern "C" int vfvm_set_physics(vfvm_handle* h, int slot, int id, const double* 
         if (id == VFVM_REACTION_SINH) need = n;
         if (id == VFVM_REACTION_AFFINE) need = n * n + n;
         if (id == VFVM_REACTION_BILINEAR2) need = 1;
+        if (id == VFVM_REACTION_REGION_AFFINE) {
+            if (np < 1 || (int)params[0] < 1 || np != 1 + (int)params[0] * (n * n + n)) return vfvm_fail(h, VFVM_ERR_ARG, "region-affine reaction: params = nreg, then nreg x (R[n*n], r0[n])");
+            need = np;
+        }
         if (id == VFVM_REACTION_BILINEAR2 && n != 2) return vfvm_fail(h, VFVM_ERR_UNSUPPORTED, "bilinear reaction: exactly 2 species");
         if (id == VFVM_REACTION_BIPOLAR) {
             if (n != 3 || np < 9 || params[5] != 0 || params[6] != 1 || params[7] != 2 || np != 9 + (int)params[8])

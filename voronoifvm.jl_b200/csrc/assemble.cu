@@ -48,6 +48,9 @@ struct AsmArgs {
     int slice0, nslices, cF, cD, the_region;  // this launch handles the slices [slice0, nslices)
     double time, tstepinv, lambda;
     signed char idxF[100], idxD[100];
+    // masked systems (species not enabled in every cell region): enabled-species bits per cell region, species defined per node
+    unsigned short rsmask[VFVM_MAX_CREGIONS];
+    const int32_t* __restrict__ node_active;
 };
 
 // internal flux id: power-law diffusion with exponent exactly 2 (Example207): u*u, no pow() code in the kernel
@@ -113,8 +116,12 @@ __device__ __forceinline__ T storage_sep(int id, const double* __restrict__ p, i
 
 // SEP: every coupling mask is exactly the species diagonal (plane i <-> (i,i)) and flux / reaction / storage are species-
 // separable: the fast path of cfg1/2/3/5.  Otherwise the general path with Dual<2 NS> and the runtime plane tables.
-template <int NS, int FLUX, bool MULTIREG, bool SEP, bool LIGHT>
-__global__ void __launch_bounds__(ASM_THREADS, (SEP && LIGHT && NS == 1) ? 4 : ((!SEP && NS <= 3) ? 2 : 1)) k_assemble_rows(const AsmArgs a) {
+// MASKED (only with MULTIREG, !SEP): species are enabled per cell region (enable_species!(sys, i, regions)).  An (edge, region)
+// or (node, region) item contributes to species i only where region_species[i, region] holds, and to the coupling (i,j) only
+// where both hold (assemble_res_jac, src/vfvm_assemblydata.jl:245-270, 350-382); dofs of species that are not defined at a node
+// get the identity row F = u - uold, A_ii = 1 (_eval_and_assemble_inactive_species, src/vfvm_system.jl:1012-1026).
+template <int NS, int FLUX, bool MULTIREG, bool SEP, bool LIGHT, bool MASKED = false>
+__global__ void __launch_bounds__(ASM_THREADS, (SEP && LIGHT && NS == 1) ? 4 : ((!SEP && NS <= 3 && !MASKED) ? 2 : 1)) k_assemble_rows(const AsmArgs a) {
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5, nwarps = gridDim.x * wpb;
     const PhysicsDev& ph = *a.ph;
@@ -147,7 +154,7 @@ __global__ void __launch_bounds__(ASM_THREADS, (SEP && LIGHT && NS == 1) ? 4 : (
         if constexpr (!MULTIREG) nfac0 = a.nf_fac[r];
 #pragma unroll
         for (int i = 0; i < NS; i++) {
-            uo_r[i] = has_storage ? a.UOld[r * NS + i] : 0.0;
+            uo_r[i] = (has_storage || MASKED) ? a.UOld[r * NS + i] : 0.0;
             src_r[i] = a.src ? a.src[r * NS + i] : 0.0;
         }
         constexpr int ND = SEP ? NS : NS * NS;
@@ -179,6 +186,29 @@ __global__ void __launch_bounds__(ASM_THREADS, (SEP && LIGHT && NS == 1) ? 4 : (
                 const int L = Lc[b];
                 const double* uc = ucb[b];
                 const double fac = fc[b];
+                // masked: form factor summed over the cell regions of the edge in which species i / both species (i,j) are enabled
+                double wsp[MASKED ? NS : 1], wpair[MASKED ? NS * NS : 1];
+                if constexpr (MASKED) {
+#pragma unroll
+                    for (int i = 0; i < NS; i++) wsp[i] = 0.0;
+#pragma unroll
+                    for (int i = 0; i < NS * NS; i++) wpair[i] = 0.0;
+                    const int ed = a.nz_edge[e];
+                    if (ed >= 0) {
+                        for (int64_t q = a.ef_colptr[ed]; q < a.ef_colptr[ed + 1]; q++) {
+                            const unsigned m = a.rsmask[a.ef_region[q] - 1];
+                            const double fq = a.ef_fac[q];
+#pragma unroll
+                            for (int i = 0; i < NS; i++) {
+                                if (!((m >> i) & 1u)) continue;
+                                wsp[i] += fq;
+#pragma unroll
+                                for (int jj = 0; jj < NS; jj++)
+                                    if ((m >> jj) & 1u) wpair[i * NS + jj] += fq;
+                            }
+                        }
+                    }
+                }
                 {
                     constexpr bool first = true;
                     if constexpr (flux_separable(FLUX)) {
@@ -189,6 +219,15 @@ __global__ void __launch_bounds__(ASM_THREADS, (SEP && LIGHT && NS == 1) ? 4 : (
                             y.d[1] = 1.0;
                             const Dual<2> f = eval_flux_sep<FLUX>(Dcoef[i], mexp, x, y);
                             nan_seen |= (f.d[0] != f.d[0]) | (f.d[1] != f.d[1]);
+                            if constexpr (MASKED) {
+                                Fr[i] += wsp[i] * f.v;
+                                const int p = a.idxF[i * NS + i];
+                                if (p >= 0) {
+                                    Dr[i * NS + i] += wsp[i] * f.d[0];
+                                    a.offval[(int64_t)p * nnz + e] = wsp[i] * f.d[1];
+                                }
+                                continue;
+                            }
                             Fr[i] += fac * f.v;
                             if constexpr (SEP) {
                                 Dr[i] += fac * f.d[0];
@@ -219,16 +258,18 @@ __global__ void __launch_bounds__(ASM_THREADS, (SEP && LIGHT && NS == 1) ? 4 : (
                         eval_flux<FLUX, NS>(pf, f, x, y);
 #pragma unroll
                         for (int i = 0; i < NS; i++) {
-                            Fr[i] += sfac * f[i].v;
+                            const double si = MASKED ? (pos ? wsp[i] : -wsp[i]) : sfac;
+                            Fr[i] += si * f[i].v;
 #pragma unroll
                             for (int jj = 0; jj < NS; jj++) {
                                 const int p = a.idxF[i * NS + jj];
                                 if (p < 0) continue;
                                 const double drow = pos ? f[i].d[jj] : f[i].d[NS + jj], dcol = pos ? f[i].d[NS + jj] : f[i].d[jj];
                                 nan_seen |= (drow != drow) | (dcol != dcol);
-                                Dr[i * NS + jj] += sfac * drow;
-                                if (first) a.offval[(int64_t)p * nnz + e] = sfac * dcol;
-                                else a.offval[(int64_t)p * nnz + e] += sfac * dcol;
+                                const double sij = MASKED ? (pos ? wpair[i * NS + jj] : -wpair[i * NS + jj]) : sfac;
+                                Dr[i * NS + jj] += sij * drow;
+                                if (first) a.offval[(int64_t)p * nnz + e] = sij * dcol;
+                                else a.offval[(int64_t)p * nnz + e] += sij * dcol;
                             }
                         }
                     }
@@ -288,16 +329,29 @@ __global__ void __launch_bounds__(ASM_THREADS, (SEP && LIGHT && NS == 1) ? 4 : (
                         eval_storage<NS>(sid, ps, stor, u);
                         eval_storage<NS>(sid, ps, ostor, uo);
                     }
+                    const unsigned rm = MASKED ? a.rsmask[region - 1] : 0xffffu;
 #pragma unroll
                     for (int i = 0; i < NS; i++) {
+                        if (MASKED && !((rm >> i) & 1u)) continue;
                         Fr[i] += fac * (rea[i].v - srcv[i] + (stor[i].v - ostor[i]) * a.tstepinv);
 #pragma unroll
                         for (int jj = 0; jj < NS; jj++) {
+                            if (MASKED && !((rm >> jj) & 1u)) continue;
                             const double jv = rea[i].d[jj] + stor[i].d[jj] * a.tstepinv;
                             nan_seen |= (jv != jv);
                             Dr[i * NS + jj] += jv * fac;
                         }
                     }
+                }
+                if constexpr (MASKED) {  // dofs of species that are not defined at this node: identity row
+                    const unsigned act = (unsigned)a.node_active[r];
+#pragma unroll
+                    for (int i = 0; i < NS; i++)
+                        if (!((act >> i) & 1u)) {
+                            Fr[i] = u_r[i] - uo_r[i];
+#pragma unroll
+                            for (int jj = 0; jj < NS; jj++) Dr[i * NS + jj] = (i == jj) ? 1.0 : 0.0;
+                        }
                 }
 #pragma unroll
                 for (int i = 0; i < NS; i++) {
@@ -668,6 +722,7 @@ struct BNodeArgs {
     int dim;
     double time, lambda;
     signed char idxD[100];
+    const int32_t* __restrict__ node_active;  // masked systems: species defined at the node (isnodespecies, src/vfvm_assemblydata.jl:286-292), else null
 };
 
 template <int NS>
@@ -686,6 +741,7 @@ __global__ void k_assemble_bnodes(const BNodeArgs a) {
         Fk[i] = a.F[(int64_t)K * NS + i];
     }
     bool nan_seen = false;
+    const unsigned act = a.node_active ? (unsigned)a.node_active[K] : 0xffffu;
     for (int q = a.bn_ptr[b]; q < a.bn_ptr[b + 1]; q++) {
         const int ibf = a.bn_bface[q];
         const int region = a.bfaceregions[ibf];
@@ -695,6 +751,7 @@ __global__ void k_assemble_bnodes(const BNodeArgs a) {
             Dirichlet = 1.0e30 / fac;
 #pragma unroll
             for (int i = 0; i < NS; i++) {
+                if (!((act >> i) & 1u)) continue;
                 const double bf = ph.bfactors[(region - 1) * NS + i], bv = ph.bvalues[(region - 1) * NS + i];
                 const int pD = a.idxD[i * NS + i];
                 if (bf == 1.0e30) {
@@ -712,9 +769,11 @@ __global__ void k_assemble_bnodes(const BNodeArgs a) {
         eval_breaction<NS>(ph, res, u, region, a.time, Dirichlet, (double*)nullptr);
 #pragma unroll
         for (int i = 0; i < NS; i++) {  // src/vfvm_assembly.jl:399-401
+            if (!((act >> i) & 1u)) continue;
             Fk[i] += fac * res[i].v;
 #pragma unroll
             for (int j = 0; j < NS; j++) {
+                if (!((act >> j) & 1u)) continue;
                 const double jv = res[i].d[j];
                 nan_seen |= (jv != jv);
                 const int pD = a.idxD[i * NS + j];
@@ -725,6 +784,15 @@ __global__ void k_assemble_bnodes(const BNodeArgs a) {
 #pragma unroll
     for (int i = 0; i < NS; i++) a.F[(int64_t)K * NS + i] = Fk[i];
     if (nan_seen) atomicOr(a.flags, 1);
+}
+
+// _initialize_inactive_dof! src/vfvm_system.jl:1030-1042: dofs of species that are not defined at a node are zero
+__global__ void k_zero_inactive(int64_t Nown, int ns, const int32_t* __restrict__ node_active, double* __restrict__ U) {
+    const int64_t K = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (K >= Nown) return;
+    const unsigned act = (unsigned)node_active[K];
+    for (int i = 0; i < ns; i++)
+        if (!((act >> i) & 1u)) U[K * ns + i] = 0.0;
 }
 
 // _initialize_dirichlet! src/vfvm_system.jl:947-1003: later items overwrite earlier ones (loop order = bface order)
@@ -748,6 +816,7 @@ __global__ void k_init_dirichlet(const BNodeArgs a) {
         eval_breaction<NS>(ph, y, u, region, a.time, 1.0e30, dv);
 #pragma unroll
         for (int i = 0; i < NS; i++) {
+            if (a.node_active && !(((unsigned)a.node_active[K] >> i) & 1u)) continue;
             if (!isinf(dv[i])) u[i] = dv[i];
             if (ph.has_legacy_bc) {
                 const double bf = ph.bfactors[(region - 1) * NS + i];
@@ -812,6 +881,7 @@ static void launch_slices_sep(vfvm_handle* h, Kern kern, int& plan, const AsmArg
 // ---- host dispatch -------------------------------------------------------------------------------------------
 // the separable fast path applies when every coupling mask is exactly the species diagonal
 static bool fast_path_ok(const vfvm_handle* h) {
+    if (h->masked) return false;
     const int n = h->n, fid = h->phys.slot[VFVM_SLOT_FLUX].id, rid = h->phys.slot[VFVM_SLOT_REACTION].id, sid = h->phys.slot[VFVM_SLOT_STORAGE].id;
     if (!h->single_region || !(fid == VFVM_FLUX_DIFFUSION || fid == VFVM_FLUX_POWDIFF)) return false;
     if (!(rid == VFVM_NONE || rid == VFVM_REACTION_POW || rid == VFVM_REACTION_SINH || (rid == VFVM_REACTION_AFFINE && n == 1))) return false;
@@ -874,8 +944,9 @@ static void launch_rows(vfvm_handle* h, const AsmArgs& a) {
         }
     }
     if constexpr (flux_supported(FLUX, NS)) {
-        static int occ0 = 0, occ1 = 0;
-        if (h->single_region) launch_slices(h, k_assemble_rows<NS, FLUX, false, false, false>, occ0, a);
+        static int occ0 = 0, occ1 = 0, occm = 0;
+        if (h->masked) launch_slices(h, k_assemble_rows<NS, FLUX, true, false, false, true>, occm, a);
+        else if (h->single_region) launch_slices(h, k_assemble_rows<NS, FLUX, false, false, false>, occ0, a);
         else launch_slices(h, k_assemble_rows<NS, FLUX, true, false, false>, occ1, a);
     } else {
         throw std::string("flux id ") + std::to_string(FLUX) + " has no device instantiation for " + std::to_string(NS) + " species";
@@ -953,7 +1024,14 @@ static void fill_asm_args(vfvm_handle* h, AsmArgs& a, double time, double tstepi
         a.idxF[b] = (signed char)(b < h->n * h->n ? h->idxF[b] : -1);
         a.idxD[b] = (signed char)(b < h->n * h->n ? h->idxD[b] : -1);
     }
-    if (flux_node_transform(h->phys.slot[VFVM_SLOT_FLUX].id) && !getenv("VFVM_GENERIC_DUAL_FLUX")) {  // env: parity probe of the generic Dual<2n> path
+    for (int r = 0; r < VFVM_MAX_CREGIONS; r++) {
+        unsigned short m = 0;
+        for (int i = 0; i < h->n && r < h->ncellregions; i++)
+            if (h->region_species[(size_t)r * h->n + i]) m |= (unsigned short)(1u << i);
+        a.rsmask[r] = m;
+    }
+    a.node_active = h->node_active.p;
+    if (flux_node_transform(h->phys.slot[VFVM_SLOT_FLUX].id) && !h->masked && !getenv("VFVM_GENERIC_DUAL_FLUX")) {  // env: parity probe of the generic Dual<2n> path
         h->node_q.alloc((size_t)h->n * h->N);
         a.Q = h->node_q.p;
     }
@@ -978,6 +1056,7 @@ static void fill_bnode_args(vfvm_handle* h, BNodeArgs& b, const AsmArgs& a, doub
     b.time = time;
     b.lambda = lambda;
     memcpy(b.idxD, a.idxD, sizeof(b.idxD));
+    b.node_active = h->masked ? h->node_active.p : nullptr;
 }
 
 // q(u) of the nodes [K0, K1) (only for flux_node_transform fluxes)
@@ -1181,7 +1260,16 @@ int vfvm_assemble_finish(vfvm_handle* h) {
     return VFVM_OK;
 }
 
+// masked systems: dofs of species that are not defined at a node are kept at exactly zero (a Krylov solve of their identity rows
+// may leave rounding noise)
+void vfvm_zero_inactive(vfvm_handle* h, double* vec) {
+    if (!h->masked) return;
+    k_zero_inactive<<<cdiv(h->Nown, 256), 256, 0, h->stream>>>(h->Nown, h->n, h->node_active.p, vec);
+    h->launches++;
+}
+
 int vfvm_init_dirichlet_impl(vfvm_handle* h, double time, double lambda) {
+    vfvm_zero_inactive(h, h->vec[VFVM_VEC_SOLUTION].p);
     if (!h->nbnodes) return VFVM_OK;
     BNodeArgs b;
     memset(&b, 0, sizeof(b));
@@ -1198,6 +1286,7 @@ int vfvm_init_dirichlet_impl(vfvm_handle* h, double time, double lambda) {
     b.dim = h->dim;
     b.time = time;
     b.lambda = lambda;
+    b.node_active = h->masked ? h->node_active.p : nullptr;
     NS_DISPATCH(h->n, (k_init_dirichlet<NS><<<cdiv(h->nbnodes, 128), 128, 0, h->stream>>>(b)));
     h->launches++;
     CK(cudaStreamSynchronize(h->stream));

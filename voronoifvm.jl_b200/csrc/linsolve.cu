@@ -17,7 +17,7 @@
 #define LS_RMAX 256
 
 // device scalar slots
-enum { S_RHO = 0, S_RHO_OLD, S_ALPHA, S_OMEGA, S_BETA, S_RV, S_TS, S_TT, S_RR, S_BB, S_PAP, S_RZ, S_RZ_OLD, S_TMP0, S_TMP1, S_COUNT = 16 };
+enum { S_RHO = 0, S_RHO_OLD, S_ALPHA, S_OMEGA, S_BETA, S_RV, S_RESTART, S_RHAT2, S_RR, S_BB, S_PAP, S_RZ, S_RZ_OLD, S_TMP0, S_TMP1, S_COUNT = 16 };
 
 int vfvm_comm_allreduce_sum(vfvm_handle* h, double* dev, int count);
 int vfvm_comm_allreduce_max(vfvm_handle* h, double* dev, int count);
@@ -195,6 +195,8 @@ __device__ void scalar_update(int op, double* __restrict__ sc, int32_t* __restri
             sc[S_ALPHA] = 1.0;
             sc[S_OMEGA] = 1.0;
             sc[S_BETA] = 0.0;
+            sc[S_RESTART] = 0.0;
+            sc[S_RHAT2] = sc[S_TMP0];
             break;
         case OP_BICG_ALPHA:  // TMP0 = (rhat, v)
             sc[S_RV] = sc[S_TMP0];
@@ -205,10 +207,20 @@ __device__ void scalar_update(int op, double* __restrict__ sc, int32_t* __restri
             sc[S_OMEGA] = (sc[S_TMP1] > 0.0) ? sc[S_TMP0] / sc[S_TMP1] : 0.0;
             break;
         case OP_BICG_NEXT: {  // TMP0 = (rhat, r_new), TMP1 = (r_new, r_new): beta for the next iteration
-            const double rho_new = sc[S_TMP0];
-            sc[S_BETA] = (rho_new / sc[S_RHO]) * (sc[S_ALPHA] / sc[S_OMEGA]);
-            sc[S_RHO] = rho_new;
-            sc[S_RR] = sc[S_TMP1];
+            const double rho_new = sc[S_TMP0], rr = sc[S_TMP1];
+            sc[S_RR] = rr;
+            // near-breakdown: the shadow residual has become (numerically) orthogonal to the residual, rho would underflow
+            // within a few iterations.  Restart with rhat = r (done by the next k_bicg_p): rho = (r,r), beta = 0.
+            if (rho_new * rho_new < 1.0e-16 * rr * sc[S_RHAT2] || !(fabs(sc[S_OMEGA]) > 0.0)) {
+                sc[S_RESTART] = 1.0;
+                sc[S_RHAT2] = rr;
+                sc[S_RHO] = rr;
+                sc[S_BETA] = 0.0;
+            } else {
+                sc[S_RESTART] = 0.0;
+                sc[S_BETA] = (rho_new / sc[S_RHO]) * (sc[S_ALPHA] / sc[S_OMEGA]);
+                sc[S_RHO] = rho_new;
+            }
             break;
         }
         case OP_CG_INIT:  // TMP0 = (z,r), TMP1 = (r,r)
@@ -278,10 +290,12 @@ __global__ void k_finalize_op_peer(const double* __restrict__ part, int nparts, 
 // `dinv` = reciprocal point diagonal (Jacobi) or null (identity): the preconditioned vector is produced in the same pass
 // BiCGStab: p = r + beta (p - omega v) ; phat = M^-1 p
 __global__ void k_bicg_p(int64_t n, const double* __restrict__ sc, const double* __restrict__ r, const double* __restrict__ v, double* __restrict__ p,
-                         const double* __restrict__ dinv, double* __restrict__ phat) {
+                         const double* __restrict__ dinv, double* __restrict__ phat, double* __restrict__ rhat) {
     const double beta = sc[S_BETA], omega = sc[S_OMEGA];
+    const bool restart = sc[S_RESTART] != 0.0;  // near-breakdown detected by the last scalar update: new shadow residual
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const double pi = r[i] + beta * (p[i] - omega * v[i]);
+        if (restart) rhat[i] = r[i];
+        const double pi = restart ? r[i] : r[i] + beta * (p[i] - omega * v[i]);
         p[i] = pi;
         if (phat) phat[i] = dinv ? pi * dinv[i] : pi;
     }
@@ -771,7 +785,7 @@ extern "C" int vfvm_linsolve(vfvm_handle* h, double abstol, double reltol, int m
             converged = sqrt(rr) <= tol;
             while (!converged && !breakdown && it < maxiters) {
                 it++;
-                k_bicg_p<<<VEC_GRID, LS_THREADS, 0, st>>>(nd, h->red.p, r, v, p, dinv, fusedpc ? phat : nullptr);
+                k_bicg_p<<<VEC_GRID, LS_THREADS, 0, st>>>(nd, h->red.p, r, v, p, dinv, fusedpc ? phat : nullptr, rhat);
                 h->launches++;
                 if (!fusedpc) precond_apply(h, p, phat);
                 spmv(h, phat, v, rhat, OP_BICG_ALPHA);  // (v, rhat)
@@ -988,6 +1002,7 @@ extern "C" int vfvm_newton_update(vfvm_handle* h, double damp, double* update_no
         const int64_t nd = h->Nown * h->n;
         if (h->work[11].n < (size_t)4 * VEC_GRID) h->work[11].alloc((size_t)4 * VEC_GRID);
         double* part = h->work[11].p;
+        vfvm_zero_inactive(h, h->vec[VFVM_VEC_UPDATE].p);
         k_newton_update<<<VEC_GRID, LS_THREADS, 0, h->stream>>>(nd, damp, h->vec[VFVM_VEC_UPDATE].p, h->vec[VFVM_VEC_SOLUTION].p, part);
         k_finalize_max<<<1, 1024, 0, h->stream>>>(part, VEC_GRID, h->red.p + S_TMP0);
         k_finalize<<<1, 1024, 0, h->stream>>>(part + VEC_GRID, VEC_GRID, 1, h->red.p + S_TMP1);

@@ -150,6 +150,13 @@ int vfvm_physics_masks(vfvm_handle* h) {
                 for (int i = 0; i < n * n; i++)
                     if (p[i] != 0.0) mask_set(m.reaction, i);
                 break;
+            case VFVM_REACTION_REGION_AFFINE: {
+                const int nreg = (int)p[0];
+                for (int r = 0; r < nreg; r++)
+                    for (int i = 0; i < n * n; i++)
+                        if (p[1 + r * (n * n + n) + i] != 0.0) mask_set(m.reaction, i);
+                break;
+            }
             case VFVM_REACTION_BILINEAR2:
             case VFVM_REACTION_BIPOLAR: full(m.reaction); break;
             default: return VFVM_ERR_UNREGISTERED;
@@ -337,6 +344,17 @@ int vfvm_pattern_build(vfvm_handle* h) {
         ptr.push_back((int32_t)items.size());
         h->nbnodes = (int64_t)node.size();
         h->nbitems = (int64_t)items.size();
+        if (h->masked) {  // species defined per node = union over the cell regions the node touches (node_dof, src/vfvm_system.jl:445-456)
+            std::vector<int64_t> cp = h->nf_colptr.to_host(s);
+            std::vector<int32_t> rg = h->nf_region.to_host(s), act((size_t)h->N, 0);
+            for (int64_t K = 0; K < h->N; K++)
+                for (int64_t q = cp[K]; q < cp[K + 1]; q++)
+                    for (int i = 0; i < h->n; i++)
+                        if (h->region_species[(size_t)(rg[q] - 1) * h->n + i]) act[K] |= (1 << i);
+            h->node_active.upload(act.data(), act.size(), s);
+        } else {
+            h->node_active.release();
+        }
         h->bn_node_host = node;
         h->pipe.valid = false;
         h->bn_node.upload(node.data(), node.size(), s);
@@ -384,6 +402,22 @@ static void build_scalar(vfvm_handle* h, ScalarPattern& sp) {
                          sl = h->sell_ptr.to_host(h->stream);
     std::vector<int64_t> bnode_of(Nown, -1);
     for (size_t b = 0; b < bn.size(); b++) bnode_of[bn[b]] = (int64_t)b;
+    // masked systems: species pairs that share a cell region at the node / on the edge (the reference never touches other entries)
+    std::vector<int64_t> nfp, efp;
+    std::vector<int32_t> nfr, efr, nze;
+    if (h->masked) {
+        nfp = h->nf_colptr.to_host(h->stream);
+        nfr = h->nf_region.to_host(h->stream);
+        efp = h->ef_colptr.to_host(h->stream);
+        efr = h->ef_region.to_host(h->stream);
+        nze = h->nz_edge.to_host(h->stream);
+    }
+    auto pair_ok = [&](const std::vector<int64_t>& ptr, const std::vector<int32_t>& reg, int64_t item, int i, int j) {
+        if (!h->masked) return true;
+        for (int64_t q = ptr[item]; q < ptr[item + 1]; q++)
+            if (h->region_species[(size_t)(reg[q] - 1) * n + i] && h->region_species[(size_t)(reg[q] - 1) * n + j]) return true;
+        return false;
+    };
     sp.rowptr.assign((size_t)Nown * n + 1, 0);
     sp.colidx.clear();
     sp.src.clear();
@@ -403,9 +437,10 @@ static void build_scalar(vfvm_handle* h, ScalarPattern& sp) {
         const int64_t ebase = (int64_t)sl[K >> 5] + (K & 31);
         for (int i = 0; i < n; i++) {
             bool diag_done = false;
+            const bool inactive = h->masked && !pair_ok(nfp, nfr, K, i, i);  // identity row
             auto emit_diag = [&]() {
                 for (int j = 0; j < n; j++)
-                    if (mask_get(dm, i * n + j)) {
+                    if (inactive ? (i == j) : (mask_get(dm, i * n + j) && pair_ok(nfp, nfr, K, i, j))) {
                         sp.colidx.push_back(K * n + j);
                         sp.src.push_back(-(1 + (int64_t)h->idxD[i * n + j] * Nown + K));
                     }
@@ -416,7 +451,7 @@ static void build_scalar(vfvm_handle* h, ScalarPattern& sp) {
                 const int64_t L = ci[e];
                 if (!diag_done && L > K) emit_diag();
                 for (int j = 0; j < n; j++)
-                    if (mask_get(h->masks.flux, i * n + j)) {
+                    if (mask_get(h->masks.flux, i * n + j) && (!h->masked || (nze[e] >= 0 && pair_ok(efp, efr, nze[e], i, j)))) {
                         sp.colidx.push_back(L * n + j);
                         sp.src.push_back((int64_t)h->idxF[i * n + j] * h->nnz_sell + e);
                     }

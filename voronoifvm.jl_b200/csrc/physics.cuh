@@ -131,6 +131,23 @@ __device__ __forceinline__ void eval_reaction(int id, const double* __restrict__
                 f[i] = acc;
             }
             break;
+        case VFVM_REACTION_REGION_AFFINE: {
+            const int nreg = (int)p[0];
+            if (region >= 1 && region <= nreg) {
+                const double* q = p + 1 + (region - 1) * (NS * NS + NS);
+#pragma unroll
+                for (int i = 0; i < NS; i++) {
+                    T acc(q[NS * NS + i]);
+#pragma unroll
+                    for (int j = 0; j < NS; j++) {
+                        const double r = q[i * NS + j];
+                        if (r != 0.0) acc = acc + r * u[j];
+                    }
+                    f[i] = acc;
+                }
+            }
+            break;
+        }
         case VFVM_REACTION_BILINEAR2:
             if constexpr (NS == 2) {
                 f[0] = p[0] * (u[0] * u[1]);

@@ -14,6 +14,7 @@
 #define VFVM_MAX_PARAMS 160
 #define VFVM_MAX_BC 32
 #define VFVM_MAX_BREGIONS 16
+#define VFVM_MAX_CREGIONS 32
 
 // ------------------------------------------------------------------------------------------------ device buffers
 template <class T>
@@ -133,6 +134,9 @@ struct vfvm_handle {
 
     // system
     int n = 0;
+    std::vector<uint8_t> region_species;  // n x ncellregions: species enabled per cell region
+    bool masked = false;                   // some species is not enabled in every cell region
+    DevBuf<int32_t> node_active;           // masked systems: bit i set <=> species i is defined at the node (node_dof, src/vfvm_system.jl:445-456)
     PhysicsDev phys;
     DevBuf<PhysicsDev> phys_dev;  // device copy, refreshed by vfvm_sync_physics
     bool phys_dirty = true;
@@ -250,6 +254,7 @@ int vfvm_physics_masks(vfvm_handle* h);
 void vfvm_spmv_impl(vfvm_handle* h, const double* x, double* y);
 void vfvm_sync_physics(vfvm_handle* h);
 void vfvm_source_cache(vfvm_handle* h);
+void vfvm_zero_inactive(vfvm_handle* h, double* vec);
 SpmvArgs vfvm_spmv_args(vfvm_handle* h);
 void vfvm_spmv_level(vfvm_handle* h, SpmvArgs a, const double* x, double* y);
 void vfvm_blockinv_level(vfvm_handle* h, const SpmvArgs& a, int64_t N, const double* diagval, double* inv);

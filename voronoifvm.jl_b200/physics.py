@@ -19,7 +19,7 @@ SLOT_FLUX, SLOT_REACTION, SLOT_STORAGE, SLOT_SOURCE, SLOT_BREACTION = range(5)
 SLOT_NAMES = ("flux", "reaction", "storage", "source", "breaction")
 
 FLUX_DIFFUSION, FLUX_POWDIFF, FLUX_CROSSDIFF2, FLUX_SG_UNIPOLAR, FLUX_SEDAN, FLUX_SG_BIPOLAR = 1, 2, 3, 4, 5, 6
-REACTION_POW, REACTION_SINH, REACTION_AFFINE, REACTION_BILINEAR2, REACTION_BIPOLAR = 1, 2, 3, 4, 5
+REACTION_POW, REACTION_SINH, REACTION_AFFINE, REACTION_BILINEAR2, REACTION_BIPOLAR, REACTION_REGION_AFFINE = 1, 2, 3, 4, 5, 6
 STORAGE_LINEAR, STORAGE_POW, STORAGE_BIPOLAR = 1, 2, 3
 SOURCE_CONST, SOURCE_GAUSS, SOURCE_XSINYEXPZ, SOURCE_STEP1D, SOURCE_AFFINE_X, SOURCE_NODAL = 1, 2, 3, 4, 5, 6
 BREACTION_LINEAR = 1
@@ -174,6 +174,23 @@ class BilinearReaction2(RegisteredPhysics):
 
     def params(self, n):
         return np.array([self.k], dtype=np.float64)
+
+
+class RegionAffineReaction(RegisteredPhysics):
+    """f = R_r u + r0_r in cell region r: one affine map per region (Example221 reaction :54-66)"""
+
+    slot, id = SLOT_REACTION, REACTION_REGION_AFFINE
+
+    def __init__(self, R, r0=None):
+        self.R = [np.asarray(m, dtype=np.float64) for m in R]
+        self.r0 = [None] * len(self.R) if r0 is None else list(r0)
+
+    def params(self, n):
+        out = [np.array([float(len(self.R))])]
+        for m, c in zip(self.R, self.r0):
+            assert m.shape == (n, n)
+            out += [m.ravel(), np.zeros(n) if c is None else _vec(c, n)]
+        return np.concatenate(out)
 
 
 class BipolarReaction(RegisteredPhysics):
