@@ -1,0 +1,7 @@
+#!/bin/bash
+N=${1:-2}
+T="timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
+$T --master-port 29512 tests/mgpu_check.py > gpurun_out/mgpu_peer.log 2>&1; grep "mgpu_check\|MGPU_OK\|Error\|error" gpurun_out/mgpu_peer.log | head -8
+VFVM_NO_PEER=1 $T --master-port 29513 tests/mgpu_check.py > gpurun_out/mgpu_nccl.log 2>&1; grep "mgpu_check\|MGPU_OK\|Error\|error" gpurun_out/mgpu_nccl.log | head -5
+$T --master-port 29514 bench.py --gpus $N --no-cpu --steps 10 > gpurun_out/bench_${N}gpu_peer.log 2>&1; tail -1 gpurun_out/bench_${N}gpu_peer.log
+VFVM_AMG_COARSE_SWEEPS=4 $T --master-port 29515 bench.py --gpus $N --no-cpu --steps 10 > gpurun_out/bench_${N}gpu_peer_cs4.log 2>&1; tail -1 gpurun_out/bench_${N}gpu_peer_cs4.log

@@ -16,9 +16,14 @@
 //   numeric phase (every new Jacobian): A_c(I,J) = sum of the fine blocks (K,L), K in I, L in J, plane by plane, as a GATHER
 //     in the fixed sorted order (no atomics => bitwise reproducible); block inverses of the diagonal for the smoother.
 //   cycle: damped block-Jacobi pre-/post-smoothing (symmetric, so CG stays applicable), residual fused into the restriction,
-//     over-weighted coarse correction (plain aggregation under-estimates smooth corrections), a few sweeps on the coarsest level.
-// With several ranks the hierarchy is built on the rank's own diagonal block (halo columns dropped): block-Jacobi across
-// ranks with AMG inside, no communication inside the preconditioner.
+//     over-weighted coarse correction (plain aggregation under-estimates smooth corrections), four sweeps on the coarsest level.
+// With several ranks the hierarchy is distributed: aggregates never cross a partition boundary (every rank aggregates its owned
+// nodes), but the couplings across the boundary are kept on every level.  A rank learns the aggregate of each of its halo nodes
+// from the owner (one halo exchange of the aggregate ids per level); the distinct aggregates per neighbour, in ascending order,
+// are the halo of the next level -- and the owner derives the matching send list from the same ids without a second exchange.
+// Restriction, prolongation, Galerkin product and smoothing are rank-local; every SpMV of the cycle refreshes the halo of its
+// input (level 0: fused into the SpMV kernel over the peer mailboxes; coarser levels: one push/wait/unpack kernel through the
+// same mailboxes, or NCCL).  VFVM_AMG_LOCAL=1 drops the halo couplings instead (block-Jacobi across ranks with AMG inside).
 #include <algorithm>
 #include <cub/cub.cuh>
 
@@ -48,14 +53,17 @@ struct Level {
     DevBuf<int32_t> gal_ptr, gal_src, gal_dst;  // coarse entry u <- fine entries gal_src[gal_ptr[u] .. gal_ptr[u+1]); dst >= 0: SELL position, < 0: diagonal of node -dst-1
     // work vectors (n x Nvec)
     DevBuf<double> x, b, t;
+    // several ranks: halo of this level (level 0 uses the handle's lists)
+    LevelHalo halo;
+    std::vector<int32_t> send_idx_host;
 };
 
 struct Amg {
     std::vector<Level*> L;
-    bool struct_valid = false;
+    bool struct_valid = false, distributed = false;
     int64_t pattern_nnz = -1, pattern_N = -1;
     double omega = 0.8, alpha = 1.75, theta = 0.08;  // alpha: measured on cfg3 (CG iterations 153 / 101 / 79 / 71 / 69 for alpha = 1 / 1.25 / 1.5 / 1.75 / 2)
-    int coarse_sweeps = 8, max_levels = 20, sweeps = 1;  // sweeps: pre- and post-smoothing steps per level
+    int coarse_sweeps = 4, max_levels = 20, sweeps = 1;  // sweeps: pre- and post-smoothing steps per level
     ~Amg() {
         for (Level* l : L) delete l;
     }
@@ -195,6 +203,10 @@ __global__ void k_agg_join(int64_t N, int nsl, const int32_t* __restrict__ sell_
     if (valid) out[K] = mine == -1 ? target : mine;  // target -1: still undecided
 }
 
+__global__ void k_agg_to_vec(int64_t N, int ns, const int32_t* __restrict__ agg, double* __restrict__ out) {  // aggregate id of each owned node as the first component of a level vector
+    const int64_t K = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (K < N) out[K * ns] = (double)agg[K];
+}
 __global__ void k_agg_rest(int64_t N, int32_t* __restrict__ agg, int32_t* __restrict__ isroot) {
     const int64_t K = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (K >= N) return;
@@ -224,7 +236,9 @@ __global__ void k_lower_bounds32(int n, const int32_t* __restrict__ sorted, int6
 
 // ------------------------------------------------------------------------------------------------ coarse pattern kernels
 #define KEY_SENTINEL 0xffffffffffffffffull
-__global__ void k_pair_keys(int64_t N, int nsl, const int32_t* __restrict__ sell_ptr, const int32_t* __restrict__ colidx, const int32_t* __restrict__ agg, int64_t Nc,
+// Nc here = number of coarse COLUMNS (owned aggregates + coarse halo), the multiplier of the (row, column) key; columns up to
+// Ncols_f (fine owned + halo nodes) take part, their aggregate ids come from `agg` (halo part filled by the owner's ids)
+__global__ void k_pair_keys(int64_t N, int64_t Ncols_f, int nsl, const int32_t* __restrict__ sell_ptr, const int32_t* __restrict__ colidx, const int32_t* __restrict__ agg, int64_t Nc,
                             unsigned long long* __restrict__ keys, int32_t* __restrict__ vals) {
     ROW_LOOP_BEGIN(N, nsl)
     const int I = valid ? agg[K] : -1;
@@ -232,7 +246,7 @@ __global__ void k_pair_keys(int64_t N, int nsl, const int32_t* __restrict__ sell
         const int e = base + 32 * j + lane;
         const int L = colidx[e];
         unsigned long long key = KEY_SENTINEL;
-        if (valid && I >= 0 && L != K && L < N) {
+        if (valid && I >= 0 && L != K && L < Ncols_f) {
             const int J = agg[L];
             if (J >= 0) key = (unsigned long long)I * (unsigned long long)Nc + (unsigned long long)J;
         }
@@ -265,9 +279,9 @@ __device__ __forceinline__ int64_t lb64(const unsigned long long* __restrict__ a
 }
 __global__ void k_first_sentinel(const unsigned long long* __restrict__ a, int64_t n, int32_t* __restrict__ out) { *out = (int32_t)lb64(a, n, KEY_SENTINEL); }
 // off-diagonal row lengths of the coarse matrix from the sorted unique (I,J) keys
-__global__ void k_coarse_rowlen(int64_t Nc, const unsigned long long* __restrict__ ukey, int64_t nuniq, int32_t* __restrict__ rowlen) {
+__global__ void k_coarse_rowlen(int64_t Nrows, int64_t Nc, const unsigned long long* __restrict__ ukey, int64_t nuniq, int32_t* __restrict__ rowlen) {
     const int64_t I = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (I >= Nc) return;
+    if (I >= Nrows) return;
     const int64_t f = lb64(ukey, nuniq, (unsigned long long)I * Nc), g = lb64(ukey, nuniq, (unsigned long long)(I + 1) * Nc);
     const unsigned long long dk = (unsigned long long)I * Nc + I;
     const int64_t dpos = lb64(ukey, nuniq, dk);
@@ -440,7 +454,8 @@ int64_t aggregate(vfvm_handle* h, Amg& A, Level& l, bool level0) {
     d.alloc(N);
     SpmvArgs a = level_args(h, l);
     NS_SWITCH(h->n, (k_node_weight<NS><<<gridw, 256, 0, s>>>(N, nsl, l.sell_ptr, l.colidx, l.w, l.diagval, a, level0 ? 1 : 0, d.p)));
-    l.agg.alloc(N);
+    l.agg.alloc(l.Nvec);
+    CK(cudaMemsetAsync(l.agg.p, 0xff, l.Nvec * sizeof(int32_t), s));  // halo part: -1 until the owners' ids arrive
     k_agg_init<<<gridw, 256, 0, s>>>(N, nsl, l.sell_ptr, l.colidx, l.w, d.p, th2, l.agg.p);
     DevBuf<unsigned long long> ep, m1;
     ep.alloc(N);
@@ -494,16 +509,18 @@ int64_t aggregate(vfvm_handle* h, Amg& A, Level& l, bool level0) {
 // pattern of the next level + gather maps of the Galerkin product
 void coarsen_pattern(vfvm_handle* h, Level& f, Level& c) {
     cudaStream_t s = h->stream;
-    const int64_t Nc = f.Nc, nnz = f.nnz_sell;
-    c.N = c.Nvec = Nc;
-    c.nslices = cdiv(Nc, 32);
+    const int64_t Nrows = f.Nc, nnz = f.nnz_sell;
+    c.N = Nrows;
+    c.Nvec = Nrows + c.halo.nhalo;   // owned aggregates + coarse halo
+    const int64_t Nc = c.Nvec;        // number of coarse columns = multiplier of the (row, column) keys
+    c.nslices = cdiv(Nrows, 32);
     DevBuf<unsigned long long> keys, keys_s, ukey;
     DevBuf<int32_t> vals, flag, uid;
     keys.alloc(nnz);
     keys_s.alloc(nnz);
     vals.alloc(nnz);
     f.gal_src.alloc(nnz);
-    k_pair_keys<<<cdiv(f.nslices, 8), 256, 0, s>>>(f.N, f.nslices, f.sell_ptr, f.colidx, f.agg.p, Nc, keys.p, vals.p);
+    k_pair_keys<<<cdiv(f.nslices, 8), 256, 0, s>>>(f.N, f.Nvec, f.nslices, f.sell_ptr, f.colidx, f.agg.p, Nc, keys.p, vals.p);
     size_t tb = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tb, keys.p, keys_s.p, vals.p, f.gal_src.p, (int)nnz, 0, 64, s);
     DevBuf<char> tmp;
@@ -532,11 +549,13 @@ void coarsen_pattern(vfvm_handle* h, Level& f, Level& c) {
         CK(cudaStreamSynchronize(s));
     }
     DevBuf<int32_t> rowlen, width32;
-    rowlen.alloc(Nc);
+    rowlen.alloc(std::max<int64_t>(1, Nrows));
     width32.alloc(c.nslices + 1);
     CK(cudaMemsetAsync(width32.p, 0, (c.nslices + 1) * sizeof(int32_t), s));
-    k_coarse_rowlen<<<cdiv(Nc, 256), 256, 0, s>>>(Nc, ukey.p, nuniq, rowlen.p);
-    k_slice_width<<<cdiv(c.nslices, 8), 256, 0, s>>>(c.nslices, Nc, rowlen.p, width32.p);
+    if (Nrows) {
+        k_coarse_rowlen<<<cdiv(Nrows, 256), 256, 0, s>>>(Nrows, Nc, ukey.p, nuniq, rowlen.p);
+        k_slice_width<<<cdiv(c.nslices, 8), 256, 0, s>>>(c.nslices, Nrows, rowlen.p, width32.p);
+    }
     c.sell_ptr_b.alloc(c.nslices + 1);
     cub::DeviceScan::ExclusiveSum(nullptr, tb, width32.p, c.sell_ptr_b.p, c.nslices + 1, s);
     tmp.alloc(tb + 16);
@@ -545,7 +564,7 @@ void coarsen_pattern(vfvm_handle* h, Level& f, Level& c) {
     c.colidx_b.alloc(std::max<int64_t>(1, c.nnz_sell));
     c.w_b.alloc(std::max<int64_t>(1, c.nnz_sell));
     CK(cudaMemsetAsync(c.w_b.p, 0, std::max<int64_t>(1, c.nnz_sell) * sizeof(double), s));
-    k_fill_rowid<<<cdiv(c.nslices, 8), 256, 0, s>>>(c.nslices, c.sell_ptr_b.p, c.colidx_b.p);
+    if (c.nslices) k_fill_rowid<<<cdiv(c.nslices, 8), 256, 0, s>>>(c.nslices, c.sell_ptr_b.p, c.colidx_b.p);
     if (nuniq) {
         k_place_uniques<<<cdiv(nuniq, 256), 256, 0, s>>>(nuniq, Nc, ukey.p, c.sell_ptr_b.p, c.colidx_b.p, f.gal_dst.p);
         k_gal_weight<<<cdiv(nuniq, 256), 256, 0, s>>>(nuniq, f.gal_ptr.p, f.gal_src.p, f.gal_dst.p, f.w, c.w_b.p);
@@ -553,7 +572,7 @@ void coarsen_pattern(vfvm_handle* h, Level& f, Level& c) {
     h->launches += 10;
     c.offval_b.alloc((size_t)std::max(1, h->cF) * std::max<int64_t>(1, c.nnz_sell));
     CK(cudaMemsetAsync(c.offval_b.p, 0, c.offval_b.n * sizeof(double), s));  // padding entries stay exact zeros
-    c.diagval_b.alloc((size_t)std::max(1, h->cD) * Nc);
+    c.diagval_b.alloc((size_t)std::max(1, h->cD) * std::max<int64_t>(1, Nrows));
     c.sell_ptr = c.sell_ptr_b.p;
     c.colidx = c.colidx_b.p;
     c.offval = c.offval_b.p;
@@ -562,9 +581,81 @@ void coarsen_pattern(vfvm_handle* h, Level& f, Level& c) {
     CK(cudaStreamSynchronize(s));
 }
 
+// sum over the ranks of a host value (collective; identity on one rank)
+double global_sum(vfvm_handle* h, double v) {
+    if (h->nranks <= 1) return v;
+    DevBuf<double> d;
+    d.alloc(1);
+    CK(cudaMemcpyAsync(d.p, &v, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    vfvm_comm_allreduce_sum(h, d.p, 1);
+    return fetch(d.p, h->stream);
+}
+
+void exchange(vfvm_handle* h, Amg& A, size_t i, double* x) {  // halo refresh of a level vector
+    if (!A.distributed) return;
+    if (i == 0) vfvm_halo_exchange_ptr(h, x);
+    else vfvm_halo_exchange_level(h, A.L[i]->halo, x);
+}
+
+// Halo of the next level (several ranks).  Every rank sends the aggregate ids of its boundary nodes to the neighbours (one halo
+// exchange on level f); the distinct ids per neighbour, ascending, are the coarse halo nodes, and the owner builds the matching
+// send list from the same ids -- both sides see the same multiset in the same order, so no second exchange is needed.
+void build_coarse_halo(vfvm_handle* h, Amg& A, size_t fi, Level& f, Level& c) {
+    cudaStream_t s = h->stream;
+    const int n = h->n, nn = (int)h->nb_ranks.size();
+    const std::vector<int64_t>& fsp = fi == 0 ? h->send_ptr : f.halo.send_ptr;
+    const std::vector<int64_t>& frp = fi == 0 ? h->recv_ptr : f.halo.recv_ptr;
+    if (fi == 0) f.send_idx_host = h->send_idx.to_host(s);
+    const int64_t nhalo_f = f.Nvec - f.N;
+    DevBuf<double> T;
+    T.alloc((size_t)n * f.Nvec);
+    CK(cudaMemsetAsync(T.p, 0, T.n * sizeof(double), s));
+    if (f.N) k_agg_to_vec<<<cdiv(f.N, 256), 256, 0, s>>>(f.N, n, f.agg.p, T.p);
+    exchange(h, A, fi, T.p);
+    std::vector<double> Th = T.to_host(s);
+    std::vector<int32_t> aggh = f.agg.to_host(s);
+    // receiver side
+    std::vector<int32_t> halo_agg((size_t)std::max<int64_t>(1, nhalo_f), -1);
+    c.halo.recv_ptr.assign(nn + 1, 0);
+    for (int r = 0; r < nn; r++) {
+        std::vector<int32_t> ids;
+        for (int64_t q = frp[r]; q < frp[r + 1]; q++) {
+            const int32_t a = (int32_t)Th[(size_t)(f.N + q) * n];
+            if (a >= 0) ids.push_back(a);
+        }
+        std::sort(ids.begin(), ids.end());
+        ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
+        for (int64_t q = frp[r]; q < frp[r + 1]; q++) {
+            const int32_t a = (int32_t)Th[(size_t)(f.N + q) * n];
+            if (a >= 0) halo_agg[q] = (int32_t)(f.Nc + c.halo.recv_ptr[r] + (std::lower_bound(ids.begin(), ids.end(), a) - ids.begin()));
+        }
+        c.halo.recv_ptr[r + 1] = c.halo.recv_ptr[r] + (int64_t)ids.size();
+    }
+    if (nhalo_f) CK(cudaMemcpyAsync(f.agg.p + f.N, halo_agg.data(), nhalo_f * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    // owner side
+    c.halo.send_ptr.assign(nn + 1, 0);
+    c.send_idx_host.clear();
+    for (int r = 0; r < nn; r++) {
+        std::vector<int32_t> ids;
+        for (int64_t q = fsp[r]; q < fsp[r + 1]; q++) {
+            const int32_t a = aggh[f.send_idx_host[q]];
+            if (a >= 0) ids.push_back(a);
+        }
+        std::sort(ids.begin(), ids.end());
+        ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
+        c.send_idx_host.insert(c.send_idx_host.end(), ids.begin(), ids.end());
+        c.halo.send_ptr[r + 1] = (int64_t)c.send_idx_host.size();
+    }
+    c.halo.Nown = f.Nc;
+    c.halo.nhalo = c.halo.recv_ptr[nn];
+    c.halo.send_idx.upload(c.send_idx_host.data(), c.send_idx_host.size(), s);
+    CK(cudaStreamSynchronize(s));
+}
+
 void build_hierarchy(vfvm_handle* h, Amg& A) {
     for (Level* l : A.L) delete l;
     A.L.clear();
+    A.distributed = h->nranks > 1 && !h->nb_ranks.empty() && !getenv("VFVM_AMG_LOCAL");
     Level* l0 = new Level();
     l0->N = h->Nown;
     l0->Nvec = h->N;
@@ -578,13 +669,23 @@ void build_hierarchy(vfvm_handle* h, Amg& A) {
     A.L.push_back(l0);
     while ((int)A.L.size() < A.max_levels) {
         Level& f = *A.L.back();
-        if (f.N <= 64) break;
-        const int64_t Nc = aggregate(h, A, f, A.L.size() == 1);
-        if (Nc < 1 || Nc > (int64_t)(0.8 * f.N)) {  // no real coarsening any more: this level is the coarsest
+        // every decision about the depth is taken on rank-summed numbers: all ranks must build the same number of levels
+        const double Nglob = global_sum(h, (double)f.N);
+        if (Nglob <= 64.0 * h->nranks) break;
+        const int64_t Nc = f.N > 0 ? aggregate(h, A, f, A.L.size() == 1) : 0;
+        if (f.N == 0) {
+            f.agg.alloc(std::max<int64_t>(1, f.Nvec));
+            f.agg_ptr.alloc(1);
+            CK(cudaMemsetAsync(f.agg_ptr.p, 0, sizeof(int32_t), h->stream));
+            f.Nc = 0;
+        }
+        const double Ncglob = global_sum(h, (double)Nc);
+        if (Ncglob < 1.0 || Ncglob > 0.8 * Nglob) {  // no real coarsening any more: this level is the coarsest
             f.Nc = 0;
             break;
         }
         Level* c = new Level();
+        if (A.distributed) build_coarse_halo(h, A, A.L.size() - 1, f, *c);
         coarsen_pattern(h, f, *c);
         A.L.push_back(c);
     }
@@ -592,18 +693,18 @@ void build_hierarchy(vfvm_handle* h, Amg& A) {
     const int n = h->n;
     for (size_t i = 0; i < A.L.size(); i++) {
         Level& l = *A.L[i];
-        l.binv.alloc((size_t)n * n * l.N);
-        l.x.alloc((size_t)n * l.Nvec);
-        l.t.alloc((size_t)n * l.Nvec);
+        l.binv.alloc((size_t)n * n * std::max<int64_t>(1, l.N));
+        l.x.alloc((size_t)n * std::max<int64_t>(1, l.Nvec));
+        l.t.alloc((size_t)n * std::max<int64_t>(1, l.Nvec));
         CK(cudaMemsetAsync(l.x.p, 0, l.x.n * sizeof(double), h->stream));
-        if (i > 0) l.b.alloc((size_t)n * l.Nvec);
+        if (i > 0) l.b.alloc((size_t)n * std::max<int64_t>(1, l.Nvec));
     }
     A.struct_valid = true;
     A.pattern_nnz = h->nnz_sell;
     A.pattern_N = h->Nown;
     if (getenv("VFVM_AMG_VERBOSE")) {
-        fprintf(stderr, "[vfvm amg] levels:");
-        for (Level* l : A.L) fprintf(stderr, " %lld(%lld)", (long long)l->N, (long long)l->nnz_sell);
+        fprintf(stderr, "[vfvm amg] rank %d %s levels (nodes+halo(stored blocks)):", h->rank, A.distributed ? "distributed" : "local");
+        for (Level* l : A.L) fprintf(stderr, " %lld+%lld(%lld)", (long long)l->N, (long long)(l->Nvec - l->N), (long long)l->nnz_sell);
         fprintf(stderr, "\n");
     }
 }
@@ -617,17 +718,32 @@ void numeric_setup(vfvm_handle* h, Amg& A) {
     A.L[0]->diagval = h->diagval.p;
     for (size_t i = 0; i + 1 < A.L.size(); i++) {
         Level &f = *A.L[i], &c = *A.L[i + 1];
-        k_gal_diag<<<cdiv(c.N, 128), 128, 0, s>>>(c.N, h->cD, f.agg_ptr.p, f.agg_nodes.p, f.diagval, f.N, c.diagval_b.p);
+        if (c.N) k_gal_diag<<<cdiv(c.N, 128), 128, 0, s>>>(c.N, h->cD, f.agg_ptr.p, f.agg_nodes.p, f.diagval, f.N, c.diagval_b.p);
         if (f.nuniq)
             k_gal_off<<<cdiv(f.nuniq, 128), 128, 0, s>>>(f.nuniq, pm, f.gal_ptr.p, f.gal_src.p, f.gal_dst.p, f.offval, f.nnz_sell, c.offval_b.p, c.nnz_sell, c.diagval_b.p, c.N);
         h->launches += 2;
     }
-    for (Level* l : A.L) vfvm_blockinv_level(h, level_args(h, *l), l->N, l->diagval, l->binv.p);
+    for (Level* l : A.L)
+        if (l->N) vfvm_blockinv_level(h, level_args(h, *l), l->N, l->diagval, l->binv.p);
 }
 
-void smooth(vfvm_handle* h, Amg& A, Level& l, const double* b, bool first, double* out) {
+// t = A_l x_l with the halo of x_l refreshed first (several ranks); level 0 goes through the handle's SpMV, whose kernel
+// carries the exchange itself over the peer mailboxes
+void level_spmv(vfvm_handle* h, Amg& A, size_t i) {
+    Level& l = *A.L[i];
+    if (A.distributed && i == 0) {
+        vfvm_spmv_impl(h, l.x.p, l.t.p);
+        return;
+    }
+    if (A.distributed) vfvm_spmv_level_halo(h, level_args(h, l), l.halo, l.x.p, l.t.p);
+    else if (l.N) vfvm_spmv_level(h, level_args(h, l), l.x.p, l.t.p);
+}
+
+void smooth(vfvm_handle* h, Amg& A, size_t i, const double* b, bool first, double* out) {
     cudaStream_t s = h->stream;
-    if (!first) vfvm_spmv_level(h, level_args(h, l), l.x.p, l.t.p);
+    Level& l = *A.L[i];
+    if (!first) level_spmv(h, A, i);
+    if (!l.N) return;
     NS_SWITCH(h->n, (k_smooth<NS><<<cdiv(l.N, 128), 128, 0, s>>>(l.N, A.omega, l.binv.p, b, first ? nullptr : l.t.p, l.x.p, out)));
     h->launches++;
 }
@@ -636,19 +752,19 @@ void cycle(vfvm_handle* h, Amg& A, size_t i, const double* b, double* out) {
     cudaStream_t s = h->stream;
     Level& l = *A.L[i];
     if (i + 1 == A.L.size()) {  // coarsest level: a few sweeps
-        for (int k = 0; k < A.coarse_sweeps; k++) smooth(h, A, l, b, k == 0, k + 1 == A.coarse_sweeps ? out : nullptr);
+        for (int k = 0; k < A.coarse_sweeps; k++) smooth(h, A, i, b, k == 0, k + 1 == A.coarse_sweeps ? out : nullptr);
         return;
     }
     Level& c = *A.L[i + 1];
-    smooth(h, A, l, b, true, nullptr);
-    for (int k = 1; k < A.sweeps; k++) smooth(h, A, l, b, false, nullptr);
-    vfvm_spmv_level(h, level_args(h, l), l.x.p, l.t.p);
-    NS_SWITCH(h->n, (k_restrict<NS><<<cdiv(c.N, 128), 128, 0, s>>>(c.N, l.agg_ptr.p, l.agg_nodes.p, b, l.t.p, c.b.p)));
+    smooth(h, A, i, b, true, nullptr);
+    for (int k = 1; k < A.sweeps; k++) smooth(h, A, i, b, false, nullptr);
+    level_spmv(h, A, i);
+    if (c.N) NS_SWITCH(h->n, (k_restrict<NS><<<cdiv(c.N, 128), 128, 0, s>>>(c.N, l.agg_ptr.p, l.agg_nodes.p, b, l.t.p, c.b.p)));
     cycle(h, A, i + 1, c.b.p, nullptr);
-    NS_SWITCH(h->n, (k_prolong<NS><<<cdiv(l.N, 256), 256, 0, s>>>(l.N, A.alpha, l.agg.p, c.x.p, l.x.p)));
+    if (l.N) NS_SWITCH(h->n, (k_prolong<NS><<<cdiv(l.N, 256), 256, 0, s>>>(l.N, A.alpha, l.agg.p, c.x.p, l.x.p)));
     h->launches += 2;
-    for (int k = 1; k < A.sweeps; k++) smooth(h, A, l, b, false, nullptr);
-    smooth(h, A, l, b, false, out);
+    for (int k = 1; k < A.sweeps; k++) smooth(h, A, i, b, false, nullptr);
+    smooth(h, A, i, b, false, out);
 }
 
 }  // namespace
@@ -664,6 +780,9 @@ void vfvm_amg_setup(vfvm_handle* h) {
         if (const char* e = getenv("VFVM_AMG_THETA")) A.theta = atof(e);
         if (const char* e = getenv("VFVM_AMG_COARSE_SWEEPS")) A.coarse_sweeps = std::max(1, atoi(e));
         if (const char* e = getenv("VFVM_AMG_SWEEPS")) A.sweeps = std::max(1, atoi(e));
+        const int ml_old = A.max_levels;
+        if (const char* e = getenv("VFVM_AMG_MAX_LEVELS")) A.max_levels = std::max(1, atoi(e));
+        if (A.max_levels != ml_old) A.struct_valid = false;
         if (A.theta != theta_old) A.struct_valid = false;
     }
     if (!A.struct_valid || A.pattern_nnz != h->nnz_sell || A.pattern_N != h->Nown || A.L.empty() || A.L[0]->sell_ptr != h->sell_ptr.p) build_hierarchy(h, A);

@@ -98,7 +98,10 @@ __global__ void k_peer_halo(const PeerArgs P, double* __restrict__ x) {
     if (threadIdx.x < P.nn) peer_wait(P.hflag_local + threadIdx.x, P.seq, P.err);
     __syncthreads();
     const int64_t total = P.nhalo * NS;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) x[P.Nown * NS + i] = peer_ld_data(P.halo_local + i);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t c = i / NS;
+        x[P.Nown * NS + i] = peer_ld_data(P.halo_local + peer_halo_pos(P, c) * NS + (i - c * NS));
+    }
 }
 
 // in-place all-reduce (sum or max) of `count` <= VFVM_PEER_RED_W device values: store my values into every rank's box, wait
@@ -130,7 +133,10 @@ static void fill_peer_common(vfvm_handle* h, PeerArgs& P) {
     P.nranks = h->nranks;
     P.rank = h->rank;
     P.ns = h->n;
-    for (int r = 0; r <= P.nn; r++) P.send_ptr[r] = h->send_ptr[r];
+    for (int r = 0; r <= P.nn; r++) {
+        P.send_ptr[r] = h->send_ptr[r];
+        P.recv_ptr0[r] = P.recv_ptrl[r] = h->recv_ptr[r];
+    }
     P.send_idx = h->send_idx.p;
     P.Nown = h->Nown;
     P.nhalo = h->N - h->Nown;
@@ -345,6 +351,57 @@ int vfvm_halo_exchange_ptr(vfvm_handle* h, double* x) {
     }
     int rc = g_nccl.GroupEnd();
     if (rc != ncclSuccess) throw std::string("NCCL halo exchange: ") + g_nccl.GetErrorString(rc);
+    return VFVM_OK;
+}
+
+// exchange arguments of a coarser AMG level: same mailboxes and neighbours as level 0, the level's own (shorter) lists
+PeerArgs vfvm_peer_args_halo_level(vfvm_handle* h, const LevelHalo& c) {
+    PeerArgs P = vfvm_peer_args_halo(h);
+    for (int r = 0; r <= P.nn; r++) {
+        P.send_ptr[r] = c.send_ptr[r];
+        P.recv_ptrl[r] = c.recv_ptr[r];
+    }
+    P.send_idx = c.send_idx.p;
+    P.Nown = c.Nown;
+    P.nhalo = c.nhalo;
+    return P;
+}
+
+// halo refresh of a vector of a coarser AMG level (same neighbours as level 0, shorter lists)
+int vfvm_halo_exchange_level(vfvm_handle* h, LevelHalo& c, double* x) {
+    if (h->nranks <= 1 || h->nb_ranks.empty()) return VFVM_OK;
+    const int ns = h->n, nn = (int)h->nb_ranks.size();
+    if (h->peer_ok) {
+        const PeerArgs P = vfvm_peer_args_halo_level(h, c);
+        const int64_t work = std::max<int64_t>(c.send_ptr[nn], c.nhalo) * ns;
+        const int grid = std::max(1, std::min(cdiv(work, 256), 148));
+        switch (ns) {
+            case 1: k_peer_halo<1><<<grid, 256, 0, h->stream>>>(P, x); break;
+            case 2: k_peer_halo<2><<<grid, 256, 0, h->stream>>>(P, x); break;
+            case 3: k_peer_halo<3><<<grid, 256, 0, h->stream>>>(P, x); break;
+            case 4: k_peer_halo<4><<<grid, 256, 0, h->stream>>>(P, x); break;
+            case 5: k_peer_halo<5><<<grid, 256, 0, h->stream>>>(P, x); break;
+            case 10: k_peer_halo<10><<<grid, 256, 0, h->stream>>>(P, x); break;
+            default: throw std::string("number of species without device instantiation");
+        }
+        h->launches++;
+        return VFVM_OK;
+    }
+    const int64_t nsend = c.send_ptr[nn];
+    if (c.send_buf.n < (size_t)std::max<int64_t>(1, nsend) * ns) c.send_buf.alloc((size_t)std::max<int64_t>(1, nsend) * ns);
+    if (nsend) {
+        k_pack<<<cdiv(nsend * ns, 256), 256, 0, h->stream>>>(nsend, ns, c.send_idx.p, x, c.send_buf.p);
+        h->launches++;
+    }
+    ncclComm_t comm = (ncclComm_t)h->nccl;
+    g_nccl.GroupStart();
+    for (int r = 0; r < nn; r++) {
+        const int64_t s0 = c.send_ptr[r], s1 = c.send_ptr[r + 1], r0 = c.recv_ptr[r], r1 = c.recv_ptr[r + 1];
+        if (s1 > s0) g_nccl.Send(c.send_buf.p + s0 * ns, (size_t)(s1 - s0) * ns, ncclFloat64, h->nb_ranks[r], comm, h->stream);
+        if (r1 > r0) g_nccl.Recv(x + (c.Nown + r0) * ns, (size_t)(r1 - r0) * ns, ncclFloat64, h->nb_ranks[r], comm, h->stream);
+    }
+    int rc = g_nccl.GroupEnd();
+    if (rc != ncclSuccess) throw std::string("NCCL halo exchange (AMG level): ") + g_nccl.GetErrorString(rc);
     return VFVM_OK;
 }
 

@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(LS_THREADS) k_spmv(const SpmvArgs a, const Pee
                 for (int b = 0; b < BATCH; b++)
 #pragma unroll
                     for (int jj = 0; jj < NS; jj++)
-                        xl[b][jj] = Lc[b] >= a.Nown ? peer_ld_data(P.halo_local + (int64_t)(Lc[b] - a.Nown) * NS + jj) : a.x[(int64_t)Lc[b] * NS + jj];
+                        xl[b][jj] = Lc[b] >= a.Nown ? peer_ld_data(P.halo_local + peer_halo_pos(P, Lc[b] - a.Nown) * NS + jj) : a.x[(int64_t)Lc[b] * NS + jj];
             } else {
 #pragma unroll
                 for (int b = 0; b < BATCH; b++)
@@ -579,7 +579,7 @@ void finalize(vfvm_handle* h, const double* part, int nparts, int nvals, int op)
 }
 
 template <int NS, bool DIAGMASK, bool PEER>
-void launch_spmv_k(vfvm_handle* h, SpmvArgs& a, int op) {
+void launch_spmv_k(vfvm_handle* h, SpmvArgs& a, int op, const LevelHalo* lh = nullptr) {
     auto kern = k_spmv<NS, DIAGMASK, PEER>;
     static int occ = 0;
     if (occ == 0) {
@@ -594,7 +594,7 @@ void launch_spmv_k(vfvm_handle* h, SpmvArgs& a, int op) {
         a.part = h->work[10].p;
     }
     PeerArgs P;
-    if constexpr (PEER) P = vfvm_peer_args_halo(h);  // the grid is one resident wave, so the block that finishes the push last can raise the flags
+    if constexpr (PEER) P = lh ? vfvm_peer_args_halo_level(h, *lh) : vfvm_peer_args_halo(h);  // the grid is one resident wave, so the block that finishes the push last can raise the flags
     else memset(&P, 0, sizeof(P));
     kern<<<grid, LS_THREADS, 0, h->stream>>>(a, P);
     h->launches++;
@@ -709,6 +709,25 @@ void vfvm_spmv_level(vfvm_handle* h, SpmvArgs a, const double* x, double* y) {
         NS_DISPATCH(h->n, (launch_spmv_k<NS, true, false>(h, a, OP_NONE)));
     } else {
         NS_DISPATCH(h->n, (launch_spmv_k<NS, false, false>(h, a, OP_NONE)));
+    }
+}
+// the same with the halo of x refreshed first (coarser AMG levels of a distributed hierarchy): over the peer mailboxes the exchange
+// is part of the SpMV kernel, otherwise an NCCL exchange precedes it
+void vfvm_spmv_level_halo(vfvm_handle* h, SpmvArgs a, LevelHalo& lh, double* x, double* y) {
+    if (!h->peer_ok) {
+        vfvm_halo_exchange_level(h, lh, x);
+        vfvm_spmv_level(h, a, x, y);
+        return;
+    }
+    a.x = x;
+    a.y = y;
+    a.w = nullptr;
+    bool diagmask = (h->cF == h->n && h->cD == h->n);
+    for (int i = 0; i < h->n && diagmask; i++) diagmask = (h->idxF[i * h->n + i] == i && h->idxD[i * h->n + i] == i);
+    if (diagmask) {
+        NS_DISPATCH(h->n, (launch_spmv_k<NS, true, true>(h, a, OP_NONE, &lh)));
+    } else {
+        NS_DISPATCH(h->n, (launch_spmv_k<NS, false, true>(h, a, OP_NONE, &lh)));
     }
 }
 SpmvArgs vfvm_spmv_args(vfvm_handle* h) { return make_spmv_args(h); }

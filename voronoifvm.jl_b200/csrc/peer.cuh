@@ -26,6 +26,9 @@ struct PeerArgs {
     int64_t send_ptr[VFVM_PEER_MAX + 1];  // my send list, grouped by neighbour slot
     const int32_t* send_idx;
     int64_t Nown, nhalo;
+    // generic exchange of a coarser level through the level-0 mailbox: neighbour r's values start at recv_ptr0[r] in the mailbox and
+    // at recv_ptrl[r] in the local halo order (equal on level 0)
+    int64_t recv_ptr0[VFVM_PEER_MAX + 1], recv_ptrl[VFVM_PEER_MAX + 1];
     // remote (peer-mapped) addresses per neighbour slot: where MY boundary values / my flag go
     double* halo_dst[VFVM_PEER_MAX];
     unsigned long long* hflag_dst[VFVM_PEER_MAX];
@@ -77,6 +80,13 @@ __device__ __forceinline__ void peer_push(const PeerArgs& P, const double* __res
             for (int r = 0; r < P.nn; r++) peer_st_flag(P.hflag_dst[r], P.seq);
         }
     }
+}
+
+// mailbox position of local halo node c (level 0: the identity)
+__device__ __forceinline__ int64_t peer_halo_pos(const PeerArgs& P, int64_t c) {
+    int r = 0;
+    while (c >= P.recv_ptrl[r + 1]) r++;
+    return P.recv_ptr0[r] + (c - P.recv_ptrl[r]);
 }
 
 // spin until *flag >= seq (bounded); returns false on timeout

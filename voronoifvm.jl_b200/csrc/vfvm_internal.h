@@ -91,6 +91,14 @@ struct Masks {
 static inline bool mask_get(const uint64_t* m, int bit) { return (m[bit >> 6] >> (bit & 63)) & 1ull; }
 static inline void mask_set(uint64_t* m, int bit) { m[bit >> 6] |= (1ull << (bit & 63)); }
 
+// halo description of a coarser AMG level: same neighbour ranks as level 0 (handle), shorter lists
+struct LevelHalo {
+    int64_t Nown = 0, nhalo = 0;
+    std::vector<int64_t> send_ptr, recv_ptr;  // per neighbour slot, nn+1 entries
+    DevBuf<int32_t> send_idx;                 // owned nodes of this level to send, grouped by neighbour
+    DevBuf<double> send_buf;                  // NCCL transport: packed values
+};
+
 // chunking of the pipelined host-vector assembly (vfvm_eval_res_jac with VFVM_HOST)
 struct PipePlan {
     bool valid = false;
@@ -261,6 +269,11 @@ void vfvm_blockinv_level(vfvm_handle* h, const SpmvArgs& a, int64_t N, const dou
 void vfvm_amg_setup(vfvm_handle* h);
 void vfvm_amg_apply(vfvm_handle* h, const double* in, double* out);
 void vfvm_amg_free(vfvm_handle* h);
+int vfvm_halo_exchange_level(vfvm_handle* h, LevelHalo& c, double* x);
+PeerArgs vfvm_peer_args_halo_level(vfvm_handle* h, const LevelHalo& c);
+void vfvm_spmv_level_halo(vfvm_handle* h, SpmvArgs a, LevelHalo& lh, double* x, double* y);
+int vfvm_halo_exchange_ptr(vfvm_handle* h, double* x);
+int vfvm_comm_allreduce_sum(vfvm_handle* h, double* dev, int count);
 PeerArgs vfvm_peer_args_halo(vfvm_handle* h);    // starts a new halo exchange (advances the sequence number)
 PeerArgs vfvm_peer_args_reduce(vfvm_handle* h);  // starts a new reduction
 
