@@ -1,9 +1,7 @@
 #!/bin/bash
-# N-GPU checks (N = $1): parity with peer mailboxes, then the cfg3 bench line with both transports
+# N-GPU run (N = $1): parity script, then the cfg3 bench line with both transports
 N=${1:-8}
 T="timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 $T --master-port 29512 tests/mgpu_check.py > gpurun_out/mgpu_peer_$N.log 2>&1; grep "mgpu_check\|MGPU_OK\|Error\|error" gpurun_out/mgpu_peer_$N.log | head -5
 $T --master-port 29514 bench.py --gpus $N --no-cpu > gpurun_out/bench_${N}gpu_peer.log 2>&1; tail -1 gpurun_out/bench_${N}gpu_peer.log
 VFVM_NO_PEER=1 $T --master-port 29515 bench.py --gpus $N --no-cpu > gpurun_out/bench_${N}gpu_nccl.log 2>&1; tail -1 gpurun_out/bench_${N}gpu_nccl.log
-VFVM_BENCH_PRECON=jacobi $T --master-port 29516 bench.py --gpus $N --no-cpu > gpurun_out/bench_${N}gpu_peer_jacobi.log 2>&1; tail -1 gpurun_out/bench_${N}gpu_peer_jacobi.log
-VFVM_BENCH_PRECON=jacobi VFVM_NO_PEER=1 $T --master-port 29517 bench.py --gpus $N --no-cpu > gpurun_out/bench_${N}gpu_nccl_jacobi.log 2>&1; tail -1 gpurun_out/bench_${N}gpu_nccl_jacobi.log
