@@ -168,3 +168,50 @@ def test_pipelined_bipolar_chunks(chunks, monkeypatch):
         assert np.array_equal(F0, F1) and np.array_equal(A0, A1)
     finally:
         st.close()
+
+
+def _assert_matches_oracle(st, s, U, Uold, tstep, rowscale):
+    F = st.eval_res_jac(U, Uold, tstep=tstep)
+    A = st.matrix("csc")
+    o = O.OracleSystem(s)
+    Fo, Ao = o.assemble(U, Uold, tstep=tstep, nthreads=O.lib().vo_max_threads())
+    assert np.array_equal(A.indptr, Ao.indptr) and np.array_equal(A.indices, Ao.indices)
+    coo = Ao.tocoo()
+    mag = np.where(np.abs(coo.data) < 1e29, np.abs(coo.data), 0.0)
+    termscale = np.bincount(coo.row, weights=mag, minlength=Ao.shape[0])  # magnitude of the summed terms of each row (cancellation allowance)
+    err = np.abs(A.data - Ao.data)
+    assert np.all(err <= 1e-12 * np.abs(Ao.data) + 8 * np.finfo(float).eps * termscale[coo.row])
+    f, fo = F.ravel(order="F"), Fo.ravel(order="F")
+    assert np.all(np.abs(f - fo) <= 1e-12 * np.abs(fo) + 8 * np.finfo(float).eps * (termscale * max(1.0, np.abs(U).max()) + np.abs(fo)))
+
+
+def test_cfg4_full_size_against_oracle():
+    """cfg4 (bipolar drift-diffusion, 129^3 nodes, 3 species, 3 cell regions, implicit Euler): every residual and Jacobian entry of
+    the analytic node-transformed device kernel against the oracle's Dual<6> evaluation of the reference's flux"""
+    import bench
+
+    s, kw, _ = bench.make_system("cfg4", None)
+    st = v.SystemState(s)
+    try:
+        assert st.num_edges == 14827904
+        # a random state: on a smooth field neighbouring nodes with identical values make some Scharfetter-Gummel derivatives exactly
+        # zero, and the reference (and the oracle) do not insert exact zeros (_addnz, src/vfvm_assembly.jl:21-28) while the
+        # device pattern is value independent -- the values agree either way, only explicit zeros would differ
+        U = np.asfortranarray(np.random.default_rng(20261017).uniform(-0.5, 0.5, (3, s.grid.num_nodes)))
+        Uold = np.asfortranarray(U * 0.9 + 0.01)
+        _assert_matches_oracle(st, s, U, Uold, kw["tstep"], 0.1)
+    finally:
+        st.close()
+
+
+def test_cfg5_full_size_against_oracle():
+    """cfg5 (10 decoupled species, 97^3 nodes, implicit Euler): chunked separable kernel against the oracle"""
+    import bench
+
+    s, kw, _ = bench.make_system("cfg5", None)
+    st = v.SystemState(s)
+    try:
+        U = bench.generic_state(s)
+        _assert_matches_oracle(st, s, U, np.asfortranarray(U * 0.5), kw["tstep"], 0.1)
+    finally:
+        st.close()
