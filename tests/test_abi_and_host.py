@@ -105,3 +105,20 @@ def test_system_mirror_bookkeeping():
     assert s.boundary_factors[1, 0] == 0.5 and s.has_legacy_bc()
     u = v.unknowns(s, 0.5)
     assert u.shape == (2, 16) and u.flags.f_contiguous and v.num_dof(s) == 32
+
+
+def test_golden_file_is_consistent():
+    """tests/golden/reference_known_answers.json: every value is asserted by the oracle tests, and (build container only) the literal
+    stands at the cited line of the reference"""
+    import json
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    gold = json.load(open(os.path.join(here, "golden", "reference_known_answers.json")))
+    tests_text = open(os.path.join(here, "test_oracle_golden.py")).read()
+    for key, g in gold.items():
+        assert g["literal"] in tests_text, key
+        assert float(g["literal"]) == g["value"]
+        path, line = g["reference"].rsplit(":", 1)
+        full = os.path.join("/root/reference", path)
+        if os.path.exists(full):
+            assert g["literal"] in open(full).read().splitlines()[int(line) - 1], key
