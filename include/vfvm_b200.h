@@ -203,6 +203,10 @@ int vfvm_linsolve(vfvm_handle* h, double abstol, double reltol, int maxiters, in
 /* y = A x for parity tests of the SpMV kernel; x, y in the given memspace, length = nrows */
 int vfvm_spmv(vfvm_handle* h, const double* x, double* y, int memspace);
 
+/* options of VFVM_PRECON_AMG: opts = {omega, alpha, theta, sweeps, coarse_sweeps, wdepth}, NaN (or a shorter array) keeps a value;
+ * the keyword arguments of AMGPreconBuilder on the host side */
+int vfvm_amg_set_options(vfvm_handle* h, const double* opts, int nopts);
+
 /* ---- K11: Newton update + norms (src/vfvm_solver.jl:116-132) ----------------------------------------- */
 /* SOLUTION -= damp * UPDATE; returns ||UPDATE||_inf and ||SOLUTION_new||_1 */
 int vfvm_newton_update(vfvm_handle* h, double damp, double* update_norm_inf, double* solution_norm1);

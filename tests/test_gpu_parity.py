@@ -553,7 +553,7 @@ def test_amg_multilevel_matches_direct_solve_and_beats_jacobi():
     v.boundary_dirichlet(sys, 1, 6, 0.0)
     ref = O.OracleSystem(sys).solve_step(v.unknowns(sys))
     its = {}
-    for name, pc in (("jacobi", v.JacobiPreconBuilder()), ("amg", v.AMGPreconBuilder())):
+    for name, pc in (("jacobi", v.JacobiPreconBuilder()), ("amg", v.AMGPreconBuilder()), ("amg_w", v.AMGPreconBuilder(wdepth=2, alpha=2.0))):
         st = v.SystemState(sys)
         try:
             sol = v.solve(sys, state=st, inival=0.0, method_linear=v.KrylovJL_CG(precs=pc), reltol_linear=1e-13, abstol_linear=0.0, maxiters_linear=3000)
@@ -562,6 +562,7 @@ def test_amg_multilevel_matches_direct_solve_and_beats_jacobi():
             st.close()
         assert np.max(np.abs(sol - ref)) < TOL_NEWTON, name
     assert 0 < its["amg"] * 3 < its["jacobi"], its
+    assert 0 < its["amg_w"] <= its["amg"], its
 
 
 def test_amg_block_system_bipolar_newton():

@@ -56,6 +56,10 @@ class AMGPreconBuilder:
     examples/DevEx003_Solvers.jl:149-169, examples/DevEx004_EquationBlock3D.jl:225-251"""
     precon = _lib.PRECON_AMG
 
+    def __init__(self, omega=None, alpha=None, theta=None, sweeps=None, coarse_sweeps=None, wdepth=None):
+        nan = float("nan")
+        self.options = [nan if o is None else float(o) for o in (omega, alpha, theta, sweeps, coarse_sweeps, wdepth)]
+
 
 SmoothedAggregationPreconBuilder = AMGPreconBuilder  # same entry point; the device hierarchy uses plain aggregation with an over-weighted correction
 
@@ -188,9 +192,13 @@ def _linear_setup(state: SystemState, control: SolverControl):
         m = DeviceDirectLike()
     if not isinstance(m, _Krylov):
         raise TypeError("method_linear must be one of the device Krylov stand-ins (KrylovJL_BICGSTAB/CG/GMRES) or None")
-    key = (m.krylov, m.precon, getattr(m, "restart", 30))
+    key = (m.krylov, m.precon, getattr(m, "restart", 30), repr(getattr(getattr(m, "precs", None), "options", None)))
     if state.linear_cache != key:
         check(state.h, state.L.vfvm_linsolve_setup(state.h, m.krylov, m.precon, getattr(m, "restart", 30)))
+        opts = getattr(getattr(m, "precs", None), "options", None)
+        if opts is not None:
+            arr = (C.c_double * len(opts))(*opts)
+            check(state.h, state.L.vfvm_amg_set_options(state.h, arr, len(opts)))
         state.linear_cache = key
         fresh = True
     else:
