@@ -400,9 +400,14 @@ def _newton_step(st, system, U, tstep, world):
     if os.environ.get("VFVM_BENCH_PRECON", "amg") == "amg":
         precon = v._lib.PRECON_AMG  # aggregation AMG (csrc/amg.cu); VFVM_BENCH_PRECON=jacobi gives the one-level baseline
     v._lib.check(h, L.vfvm_linsolve_setup(h, krylov, precon, 0))
-    wcycle = precon == v._lib.PRECON_AMG and world == 1 and spd and system.grid.dim == 3 and system.num_species == 1
-    if wcycle:  # W-cycle on the two top coarse levels: halves the CG iterations of the 3D Laplace problem
-        opts = (C.c_double * 6)(*([float("nan")] * 5 + [2.0]))
+    # W-cycle on the top coarse levels where it pays (measured): the single-GPU scalar problems cfg3 (3D Laplace,
+    # two levels) and cfg2 (2D nonlinear Poisson, three levels); V-cycle everywhere else
+    wdepth = 0
+    if precon == v._lib.PRECON_AMG and world == 1 and system.num_species == 1:
+        wdepth = 2 if (spd and system.grid.dim == 3) else (3 if (not spd and system.grid.dim == 2) else 0)
+    wcycle = wdepth > 0
+    if wcycle:
+        opts = (C.c_double * 6)(*([float("nan")] * 5 + [float(wdepth)]))
         v._lib.check(h, L.vfvm_amg_set_options(h, opts, 6))
     iters, resn = C.c_int(), C.c_double()
     assert L.vfvm_assemble(h, 0.0, tstep, 0.0) == 0
@@ -415,7 +420,7 @@ def _newton_step(st, system, U, tstep, world):
     L.vfvm_newton_update(h, 1.0, C.byref(ninf), C.byref(n1))
     dt = time.perf_counter() - t0
     t = st.timings()
-    return {"ms": dt * 1e3, "assemble_ms": float(t[0]), "linsolve_ms": float(t[1] + t[2]), "krylov": ("CG" if spd else "BiCGStab") + {v._lib.PRECON_JACOBI: "+Jacobi", v._lib.PRECON_BLOCKJACOBI: "+block-Jacobi", v._lib.PRECON_AMG: "+aggregation-AMG"}[precon] + (" (W-cycle on levels 1-2)" if wcycle else ""), "reltol": 1e-10, "iters": iters.value,
+    return {"ms": dt * 1e3, "assemble_ms": float(t[0]), "linsolve_ms": float(t[1] + t[2]), "krylov": ("CG" if spd else "BiCGStab") + {v._lib.PRECON_JACOBI: "+Jacobi", v._lib.PRECON_BLOCKJACOBI: "+block-Jacobi", v._lib.PRECON_AMG: "+aggregation-AMG"}[precon] + (f" (W-cycle on levels 1-{wdepth})" if wcycle else ""), "reltol": 1e-10, "iters": iters.value,
             "resnorm": resn.value, "update_norm_inf": ninf.value, "rc": rc}
 
 

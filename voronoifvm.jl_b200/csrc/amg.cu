@@ -58,14 +58,33 @@ struct Level {
     std::vector<int32_t> send_idx_host;
 };
 
+// one captured V-/W-cycle per (input, output) vector pair: Krylov methods call the preconditioner with the same few pairs in every
+// iteration, and the coarse levels are launch-latency bound (a W-cycle on cfg3 is 260 launches), so replaying a CUDA graph
+// removes most of the launch overhead.  Single rank only: the peer exchanges carry a sequence number in their arguments.
+struct CycleGraph {
+    const double* in = nullptr;
+    double* out = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    int64_t launches = 0;
+};
+
 struct Amg {
     std::vector<Level*> L;
+    std::vector<CycleGraph> graphs;
+    int applies = 0;  // applications since the last (re)build of the cycle
+    void drop_graphs() {
+        for (CycleGraph& g : graphs)
+            if (g.exec) cudaGraphExecDestroy(g.exec);
+        graphs.clear();
+        applies = 0;
+    }
     bool struct_valid = false, distributed = false;
     int64_t pattern_nnz = -1, pattern_N = -1;
     double omega = 0.8, alpha = 1.75, theta = 0.08;  // alpha: measured on cfg3 (CG iterations 153 / 101 / 79 / 71 / 69 for alpha = 1 / 1.25 / 1.5 / 1.75 / 2)
     int coarse_sweeps = 4, max_levels = 20, sweeps = 1;
     int wdepth = 0;  // levels 1..wdepth are visited twice per visit of their parent (W-cycle on the top of the hierarchy), 0 = V-cycle  // sweeps: pre- and post-smoothing steps per level
     ~Amg() {
+        drop_graphs();
         for (Level* l : L) delete l;
     }
 };
@@ -665,6 +684,7 @@ void build_coarse_halo(vfvm_handle* h, Amg& A, size_t fi, Level& f, Level& c) {
 }
 
 void build_hierarchy(vfvm_handle* h, Amg& A) {
+    A.drop_graphs();
     for (Level* l : A.L) delete l;
     A.L.clear();
     A.distributed = h->nranks > 1 && !h->nb_ranks.empty() && !getenv("VFVM_AMG_LOCAL");
@@ -809,6 +829,7 @@ void vfvm_amg_setup(vfvm_handle* h) {
         if (const char* e = getenv("VFVM_AMG_MAX_LEVELS")) A.max_levels = std::max(1, atoi(e));
         if (A.max_levels != ml_old) A.struct_valid = false;
         if (A.theta != theta_old) A.struct_valid = false;
+        A.drop_graphs();  // options / matrix pointers may have changed: the cycle is captured again after this setup
     }
     if (!A.struct_valid || A.pattern_nnz != h->nnz_sell || A.pattern_N != h->Nown || A.L.empty() || A.L[0]->sell_ptr != h->sell_ptr.p) build_hierarchy(h, A);
     numeric_setup(h, A);
@@ -832,13 +853,47 @@ extern "C" int vfvm_amg_set_options(vfvm_handle* h, const double* opts, int nopt
     if (have(3)) A.sweeps = std::max(1, (int)opts[3]);
     if (have(4)) A.coarse_sweeps = std::max(1, (int)opts[4]);
     if (have(5)) A.wdepth = std::max(0, (int)opts[5]);
+    A.drop_graphs();
     h->precon_valid = false;
     return VFVM_OK;
 }
 
 void vfvm_amg_apply(vfvm_handle* h, const double* in, double* out) {
     Amg& A = *(Amg*)h->amg;
-    cycle(h, A, 0, in, out);
+    static const bool no_graph = getenv("VFVM_AMG_NO_GRAPH") != nullptr;
+    if (A.distributed || h->nranks > 1 || no_graph || A.applies++ < 2) {  // the first applications run eagerly (occupancy queries, allocations)
+        cycle(h, A, 0, in, out);
+        return;
+    }
+    for (CycleGraph& g : A.graphs)
+        if (g.in == in && g.out == out) {
+            CK(cudaGraphLaunch(g.exec, h->stream));
+            h->launches += g.launches;
+            return;
+        }
+    if (A.graphs.size() >= 8) {  // unexpected number of vector pairs: stay eager
+        cycle(h, A, 0, in, out);
+        return;
+    }
+    CycleGraph g;
+    g.in = in;
+    g.out = out;
+    const int64_t before = h->launches;
+    cudaGraph_t graph = nullptr;
+    CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    try {
+        cycle(h, A, 0, in, out);
+    } catch (...) {
+        cudaStreamEndCapture(h->stream, &graph);
+        if (graph) cudaGraphDestroy(graph);
+        throw;
+    }
+    CK(cudaStreamEndCapture(h->stream, &graph));
+    g.launches = h->launches - before;
+    CK(cudaGraphInstantiate(&g.exec, graph, 0));
+    CK(cudaGraphDestroy(graph));
+    A.graphs.push_back(g);
+    CK(cudaGraphLaunch(g.exec, h->stream));
 }
 
 void vfvm_amg_free(vfvm_handle* h) {
