@@ -7,7 +7,7 @@ nx^3 tensor simplex grid), for anyone who has Julia + VoronoiFVM.jl:
     julia -t auto baseline/reference_timing.jl 65      # nx = 65 is the sample bench.py's CPU baseline uses
 
 It prints the same two figures bench.py reports for its CPU arm: residual+Jacobian assembly throughput in Medges/s
-(evaluate_residual_and_jacobian, src/vfvm_solver.jl:256-260, which calls eval_and_assemble, src/vfvm_assembly.jl:520-643)
+(evaluate_residual_and_jacobian!, src/vfvm_solver.jl:224-243, which calls eval_and_assemble, src/vfvm_assembly.jl:520-643)
 and the time of one Newton step (solve, src/vfvm_solver.jl:665-668; the problem is linear, so one step).
 =#
 using VoronoiFVM, ExtendableGrids, LinearAlgebra, Printf
@@ -25,9 +25,10 @@ function main(nx)
     boundary_dirichlet!(sys, 1, 5, 0.0)
     boundary_dirichlet!(sys, 1, 6, 0.0)
     U = unknowns(sys; inival = 0.5)
-    evaluate_residual_and_jacobian(sys, U)           # first call: pattern build + compilation
+    state = VoronoiFVM.SystemState(sys)               # the matrix pattern lives in the state: steady-state assemblies below
+    VoronoiFVM.evaluate_residual_and_jacobian!(state, U)   # first call: pattern build + compilation (src/vfvm_solver.jl:224-243)
     nedges = num_edges(grid)
-    t = minimum(@elapsed(evaluate_residual_and_jacobian(sys, U)) for _ in 1:3)
+    t = minimum(@elapsed(VoronoiFVM.evaluate_residual_and_jacobian!(state, U)) for _ in 1:3)
     @printf("assembly: %d edges, %.3f ms, %.1f Medges/s on %d threads\n", nedges, 1e3 * t, nedges / t / 1e6, Threads.nthreads())
     solve(sys; inival = 0.0)                          # compilation
     t = @elapsed sol = solve(sys; inival = 0.0, log = true)
