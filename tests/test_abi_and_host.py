@@ -122,3 +122,30 @@ def test_golden_file_is_consistent():
         full = os.path.join("/root/reference", path)
         if os.path.exists(full):
             assert g["literal"] in open(full).read().splitlines()[int(line) - 1], key
+
+
+def test_postprocess_rejects_unregistered_functions_before_touching_the_device():
+    """integrate / edgeintegrate take registered physics objects only (no silent CPU evaluation of arbitrary callbacks)"""
+    X = np.linspace(0, 1, 5)
+    s = v.System(v.simplexgrid(X, X), species=[1])
+    U = np.zeros((1, s.grid.num_nodes))
+    with pytest.raises(v.UnregisteredPhysicsError):
+        v.integrate(s, lambda y, u, node, data=None: None, U)
+    with pytest.raises(v.UnregisteredPhysicsError):
+        v.edgeintegrate(s, lambda y, u, edge, data=None: None, U)
+    with pytest.raises(v.UnregisteredPhysicsError):
+        v.integrate(s, ph.LinearDiffusion(), U)  # a flux is not a node function
+
+
+def test_region_affine_reaction_parameter_block():
+    r = ph.RegionAffineReaction([np.eye(2), 2 * np.eye(2)], [None, [1.0, 2.0]])
+    p = r.params(2)
+    assert p[0] == 2 and p.size == 1 + 2 * (4 + 2)
+    assert np.array_equal(p[1:5], [1, 0, 0, 1]) and np.array_equal(p[5:7], [0, 0]) and np.array_equal(p[11:13], [1, 2])
+
+
+def test_amg_builder_options_vector():
+    b = v.AMGPreconBuilder(wdepth=2, alpha=2.0)
+    assert b.precon == v._lib.PRECON_AMG and len(b.options) == 6
+    assert b.options[1] == 2.0 and b.options[5] == 2.0 and all(o != o for o in (b.options[0], b.options[2], b.options[3], b.options[4]))
+    assert v.SmoothedAggregationPreconBuilder is v.AMGPreconBuilder

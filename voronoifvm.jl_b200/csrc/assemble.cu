@@ -1197,6 +1197,10 @@ int vfvm_eval_res_jac_pipelined(vfvm_handle* h, const double* U, const double* U
     // exactly the kernels' run time).  On 30 % of the grid the chunk kernels still keep up with PCIe and the copies run at
     // full rate beside them (cfg3: 2.51 ms unpipelined, 1.76 ms pipelined on the full grid, 1.5 ms on 30 %).
     const char* gp = getenv("VFVM_PIPE_GRID_PCT");
+    struct GridShare {  // restored on every exit path, also when a launch throws
+        vfvm_handle* h;
+        ~GridShare() { h->grid_pct = 100; }
+    } grid_share{h};
     h->grid_pct = gp ? std::max(1, std::min(100, atoi(gp))) : 30;
     int arrived = -1;  // last piece the main stream has waited for
     for (int c = 0; c < K; c++) {
