@@ -371,8 +371,10 @@ __global__ void __launch_bounds__(ASM_THREADS, (SEP && LIGHT && NS == 1) ? 4 : (
 // Separable fast path (every coupling mask = species diagonal; cfg1/2/3/5).  Species are independent scalar problems on the
 // same graph, so they are processed in chunks of CH species (blockIdx.y = chunk): registers stay low for many-species
 // systems (cfg5: 10 species -> 2 chunks of 5) at the price of re-reading the 12 B/entry index+factor stream per chunk.
-template <int NS, int CH, int FLUX, bool LIGHT>
-__global__ void __launch_bounds__(ASM_THREADS, (LIGHT && CH == 1) ? 4 : (CH <= 5 ? 2 : 1)) k_assemble_rows_sep(const AsmArgs a) {
+// BT: entries per lane in flight (0 = default for the chunk size); rows of 2D grids have at most 6 neighbours, a batch of 6 covers
+// them in one pass without the spills of the 8-wide default
+template <int NS, int CH, int FLUX, bool LIGHT, int BT = 0>
+__global__ void __launch_bounds__(ASM_THREADS, ((LIGHT && CH == 1) || CH == 2) ? 4 : (CH <= 5 ? 2 : 1)) k_assemble_rows_sep(const AsmArgs a) {
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5, nwarps = gridDim.x * wpb;
     const int c0 = blockIdx.y * CH;
@@ -405,7 +407,7 @@ __global__ void __launch_bounds__(ASM_THREADS, (LIGHT && CH == 1) ? 4 : (CH <= 5
             Fr[i] = 0.0;
             Dr[i] = 0.0;
         }
-        constexpr int BATCH = CH == 1 ? 8 : (CH <= 3 ? 4 : 2);
+        constexpr int BATCH = BT ? BT : (CH == 1 ? 8 : (CH <= 3 ? 4 : 2));
         for (int j0 = 0; j0 < w; j0 += BATCH) {
             int Lc[BATCH];
             double fc[BATCH];
@@ -925,7 +927,21 @@ static void launch_rows(vfvm_handle* h, const AsmArgs& a) {
             if constexpr (FLUX == VFVM_FLUX_POWDIFF) {
                 const double m = h->phys.params[h->phys.slot[VFVM_SLOT_FLUX].off + NS];
                 if (m == 2.0 && light) {
+                    if constexpr (NS == 1) {
+                        if (h->group_maxnnz <= 6 && !getenv("VFVM_SEP_BATCH8")) {  // 2D grids: one batch of 6 per row
+                            static int plan6 = 0;
+                            launch_slices_sep(h, k_assemble_rows_sep<NS, CH, FLUX_POWDIFF_SQ, true, 6>, plan6, a, NS / CH);
+                            return;
+                        }
+                    }
                     launch_slices_sep(h, k_assemble_rows_sep<NS, CH, FLUX_POWDIFF_SQ, true>, plan[2], a, NS / CH);
+                    return;
+                }
+            }
+            if constexpr (NS == 10 && FLUX == VFVM_FLUX_DIFFUSION) {
+                if (light && getenv("VFVM_SEP_CH2")) {  // tuning probe: 5 chunks of 2 species, 4 blocks per SM
+                    static int plan2 = 0;
+                    launch_slices_sep(h, k_assemble_rows_sep<NS, 2, FLUX, true>, plan2, a, NS / 2);
                     return;
                 }
             }

@@ -318,6 +318,9 @@ int vfvm_pattern_build(vfvm_handle* h) {
                                                      h->colidx.p, h->nz_edge.p, h->nzfac.p, h->upos.p);
         h->launches++;
         CK(cudaStreamSynchronize(s));
+        std::vector<int32_t> sl = h->sell_ptr.to_host(s);  // widest slice = longest row: the row kernels pick their batch size by it
+        h->group_maxnnz = 0;
+        for (int g = 0; g < nslices; g++) h->group_maxnnz = std::max(h->group_maxnnz, (sl[g + 1] - sl[g]) / 32);
     }
     keys.release();
     vals.release();
