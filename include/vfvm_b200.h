@@ -221,6 +221,10 @@ int vfvm_vector_diffnorm(vfvm_handle* h, int which_a, int which_b, double* norm_
  * (w1pseminorm, :300-312), -2 = the edge average (u_K + u_L) / 2 (test/test120_norms.jl:35-38).  Collective with several ranks. */
 int vfvm_integrate(vfvm_handle* h, int slot, int id, const double* params, int np, int which, double* out);
 int vfvm_edgeintegrate(vfvm_handle* h, int id, const double* params, int np, int which, double* out);
+/* mass_matrix(state), src/vfvm_diffeq_interface.jl:60-101: Jacobian of the registered storage at U = 0 times the node factors;
+ * out (host): one n x n block per owned node, out[(K*n + i)*n + j] = M[(K,i),(K,j)].  eval_rhs! / eval_jacobian! of the ODE
+ * interface (:27-52) are vfvm_eval_res_jac with tstep = Inf and a sign flip on the host side. */
+int vfvm_mass_matrix(vfvm_handle* h, double* out);
 
 /* ---- multi-GPU (one process per GPU; the host shares the NCCL id through its own rendezvous) ------- */
 int vfvm_comm_unique_id(char id_out[128]);

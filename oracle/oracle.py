@@ -181,6 +181,12 @@ class OracleSystem:
         assert self.L.vo_edgeintegrate(self.h, pid, _p(prm, C.c_double), prm.size, _p(u, C.c_double), _p(out, C.c_double)) == 0
         return out.reshape((self.n, self.g.num_cellregions), order="F")
 
+    def mass_matrix(self):
+        """mass_matrix(state) src/vfvm_diffeq_interface.jl:60-101 -> (N, n, n) node blocks"""
+        out = np.zeros(self.n * self.n * self.g.num_nodes)
+        assert self.L.vo_mass_matrix(self.h, _p(out, C.c_double)) == 0
+        return out.reshape((self.g.num_nodes, self.n, self.n))
+
     def initialize(self, U, time=0.0, embed=0.0):
         u = np.asfortranarray(U, dtype=np.float64).ravel(order="F").copy()
         self.L.vo_initialize(self.h, _p(u, C.c_double), C.c_double(time), C.c_double(embed))

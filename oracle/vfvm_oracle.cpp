@@ -35,6 +35,7 @@
 #include <cstring>
 #include <string>
 #include <utility>
+#include <type_traits>
 #include <vector>
 
 #ifdef _OPENMP
@@ -908,6 +909,49 @@ int vo_edgeintegrate(void* h, int id, const double* params, int np, const double
             for (int i = 0; i < n; i++)
                 if (rs[i]) out[(size_t)(edge.region - 1) * n + i] += hh * hh * edge.fac * res[i] / g.dim;  // :138
         }
+    return 0;
+}
+
+// mass_matrix(state), src/vfvm_diffeq_interface.jl:60-101: Jacobian of the storage term at U = 0, weighted by the node factors.
+// out: n x n x N (out[(K*n + i)*n + j] = M[(K,i),(K,j)]); bstorage is not part of the registered library.
+int vo_mass_matrix(void* h, double* out) {
+    System& s = *(System*)h;
+    const Grid& g = s.g;
+    const int n = s.n;
+    std::fill(out, out + (size_t)n * n * g.N, 0.0);
+    NodeCtx node;
+    node.dim = g.dim;
+    auto run = [&](auto tag) {
+        constexpr int NS = decltype(tag)::value;
+        typedef Dual<NS> D;
+        D u[NS], st[NS];
+        for (int K = 0; K < g.N; K++)
+            for (int64_t k = s.nodefactors.colptr[K]; k < s.nodefactors.colptr[K + 1]; k++) {
+                node.index = K;
+                node.region = s.nodefactors.region[k];
+                node.fac = s.nodefactors.fac[k];
+                node.x = &g.coord[(size_t)K * g.dim];
+                for (int i = 0; i < NS; i++) {
+                    u[i] = D(0.0);
+                    u[i].d[i] = 1.0;
+                    st[i] = D(0.0);
+                }
+                eval_storage(s.ph.slot[VFVM_SLOT_STORAGE], NS, st, u, node);
+                const uint8_t* rs = &s.region_species[(size_t)(node.region - 1) * NS];
+                for (int i = 0; i < NS; i++)
+                    for (int j = 0; j < NS; j++)
+                        if (rs[i] && rs[j]) out[((size_t)K * NS + i) * NS + j] += st[i].d[j] * node.fac;
+            }
+    };
+    switch (n) {
+        case 1: run(std::integral_constant<int, 1>()); break;
+        case 2: run(std::integral_constant<int, 2>()); break;
+        case 3: run(std::integral_constant<int, 3>()); break;
+        case 4: run(std::integral_constant<int, 4>()); break;
+        case 5: run(std::integral_constant<int, 5>()); break;
+        case 10: run(std::integral_constant<int, 10>()); break;
+        default: return VFVM_ERR_UNSUPPORTED;
+    }
     return 0;
 }
 

@@ -66,3 +66,44 @@ def test_integrate_rejects_unregistered_functions():
     sys = v.System(_grid(2), species=[1])
     with pytest.raises(v.UnregisteredPhysicsError):
         v.integrate(sys, lambda y, u, node, data=None: None, np.zeros((1, sys.grid.num_nodes)))
+
+
+def test_ode_interface_entry_points():
+    """eval_rhs! / eval_jacobian! / mass_matrix (src/vfvm_diffeq_interface.jl:27-101): -F, -J of the stationary operator and the
+    storage Jacobian at 0 times the node volumes, against the oracle"""
+    X = np.linspace(0, 1, 9)
+    g = v.simplexgrid(X, X)
+    v.cellmask(g, [0.0, 0.0], [0.5, 1.0], 2)
+    s = v.System(g, flux=ph.CrossDiffusion2([1.0, 0.5], 0.1), reaction=ph.BilinearReaction2(0.3), storage=ph.LinearStorage([1.0, 2.0]), species=[1, 2])
+    v.boundary_dirichlet(s, 1, 2, 1.0)
+    rng = np.random.default_rng(2)
+    U = np.asfortranarray(rng.uniform(0.1, 1.0, (2, g.num_nodes)))
+    o = O.OracleSystem(s)
+    Fo, Ao = o.assemble(U, U)
+    st = v.SystemState(s)
+    try:
+        du = v.eval_rhs(st, U.ravel(order="F"))
+        J = v.eval_jacobian(st, U.ravel(order="F"))
+        assert np.allclose(du, -Fo.ravel(order="F"), rtol=1e-12, atol=1e-13)
+        assert np.array_equal(J.indices, Ao.indices) and np.allclose(J.data, -Ao.data, rtol=1e-12, atol=1e-13)
+        M = v.mass_matrix(st)
+        Mo = o.mass_matrix()
+        assert M.ndim == 1  # linear storage: diagonal, like the reference's Diagonal
+        assert np.allclose(M.reshape(g.num_nodes, 2), Mo[:, [0, 1], [0, 1]], rtol=1e-14)
+        assert M.reshape(g.num_nodes, 2)[:, 0].sum() == pytest.approx(1.0, rel=1e-12)  # storage coefficient 1 x volume of the unit square
+    finally:
+        st.close()
+    # non-diagonal storage (bipolar) with three cell regions -> sparse block-diagonal matrix
+    g3 = v.simplexgrid(X, X, X)
+    v.cellmask(g3, [0, 0, 0.3], [1, 1, 0.72], 2)
+    s3 = v.System(g3, flux=ph.BipolarSGFlux(), reaction=ph.BipolarReaction([10.0, 0.0, -10.0]), storage=ph.BipolarStorage(), species=[1, 2, 3])
+    st3 = v.SystemState(s3)
+    try:
+        M3 = v.mass_matrix(st3)
+        Mo3 = O.OracleSystem(s3).mass_matrix()
+        assert not isinstance(M3, np.ndarray)
+        B = M3.toarray() if g3.num_nodes * 3 < 3000 else None
+        d = np.array([M3[3 * K : 3 * K + 3, 3 * K : 3 * K + 3].toarray() for K in range(0, g3.num_nodes, 37)])
+        assert np.allclose(d, Mo3[::37], rtol=1e-13, atol=0)
+    finally:
+        st3.close()

@@ -113,6 +113,37 @@ __global__ void k_integrate_edges(int64_t E, int64_t Nown, int region, int dim, 
     }
 }
 
+// mass_matrix(state), src/vfvm_diffeq_interface.jl:60-101: storage Jacobian at U = 0 times the node factors, one n x n block per node
+template <int NS>
+__global__ void k_mass_matrix(int64_t Nown, const int64_t* __restrict__ colptr, const int32_t* __restrict__ nregion, const double* __restrict__ nfac,
+                              const PhysicsDev* __restrict__ ph, const unsigned short* __restrict__ rsmask, double* __restrict__ out) {
+    const int64_t K = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (K >= Nown) return;
+    typedef Dual<NS> D;
+    D u[NS], st[NS];
+#pragma unroll
+    for (int i = 0; i < NS; i++) {
+        u[i] = D(0.0);
+        u[i].d[i] = 1.0;
+        st[i] = D(0.0);
+    }
+    eval_storage<NS>(ph->slot[VFVM_SLOT_STORAGE].id, ph->params + ph->slot[VFVM_SLOT_STORAGE].off, st, u);  // the registered storages do not depend on the region
+    double M[NS * NS];
+#pragma unroll
+    for (int i = 0; i < NS * NS; i++) M[i] = 0.0;
+    for (int64_t q = colptr[K]; q < colptr[K + 1]; q++) {
+        const unsigned m = rsmask[nregion[q] - 1];
+        const double fac = nfac[q];
+#pragma unroll
+        for (int i = 0; i < NS; i++)
+#pragma unroll
+            for (int j = 0; j < NS; j++)
+                if (((m >> i) & 1u) && ((m >> j) & 1u)) M[i * NS + j] += st[i].d[j] * fac;
+    }
+#pragma unroll
+    for (int i = 0; i < NS * NS; i++) out[K * NS * NS + i] = M[i];
+}
+
 __global__ void k_pp_finalize(const double* __restrict__ part, int nparts, int nvals, double* __restrict__ out) {
     __shared__ double red[32];
     for (int v = 0; v < nvals; v++) {
@@ -200,6 +231,29 @@ extern "C" int vfvm_integrate(vfvm_handle* h, int slot, int id, const double* pa
         CK(cudaSetDevice(h->device));
         return integrate_impl(h, false, slot, id, params, np, which, out);
     })
+}
+
+extern "C" int vfvm_mass_matrix(vfvm_handle* h, double* out) {
+    if (!h || !h->have_geometry || !h->have_system || !out) return vfvm_fail(h, VFVM_ERR_ARG, "vfvm_mass_matrix: geometry and system first");
+    VFVM_TRY(h, {
+        CK(cudaSetDevice(h->device));
+        vfvm_sync_physics(h);
+        const int n = h->n;
+        std::vector<unsigned short> rs(VFVM_MAX_CREGIONS, 0);
+        for (int r = 0; r < h->ncellregions; r++)
+            for (int i = 0; i < n; i++)
+                if (h->region_species[(size_t)r * n + i]) rs[r] |= (unsigned short)(1u << i);
+        DevBuf<unsigned short> drs;
+        drs.upload(rs.data(), rs.size(), h->stream);
+        DevBuf<double> res;
+        res.alloc((size_t)n * n * h->Nown);
+        PP_NS(n, (k_mass_matrix<NS><<<cdiv(h->Nown, 128), 128, 0, h->stream>>>(h->Nown, h->nf_colptr.p, h->nf_region.p, h->nf_fac.p, h->phys_dev.p, drs.p, res.p)));
+        h->launches++;
+        CK(cudaMemcpyAsync(out, res.p, sizeof(double) * n * n * h->Nown, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        CK(cudaGetLastError());
+    })
+    return VFVM_OK;
 }
 
 extern "C" int vfvm_edgeintegrate(vfvm_handle* h, int id, const double* params, int np, int which, double* out) {

@@ -127,3 +127,34 @@ def nodevolumes(system: System, state: SystemState | None = None):
     finally:
         if own:
             st.close()
+
+
+# ---- ODE interface entry points (src/vfvm_diffeq_interface.jl:10-101) on the device twin ---------------------------------
+def eval_rhs(state: SystemState, u, t=0.0):
+    """`eval_rhs!(du, u, state, t)`: du = -residual of the stationary operator (tstep = Inf; the ODE solver owns the time derivative)"""
+    U = np.asarray(u, dtype=np.float64).reshape((state.n, state.N), order="F")
+    return -state.eval_res_jac(U, time=float(t)).ravel(order="F")
+
+
+def eval_jacobian(state: SystemState, u, t=0.0):
+    """`eval_jacobian!(J, u, state, t)`: J = -Jacobian of the stationary operator (CSC, the reference's pattern)"""
+    U = np.asarray(u, dtype=np.float64).reshape((state.n, state.N), order="F")
+    state.eval_res_jac(U, time=float(t))
+    return -state.matrix("csc")
+
+
+def mass_matrix(state: SystemState):
+    """`mass_matrix(state)`: storage Jacobian at U = 0 times the node volumes; a 1D array (the diagonal) if it is diagonal, like the
+    reference's `Diagonal`, else a sparse block-diagonal matrix"""
+    import scipy.sparse as sp
+
+    state.sync()
+    n, N = state.n, state.Nown
+    out = np.zeros(N * n * n)
+    check(state.h, state.L.vfvm_mass_matrix(state.h, out.ctypes.data))
+    blocks = out.reshape((N, n, n))
+    off = blocks.copy()
+    off[:, np.arange(n), np.arange(n)] = 0.0
+    if not off.any():
+        return blocks[:, np.arange(n), np.arange(n)].ravel()
+    return sp.bsr_matrix((blocks, np.arange(N), np.arange(N + 1)), shape=(N * n, N * n)).tocsc()
