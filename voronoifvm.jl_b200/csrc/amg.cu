@@ -72,6 +72,15 @@ struct Amg {
     std::vector<Level*> L;
     std::vector<CycleGraph> graphs;
     int applies = 0;  // applications since the last (re)build of the cycle
+    // what a captured cycle bakes into its kernel arguments: a graph stays valid across numeric setups as long as none of it changes
+    struct Signature {
+        double omega = 0, alpha = 0;
+        int sweeps = 0, coarse_sweeps = 0, wdepth = 0;
+        const void *off0 = nullptr, *diag0 = nullptr;
+        bool operator==(const Signature& o) const {
+            return omega == o.omega && alpha == o.alpha && sweeps == o.sweeps && coarse_sweeps == o.coarse_sweeps && wdepth == o.wdepth && off0 == o.off0 && diag0 == o.diag0;
+        }
+    } captured;
     void drop_graphs() {
         for (CycleGraph& g : graphs)
             if (g.exec) cudaGraphExecDestroy(g.exec);
@@ -829,10 +838,21 @@ void vfvm_amg_setup(vfvm_handle* h) {
         if (const char* e = getenv("VFVM_AMG_MAX_LEVELS")) A.max_levels = std::max(1, atoi(e));
         if (A.max_levels != ml_old) A.struct_valid = false;
         if (A.theta != theta_old) A.struct_valid = false;
-        A.drop_graphs();  // options / matrix pointers may have changed: the cycle is captured again after this setup
     }
     if (!A.struct_valid || A.pattern_nnz != h->nnz_sell || A.pattern_N != h->Nown || A.L.empty() || A.L[0]->sell_ptr != h->sell_ptr.p) build_hierarchy(h, A);
     numeric_setup(h, A);
+    Amg::Signature sig;
+    sig.omega = A.omega;
+    sig.alpha = A.alpha;
+    sig.sweeps = A.sweeps;
+    sig.coarse_sweeps = A.coarse_sweeps;
+    sig.wdepth = A.wdepth;
+    sig.off0 = h->offval.p;
+    sig.diag0 = h->diagval.p;
+    if (!(sig == A.captured)) {  // a new Jacobian in the same buffers keeps the captured cycles; new options or buffers do not
+        A.drop_graphs();
+        A.captured = sig;
+    }
 }
 
 // options of the AMG preconditioner: omega (smoother damping), alpha (weight of the coarse correction), theta (strength threshold),
@@ -853,7 +873,6 @@ extern "C" int vfvm_amg_set_options(vfvm_handle* h, const double* opts, int nopt
     if (have(3)) A.sweeps = std::max(1, (int)opts[3]);
     if (have(4)) A.coarse_sweeps = std::max(1, (int)opts[4]);
     if (have(5)) A.wdepth = std::max(0, (int)opts[5]);
-    A.drop_graphs();
     h->precon_valid = false;
     return VFVM_OK;
 }
