@@ -713,6 +713,7 @@ void build_hierarchy(vfvm_handle* h, Amg& A) {
         // every decision about the depth is taken on rank-summed numbers: all ranks must build the same number of levels
         const double Nglob = global_sum(h, (double)f.N);
         if (Nglob <= 64.0 * h->nranks) break;
+        if (global_sum(h, f.N < 16 ? 1.0 : 0.0) > 0.0) break;  // some rank has (almost) run out of nodes: this level is the coarsest everywhere
         const int64_t Nc = f.N > 0 ? aggregate(h, A, f, A.L.size() == 1) : 0;
         if (f.N == 0) {
             f.agg.alloc(std::max<int64_t>(1, f.Nvec));
