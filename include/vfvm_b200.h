@@ -225,6 +225,10 @@ int vfvm_edgeintegrate(vfvm_handle* h, int id, const double* params, int np, int
  * out (host): one n x n block per owned node, out[(K*n + i)*n + j] = M[(K,i),(K,j)].  eval_rhs! / eval_jacobian! of the ODE
  * interface (:27-52) are vfvm_eval_res_jac with tstep = Inf and a sign flip on the host side. */
 int vfvm_mass_matrix(vfvm_handle* h, double* out);
+/* flux callback of every edge of a resident vector, without form factor: out (host) n x E, out[e*n + i] = flux(u_K, u_L)_i with
+ * K = edge.node[1], L = edge.node[2] -- the edge loop of nodeflux (src/vfvm_postprocess.jl:191-207); the accumulation over the
+ * nodes with the Voronoi face centres is host-side post-processing (voronoifvm.jl_b200/postprocess.py:nodeflux) */
+int vfvm_edgeflux(vfvm_handle* h, int id, const double* params, int np, int which, double* out);
 
 /* ---- multi-GPU (one process per GPU; the host shares the NCCL id through its own rendezvous) ------- */
 int vfvm_comm_unique_id(char id_out[128]);

@@ -181,6 +181,14 @@ class OracleSystem:
         assert self.L.vo_edgeintegrate(self.h, pid, _p(prm, C.c_double), prm.size, _p(u, C.c_double), _p(out, C.c_double)) == 0
         return out.reshape((self.n, self.g.num_cellregions), order="F")
 
+    def edgeflux(self, U, pid, params=()):
+        """flux callback of every edge (no form factor) -> (n, E); the edge loop of nodeflux, src/vfvm_postprocess.jl:191-207"""
+        u = np.ascontiguousarray(np.asarray(U, dtype=np.float64).T).ravel()
+        prm = np.ascontiguousarray(params, dtype=np.float64)
+        out = np.zeros(self.n * self.num_edges)
+        assert self.L.vo_edgeflux(self.h, pid, _p(prm, C.c_double), prm.size, _p(u, C.c_double), _p(out, C.c_double)) == 0
+        return out.reshape((self.n, self.num_edges), order="F")
+
     def mass_matrix(self):
         """mass_matrix(state) src/vfvm_diffeq_interface.jl:60-101 -> (N, n, n) node blocks"""
         out = np.zeros(self.n * self.n * self.g.num_nodes)

@@ -912,6 +912,37 @@ int vo_edgeintegrate(void* h, int id, const double* params, int np, const double
     return 0;
 }
 
+// flux callback of every edge without form factor: out[e*n + i] = flux(u_K, u_L)_i, K = edge.node[1], L = edge.node[2]
+// (the edge loop of nodeflux, src/vfvm_postprocess.jl:191-207)
+int vo_edgeflux(void* h, int id, const double* params, int np, const double* U, double* out) {
+    System& s = *(System*)h;
+    const Grid& g = s.g;
+    const int n = s.n;
+    PhysSlot ps;
+    ps.id = id;
+    ps.p.assign(params, params + np);
+    EdgeCtx edge;
+    edge.dim = g.dim;
+    std::vector<double> res(n), uK(n), uL(n);
+    for (int ie = 0; ie < g.E; ie++) {
+        const int K = g.edgenodes[2 * (size_t)ie], L = g.edgenodes[2 * (size_t)ie + 1];
+        edge.index = ie;
+        edge.nodeK = K;
+        edge.nodeL = L;
+        edge.region = 1;
+        edge.xK = &g.coord[(size_t)K * g.dim];
+        edge.xL = &g.coord[(size_t)L * g.dim];
+        for (int i = 0; i < n; i++) {
+            uK[i] = U[(size_t)K * n + i];
+            uL[i] = U[(size_t)L * n + i];
+            res[i] = 0.0;
+        }
+        eval_flux(ps, n, res.data(), uK.data(), uL.data(), edge);
+        for (int i = 0; i < n; i++) out[(size_t)ie * n + i] = res[i];
+    }
+    return 0;
+}
+
 // mass_matrix(state), src/vfvm_diffeq_interface.jl:60-101: Jacobian of the storage term at U = 0, weighted by the node factors.
 // out: n x n x N (out[(K*n + i)*n + j] = M[(K,i),(K,j)]); bstorage is not part of the registered library.
 int vo_mass_matrix(void* h, double* out) {

@@ -107,3 +107,35 @@ def test_ode_interface_entry_points():
         assert np.allclose(d, Mo3[::37], rtol=1e-13, atol=0)
     finally:
         st3.close()
+
+
+def test_example201_nodeflux_device():
+    """examples/Example201_Laplace2D.jl:33-47 through the device path: solve, nodeflux (flux callback on the device), known answer;
+    and the device edge fluxes against the oracle's on a non-uniform grid with a nonlinear flux"""
+    from test_oracle_golden import example201_system
+
+    s = example201_system()
+    st = v.SystemState(s)
+    try:
+        sol = v.solve(s, state=st, inival=0.0)
+        nf = v.nodeflux(s, sol, state=st)
+        assert nf.shape == (2, 1, s.grid.num_nodes)
+        assert np.linalg.norm(sol) + np.linalg.norm(nf) == pytest.approx(9.63318042491699, rel=1e-12)
+    finally:
+        st.close()
+    X = np.linspace(0, 1, 8) ** 1.5
+    g = v.simplexgrid(X, X)
+    s2 = v.System(g, flux=ph.PowerDiffusion([0.3, 2.0], 3.0), species=[1, 2])
+    U = np.asfortranarray(np.random.default_rng(8).uniform(0.2, 1.0, (2, g.num_nodes)))
+    st2 = v.SystemState(s2)
+    try:
+        prm = np.ascontiguousarray(s2.physics.flux.params(2))
+        dev = np.zeros(2 * st2.num_edges)
+        st2.set_vector(v._lib.VEC_UPDATE, U)
+        v._lib.check(st2.h, st2.L.vfvm_edgeflux(st2.h, s2.physics.flux.id, prm.ctypes.data, prm.size, v._lib.VEC_UPDATE, dev.ctypes.data))
+        ref = O.OracleSystem(s2).edgeflux(U, s2.physics.flux.id, prm)
+        assert np.allclose(dev.reshape((2, st2.num_edges), order="F"), ref, rtol=1e-13, atol=1e-15)
+        nf2 = v.nodeflux(s2, U, state=st2)
+        assert nf2.shape == (2, 2, g.num_nodes) and np.all(np.isfinite(nf2))
+    finally:
+        st2.close()

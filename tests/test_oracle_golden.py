@@ -284,3 +284,33 @@ def test_example221_species_per_region(dim, expected):
     assert sol[1].sum() == pytest.approx(expected, rel=1e-9 if dim < 3 else 5e-5)
     nd = s.node_dof()
     assert np.all(sol[~nd] == 0.0)  # inactive dofs stay zero
+
+
+def example201_system(n=5):
+    """examples/Example201_Laplace2D.jl:22-33 (the Metis partition there only renumbers; the norms do not see it)"""
+    X = np.linspace(0, 1, n + 1)
+    s = v.System(v.simplexgrid(X, X), flux=ph.LinearDiffusion(), is_linear=True)
+    v.enable_species(s, 1, [1])
+    v.boundary_dirichlet(s, 1, 1, 0.0)
+    v.boundary_dirichlet(s, 1, 3, 1.0)
+    return s
+
+
+def test_example201_laplace2d_nodeflux():
+    """examples/Example201_Laplace2D.jl:47: norm(solution) + norm(nodeflux) = 9.63318042491699 (nodeflux restated with the oracle's edge
+    fluxes and the Voronoi face centres of voronoifvm.jl_b200/postprocess.py)"""
+    from vfvm_b200 import postprocess as pp
+
+    s = example201_system()
+    g = s.grid
+    o = O.OracleSystem(s)
+    sol = o.solve_step(v.unknowns(s, inival=0.0))
+    fl = o.edgeflux(sol, ph.FLUX_DIFFUSION, [1.0])
+    en = o.edgenodes()
+    cp, _, ef = o.edgefactors()
+    efac = np.add.reduceat(np.append(ef, 0.0), cp[:-1]) * (cp[1:] > cp[:-1])
+    ncp, _, nf = o.nodefactors()
+    nfl = pp._nodeflux_from_edgeflux(g, en, pp.voronoi_face_centers(g, en, o.celledges()), efac, np.add.reduceat(nf, ncp[:-1]), fl)
+    assert nfl.shape == (2, 1, g.num_nodes)
+    assert np.linalg.norm(sol) + np.linalg.norm(nfl) == pytest.approx(9.63318042491699, rel=1e-13)
+    assert np.allclose(nfl[1, 0], -1.0, atol=1e-13) and np.allclose(nfl[0, 0], 0.0, atol=1e-13)  # exact for the linear solution u = y

@@ -16,4 +16,4 @@ from .solver import (SolverControl, NewtonSolverHistory, TransientSolution, solv
                      KrylovJL_BICGSTAB, KrylovJL_CG, KrylovJL_GMRES, JacobiPreconBuilder, BlockPreconBuilder, ILUZeroPreconBuilder, AMGPreconBuilder, SmoothedAggregationPreconBuilder,
                      DeviceDirectLike)
 from . import postprocess  # noqa: F401,E402
-from .postprocess import (integrate, edgeintegrate, lpnorm, l2norm, w1pseminorm, h1seminorm, w1pnorm, h1norm, nodevolumes, eval_rhs, eval_jacobian, mass_matrix)  # noqa: F401,E402
+from .postprocess import (integrate, edgeintegrate, lpnorm, l2norm, w1pseminorm, h1seminorm, w1pnorm, h1norm, nodevolumes, eval_rhs, eval_jacobian, mass_matrix, nodeflux)  # noqa: F401,E402

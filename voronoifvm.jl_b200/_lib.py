@@ -59,6 +59,7 @@ SIGNATURES = {
     "vfvm_init_dirichlet": [_H, C.c_double, C.c_double],
     "vfvm_assemble": [_H, C.c_double, C.c_double, C.c_double],
     "vfvm_mass_matrix": [_H, C.c_void_p],
+    "vfvm_edgeflux": [_H, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p],
     "vfvm_amg_set_options": [_H, C.c_void_p, C.c_int],
     "vfvm_integrate": [_H, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p],
     "vfvm_edgeintegrate": [_H, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p],

@@ -144,6 +144,24 @@ __global__ void k_mass_matrix(int64_t Nown, const int64_t* __restrict__ colptr, 
     for (int i = 0; i < NS * NS; i++) out[K * NS * NS + i] = M[i];
 }
 
+// flux callback of every edge without form factor (edge loop of nodeflux, src/vfvm_postprocess.jl:191-207): out[e*NS + i]
+template <int NS, int FLUX>
+__global__ void k_edge_flux(int64_t E, const int32_t* __restrict__ edgenodes, const double* __restrict__ U, const FnArgs fn, double* __restrict__ out) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    const int K = edgenodes[2 * e], L = edgenodes[2 * e + 1];
+    double uK[NS], uL[NS], f[NS];
+#pragma unroll
+    for (int i = 0; i < NS; i++) {
+        uK[i] = U[(int64_t)K * NS + i];
+        uL[i] = U[(int64_t)L * NS + i];
+        f[i] = 0.0;
+    }
+    eval_flux<FLUX, NS>(fn.p, f, uK, uL);
+#pragma unroll
+    for (int i = 0; i < NS; i++) out[e * NS + i] = f[i];
+}
+
 __global__ void k_pp_finalize(const double* __restrict__ part, int nparts, int nvals, double* __restrict__ out) {
     __shared__ double red[32];
     for (int v = 0; v < nvals; v++) {
@@ -192,6 +210,27 @@ void launch_edges_ns(vfvm_handle* h, int region, const double* U, const FnArgs& 
     }
 }
 
+template <int NS, int FLUX>
+void launch_edge_flux(vfvm_handle* h, const double* U, const FnArgs& fn, double* out) {
+    if constexpr (flux_supported(FLUX, NS)) {
+        k_edge_flux<NS, FLUX><<<cdiv(h->E, 256), 256, 0, h->stream>>>(h->E, h->edgenodes.p, U, fn, out);
+    } else {
+        throw std::string("flux id ") + std::to_string(FLUX) + " has no device instantiation for " + std::to_string(NS) + " species";
+    }
+}
+template <int NS>
+void launch_edge_flux_ns(vfvm_handle* h, const double* U, const FnArgs& fn, double* out) {
+    switch (fn.id) {
+        case VFVM_FLUX_DIFFUSION: launch_edge_flux<NS, VFVM_FLUX_DIFFUSION>(h, U, fn, out); break;
+        case VFVM_FLUX_POWDIFF: launch_edge_flux<NS, VFVM_FLUX_POWDIFF>(h, U, fn, out); break;
+        case VFVM_FLUX_CROSSDIFF2: launch_edge_flux<NS, VFVM_FLUX_CROSSDIFF2>(h, U, fn, out); break;
+        case VFVM_FLUX_SG_UNIPOLAR: launch_edge_flux<NS, VFVM_FLUX_SG_UNIPOLAR>(h, U, fn, out); break;
+        case VFVM_FLUX_SEDAN: launch_edge_flux<NS, VFVM_FLUX_SEDAN>(h, U, fn, out); break;
+        case VFVM_FLUX_SG_BIPOLAR: launch_edge_flux<NS, VFVM_FLUX_SG_BIPOLAR>(h, U, fn, out); break;
+        default: throw std::string("unregistered flux id");
+    }
+}
+
 int integrate_impl(vfvm_handle* h, bool edges, int slot, int id, const double* params, int np, int which, double* out) {
     if (np < 0 || np > VFVM_MAX_PARAMS) return vfvm_fail(h, VFVM_ERR_ARG, "too many parameters");
     FnArgs fn;
@@ -231,6 +270,29 @@ extern "C" int vfvm_integrate(vfvm_handle* h, int slot, int id, const double* pa
         CK(cudaSetDevice(h->device));
         return integrate_impl(h, false, slot, id, params, np, which, out);
     })
+}
+
+extern "C" int vfvm_edgeflux(vfvm_handle* h, int id, const double* params, int np, int which, double* out) {
+    if (!h || !h->have_geometry || !h->have_system || !out || which < 0 || which > 3 || np < 0 || np > VFVM_MAX_PARAMS)
+        return vfvm_fail(h, VFVM_ERR_ARG, "vfvm_edgeflux: geometry and system first; vector id 0..3");
+    if (!h->vec[which].p) return vfvm_fail(h, VFVM_ERR_STATE, "vector not set (vfvm_build_pattern allocates the resident vectors)");
+    VFVM_TRY(h, {
+        CK(cudaSetDevice(h->device));
+        FnArgs fn;
+        memset(&fn, 0, sizeof(fn));
+        fn.slot = VFVM_SLOT_FLUX;
+        fn.id = id;
+        fn.np = np;
+        for (int i = 0; i < np; i++) fn.p[i] = params[i];
+        DevBuf<double> res;
+        res.alloc((size_t)h->n * std::max<int64_t>(1, h->E));
+        if (h->E) PP_NS(h->n, (launch_edge_flux_ns<NS>(h, h->vec[which].p, fn, res.p)));
+        h->launches++;
+        CK(cudaMemcpyAsync(out, res.p, sizeof(double) * h->n * h->E, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        CK(cudaGetLastError());
+    })
+    return VFVM_OK;
 }
 
 extern "C" int vfvm_mass_matrix(vfvm_handle* h, double* out) {

@@ -158,3 +158,67 @@ def mass_matrix(state: SystemState):
     if not off.any():
         return blocks[:, np.arange(n), np.arange(n)].ravel()
     return sp.bsr_matrix((blocks, np.arange(N), np.arange(N + 1)), shape=(N * n, N * n)).tocsc()
+
+
+# ---- nodeflux (src/vfvm_postprocess.jl:167-252) ------------------------------------------------------------------------------
+def voronoi_face_centers(grid, edgenodes, celledges):
+    """x_sigma per edge, the point of the Voronoi face the "magic formula" (Eymard/Gallouet/Herbin 2006, Lemma 2.4) is evaluated at.
+    ExtendableGrids' `VoronoiFaceCenters` is not under /root/reference; restated here as: 1D the edge midpoint; 2D the midpoint of the
+    two adjacent triangles' circumcentres for interior edges and the edge midpoint for boundary edges.  PARITY UNPINNED beyond the
+    reference's known answer of Example201 (uniform grid, where every consistent choice coincides); 3D is not provided."""
+    x = grid.coord
+    mid = 0.5 * (x[:, edgenodes[0]] + x[:, edgenodes[1]])
+    if grid.dim == 1:
+        return mid
+    if grid.dim != 2:
+        raise NotImplementedError("nodeflux: Voronoi face centres are restated for 1D and 2D grids only")
+    a, b, c = (x[:, grid.cellnodes[k]] for k in range(3))
+    d = 2.0 * (a[0] * (b[1] - c[1]) + b[0] * (c[1] - a[1]) + c[0] * (a[1] - b[1]))
+    a2, b2, c2 = (a * a).sum(0), (b * b).sum(0), (c * c).sum(0)
+    cc = np.stack([(a2 * (b[1] - c[1]) + b2 * (c[1] - a[1]) + c2 * (a[1] - b[1])) / d, (a2 * (c[0] - b[0]) + b2 * (a[0] - c[0]) + c2 * (b[0] - a[0])) / d])
+    E = edgenodes.shape[1]
+    acc, cnt = np.zeros((2, E)), np.zeros(E)
+    for k in range(3):
+        np.add.at(acc[0], celledges[k], cc[0])
+        np.add.at(acc[1], celledges[k], cc[1])
+        np.add.at(cnt, celledges[k], 1.0)
+    return np.where(cnt >= 2, acc / np.maximum(cnt, 1.0), mid)
+
+
+def _nodeflux_from_edgeflux(grid, edgenodes, xsigma, efac, nodevol, flux):
+    """nodeflux[:, i, K] += fac f_i (x_sigma - x_K), nodeflux[:, i, L] -= fac f_i (x_sigma - x_L), then / nodevol (:204-217)"""
+    n, dim, N = flux.shape[0], grid.dim, grid.num_nodes
+    K, L = edgenodes[0], edgenodes[1]
+    out = np.zeros((dim, n, N))
+    dK, dL = xsigma - grid.coord[:, K], xsigma - grid.coord[:, L]
+    for d in range(dim):
+        for i in range(n):
+            w = efac * flux[i]
+            np.add.at(out[d, i], K, w * dK[d])
+            np.add.at(out[d, i], L, -w * dL[d])
+    return out / nodevol[None, None, :]
+
+
+def nodeflux(system: System, U, F=None, state: SystemState | None = None):
+    """`nodeflux(system, U)` / `nodeflux(system, F, U)`: reconstruction of the edge flux as a vector field on the nodes -> (dim, nspecies, nnodes).
+    The flux callback runs on the device (`vfvm_edgeflux`); the accumulation with the Voronoi face centres is host-side post-processing."""
+    F = system.physics.flux if F is None else F
+    if not (isinstance(F, RegisteredPhysics) and F.slot == SLOT_FLUX):
+        raise UnregisteredPhysicsError("nodeflux: the flux must be a registered flux object")
+    st, own = _with_state(system, state)
+    try:
+        st.sync()
+        st.set_vector(_lib.VEC_UPDATE, np.asfortranarray(np.asarray(U, dtype=np.float64)))
+        prm = np.ascontiguousarray(F.params(system.num_species), dtype=np.float64)
+        flux = np.zeros(st.n * st.num_edges)
+        check(st.h, st.L.vfvm_edgeflux(st.h, F.id, prm.ctypes.data if prm.size else None, prm.size, _lib.VEC_UPDATE, flux.ctypes.data))
+        en = st.edgenodes()
+        cp, _, ef = st.edgefactors()
+        efac = np.add.reduceat(np.append(ef, 0.0), cp[:-1]) * (cp[1:] > cp[:-1])
+        np_, _, nf = st.nodefactors()
+        nodevol = np.add.reduceat(nf, np_[:-1])
+        xs = voronoi_face_centers(system.grid, en, st.celledges())
+        return _nodeflux_from_edgeflux(system.grid, en, xs, efac, nodevol, flux.reshape((st.n, st.num_edges), order="F"))
+    finally:
+        if own:
+            st.close()
