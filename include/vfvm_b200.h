@@ -195,11 +195,19 @@ int vfvm_eval_res_jac(vfvm_handle* h, const double* U, const double* UOld, doubl
                       double time, double tstep, double lambda);
 int vfvm_get_nzval_csr(vfvm_handle* h, double* nzval, int memspace);
 int vfvm_get_nzval_csc(vfvm_handle* h, double* nzval, int memspace);
+/* scalar CSR rows (pattern + values) of the owned nodes [node0, node1) only: the rows SparseMatrixCSC(flush!(matrix)) holds for these
+ * nodes (src/vfvm_solver.jl:242), without moving the whole Jacobian to the host.  Call with colidx == NULL to get *nnz first;
+ * rowptr has (node1 - node0) * nspecies + 1 offsets starting at 0, colidx are local dof numbers. */
+int vfvm_get_rows_csr(vfvm_handle* h, int64_t node0, int64_t node1, int64_t* nnz, int64_t* rowptr, int64_t* colidx, double* nzval);
 
 /* ---- K8-K10: _solve_linear! (src/vfvm_linsolve.jl:6-61): solve A * UPDATE = RESIDUAL --------------- */
 int vfvm_linsolve_setup(vfvm_handle* h, int krylov, int precon, int gmres_restart);
 int vfvm_linsolve(vfvm_handle* h, double abstol, double reltol, int maxiters, int reuse_precs, int* iters,
                   double* resnorm);
+/* did the last vfvm_linsolve reach its tolerance (1) or stop at maxiters (0)?  rhs_norm = ||RESIDUAL||_2 it was measured against.
+ * Hitting maxiters is not an error of vfvm_linsolve (Krylov.jl under LinearSolve behaves the same, the Newton loop judges the update);
+ * the stand-in for the reference's default direct solver (UMFPACK, src/vfvm_solver.jl:34-41) turns it into a LinearSolverError. */
+int vfvm_linsolve_status(vfvm_handle* h, int* converged, double* rhs_norm);
 /* y = A x for parity tests of the SpMV kernel; x, y in the given memspace, length = nrows */
 int vfvm_spmv(vfvm_handle* h, const double* x, double* y, int memspace);
 

@@ -62,6 +62,36 @@ def test_integrals_match_the_oracle_multiregion_multispecies():
         st.close()
 
 
+def test_integrals_respect_species_enabled_per_region():
+    """enable_species!(sys, i, regions): a species contributes to integral[i, region] only where it is enabled
+    (assemble_res -> isregionspecies, src/vfvm_assemblydata.jl:310-332, 385-405); affine node function with F(0) != 0"""
+    X = np.linspace(0, 1, 11)
+    g = v.simplexgrid(X, X, X)
+    v.cellmask(g, [0, 0, 0.3], [1, 1, 0.7], 2)
+    v.cellmask(g, [0, 0, 0.7], [1, 1, 1.0], 3)
+    R = np.array([[1.0, 0.2, 0.0], [0.1, 2.0, 0.3], [0.0, 0.4, 3.0]])
+    sys = v.System(g, flux=ph.LinearDiffusion([1.0, 2.0, 3.0]), reaction=ph.AffineReaction(R, [0.5, -0.25, 1.5]))
+    v.enable_species(sys, 1, [1])
+    v.enable_species(sys, 2, [1, 2, 3])
+    v.enable_species(sys, 3, [3])
+    U = np.asfortranarray(np.random.default_rng(5).uniform(0.1, 1.0, (3, g.num_nodes)))
+    o = O.OracleSystem(sys)
+    st = v.SystemState(sys)
+    try:
+        for F in (None, sys.physics.reaction):
+            dev = v.integrate(sys, U, state=st) if F is None else v.integrate(sys, F, U, state=st)
+            ref = o.integrate(U) if F is None else o.integrate(U, F.slot, F.id, F.params(3))
+            assert np.all(np.abs(dev - ref) <= 1e-12 * np.abs(ref) + 1e-14), (F, dev, ref)
+            assert dev[0, 1] == 0.0 and dev[0, 2] == 0.0 and dev[2, 0] == 0.0 and dev[2, 1] == 0.0  # disabled (species, region) pairs stay empty
+        for F in (sys.physics.flux, v.postprocess.W1pIntegrand(2.0), v.postprocess.EdgeAverage()):
+            dev = v.edgeintegrate(sys, F, U, state=st)
+            ref = o.edgeintegrate(U, F.id, F.params(3))
+            assert np.all(np.abs(dev - ref) <= 1e-12 * np.abs(ref) + 1e-13), (F, dev, ref)
+            assert dev[0, 1] == 0.0 and dev[2, 0] == 0.0
+    finally:
+        st.close()
+
+
 def test_integrate_rejects_unregistered_functions():
     sys = v.System(_grid(2), species=[1])
     with pytest.raises(v.UnregisteredPhysicsError):

@@ -71,8 +71,10 @@ SIGNATURES = {
     "vfvm_eval_res_jac": [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double],
     "vfvm_get_nzval_csr": [_H, C.c_void_p, C.c_int],
     "vfvm_get_nzval_csc": [_H, C.c_void_p, C.c_int],
+    "vfvm_get_rows_csr": [_H, C.c_int64, C.c_int64, _I64, _I64, _I64, _D],
     "vfvm_linsolve_setup": [_H, C.c_int, C.c_int, C.c_int],
     "vfvm_linsolve": [_H, C.c_double, C.c_double, C.c_int, C.c_int, _p(C.c_int), _D],
+    "vfvm_linsolve_status": [_H, _p(C.c_int), _D],
     "vfvm_spmv": [_H, C.c_void_p, C.c_void_p, C.c_int],
     "vfvm_newton_update": [_H, C.c_double, _D, _D],
     "vfvm_vector_norms": [_H, C.c_int, _D, _D],

@@ -81,11 +81,13 @@ struct Amg {
             return omega == o.omega && alpha == o.alpha && sweeps == o.sweeps && coarse_sweeps == o.coarse_sweeps && wdepth == o.wdepth && off0 == o.off0 && diag0 == o.diag0;
         }
     } captured;
+    vfvm_handle* owner = nullptr;
     void drop_graphs() {
         for (CycleGraph& g : graphs)
             if (g.exec) cudaGraphExecDestroy(g.exec);
         graphs.clear();
         applies = 0;
+        if (owner) owner->graph_epoch++;  // a captured Krylov iteration contains this cycle
     }
     bool struct_valid = false, distributed = false;
     int64_t pattern_nnz = -1, pattern_N = -1;
@@ -827,6 +829,7 @@ void vfvm_amg_setup(vfvm_handle* h) {
     if (!h->nzfac.p) throw std::string("AMG needs the edge-factor plane of the pattern");
     if (!h->amg) h->amg = new Amg();
     Amg& A = *(Amg*)h->amg;
+    A.owner = h;
     {  // tuning knobs (read at every setup so that a probe can sweep them)
         const double theta_old = A.theta;
         if (const char* e = getenv("VFVM_AMG_OMEGA")) A.omega = atof(e);
@@ -864,6 +867,8 @@ extern "C" int vfvm_amg_set_options(vfvm_handle* h, const double* opts, int nopt
     if (!h || !opts || nopts < 0 || nopts > 6) return VFVM_ERR_ARG;
     if (!h->amg) h->amg = new Amg();
     Amg& A = *(Amg*)h->amg;
+    A.owner = h;
+    h->graph_epoch++;
     auto have = [&](int k) { return k < nopts && opts[k] == opts[k]; };
     if (have(0)) A.omega = opts[0];
     if (have(1)) A.alpha = opts[1];
@@ -881,6 +886,10 @@ extern "C" int vfvm_amg_set_options(vfvm_handle* h, const double* opts, int nopt
 void vfvm_amg_apply(vfvm_handle* h, const double* in, double* out) {
     Amg& A = *(Amg*)h->amg;
     static const bool no_graph = getenv("VFVM_AMG_NO_GRAPH") != nullptr;
+    if (h->in_capture) {  // part of a captured Krylov iteration (linsolve.cu): plain kernels
+        cycle(h, A, 0, in, out);
+        return;
+    }
     if (A.distributed || h->nranks > 1 || no_graph || A.applies++ < 2) {  // the first applications run eagerly (occupancy queries, allocations)
         cycle(h, A, 0, in, out);
         return;

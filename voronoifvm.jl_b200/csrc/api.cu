@@ -60,6 +60,7 @@ extern "C" void vfvm_destroy(vfvm_handle* h) {
     vfvm_comm_destroy(h);
     if (h->stream) cudaStreamSynchronize(h->stream);
     vfvm_amg_free(h);
+    if (h->iter_graph) cudaGraphExecDestroy((cudaGraphExec_t)h->iter_graph);
     if (h->flags_host) cudaFreeHost(h->flags_host);
     if (h->red_host) cudaFreeHost(h->red_host);
     for (cudaEvent_t e : h->pipe_ev) cudaEventDestroy(e);
@@ -397,6 +398,7 @@ extern "C" int vfvm_init_dirichlet(vfvm_handle* h, double time, double lambda) {
         if (rc == VFVM_OK && h->nranks > 1) {  // halo copies of Dirichlet nodes follow their owners
             vfvm_halo_exchange_ptr(h, h->vec[VFVM_VEC_SOLUTION].p);
             CK(cudaStreamSynchronize(h->stream));
+            if (int prc = vfvm_peer_check(h)) return prc;
         }
         return rc;
     })

@@ -1112,7 +1112,8 @@ int vfvm_assemble_impl(vfvm_handle* h, double time, double tstep, double lambda,
         launch_bnodes_range(h, b, 0, h->nbnodes);
     }
     CK(cudaEventRecord(h->ev2, s));
-    h->precon_valid = false;
+    // the preconditioner of the previous Jacobian stays valid for `reuse_precs` solves (factorize_every_newtonstep = false,
+    // src/vfvm_solver.jl:99): it is rebuilt whenever vfvm_linsolve is called without reuse, and invalidated by pattern / option changes
     h->asm_pending = true;
     if (async) return VFVM_OK;
     return vfvm_assemble_finish(h);
@@ -1236,7 +1237,6 @@ int vfvm_eval_res_jac_pipelined(vfvm_handle* h, const double* U, const double* U
     CK(cudaEventRecord(h->ev1, s));
     CK(cudaEventRecord(h->ev2, s));
     if (!have_old) CK(cudaMemcpyAsync(dO, dU, sizeof(double) * n * h->N, cudaMemcpyDeviceToDevice, s));
-    h->precon_valid = false;
     h->asm_pending = true;
     static const bool trace = getenv("VFVM_PIPE_TRACE") != nullptr;  // diagnostic: when each stream finished, relative to the start
     cudaEvent_t t_in = nullptr, t_out = nullptr;

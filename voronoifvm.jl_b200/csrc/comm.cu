@@ -75,6 +75,8 @@ __global__ void k_pack(int64_t cnt, int ns, const int32_t* __restrict__ idx, con
     buf[i] = x[(int64_t)idx[q] * ns + s];
 }
 
+__global__ void k_clear_bits(int32_t* w, int32_t bits) { atomicAnd(w, ~bits); }
+
 // ---- peer mailboxes (peer.cuh) ---------------------------------------------------------------------------------------
 struct BoxLayout {
     size_t dir, hflag, rflag, red, halo;
@@ -94,13 +96,15 @@ BoxLayout box_layout(int R) {
 // generic halo refresh of a vector through the mailboxes, one kernel: push, raise flags, wait for the neighbours, unpack
 template <int NS>
 __global__ void k_peer_halo(const PeerArgs P, double* __restrict__ x) {
-    peer_push<NS>(P, x);
-    if (threadIdx.x < P.nn) peer_wait(P.hflag_local + threadIdx.x, P.seq, P.err);
+    const unsigned long long seq = peer_seq(P);
+    peer_push<NS>(P, seq, x);
+    if (threadIdx.x < P.nn) peer_wait(peer_hflag_local(P, seq) + threadIdx.x, seq, P.err, P.timeout_ns);
     __syncthreads();
     const int64_t total = P.nhalo * NS;
+    const double* __restrict__ box = peer_halo_local(P, seq);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t c = i / NS;
-        x[P.Nown * NS + i] = peer_ld_data(P.halo_local + peer_halo_pos(P, c) * NS + (i - c * NS));
+        x[P.Nown * NS + i] = peer_ld_data(box + peer_halo_pos(P, c) * NS + (i - c * NS));
     }
 }
 
@@ -108,17 +112,12 @@ __global__ void k_peer_halo(const PeerArgs P, double* __restrict__ x) {
 // for every rank's values in mine, combine in rank order
 __global__ void k_peer_allreduce(const PeerArgs P, double* __restrict__ vals, int count, int ismax) {
     const int t = threadIdx.x;
-    if (t < P.nranks) {
-        for (int v = 0; v < count; v++) P.red_dst[t][v] = vals[v];
-        __threadfence_system();
-        peer_st_flag(P.rflag_dst[t], P.seq);
-        peer_wait(P.rflag_local + t, P.seq, P.err);
-    }
-    __syncthreads();
+    const unsigned long long seq = peer_seq(P);
+    const double* red = peer_reduce_exchange(P, seq, vals, count);
     if (t < count) {
-        double acc = peer_ld_data(P.red_local + t);
+        double acc = peer_ld_data(red + t);
         for (int q = 1; q < P.nranks; q++) {
-            const double v = peer_ld_data(P.red_local + (size_t)q * VFVM_PEER_RED_W + t);
+            const double v = peer_ld_data(red + (size_t)q * VFVM_PEER_RED_W + t);
             acc = ismax ? fmax(acc, v) : acc + v;
         }
         vals[t] = acc;
@@ -142,37 +141,40 @@ static void fill_peer_common(vfvm_handle* h, PeerArgs& P) {
     P.nhalo = h->N - h->Nown;
     P.push_count = h->peer_counter.p;
     P.err = h->flags.p;
+    P.timeout_ns = h->peer_timeout_ns;
 }
 
 PeerArgs vfvm_peer_args_halo(vfvm_handle* h) {
     PeerArgs P;
     fill_peer_common(h, P);
-    P.seq = ++h->halo_seq;
-    const int par = (int)(P.seq & 1), R = h->nranks;
+    P.seq_ctr = h->peer_seq.p;
+    const int R = h->nranks;
     const BoxLayout b = box_layout(R);
     for (int r = 0; r < P.nn; r++) {
         char* base = h->peer_base[h->nb_ranks[r]];
-        P.halo_dst[r] = (double*)(base + b.halo) + (size_t)par * h->peer_halo_doubles[r] + (size_t)h->peer_recv_off[r] * h->n;
-        P.hflag_dst[r] = (unsigned long long*)(base + b.hflag) + (size_t)par * R + h->peer_slot[r];
+        P.halo_dst[r] = (double*)(base + b.halo) + (size_t)h->peer_recv_off[r] * h->n;
+        P.halo_dst_stride[r] = h->peer_halo_doubles[r];
+        P.hflag_dst[r] = (unsigned long long*)(base + b.hflag) + h->peer_slot[r];
     }
-    P.halo_local = (const double*)(h->peer_box + b.halo) + (size_t)par * (size_t)P.nhalo * h->n;
-    P.hflag_local = (const unsigned long long*)(h->peer_box + b.hflag) + (size_t)par * R;
+    P.halo_local = (const double*)(h->peer_box + b.halo);
+    P.halo_local_stride = (h->N - h->Nown) * h->n;
+    P.hflag_local = (const unsigned long long*)(h->peer_box + b.hflag);
     return P;
 }
 
 PeerArgs vfvm_peer_args_reduce(vfvm_handle* h) {
     PeerArgs P;
     fill_peer_common(h, P);
-    P.seq = ++h->red_seq;
-    const int par = (int)(P.seq & 1), R = h->nranks;
+    P.seq_ctr = h->peer_seq.p + 1;
+    const int R = h->nranks;
     const BoxLayout b = box_layout(R);
     for (int q = 0; q < R; q++) {
         char* base = h->peer_base[q];
-        P.red_dst[q] = (double*)(base + b.red) + ((size_t)par * R + h->rank) * VFVM_PEER_RED_W;
-        P.rflag_dst[q] = (unsigned long long*)(base + b.rflag) + (size_t)par * R + h->rank;
+        P.red_dst[q] = (double*)(base + b.red) + (size_t)h->rank * VFVM_PEER_RED_W;
+        P.rflag_dst[q] = (unsigned long long*)(base + b.rflag) + h->rank;
     }
-    P.red_local = (const double*)(h->peer_box + b.red) + (size_t)par * R * VFVM_PEER_RED_W;
-    P.rflag_local = (const unsigned long long*)(h->peer_box + b.rflag) + (size_t)par * R;
+    P.red_local = (const double*)(h->peer_box + b.red);
+    P.rflag_local = (const unsigned long long*)(h->peer_box + b.rflag);
     return P;
 }
 
@@ -250,13 +252,30 @@ extern "C" int vfvm_peer_connect(vfvm_handle* h, const char* handles) {
             h->peer_slot[r] = dir[R + h->rank];
             h->peer_halo_doubles[r] = dir[2 * R];
         }
-        h->halo_seq = h->red_seq = 0;
+        h->peer_seq.alloc(2);  // device-resident sequence counters: [0] halo exchanges, [1] reductions
+        CK(cudaMemset(h->peer_seq.p, 0, 2 * sizeof(unsigned long long)));
+        if (const char* e = getenv("VFVM_PEER_TIMEOUT_MS")) h->peer_timeout_ns = std::max(1ll, atoll(e)) * 1000000ll;
         h->peer_ok = true;
     })
     return VFVM_OK;
 }
 
 extern "C" int vfvm_peer_active(vfvm_handle* h) { return h && h->peer_ok ? 1 : 0; }
+
+// Every entry point that ran a peer kernel calls this before it returns: a wait on a peer that timed out (bit 8 of the flag word)
+// must surface as VFVM_ERR_COMM -- stale halo values or partial sums would otherwise feed different Newton decisions on different
+// ranks without any error.  Synchronises the stream.
+int vfvm_peer_check(vfvm_handle* h) {
+    if (h->nranks <= 1 || !h->peer_ok) return VFVM_OK;
+    CK(cudaMemcpyAsync(h->flags_host + 3, h->flags.p, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->flags_host[3] & 256) {
+        k_clear_bits<<<1, 1, 0, h->stream>>>(h->flags.p, 256);
+        CK(cudaStreamSynchronize(h->stream));
+        return vfvm_fail(h, VFVM_ERR_COMM, "peer exchange timed out: a neighbouring rank did not deliver its halo / partial sums (VFVM_PEER_TIMEOUT_MS)");
+    }
+    return VFVM_OK;
+}
 
 extern "C" int vfvm_comm_unique_id(char id_out[128]) {
     std::string err;
@@ -408,10 +427,11 @@ int vfvm_halo_exchange_level(vfvm_handle* h, LevelHalo& c, double* x) {
 extern "C" int vfvm_halo_exchange(vfvm_handle* h, int which) {
     if (!h || !h->have_pattern || which < 0 || which > 3) return vfvm_fail(h, VFVM_ERR_ARG, "bad vector id or no pattern");
     VFVM_TRY(h, {
+        CK(cudaSetDevice(h->device));
         vfvm_halo_exchange_ptr(h, h->vec[which].p);
         CK(cudaStreamSynchronize(h->stream));
+        return vfvm_peer_check(h);
     })
-    return VFVM_OK;
 }
 
 int vfvm_comm_allreduce_sum(vfvm_handle* h, double* dev, int count) {

@@ -68,7 +68,13 @@ __global__ void __launch_bounds__(LS_THREADS) k_spmv(const SpmvArgs a, const Pee
     const int64_t nnz = a.nnz_sell;
     double d_yw = 0.0, d_yy = 0.0;
     bool halo_ready = false;  // warp-uniform
-    if constexpr (PEER) peer_push<NS>(P, a.x);
+    unsigned long long seq = 0;
+    const double* __restrict__ hbox = nullptr;
+    if constexpr (PEER) {
+        seq = peer_seq(P);
+        hbox = peer_halo_local(P, seq);
+        peer_push<NS>(P, seq, a.x);
+    }
     for (int g = blockIdx.x * wpb + (threadIdx.x >> 5); g < a.nslices; g += nwarps) {
         const int64_t rraw = (int64_t)g * 32 + lane;
         const bool valid = rraw < a.Nown;
@@ -95,7 +101,7 @@ __global__ void __launch_bounds__(LS_THREADS) k_spmv(const SpmvArgs a, const Pee
 #pragma unroll
                 for (int b = 0; b < BATCH; b++) need |= Lc[b] >= a.Nown;
                 if (!halo_ready && __any_sync(0xffffffffu, need)) {
-                    if (lane < P.nn) peer_wait(P.hflag_local + lane, P.seq, P.err);
+                    if (lane < P.nn) peer_wait(peer_hflag_local(P, seq) + lane, seq, P.err, P.timeout_ns);
                     __syncwarp();
                     halo_ready = true;
                 }
@@ -103,7 +109,7 @@ __global__ void __launch_bounds__(LS_THREADS) k_spmv(const SpmvArgs a, const Pee
                 for (int b = 0; b < BATCH; b++)
 #pragma unroll
                     for (int jj = 0; jj < NS; jj++)
-                        xl[b][jj] = Lc[b] >= a.Nown ? peer_ld_data(P.halo_local + peer_halo_pos(P, Lc[b] - a.Nown) * NS + jj) : a.x[(int64_t)Lc[b] * NS + jj];
+                        xl[b][jj] = Lc[b] >= a.Nown ? peer_ld_data(hbox + peer_halo_pos(P, Lc[b] - a.Nown) * NS + jj) : a.x[(int64_t)Lc[b] * NS + jj];
             } else {
 #pragma unroll
                 for (int b = 0; b < BATCH; b++)
@@ -270,16 +276,11 @@ __global__ void k_finalize_op_peer(const double* __restrict__ part, int nparts, 
         __syncthreads();
     }
     const int t = threadIdx.x;
-    if (t < P.nranks) {
-        for (int v = 0; v < nvals; v++) P.red_dst[t][v] = mine[v];
-        __threadfence_system();
-        peer_st_flag(P.rflag_dst[t], P.seq);
-        peer_wait(P.rflag_local + t, P.seq, P.err);
-    }
-    __syncthreads();
+    const unsigned long long seq = peer_seq(P);
+    const double* red_all = peer_reduce_exchange(P, seq, mine, nvals);
     if (t < nvals) {
-        double acc = peer_ld_data(P.red_local + t);
-        for (int q = 1; q < P.nranks; q++) acc += peer_ld_data(P.red_local + (size_t)q * VFVM_PEER_RED_W + t);
+        double acc = peer_ld_data(red_all + t);
+        for (int q = 1; q < P.nranks; q++) acc += peer_ld_data(red_all + (size_t)q * VFVM_PEER_RED_W + t);
         sc[S_TMP0 + t] = acc;
     }
     __syncthreads();
@@ -694,6 +695,84 @@ struct AsyncNorm {
     }
 };
 
+
+// ---- one Krylov iteration as a CUDA graph ---------------------------------------------------------------------------------------
+// Every kernel of an iteration (SpMV with its fused halo push / dots, the vector updates, the whole AMG cycle, the single-block
+// reductions with their peer all-reduce) takes arguments that do not change from one iteration to the next: the Krylov scalars and
+// the peer sequence counters live in device memory.  The first two iterations of a solve run eagerly (allocations, occupancy
+// queries), the third is captured once per (method, preconditioner, buffers) signature and kept in the handle; every later
+// iteration -- of this solve and of the following Newton steps -- is one cudaGraphLaunch.  With several ranks this removes the
+// launch gaps of the ~50 small coarse-level kernels of a distributed AMG cycle, which bounded the 8-GPU step in round 1.
+uint64_t iteration_signature(vfvm_handle* h, const double* b, const double* x, const double* part) {
+    uint64_t sig = 1469598103934665603ull;
+    auto mix = [&](uint64_t v) { sig = (sig ^ v) * 1099511628211ull; };
+    mix((uint64_t)h->krylov);
+    mix((uint64_t)h->precon);
+    mix((uint64_t)h->graph_epoch);
+    mix((uint64_t)h->Nown);
+    mix((uint64_t)h->nnz_sell);
+    mix((uint64_t)(uintptr_t)b);
+    mix((uint64_t)(uintptr_t)x);
+    mix((uint64_t)(uintptr_t)part);
+    mix((uint64_t)(uintptr_t)h->offval.p);
+    mix((uint64_t)(uintptr_t)h->diagval.p);
+    mix((uint64_t)(uintptr_t)h->pc_diag.p);
+    mix((uint64_t)(h->peer_ok ? 1 : 0));
+    for (int i = 0; i < 8; i++) mix((uint64_t)(uintptr_t)h->work[i].p);
+    mix((uint64_t)(uintptr_t)h->work[10].p);
+    return sig;
+}
+
+struct IterationGraph {
+    vfvm_handle* h;
+    const double *b, *x, *part;
+    uint64_t sig = 0;
+    bool enabled;
+    IterationGraph(vfvm_handle* hh, const double* b_, const double* x_, const double* part_) : h(hh), b(b_), x(x_), part(part_) {
+        static const bool off = getenv("VFVM_NO_KRYLOV_GRAPH") != nullptr;
+        // ILU applications launch one kernel per dependency level from host-side level lists: eager; NCCL transport: eager
+        enabled = !off && (h->nranks <= 1 || h->peer_ok) && h->precon != VFVM_PRECON_ILU0 && h->precon != VFVM_PRECON_ILU0_MC;
+    }
+    template <class Body>
+    void run(int it, Body& body) {
+        if (!enabled || it <= 2) {
+            body();
+            return;
+        }
+        if (!sig) sig = iteration_signature(h, b, x, part);  // after the eager iterations: every buffer exists now
+        if (h->iter_graph && h->iter_graph_sig == sig) {
+            CK(cudaGraphLaunch((cudaGraphExec_t)h->iter_graph, h->stream));
+            h->launches += h->iter_graph_launches;
+            return;
+        }
+        if (h->iter_graph) {
+            cudaGraphExecDestroy((cudaGraphExec_t)h->iter_graph);
+            h->iter_graph = nullptr;
+        }
+        const int64_t before = h->launches;
+        cudaGraph_t graph = nullptr;
+        CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        h->in_capture = true;
+        try {
+            body();
+        } catch (...) {
+            h->in_capture = false;
+            cudaStreamEndCapture(h->stream, &graph);
+            if (graph) cudaGraphDestroy(graph);
+            throw;
+        }
+        h->in_capture = false;
+        CK(cudaStreamEndCapture(h->stream, &graph));
+        h->iter_graph_launches = h->launches - before;
+        cudaGraphExec_t exec = nullptr;
+        CK(cudaGraphInstantiate(&exec, graph, 0));
+        CK(cudaGraphDestroy(graph));
+        h->iter_graph = exec;
+        h->iter_graph_sig = sig;
+        CK(cudaGraphLaunch(exec, h->stream));
+    }
+};
+
 }  // namespace
 
 void vfvm_spmv_impl(vfvm_handle* h, const double* x, double* y) { spmv(h, const_cast<double*>(x), y, nullptr); }
@@ -745,6 +824,7 @@ extern "C" int vfvm_linsolve_setup(vfvm_handle* h, int krylov, int precon, int g
     h->precon = precon;
     h->gmres_restart = gmres_restart > 0 ? std::min(gmres_restart, 100) : 30;
     h->precon_valid = false;
+    h->graph_epoch++;
     return VFVM_OK;
 }
 
@@ -802,8 +882,7 @@ extern "C" int vfvm_linsolve(vfvm_handle* h, double abstol, double reltol, int m
             bb = rr;
             tol = fmax(abstol, reltol * sqrt(bb));
             converged = sqrt(rr) <= tol;
-            while (!converged && !breakdown && it < maxiters) {
-                it++;
+            auto body = [&]() {
                 k_bicg_p<<<VEC_GRID, LS_THREADS, 0, st>>>(nd, h->red.p, r, v, p, dinv, fusedpc ? phat : nullptr, rhat);
                 h->launches++;
                 if (!fusedpc) precond_apply(h, p, phat);
@@ -815,6 +894,11 @@ extern "C" int vfvm_linsolve(vfvm_handle* h, double abstol, double reltol, int m
                 k_bicg_xr<<<VEC_GRID, LS_THREADS, 0, st>>>(nd, h->red.p, phat, shat, s, t, rhat, x, r, part);
                 h->launches++;
                 finalize(h, part, VEC_GRID, 2, OP_BICG_NEXT);  // (rhat, r), (r, r)
+            };
+            IterationGraph ig(h, b, x, part);
+            while (!converged && !breakdown && it < maxiters) {
+                it++;
+                ig.run(it, body);
                 an.post(it, S_RR);
                 check(it - 1);
             }
@@ -837,8 +921,7 @@ extern "C" int vfvm_linsolve(vfvm_handle* h, double abstol, double reltol, int m
             bb = rr;
             tol = fmax(abstol, reltol * sqrt(bb));
             converged = sqrt(rr) <= tol;
-            while (!converged && !breakdown && it < maxiters) {
-                it++;
+            auto body = [&]() {
                 spmv(h, p, q, p, OP_CG_ALPHA);  // (q, p)
                 k_cg_xr<<<VEC_GRID, LS_THREADS, 0, st>>>(nd, h->red.p, p, q, x, r, dinv, z, fusedpc ? 1 : 0, part);
                 h->launches++;
@@ -850,6 +933,11 @@ extern "C" int vfvm_linsolve(vfvm_handle* h, double abstol, double reltol, int m
                 finalize(h, part, VEC_GRID, 2, OP_CG_NEXT);
                 k_cg_p<<<VEC_GRID, LS_THREADS, 0, st>>>(nd, h->red.p, z, p);
                 h->launches++;
+            };
+            IterationGraph ig(h, b, x, part);
+            while (!converged && !breakdown && it < maxiters) {
+                it++;
+                ig.run(it, body);
                 an.post(it, S_RR);
                 check(it - 1);
             }
@@ -969,6 +1057,8 @@ extern "C" int vfvm_linsolve(vfvm_handle* h, double abstol, double reltol, int m
         h->times[VFVM_TIME_LINSOLVE_SOLVE] = ms;
         *iters = it;
         *resnorm = sqrt(rr);
+        h->last_converged = converged ? 1 : 0;
+        h->last_rhsnorm = sqrt(bb);
         if (breakdown) {
             h->err = "Krylov breakdown (zero pivot / NaN)";
             return VFVM_ERR_LINSOLVE;
@@ -978,9 +1068,19 @@ extern "C" int vfvm_linsolve(vfvm_handle* h, double abstol, double reltol, int m
     return VFVM_OK;
 }
 
+// outcome of the last vfvm_linsolve: hitting maxiters is not an error of the call (Krylov.jl under LinearSolve behaves the same and the
+// Newton loop judges the update), but a caller that stands in for a DIRECT solve must know whether the tolerance was reached
+extern "C" int vfvm_linsolve_status(vfvm_handle* h, int* converged, double* rhs_norm) {
+    if (!h) return VFVM_ERR_ARG;
+    if (converged) *converged = h->last_converged;
+    if (rhs_norm) *rhs_norm = h->last_rhsnorm;
+    return VFVM_OK;
+}
+
 extern "C" int vfvm_spmv(vfvm_handle* h, const double* x, double* y, int memspace) {
     if (!h || !h->have_pattern) return vfvm_fail(h, VFVM_ERR_STATE, "vfvm_build_pattern has not been called");
     VFVM_TRY(h, {
+        CK(cudaSetDevice(h->device));
         const int64_t nd = h->Nown * h->n, nall = h->N * h->n;
         if (memspace == VFVM_DEVICE) {
             spmv(h, const_cast<double*>(x), y, nullptr);
@@ -993,11 +1093,12 @@ extern "C" int vfvm_spmv(vfvm_handle* h, const double* x, double* y, int memspac
         }
         CK(cudaStreamSynchronize(h->stream));
         CK(cudaGetLastError());
+        return vfvm_peer_check(h);
     })
-    return VFVM_OK;
 }
 
 static int norms_impl(vfvm_handle* h, const double* a, const double* b, double* norm_inf, double* norm1) {
+    CK(cudaSetDevice(h->device));
     const int64_t nd = h->Nown * h->n;
     if (h->work[11].n < (size_t)4 * VEC_GRID) h->work[11].alloc((size_t)4 * VEC_GRID);
     double* part = h->work[11].p;
@@ -1012,12 +1113,13 @@ static int norms_impl(vfvm_handle* h, const double* a, const double* b, double* 
     CK(cudaGetLastError());
     if (norm_inf) *norm_inf = h->red_host[0];
     if (norm1) *norm1 = h->red_host[1];
-    return VFVM_OK;
+    return vfvm_peer_check(h);
 }
 
 extern "C" int vfvm_newton_update(vfvm_handle* h, double damp, double* update_norm_inf, double* solution_norm1) {
     if (!h || !h->have_pattern) return vfvm_fail(h, VFVM_ERR_STATE, "vfvm_build_pattern has not been called");
     VFVM_TRY(h, {
+        CK(cudaSetDevice(h->device));
         const int64_t nd = h->Nown * h->n;
         if (h->work[11].n < (size_t)4 * VEC_GRID) h->work[11].alloc((size_t)4 * VEC_GRID);
         double* part = h->work[11].p;
@@ -1034,8 +1136,8 @@ extern "C" int vfvm_newton_update(vfvm_handle* h, double damp, double* update_no
         CK(cudaGetLastError());
         if (update_norm_inf) *update_norm_inf = h->red_host[0];
         if (solution_norm1) *solution_norm1 = h->red_host[1];
+        return vfvm_peer_check(h);
     })
-    return VFVM_OK;
 }
 
 extern "C" int vfvm_vector_norms(vfvm_handle* h, int which, double* norm_inf, double* norm1) {

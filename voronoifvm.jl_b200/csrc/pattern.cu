@@ -388,6 +388,7 @@ int vfvm_pattern_build(vfvm_handle* h) {
     h->seen_transient = false;
     h->precon_valid = false;
     h->ilu_struct_valid = false;
+    h->graph_epoch++;
     h->have_pattern = true;
     return VFVM_OK;
 }
@@ -398,13 +399,28 @@ struct ScalarPattern {
     std::vector<int64_t> src;  // >= 0: offval index (plane*nnz_off + k) ; < 0: -(1 + diag index (plane*Nown + K))
 };
 
-static void build_scalar(vfvm_handle* h, ScalarPattern& sp) {
+// scalar CSR rows of the nodes [K0, K1); only the slices / planes of that range are downloaded (a probe of a few node planes of a
+// 193^3 problem must not pull the whole Jacobian over PCIe)
+template <class T>
+static std::vector<T> fetch_range(const DevBuf<T>& b, int64_t i0, int64_t i1, cudaStream_t s) {
+    std::vector<T> v((size_t)std::max<int64_t>(0, i1 - i0));
+    if (!v.empty()) CK(cudaMemcpyAsync(v.data(), b.p + i0, v.size() * sizeof(T), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return v;
+}
+
+static void build_scalar_range(vfvm_handle* h, int64_t K0, int64_t K1, ScalarPattern& sp, int64_t* e0_out = nullptr, int64_t* e1_out = nullptr) {
     const int n = h->n;
     const int64_t Nown = h->Nown;
-    std::vector<int32_t> rp = h->rowptr.to_host(h->stream), ci = h->colidx.to_host(h->stream), bn = h->bn_node.to_host(h->stream),
-                         sl = h->sell_ptr.to_host(h->stream);
-    std::vector<int64_t> bnode_of(Nown, -1);
-    for (size_t b = 0; b < bn.size(); b++) bnode_of[bn[b]] = (int64_t)b;
+    const int64_t g0 = K0 >> 5, g1 = (K1 + 31) >> 5;
+    std::vector<int32_t> rp = fetch_range(h->rowptr, K0, K1 + 1, h->stream), sl = fetch_range(h->sell_ptr, g0, g1 + 1, h->stream), bn = h->bn_node.to_host(h->stream);
+    const int64_t e0 = sl.empty() ? 0 : sl.front(), e1 = sl.empty() ? 0 : sl.back();
+    if (e0_out) *e0_out = e0;
+    if (e1_out) *e1_out = e1;
+    std::vector<int32_t> ci = fetch_range(h->colidx, e0, e1, h->stream);
+    std::vector<int64_t> bnode_of((size_t)(K1 - K0), -1);
+    for (size_t b = 0; b < bn.size(); b++)
+        if (bn[b] >= K0 && bn[b] < K1) bnode_of[bn[b] - K0] = (int64_t)b;
     // masked systems: species pairs that share a cell region at the node / on the edge (the reference never touches other entries)
     std::vector<int64_t> nfp, efp;
     std::vector<int32_t> nfr, efr, nze;
@@ -413,7 +429,7 @@ static void build_scalar(vfvm_handle* h, ScalarPattern& sp) {
         nfr = h->nf_region.to_host(h->stream);
         efp = h->ef_colptr.to_host(h->stream);
         efr = h->ef_region.to_host(h->stream);
-        nze = h->nz_edge.to_host(h->stream);
+        nze = fetch_range(h->nz_edge, e0, e1, h->stream);
     }
     auto pair_ok = [&](const std::vector<int64_t>& ptr, const std::vector<int32_t>& reg, int64_t item, int i, int j) {
         if (!h->masked) return true;
@@ -421,23 +437,23 @@ static void build_scalar(vfvm_handle* h, ScalarPattern& sp) {
             if (h->region_species[(size_t)(reg[q] - 1) * n + i] && h->region_species[(size_t)(reg[q] - 1) * n + j]) return true;
         return false;
     };
-    sp.rowptr.assign((size_t)Nown * n + 1, 0);
+    sp.rowptr.assign((size_t)(K1 - K0) * n + 1, 0);
     sp.colidx.clear();
     sp.src.clear();
-    for (int64_t K = 0; K < Nown; K++) {
+    for (int64_t K = K0; K < K1; K++) {
         uint64_t dm[2] = {h->masks.flux[0] | h->masks.reaction[0], h->masks.flux[1] | h->masks.reaction[1]};
         if (h->seen_transient) {
             dm[0] |= h->masks.storage[0];
             dm[1] |= h->masks.storage[1];
         }
-        if (bnode_of[K] >= 0) {
+        if (bnode_of[K - K0] >= 0) {
             uint64_t bits[2];
-            memcpy(bits, &h->bnode_mask_host[(size_t)bnode_of[K] * 16], 16);
+            memcpy(bits, &h->bnode_mask_host[(size_t)bnode_of[K - K0] * 16], 16);
             dm[0] |= bits[0];
             dm[1] |= bits[1];
         }
-        const int len = rp[K + 1] - rp[K];
-        const int64_t ebase = (int64_t)sl[K >> 5] + (K & 31);
+        const int len = rp[K - K0 + 1] - rp[K - K0];
+        const int64_t ebase = (int64_t)sl[(K >> 5) - g0] + (K & 31);
         for (int i = 0; i < n; i++) {
             bool diag_done = false;
             const bool inactive = h->masked && !pair_ok(nfp, nfr, K, i, i);  // identity row
@@ -451,19 +467,21 @@ static void build_scalar(vfvm_handle* h, ScalarPattern& sp) {
             };
             for (int q = 0; q < len; q++) {
                 const int64_t e = ebase + (int64_t)q * 32;
-                const int64_t L = ci[e];
+                const int64_t L = ci[e - e0];
                 if (!diag_done && L > K) emit_diag();
                 for (int j = 0; j < n; j++)
-                    if (mask_get(h->masks.flux, i * n + j) && (!h->masked || (nze[e] >= 0 && pair_ok(efp, efr, nze[e], i, j)))) {
+                    if (mask_get(h->masks.flux, i * n + j) && (!h->masked || (nze[e - e0] >= 0 && pair_ok(efp, efr, nze[e - e0], i, j)))) {
                         sp.colidx.push_back(L * n + j);
                         sp.src.push_back((int64_t)h->idxF[i * n + j] * h->nnz_sell + e);
                     }
             }
             if (!diag_done) emit_diag();
-            sp.rowptr[K * n + i + 1] = (int64_t)sp.colidx.size();
+            sp.rowptr[(K - K0) * n + i + 1] = (int64_t)sp.colidx.size();
         }
     }
 }
+
+static void build_scalar(vfvm_handle* h, ScalarPattern& sp) { build_scalar_range(h, 0, h->Nown, sp); }
 
 static int need_pattern(vfvm_handle* h) {
     if (!h || !h->have_pattern) return vfvm_fail(h, VFVM_ERR_STATE, "vfvm_build_pattern has not been called");
@@ -545,3 +563,34 @@ static int get_nzval(vfvm_handle* h, double* out, int memspace, bool csc) {
 
 extern "C" int vfvm_get_nzval_csr(vfvm_handle* h, double* nzval, int memspace) { return get_nzval(h, nzval, memspace, false); }
 extern "C" int vfvm_get_nzval_csc(vfvm_handle* h, double* nzval, int memspace) { return get_nzval(h, nzval, memspace, true); }
+
+// Scalar CSR rows of the owned nodes [node0, node1) with their values (parity probes at full problem size compare a few node
+// planes of the 193^3 Jacobians entry by entry with a CPU evaluation).  Call with colidx == NULL to get the entry count first.
+// rowptr: (node1 - node0) * n + 1 offsets starting at 0; colidx: local dof numbers.
+extern "C" int vfvm_get_rows_csr(vfvm_handle* h, int64_t node0, int64_t node1, int64_t* nnz_out, int64_t* rowptr, int64_t* colidx, double* nzval) {
+    if (int rc = need_pattern(h)) return rc;
+    if (node0 < 0 || node1 > h->Nown || node0 >= node1 || !nnz_out) return vfvm_fail(h, VFVM_ERR_ARG, "bad node range");
+    VFVM_TRY(h, {
+        CK(cudaSetDevice(h->device));
+        ScalarPattern sp;
+        int64_t e0 = 0, e1 = 0;
+        build_scalar_range(h, node0, node1, sp, &e0, &e1);
+        *nnz_out = (int64_t)sp.colidx.size();
+        if (!colidx) return VFVM_OK;
+        std::copy(sp.rowptr.begin(), sp.rowptr.end(), rowptr);
+        std::copy(sp.colidx.begin(), sp.colidx.end(), colidx);
+        std::vector<std::vector<double>> off((size_t)h->cF), dg((size_t)h->cD);
+        for (int p = 0; p < h->cF; p++) off[p] = fetch_range(h->offval, (int64_t)p * h->nnz_sell + e0, (int64_t)p * h->nnz_sell + e1, h->stream);
+        for (int p = 0; p < h->cD; p++) dg[p] = fetch_range(h->diagval, (int64_t)p * h->Nown + node0, (int64_t)p * h->Nown + node1, h->stream);
+        for (size_t k = 0; k < sp.src.size(); k++) {
+            if (sp.src[k] >= 0) {
+                const int64_t p = sp.src[k] / h->nnz_sell, e = sp.src[k] - p * h->nnz_sell;
+                nzval[k] = off[(size_t)p][(size_t)(e - e0)];
+            } else {
+                const int64_t q = -(sp.src[k] + 1), p = q / h->Nown, K = q - p * h->Nown;
+                nzval[k] = dg[(size_t)p][(size_t)(K - node0)];
+            }
+        }
+    })
+    return VFVM_OK;
+}

@@ -17,30 +17,37 @@
 
 #define VFVM_PEER_MAX 8      // ranks of one NVSwitch domain
 #define VFVM_PEER_RED_W 32   // doubles per rank in a reduction box (GMRES multi-dot needs restart+1)
-#define VFVM_PEER_SPIN_MAX (1ll << 23)  // bounded spinning: a lost peer becomes VFVM_ERR_COMM instead of a hung GPU
 
-// kernel argument of one exchange (the parity of `seq` is already selected by the host)
+// Kernel argument of one exchange.  The sequence number of the exchange lives in DEVICE memory (`seq_ctr`, one counter for the halo
+// exchanges and one for the reductions): every kernel that takes part reads it at its start, uses seq = counter + 1, and the block
+// that finishes the push phase last (by then every block has read the counter) stores seq back.  Nothing in the argument depends on
+// the sequence number -- the two parities' buffers are addressed as base + parity * stride inside the kernel -- so a captured CUDA
+// graph of a whole Krylov iteration (SpMV with its halo push, the AMG cycle with one exchange per level SpMV, the reductions) can be
+// replayed any number of times.
 struct PeerArgs {
     int nn, nranks, rank, ns;
-    unsigned long long seq;
+    unsigned long long* seq_ctr;
     int64_t send_ptr[VFVM_PEER_MAX + 1];  // my send list, grouped by neighbour slot
     const int32_t* send_idx;
     int64_t Nown, nhalo;
     // generic exchange of a coarser level through the level-0 mailbox: neighbour r's values start at recv_ptr0[r] in the mailbox and
     // at recv_ptrl[r] in the local halo order (equal on level 0)
     int64_t recv_ptr0[VFVM_PEER_MAX + 1], recv_ptrl[VFVM_PEER_MAX + 1];
-    // remote (peer-mapped) addresses per neighbour slot: where MY boundary values / my flag go
+    // remote (peer-mapped) addresses per neighbour slot, parity 0: where MY boundary values / my flag go
     double* halo_dst[VFVM_PEER_MAX];
-    unsigned long long* hflag_dst[VFVM_PEER_MAX];
-    const double* halo_local;                // my mailbox: halo values in local halo order
-    const unsigned long long* hflag_local;   // [slot]
+    int64_t halo_dst_stride[VFVM_PEER_MAX];  // doubles between the two parities in that neighbour's mailbox
+    unsigned long long* hflag_dst[VFVM_PEER_MAX];  // parity stride: nranks
+    const double* halo_local;                // my mailbox, parity 0: halo values in local halo order
+    int64_t halo_local_stride;
+    const unsigned long long* hflag_local;   // [parity][slot]
     unsigned int* push_count;                // grid-wide completion counter of the push phase
-    // reductions, per rank q (including myself): q's box row for me
+    // reductions, per rank q (including myself), parity 0: q's box row for me (parity strides: nranks * VFVM_PEER_RED_W / nranks)
     double* red_dst[VFVM_PEER_MAX];
     unsigned long long* rflag_dst[VFVM_PEER_MAX];
-    const double* red_local;                 // [rank][VFVM_PEER_RED_W]
-    const unsigned long long* rflag_local;   // [rank]
+    const double* red_local;                 // [parity][rank][VFVM_PEER_RED_W]
+    const unsigned long long* rflag_local;   // [parity][rank]
     int32_t* err;                            // device flag word: bit 8 = peer timeout
+    long long timeout_ns;                    // bound of a wait on a peer (a lost peer becomes VFVM_ERR_COMM instead of a hung GPU)
 };
 
 #ifdef __CUDACC__
@@ -57,17 +64,27 @@ __device__ __forceinline__ double peer_ld_data(const double* p) {  // mailbox da
     asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ long long peer_now_ns() {
+    long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// sequence number of the exchange this kernel performs (every thread reads the same value: the counter is only advanced once every
+// block of the kernel has read it)
+__device__ __forceinline__ unsigned long long peer_seq(const PeerArgs& P) { return *(volatile unsigned long long*)P.seq_ctr + 1ull; }
+
 // Push phase of a halo exchange, executed by every block of the calling kernel: this rank's boundary values of x go straight
-// into the neighbours' mailboxes; the block that finishes last raises this rank's flag at every neighbour.
+// into the neighbours' mailboxes; the block that finishes last raises this rank's flag at every neighbour and advances the counter.
 template <int NS>
-__device__ __forceinline__ void peer_push(const PeerArgs& P, const double* __restrict__ x) {
+__device__ __forceinline__ void peer_push(const PeerArgs& P, unsigned long long seq, const double* __restrict__ x) {
     const int64_t total = P.send_ptr[P.nn] * NS;
+    const int par = (int)(seq & 1ull);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t q = i / NS;
         const int s = (int)(i - q * NS);
         int r = 0;
         while (q >= P.send_ptr[r + 1]) r++;
-        P.halo_dst[r][(q - P.send_ptr[r]) * NS + s] = x[(int64_t)P.send_idx[q] * NS + s];
+        P.halo_dst[r][par * P.halo_dst_stride[r] + (q - P.send_ptr[r]) * NS + s] = x[(int64_t)P.send_idx[q] * NS + s];
     }
     __threadfence_system();
     __syncthreads();
@@ -75,9 +92,10 @@ __device__ __forceinline__ void peer_push(const PeerArgs& P, const double* __res
         __threadfence_system();
         const unsigned int prev = atomicAdd(P.push_count, 1u);
         if (prev == gridDim.x - 1) {
-            *P.push_count = 0;  // every block has arrived: ready for the next launch
+            *P.push_count = 0;  // every block has arrived (and has read the sequence counter): ready for the next launch
+            *P.seq_ctr = seq;
             __threadfence_system();
-            for (int r = 0; r < P.nn; r++) peer_st_flag(P.hflag_dst[r], P.seq);
+            for (int r = 0; r < P.nn; r++) peer_st_flag(P.hflag_dst[r] + par * P.nranks, seq);
         }
     }
 }
@@ -88,18 +106,38 @@ __device__ __forceinline__ int64_t peer_halo_pos(const PeerArgs& P, int64_t c) {
     while (c >= P.recv_ptrl[r + 1]) r++;
     return P.recv_ptr0[r] + (c - P.recv_ptrl[r]);
 }
+__device__ __forceinline__ const double* peer_halo_local(const PeerArgs& P, unsigned long long seq) { return P.halo_local + (int64_t)(seq & 1ull) * P.halo_local_stride; }
+__device__ __forceinline__ const unsigned long long* peer_hflag_local(const PeerArgs& P, unsigned long long seq) { return P.hflag_local + (seq & 1ull) * P.nranks; }
 
-// spin until *flag >= seq (bounded); returns false on timeout
-__device__ __forceinline__ bool peer_wait(const unsigned long long* flag, unsigned long long seq, int32_t* err) {
-    long long spins = 0;
+// spin until *flag >= seq, bounded in TIME (rank skew of seconds is legitimate, e.g. a host-side hierarchy build on one rank);
+// returns false on timeout
+__device__ __forceinline__ bool peer_wait(const unsigned long long* flag, unsigned long long seq, int32_t* err, long long timeout_ns) {
+    if (peer_ld_flag(flag) >= seq) return true;
     if (*(volatile int32_t*)err & 256) return false;  // a peer is already lost: do not wait again
+    const long long t0 = peer_now_ns();
+    int spins = 0;
     while (peer_ld_flag(flag) < seq) {
-        if (++spins > VFVM_PEER_SPIN_MAX) {
+        if ((++spins & 63) == 0 && peer_now_ns() - t0 > timeout_ns) {
             atomicOr(err, 256);
             return false;
         }
         __nanosleep(20);
     }
     return true;
+}
+// single-block all-reduce step shared by the reduction kernels: thread t < nranks delivers `count` values to rank t and waits for
+// rank t's values; afterwards red (parity-selected, [rank][VFVM_PEER_RED_W]) holds every rank's contribution
+__device__ __forceinline__ const double* peer_reduce_exchange(const PeerArgs& P, unsigned long long seq, const double* mine, int count) {
+    const int t = threadIdx.x, par = (int)(seq & 1ull);
+    if (t < P.nranks) {
+        double* dst = P.red_dst[t] + (int64_t)par * P.nranks * VFVM_PEER_RED_W;
+        for (int v = 0; v < count; v++) dst[v] = mine[v];
+        __threadfence_system();
+        peer_st_flag(P.rflag_dst[t] + par * P.nranks, seq);
+        peer_wait(P.rflag_local + par * P.nranks + t, seq, P.err, P.timeout_ns);
+    }
+    __syncthreads();
+    if (t == 0) *P.seq_ctr = seq;  // single-block kernel: every thread has read the counter before the barrier above
+    return P.red_local + (int64_t)par * P.nranks * VFVM_PEER_RED_W;
 }
 #endif

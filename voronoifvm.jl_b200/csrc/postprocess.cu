@@ -31,7 +31,8 @@ __device__ __forceinline__ double pp_block_sum(double v, double* sh) {
 
 template <int NS>
 __global__ void k_integrate_nodes(int64_t Nown, int region, const int64_t* __restrict__ colptr, const int32_t* __restrict__ nregion, const double* __restrict__ nfac,
-                                  const double* __restrict__ U, const FnArgs fn, double* __restrict__ part) {
+                                  const double* __restrict__ U, const FnArgs fn, unsigned rsm, double* __restrict__ part) {
+    // rsm: species enabled in this cell region (assemble_res goes through isregionspecies, src/vfvm_assemblydata.jl:310-332)
     __shared__ double red[32];
     double acc[NS];
 #pragma unroll
@@ -56,7 +57,8 @@ __global__ void k_integrate_nodes(int64_t Nown, int region, const int64_t* __res
             eval_reaction<NS>(fn.id, fn.p, f, u, region);
         }
 #pragma unroll
-        for (int i = 0; i < NS; i++) acc[i] += fac * f[i];
+        for (int i = 0; i < NS; i++)
+            if ((rsm >> i) & 1u) acc[i] += fac * f[i];
     }
 #pragma unroll
     for (int i = 0; i < NS; i++) {
@@ -69,7 +71,9 @@ __global__ void k_integrate_nodes(int64_t Nown, int region, const int64_t* __res
 template <int NS, int FLUX>
 __global__ void k_integrate_edges(int64_t E, int64_t Nown, int region, int dim, const int32_t* __restrict__ edgenodes, const int64_t* __restrict__ colptr,
                                   const int32_t* __restrict__ eregion, const double* __restrict__ efac, const double* __restrict__ coord, const double* __restrict__ U,
-                                  const FnArgs fn, double* __restrict__ part) {
+                                  const FnArgs fn, unsigned rsm, const int32_t* __restrict__ node_active, double* __restrict__ part) {
+    // a species takes part on an edge of this region if it is enabled in the region and defined at both end nodes
+    // (assemble_res(::Edge), src/vfvm_assemblydata.jl:385-405); node_active == null: every species everywhere
     __shared__ double red[32];
     double acc[NS];
 #pragma unroll
@@ -103,8 +107,10 @@ __global__ void k_integrate_edges(int64_t E, int64_t Nown, int region, int dim, 
         } else {
             eval_flux<FLUX, NS>(fn.p, f, uK, uL);
         }
+        const unsigned act = node_active ? (rsm & (unsigned)node_active[K] & (unsigned)node_active[L]) : rsm;
 #pragma unroll
-        for (int i = 0; i < NS; i++) acc[i] += wgt * (hh * hh * fac * f[i] / dim);
+        for (int i = 0; i < NS; i++)
+            if ((act >> i) & 1u) acc[i] += wgt * (hh * hh * fac * f[i] / dim);
     }
 #pragma unroll
     for (int i = 0; i < NS; i++) {
@@ -187,25 +193,25 @@ const int PP_GRID = 148 * 4, PP_THREADS = 256;
     }
 
 template <int NS, int FLUX>
-void launch_edges(vfvm_handle* h, int region, const double* U, const FnArgs& fn, double* part) {
+void launch_edges(vfvm_handle* h, int region, const double* U, const FnArgs& fn, unsigned rsm, double* part) {
     if constexpr (FLUX < 0 || flux_supported(FLUX, NS)) {
         k_integrate_edges<NS, FLUX><<<PP_GRID, PP_THREADS, 0, h->stream>>>(h->E, h->Nown, region, h->dim, h->edgenodes.p, h->ef_colptr.p, h->ef_region.p, h->ef_fac.p,
-                                                                           h->coord.p, U, fn, part);
+                                                                           h->coord.p, U, fn, rsm, h->masked ? h->node_active.p : nullptr, part);
     } else {
         throw std::string("flux id ") + std::to_string(FLUX) + " has no device instantiation for " + std::to_string(NS) + " species";
     }
 }
 template <int NS>
-void launch_edges_ns(vfvm_handle* h, int region, const double* U, const FnArgs& fn, double* part) {
+void launch_edges_ns(vfvm_handle* h, int region, const double* U, const FnArgs& fn, unsigned rsm, double* part) {
     switch (fn.id) {
-        case -1: launch_edges<NS, -1>(h, region, U, fn, part); break;
-        case -2: launch_edges<NS, -2>(h, region, U, fn, part); break;
-        case VFVM_FLUX_DIFFUSION: launch_edges<NS, VFVM_FLUX_DIFFUSION>(h, region, U, fn, part); break;
-        case VFVM_FLUX_POWDIFF: launch_edges<NS, VFVM_FLUX_POWDIFF>(h, region, U, fn, part); break;
-        case VFVM_FLUX_CROSSDIFF2: launch_edges<NS, VFVM_FLUX_CROSSDIFF2>(h, region, U, fn, part); break;
-        case VFVM_FLUX_SG_UNIPOLAR: launch_edges<NS, VFVM_FLUX_SG_UNIPOLAR>(h, region, U, fn, part); break;
-        case VFVM_FLUX_SEDAN: launch_edges<NS, VFVM_FLUX_SEDAN>(h, region, U, fn, part); break;
-        case VFVM_FLUX_SG_BIPOLAR: launch_edges<NS, VFVM_FLUX_SG_BIPOLAR>(h, region, U, fn, part); break;
+        case -1: launch_edges<NS, -1>(h, region, U, fn, rsm, part); break;
+        case -2: launch_edges<NS, -2>(h, region, U, fn, rsm, part); break;
+        case VFVM_FLUX_DIFFUSION: launch_edges<NS, VFVM_FLUX_DIFFUSION>(h, region, U, fn, rsm, part); break;
+        case VFVM_FLUX_POWDIFF: launch_edges<NS, VFVM_FLUX_POWDIFF>(h, region, U, fn, rsm, part); break;
+        case VFVM_FLUX_CROSSDIFF2: launch_edges<NS, VFVM_FLUX_CROSSDIFF2>(h, region, U, fn, rsm, part); break;
+        case VFVM_FLUX_SG_UNIPOLAR: launch_edges<NS, VFVM_FLUX_SG_UNIPOLAR>(h, region, U, fn, rsm, part); break;
+        case VFVM_FLUX_SEDAN: launch_edges<NS, VFVM_FLUX_SEDAN>(h, region, U, fn, rsm, part); break;
+        case VFVM_FLUX_SG_BIPOLAR: launch_edges<NS, VFVM_FLUX_SG_BIPOLAR>(h, region, U, fn, rsm, part); break;
         default: throw std::string("unregistered flux id");
     }
 }
@@ -245,10 +251,13 @@ int integrate_impl(vfvm_handle* h, bool edges, int slot, int id, const double* p
     res.alloc((size_t)n * nreg);
     const double* U = h->vec[which].p;
     for (int r = 1; r <= nreg; r++) {
+        unsigned rsm = 0;
+        for (int i = 0; i < n; i++)
+            if (h->region_species[(size_t)(r - 1) * n + i]) rsm |= 1u << i;
         if (edges) {
-            PP_NS(n, (launch_edges_ns<NS>(h, r, U, fn, part.p)));
+            PP_NS(n, (launch_edges_ns<NS>(h, r, U, fn, rsm, part.p)));
         } else {
-            PP_NS(n, (k_integrate_nodes<NS><<<PP_GRID, PP_THREADS, 0, h->stream>>>(h->Nown, r, h->nf_colptr.p, h->nf_region.p, h->nf_fac.p, U, fn, part.p)));
+            PP_NS(n, (k_integrate_nodes<NS><<<PP_GRID, PP_THREADS, 0, h->stream>>>(h->Nown, r, h->nf_colptr.p, h->nf_region.p, h->nf_fac.p, U, fn, rsm, part.p)));
         }
         k_pp_finalize<<<1, 1024, 0, h->stream>>>(part.p, PP_GRID, n, res.p + (size_t)(r - 1) * n);
         h->launches += 2;
@@ -257,7 +266,7 @@ int integrate_impl(vfvm_handle* h, bool edges, int slot, int id, const double* p
     CK(cudaMemcpyAsync(out, res.p, sizeof(double) * n * nreg, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaGetLastError());
-    return VFVM_OK;
+    return vfvm_peer_check(h);
 }
 
 }  // namespace

@@ -185,6 +185,8 @@ struct vfvm_handle {
     // linear solver
     int krylov = VFVM_KRYLOV_BICGSTAB, precon = VFVM_PRECON_JACOBI, gmres_restart = 30;
     bool precon_valid = false;
+    int last_converged = 0;      // outcome of the last vfvm_linsolve (vfvm_linsolve_status)
+    double last_rhsnorm = 0.0;
     DevBuf<double> work[12];
     DevBuf<double> pc_diag;  // (block-)Jacobi inverse blocks, n*n planes x Nown
     DevBuf<double> ilu_off, ilu_diag;
@@ -208,9 +210,16 @@ struct vfvm_handle {
     char* peer_box = nullptr;                 // my mailbox
     std::vector<char*> peer_base;             // every rank's mailbox as mapped here ([rank] = peer_box)
     std::vector<int64_t> peer_recv_off, peer_slot, peer_halo_doubles;  // per neighbour slot: my place in that neighbour's mailbox
-    unsigned long long halo_seq = 0, red_seq = 0;
+    DevBuf<unsigned long long> peer_seq;      // device-resident sequence counters: [0] halo exchanges, [1] reductions
+    long long peer_timeout_ns = 30000000000ll;  // bound of a wait on a peer (VFVM_PEER_TIMEOUT_MS)
     DevBuf<unsigned int> peer_counter;
     void* amg = nullptr;  // aggregation AMG hierarchy (amg.cu)
+    // one Krylov iteration captured as a CUDA graph (linsolve.cu): valid while its signature (method, buffers, graph_epoch) holds
+    void* iter_graph = nullptr;  // cudaGraphExec_t
+    uint64_t iter_graph_sig = 0;
+    int64_t iter_graph_launches = 0;
+    uint64_t graph_epoch = 0;  // bumped by everything that changes what a captured iteration bakes in (solver options, AMG hierarchy / options)
+    bool in_capture = false;   // the handle's stream is being captured: preconditioners must enqueue plain kernels
 };
 
 #define VFVM_TRY(h, ...)                                        \
@@ -274,6 +283,7 @@ PeerArgs vfvm_peer_args_halo_level(vfvm_handle* h, const LevelHalo& c);
 void vfvm_spmv_level_halo(vfvm_handle* h, SpmvArgs a, LevelHalo& lh, double* x, double* y);
 int vfvm_halo_exchange_ptr(vfvm_handle* h, double* x);
 int vfvm_comm_allreduce_sum(vfvm_handle* h, double* dev, int count);
-PeerArgs vfvm_peer_args_halo(vfvm_handle* h);    // starts a new halo exchange (advances the sequence number)
-PeerArgs vfvm_peer_args_reduce(vfvm_handle* h);  // starts a new reduction
+int vfvm_peer_check(vfvm_handle* h);  // after peer kernels: VFVM_ERR_COMM if a wait on a peer timed out
+PeerArgs vfvm_peer_args_halo(vfvm_handle* h);    // arguments of a halo exchange (the sequence number lives on the device)
+PeerArgs vfvm_peer_args_reduce(vfvm_handle* h);  // arguments of a reduction
 

@@ -42,23 +42,23 @@ def node_ranges(num_nodes: int, nparts: int) -> np.ndarray:
     return (np.arange(nparts + 1, dtype=np.int64) * num_nodes) // nparts
 
 
-def partition_grid(grid: Grid, rank: int, nparts: int) -> PartitionInfo:
+def subgrid_for_node_range(grid: Grid, lo: int, hi: int, rng: np.ndarray | None = None):
+    """Grid piece of the node range [lo, hi): every cell that touches one of these nodes, local numbering = [the range, ascending]
+    + [the other nodes of those cells, grouped by owner (if `rng` gives owner ranges) and ascending].  The form factors of the
+    range's nodes and of every edge with an end in the range are complete on the piece, so its operator rows equal the global rows
+    (tests/test_partition_gloo.py).  Returns (local grid, local_nodes, selected cells, selected bfaces, halo owners)."""
     N = grid.num_nodes
-    rng = node_ranges(N, nparts)
-    lo, hi = int(rng[rank]), int(rng[rank + 1])
     cn = grid.cellnodes
-    owned_mask = (cn >= lo) & (cn < hi)
-    csel = owned_mask.any(axis=0)
+    csel = ((cn >= lo) & (cn < hi)).any(axis=0)
     lcells = cn[:, csel]
     nodes = np.unique(lcells)
     is_owned = (nodes >= lo) & (nodes < hi)
-    owned = np.arange(lo, hi, dtype=np.int64)  # every owned node is kept, even if isolated
+    owned = np.arange(lo, hi, dtype=np.int64)  # every node of the range is kept, even if isolated
     halo = nodes[~is_owned].astype(np.int64)
-    halo_owner = np.searchsorted(rng, halo, side="right") - 1
+    halo_owner = np.searchsorted(rng, halo, side="right") - 1 if rng is not None else np.zeros(halo.size, np.int64)
     order = np.lexsort((halo, halo_owner))
     halo, halo_owner = halo[order], halo_owner[order]
     local_nodes = np.concatenate([owned, halo])
-    # global -> local
     g2l = np.full(N, -1, dtype=np.int64)
     g2l[local_nodes] = np.arange(local_nodes.size)
     lcellnodes = g2l[lcells].astype(np.int32)
@@ -66,9 +66,16 @@ def partition_grid(grid: Grid, rank: int, nparts: int) -> PartitionInfo:
     lbf = g2l[grid.bfacenodes[:, bsel]]
     assert (lbf >= 0).all(), "a boundary face with an owned node must belong to a local cell"
     lgrid = Grid(grid.dim, grid.coord[:, local_nodes], lcellnodes, grid.cellregions[csel], lbf.astype(np.int32), grid.bfaceregions[bsel], grid.coordsys)
-    # the grid-wide region counts must survive on every rank (physics tables are indexed by region label)
+    # the grid-wide region counts must survive on every piece (physics tables are indexed by region label)
     lgrid._num_cellregions = grid.num_cellregions
     lgrid._num_bfaceregions = grid.num_bfaceregions
+    return lgrid, local_nodes, lcells, g2l, halo_owner, int(bsel.sum())
+
+
+def partition_grid(grid: Grid, rank: int, nparts: int) -> PartitionInfo:
+    rng = node_ranges(grid.num_nodes, nparts)
+    lo, hi = int(rng[rank]), int(rng[rank + 1])
+    lgrid, local_nodes, lcells, g2l, halo_owner, nbf = subgrid_for_node_range(grid, lo, hi, rng)
     # neighbours + exchange lists
     nbr = np.unique(halo_owner).astype(np.int32)
     recv_ptr = np.concatenate([[0], np.cumsum([np.count_nonzero(halo_owner == q) for q in nbr])]).astype(np.int64)
@@ -81,7 +88,7 @@ def partition_grid(grid: Grid, rank: int, nparts: int) -> PartitionInfo:
         send_lists.append(g2l[snodes].astype(np.int32))
     send_ptr = np.concatenate([[0], np.cumsum([s.size for s in send_lists])]).astype(np.int64)
     send_idx = np.concatenate(send_lists).astype(np.int32) if send_lists else np.zeros(0, np.int32)
-    return PartitionInfo(rank, nparts, rng, local_nodes, hi - lo, nbr, send_ptr, send_idx, recv_ptr, int(bsel.sum()), lgrid)
+    return PartitionInfo(rank, nparts, rng, local_nodes, hi - lo, nbr, send_ptr, send_idx, recv_ptr, nbf, lgrid)
 
 
 def local_system(system: System, info: PartitionInfo) -> System:

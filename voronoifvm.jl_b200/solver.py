@@ -163,6 +163,7 @@ class NewtonSolverHistory:
     tlinsolve: float = 0.0
     tlinsolve_setup: float = 0.0
     tlinsolve_solve: float = 0.0
+    linres: float = 0.0  # residual norm of the last linear solve
     updatenorm: list = dataclasses.field(default_factory=list)
     l1normdiff: list = dataclasses.field(default_factory=list)
 
@@ -223,6 +224,15 @@ def _solve_linear(state: SystemState, hist: NewtonSolverHistory, control: Solver
     if rc == _lib.ERR_LINSOLVE:
         raise LinearSolverError(state.L.vfvm_last_error(state.h).decode())
     check(state.h, rc)
+    hist.linres = resn.value
+    m = control.method_linear
+    if m is None or isinstance(m, DeviceDirectLike):
+        # the stand-in for a direct solve must not hand Newton an unconverged update silently
+        conv, bnorm = C.c_int(0), C.c_double(0.0)
+        check(state.h, state.L.vfvm_linsolve_status(state.h, C.byref(conv), C.byref(bnorm)))
+        if not conv.value:
+            raise LinearSolverError(f"direct-like default solver (BiCGStab + block-Jacobi) stopped at maxiters={maxit} with |r| = {resn.value:.3e}, |b| = {bnorm.value:.3e}; "
+                                    "choose method_linear=KrylovJL_BICGSTAB/CG(precs=AMGPreconBuilder()) for this problem")
     return iters.value, resn.value
 
 

@@ -170,6 +170,16 @@ class SystemState:
         check(self.h, self.L.vfvm_get_nzval_csc(self.h, val.ctypes.data, _lib.HOST))
         return sp.csc_matrix((val, idx, ptr), shape=(nr.value, self.n * self.N))
 
+    def rows_csr(self, node0, node1):
+        """scalar CSR rows of the owned nodes [node0, node1) (local dof column numbers) without downloading the whole Jacobian"""
+        nnz = C.c_int64()
+        check(self.h, self.L.vfvm_get_rows_csr(self.h, node0, node1, C.byref(nnz), None, None, None))
+        ptr = np.zeros((node1 - node0) * self.n + 1, np.int64)
+        idx = np.zeros(nnz.value, np.int64)
+        val = np.zeros(nnz.value)
+        check(self.h, self.L.vfvm_get_rows_csr(self.h, node0, node1, C.byref(nnz), i64ptr(ptr), i64ptr(idx), dptr(val)))
+        return sp.csr_matrix((val, idx, ptr), shape=((node1 - node0) * self.n, self.n * self.N))
+
     def spmv(self, x):
         x = np.ascontiguousarray(np.asarray(x, dtype=np.float64).ravel(order="F"))
         y = np.zeros(self.n * self.Nown)
