@@ -165,6 +165,17 @@ class OracleSystem:
         self.L.vo_get_matrix_csc(self.h, _p(colptr, C.c_int64), _p(rowval, C.c_int64), _p(nzval, C.c_double))
         return sp.csc_matrix((nzval, rowval, colptr), shape=(ndof, ndof))
 
+    def krylov_solve(self, b, method="bicgstab", precon="blockjacobi", reltol=1e-10, maxiters=5000, nthreads=1):
+        """multithreaded CPU Krylov solve with the matrix of the last `assemble` (the stand-in for KrylovJL_CG / KrylovJL_BICGSTAB with
+        Jacobi / node-block preconditioning where a sparse LU is out of reach) -> (x, iterations, true relative residual, seconds)"""
+        bb = np.ascontiguousarray(np.asarray(b, dtype=np.float64).ravel(order="F"))
+        x = np.zeros_like(bb)
+        it, rel, sec = C.c_int(0), C.c_double(0.0), C.c_double(0.0)
+        rc = self.L.vo_krylov_solve(self.h, 1 if method == "cg" else 0, 1 if precon == "jacobi" else 2, _p(bb, C.c_double), _p(x, C.c_double), C.c_double(reltol), int(maxiters),
+                                    int(nthreads), C.byref(it), C.byref(rel), C.byref(sec))
+        assert rc == 0, rc
+        return x, it.value, rel.value, sec.value
+
     def integrate(self, U, slot=1, pid=0, params=()):
         """integrate(system, F, U) src/vfvm_postprocess.jl:18-67 for a registered node function (pid 0: the identity) -> n x ncellregions"""
         u = np.ascontiguousarray(np.asarray(U, dtype=np.float64).T).ravel()

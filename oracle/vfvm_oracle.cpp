@@ -1015,3 +1015,157 @@ int vo_max_threads() {
 }
 
 }  // extern "C"
+
+// ---- CPU Krylov stand-in for `_solve_linear!` at sizes where a sparse LU is out of reach (src/vfvm_linsolve.jl:6-61 with
+// method_linear = KrylovJL_CG / KrylovJL_BICGSTAB, precs = JacobiPreconBuilder / node-block BlockPreconBuilder) ---------------------
+// Works on the matrix of the last vo_assemble.  The CSC matrix is transposed once into CSR with 32-bit column indices; SpMV, dots
+// and vector updates run on `nthreads` OpenMP threads.  method: 0 BiCGStab, 1 CG; precon: 1 point Jacobi, 2 node-block (n x n) Jacobi.
+#define VFVM_MAX_SPECIES_ORACLE 50
+extern "C" int vo_krylov_solve(void* hv, int method, int precon, const double* b, double* x, double reltol, int maxit, int nthreads, int* iters_out, double* relres_out,
+                               double* seconds_out) {
+    System& s = *(System*)hv;
+    const ExtMatrix& A = s.A;
+    const int64_t nd = A.n;
+    const int n = s.n;
+    const int64_t nnz = (int64_t)A.nzval.size();
+    if (nd <= 0 || nnz == 0) return VFVM_ERR_STATE;
+    nthreads = std::max(1, nthreads);
+    // CSC -> CSR
+    std::vector<int64_t> rp((size_t)nd + 1, 0);
+    for (int64_t k = 0; k < nnz; k++) rp[(size_t)A.rowval[k] + 1]++;
+    for (int64_t i = 0; i < nd; i++) rp[i + 1] += rp[i];
+    std::vector<int> ci((size_t)nnz);
+    std::vector<double> va((size_t)nnz);
+    {
+        std::vector<int64_t> fill(rp.begin(), rp.end() - 1);
+        for (int64_t j = 0; j < nd; j++)
+            for (int64_t k = A.colptr[j]; k < A.colptr[j + 1]; k++) {
+                const int64_t o = fill[A.rowval[k]]++;
+                ci[o] = (int)j;
+                va[o] = A.nzval[k];
+            }
+    }
+    const double t_start = omp_get_wtime();
+    // inverse (block) diagonal
+    const int bs = precon == 2 ? n : 1;
+    std::vector<double> Minv((size_t)nd * bs, 0.0);
+#pragma omp parallel for schedule(static) num_threads(nthreads)
+    for (int64_t K = 0; K < nd / bs; K++) {
+        double B[VFVM_MAX_SPECIES_ORACLE][VFVM_MAX_SPECIES_ORACLE], I[VFVM_MAX_SPECIES_ORACLE][VFVM_MAX_SPECIES_ORACLE];
+        for (int i = 0; i < bs; i++)
+            for (int j = 0; j < bs; j++) {
+                B[i][j] = 0.0;
+                I[i][j] = i == j ? 1.0 : 0.0;
+            }
+        for (int i = 0; i < bs; i++)
+            for (int64_t k = rp[K * bs + i]; k < rp[K * bs + i + 1]; k++) {
+                const int64_t c = ci[k] - K * bs;
+                if (c >= 0 && c < bs) B[i][c] = va[k];
+            }
+        for (int c = 0; c < bs; c++) {  // Gauss-Jordan without pivoting, as the device's node-block Jacobi
+            const double ip = 1.0 / B[c][c];
+            for (int j = 0; j < bs; j++) {
+                B[c][j] *= ip;
+                I[c][j] *= ip;
+            }
+            for (int i = 0; i < bs; i++) {
+                if (i == c) continue;
+                const double f = B[i][c];
+                for (int j = 0; j < bs; j++) {
+                    B[i][j] -= f * B[c][j];
+                    I[i][j] -= f * I[c][j];
+                }
+            }
+        }
+        for (int i = 0; i < bs; i++)
+            for (int j = 0; j < bs; j++) Minv[(size_t)(K * bs + i) * bs + j] = I[i][j];
+    }
+    auto spmv = [&](const double* in, double* out) {
+#pragma omp parallel for schedule(static) num_threads(nthreads)
+        for (int64_t i = 0; i < nd; i++) {
+            double acc = 0.0;
+            for (int64_t k = rp[i]; k < rp[i + 1]; k++) acc += va[k] * in[ci[k]];
+            out[i] = acc;
+        }
+    };
+    auto prec = [&](const double* in, double* out) {
+#pragma omp parallel for schedule(static) num_threads(nthreads)
+        for (int64_t K = 0; K < nd / bs; K++)
+            for (int i = 0; i < bs; i++) {
+                double acc = 0.0;
+                for (int j = 0; j < bs; j++) acc += Minv[(size_t)(K * bs + i) * bs + j] * in[K * bs + j];
+                out[K * bs + i] = acc;
+            }
+    };
+    auto dot = [&](const double* a, const double* c) {
+        double acc = 0.0;
+#pragma omp parallel for schedule(static) reduction(+ : acc) num_threads(nthreads)
+        for (int64_t i = 0; i < nd; i++) acc += a[i] * c[i];
+        return acc;
+    };
+    std::vector<double> r(b, b + nd), z((size_t)nd), p((size_t)nd), q((size_t)nd);
+    std::fill(x, x + nd, 0.0);
+    const double bb = dot(b, b);
+    double rr = bb;
+    int it = 0;
+    const double tol2 = reltol * reltol * bb;
+    if (method == 1) {
+        prec(r.data(), z.data());
+        p = z;
+        double rz = dot(r.data(), z.data());
+        while (rr > tol2 && it < maxit) {
+            it++;
+            spmv(p.data(), q.data());
+            const double alpha = rz / dot(p.data(), q.data());
+#pragma omp parallel for schedule(static) num_threads(nthreads)
+            for (int64_t i = 0; i < nd; i++) {
+                x[i] += alpha * p[i];
+                r[i] -= alpha * q[i];
+            }
+            prec(r.data(), z.data());
+            const double rz_new = dot(r.data(), z.data());
+            rr = dot(r.data(), r.data());
+            const double beta = rz_new / rz;
+            rz = rz_new;
+#pragma omp parallel for schedule(static) num_threads(nthreads)
+            for (int64_t i = 0; i < nd; i++) p[i] = z[i] + beta * p[i];
+        }
+    } else {
+        std::vector<double> rhat(r), v((size_t)nd, 0.0), sv((size_t)nd), t((size_t)nd), ph((size_t)nd), sh((size_t)nd);
+        std::fill(p.begin(), p.end(), 0.0);
+        double rho = 1.0, alpha = 1.0, omega = 1.0;
+        while (rr > tol2 && it < maxit) {
+            it++;
+            const double rho_new = dot(rhat.data(), r.data());
+            if (rho_new == 0.0 || omega == 0.0) break;
+            const double beta = (rho_new / rho) * (alpha / omega);
+            rho = rho_new;
+#pragma omp parallel for schedule(static) num_threads(nthreads)
+            for (int64_t i = 0; i < nd; i++) p[i] = r[i] + beta * (p[i] - omega * v[i]);
+            prec(p.data(), ph.data());
+            spmv(ph.data(), v.data());
+            alpha = rho / dot(rhat.data(), v.data());
+#pragma omp parallel for schedule(static) num_threads(nthreads)
+            for (int64_t i = 0; i < nd; i++) sv[i] = r[i] - alpha * v[i];
+            prec(sv.data(), sh.data());
+            spmv(sh.data(), t.data());
+            const double tt = dot(t.data(), t.data());
+            omega = tt > 0.0 ? dot(t.data(), sv.data()) / tt : 0.0;
+#pragma omp parallel for schedule(static) num_threads(nthreads)
+            for (int64_t i = 0; i < nd; i++) {
+                x[i] += alpha * ph[i] + omega * sh[i];
+                r[i] = sv[i] - omega * t[i];
+            }
+            rr = dot(r.data(), r.data());
+        }
+    }
+    // true residual
+    spmv(x, q.data());
+    double tr = 0.0;
+#pragma omp parallel for schedule(static) reduction(+ : tr) num_threads(nthreads)
+    for (int64_t i = 0; i < nd; i++) tr += (b[i] - q[i]) * (b[i] - q[i]);
+    if (iters_out) *iters_out = it;
+    if (relres_out) *relres_out = bb > 0.0 ? std::sqrt(tr / bb) : 0.0;
+    if (seconds_out) *seconds_out = omp_get_wtime() - t_start;
+    return 0;
+}

@@ -1,7 +1,9 @@
-"""Multi-GPU parity script (not collected by pytest): run as
+"""Multi-GPU parity script (not collected by pytest; the same checks run inside every multi-rank bench.py line): run as
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 tests/mgpu_check.py
-Each rank assembles / solves its node-owner partition on its own GPU (NCCL halo + all-reduce); rank 0 compares the
-gathered result with the CPU oracle on the whole grid (Newton solution <= 1e-10, residual rows <= 1e-12)."""
+Each rank assembles / solves its node-owner partition on its own GPU; rank 0 compares the gathered result with the CPU oracle on the
+whole grid (Newton solution <= 1e-10, residual rows <= 1e-12) and every rank compares its own Jacobian rows with the oracle on probe
+planes.  Three systems: a scalar nonlinear problem, the three-species bipolar drift-diffusion system (analytic node-transformed row
+kernel, three cell regions) and a system with species enabled per cell region (masked row kernel, Example221-like)."""
 import math
 import os
 import sys
@@ -10,6 +12,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import torch
 import torch.distributed as dist
@@ -17,49 +20,86 @@ import torch.distributed as dist
 import vfvm_b200 as v
 from vfvm_b200 import partition as P
 from vfvm_b200 import physics as ph
+from parity_probe import probe_rows
+
+
+def scalar_system(nx=17):
+    X = np.linspace(0, 1, nx)
+    s = v.System(v.simplexgrid(X, X, X), flux=ph.PowerDiffusion(1.0e-1, 2), reaction=ph.PowerReaction(1.0, 2.0), source=ph.XSinYExpZSource(1, 5.0), storage=ph.LinearStorage(1.0))
+    v.enable_species(s, 1, [1])
+    v.boundary_dirichlet(s, 1, 5, 0.1)
+    v.boundary_dirichlet(s, 1, 6, 0.2)
+    return s, 0.05, (0.1, 1.0)
+
+
+def bipolar_system(nx=21):
+    import bench
+
+    s, kw, _ = bench.make_system("cfg4", nx)
+    return s, kw["tstep"], (-0.5, 0.5)
+
+
+def masked_system(nx=17):
+    X = np.linspace(0, 1, nx)
+    g = v.simplexgrid(X, X, X)
+    v.cellmask(g, [0, 0, 0.3], [1, 1, 0.7], 2)
+    v.cellmask(g, [0, 0, 0.7], [1, 1, 1.0], 3)
+    R = [np.array([[1.0, 0.2, 0.0], [0.1, 2.0, 0.0], [0.0, 0.0, 0.0]]), np.array([[0.0, 0.0, 0.0], [0.0, 1.5, 0.0], [0.0, 0.0, 0.0]]), np.array([[0.0, 0.0, 0.0], [0.0, 2.0, 0.3], [0.0, 0.4, 3.0]])]
+    r0 = [np.array([0.5, -0.25, 0.0]), np.array([0.0, 0.3, 0.0]), np.array([0.0, 0.1, 1.5])]
+    s = v.System(g, flux=ph.LinearDiffusion([1.0, 2.0, 3.0]), reaction=ph.RegionAffineReaction(R, r0), storage=ph.LinearStorage([1.0, 1.0, 1.0]))
+    v.enable_species(s, 1, [1])
+    v.enable_species(s, 2, [1, 2, 3])
+    v.enable_species(s, 3, [3])
+    v.boundary_dirichlet(s, 1, 5, 1.0)
+    v.boundary_dirichlet(s, 2, 5, 0.5)
+    v.boundary_dirichlet(s, 3, 6, 0.25)
+    return s, 0.1, (0.1, 1.0)
+
+
+def check(name, s, tstep, urange, rank, world, local, amg_parity=True):
+    st, info = P.partitioned_state(s, rank, world, local)
+    n, N = s.num_species, s.grid.num_nodes
+    rng = np.random.default_rng(1)
+    Ug = np.asfortranarray(rng.uniform(urange[0], urange[1], (n, N)))
+    Ul = np.asfortranarray(Ug[:, info.local_nodes])
+    own = slice(0, info.n_owned)
+    # ---- residual rows + Jacobian rows (probe planes of every rank against the oracle, entry by entry)
+    F = st.eval_res_jac(Ul, tstep=tstep)
+    pr = probe_rows(s, st, info, Ug, Ug, tstep=tstep)
+    assert pr["ok"], (name, rank, pr)
+    # ---- one implicit Euler step (Newton to convergence), default direct-like solver across ranks, then BiCGStab + distributed AMG
+    sol = v.solve_state(st, inival=Ul, tstep=tstep)
+    sol_amg = v.solve_state(st, inival=Ul, tstep=tstep, method_linear=v.KrylovJL_BICGSTAB(precs=v.AMGPreconBuilder()), reltol_linear=1e-13, abstol_linear=0.0, maxiters_linear=2000)
+    assert np.max(np.abs(sol_amg[:, own] - sol[:, own])) < 1e-10, f"{name}: AMG-preconditioned solve differs"
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (info.local_nodes[own], F[:, own], sol[:, own], pr["entries"]))
+    if rank == 0:
+        from oracle import oracle as O
+
+        Fg, solg = np.zeros((n, N)), np.zeros((n, N))
+        for nodes, f, u, _ in gathered:
+            Fg[:, nodes] = f
+            solg[:, nodes] = u
+        o = O.OracleSystem(s)
+        Fo, _ = o.assemble(Ug, Ug, tstep=tstep)
+        ref = o.solve_step(Ug, tstep=tstep)
+        ef = np.max(np.abs(Fg - Fo) / np.maximum(np.abs(Fo), 1e-3))
+        eu = np.max(np.abs(solg - ref))
+        print(f"mgpu_check[{name}] world={world} transport={'peer mailboxes' if st.peer else 'NCCL'}: residual rel err {ef:.2e}, Newton solution err {eu:.2e}, "
+              f"Jacobian entries probed {sum(g[3] for g in gathered)}", flush=True)
+        assert ef < 1e-11 and eu < 1e-10, (name, ef, eu)
+    st.close()
 
 
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    X = np.linspace(0, 1, 17)
-    s = v.System(v.simplexgrid(X, X, X), flux=ph.PowerDiffusion(1.0e-1, 2), reaction=ph.PowerReaction(1.0, 2.0), source=ph.XSinYExpZSource(1, 5.0), storage=ph.LinearStorage(1.0))
-    v.enable_species(s, 1, [1])
-    v.boundary_dirichlet(s, 1, 5, 0.1)
-    v.boundary_dirichlet(s, 1, 6, 0.2)
-    st, info = P.partitioned_state(s, rank, world, local)
-    N = s.grid.num_nodes
-    rng = np.random.default_rng(1)
-    Ug = np.asfortranarray(rng.uniform(0.1, 1.0, (1, N)))
-    # ---- residual rows
-    F = st.eval_res_jac(Ug[:, info.local_nodes], tstep=0.05)
-    # ---- one implicit Euler step (Newton to convergence) with BiCGStab + Jacobi across ranks
-    sol = v.solve_state(st, inival=np.asfortranarray(Ug[:, info.local_nodes]), tstep=0.05)
-    # the same step with rank-local aggregation AMG inside BiCGStab (block-Jacobi across ranks, no communication in the preconditioner)
-    sol_amg = v.solve_state(st, inival=np.asfortranarray(Ug[:, info.local_nodes]), tstep=0.05, method_linear=v.KrylovJL_BICGSTAB(precs=v.AMGPreconBuilder()),
-                            reltol_linear=1e-13, abstol_linear=0.0, maxiters_linear=2000)
-    own = slice(0, info.n_owned)
-    assert np.max(np.abs(sol_amg[:, own] - sol[:, own])) < 1e-10, "AMG-preconditioned solve differs"
-
-    gathered = [None] * world
-    dist.all_gather_object(gathered, (info.local_nodes[own], F[:, own], sol[:, own]))
+    for name, mk in (("scalar", scalar_system), ("bipolar", bipolar_system), ("masked", masked_system)):
+        s, tstep, ur = mk()
+        check(name, s, tstep, ur, rank, world, local)
     if rank == 0:
-        from oracle import oracle as O
-
-        Fg, solg = np.zeros((1, N)), np.zeros((1, N))
-        for nodes, f, u in gathered:
-            Fg[:, nodes] = f
-            solg[:, nodes] = u
-        o = O.OracleSystem(s)
-        Fo, _ = o.assemble(Ug, Ug, tstep=0.05)
-        ref = o.solve_step(Ug, tstep=0.05)
-        ef = np.max(np.abs(Fg - Fo) / np.maximum(np.abs(Fo), 1e-3))
-        eu = np.max(np.abs(solg - ref))
-        print(f"mgpu_check world={world} transport={'peer mailboxes' if st.peer else 'NCCL'}: residual rel err {ef:.2e}, Newton solution err {eu:.2e}")
-        assert ef < 1e-11 and eu < 1e-10
-        print("MGPU_OK")
-    st.close()
+        print("MGPU_OK", flush=True)
     dist.destroy_process_group()
 
 

@@ -74,8 +74,23 @@ def probe_rows(system, st, pinfo, Uglob, UOldglob=None, time=0.0, tstep=math.inf
         out["rows"] += m * n
         out["entries"] += int(Aog.nnz)
         if not same:
-            out["max_rel_err_entry"] = out["max_err_over_bound"] = float("inf")
-            continue
+            # The reference's pattern is value dependent (_addnz skips exact zeros, src/vfvm_assembly.jl:21-28), the device pattern
+            # is not: device entries the oracle does not hold are tolerated only if they are exactly zero; nothing may be missing.
+            ncol = n * g.num_nodes
+            kd = np.repeat(np.arange(m * n, dtype=np.int64), np.diff(Adg.indptr)) * ncol + Adg.indices
+            ko = np.repeat(np.arange(m * n, dtype=np.int64), np.diff(Aog.indptr)) * ncol + Aog.indices
+            pos = np.searchsorted(kd, ko)
+            found = (pos < kd.size) & (kd[np.minimum(pos, kd.size - 1)] == ko)
+            extra = np.ones(kd.size, bool)
+            extra[pos[found]] = False
+            if not found.all() or np.any(Adg.data[extra] != 0.0):
+                out["pattern_superset_with_zero_extras"] = False
+                out["max_rel_err_entry"] = out["max_err_over_bound"] = float("inf")
+                continue
+            out["explicit_zero_extras"] = out.get("explicit_zero_extras", 0) + int(extra.sum())
+            keep = ~extra
+            counts = np.bincount(np.repeat(np.arange(m * n), np.diff(Adg.indptr))[keep], minlength=m * n)
+            Adg = sp.csr_matrix((Adg.data[keep], Adg.indices[keep], np.concatenate([[0], np.cumsum(counts)])), shape=Adg.shape)
         rows = np.repeat(np.arange(m * n), np.diff(Aog.indptr))
         mag = np.where(np.abs(Aog.data) < 1e29, np.abs(Aog.data), 0.0)
         termscale = np.bincount(rows, weights=mag, minlength=m * n)
@@ -87,5 +102,5 @@ def probe_rows(system, st, pinfo, Uglob, UOldglob=None, time=0.0, tstep=math.inf
         fo = Fo[:, :m].ravel(order="F")
         fbound = RTOL_ASM * np.abs(fo) + 8 * EPS * (termscale * max(1.0, float(np.abs(Ul).max())) + np.abs(fo))
         out["residual_max_err_over_bound"] = max(out["residual_max_err_over_bound"], float((np.abs(f - fo) / np.maximum(fbound, 1e-300)).max()))
-    out["ok"] = bool(out["pattern_equal"] and out["max_err_over_bound"] <= 1.0 and out["residual_max_err_over_bound"] <= 1.0)
+    out["ok"] = bool((out["pattern_equal"] or out.get("pattern_superset_with_zero_extras", True)) and out["max_err_over_bound"] <= 1.0 and out["residual_max_err_over_bound"] <= 1.0)
     return out

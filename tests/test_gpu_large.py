@@ -185,12 +185,12 @@ def _assert_matches_oracle(st, s, U, Uold, tstep, rowscale):
     assert np.all(np.abs(f - fo) <= 1e-12 * np.abs(fo) + 8 * np.finfo(float).eps * (termscale * max(1.0, np.abs(U).max()) + np.abs(fo)))
 
 
-def test_cfg4_full_size_against_oracle():
-    """cfg4 (bipolar drift-diffusion, 129^3 nodes, 3 species, 3 cell regions, implicit Euler): every residual and Jacobian entry of
-    the analytic node-transformed device kernel against the oracle's Dual<6> evaluation of the reference's flux"""
+def test_cfg4_129_every_entry_against_oracle():
+    """cfg4 physics (bipolar drift-diffusion, 3 species, 3 cell regions, implicit Euler) on 129^3 nodes: every residual and Jacobian
+    entry of the analytic node-transformed device kernel against the oracle's Dual<6> evaluation of the reference's flux"""
     import bench
 
-    s, kw, _ = bench.make_system("cfg4", None)
+    s, kw, _ = bench.make_system("cfg4", 129)
     st = v.SystemState(s)
     try:
         assert st.num_edges == 14827904
@@ -202,6 +202,68 @@ def test_cfg4_full_size_against_oracle():
         _assert_matches_oracle(st, s, U, Uold, kw["tstep"], 0.1)
     finally:
         st.close()
+
+
+@pytest.fixture(scope="module")
+def cfg4_full():
+    import bench
+
+    s, kw, _ = bench.make_system("cfg4", None)
+    st = v.SystemState(s)
+    yield s, kw, st
+    st.close()
+
+
+def test_cfg4_full_size_193_rows_against_oracle(cfg4_full):
+    """the north_star target grid (193^3 nodes, 49.9 M edges, 3 species): the oracle cannot hold the whole 563 M-entry Jacobian next to
+    the device copy, so twelve pairs of node planes -- both Dirichlet faces, both region interfaces and eight others -- are compared
+    entry by entry (tests/parity_probe.py: the rows of a node range only depend on the cells touching it)"""
+    from parity_probe import probe_rows
+
+    s, kw, st = cfg4_full
+    assert st.num_edges == 49877568
+    g = s.grid
+    U = np.asfortranarray(np.random.default_rng(20261017).uniform(-0.5, 0.5, (3, g.num_nodes)))
+    Uold = np.asfortranarray(U * 0.9 + 0.01)
+    st.eval_res_jac(U, Uold, tstep=kw["tstep"])
+    plane = 193 * 193
+    zs = [0, 191, 63, 64, 65, 127, 128, 129, 17, 96, 150, 180]
+    res = probe_rows(s, st, None, U, Uold, tstep=kw["tstep"], ranges=[(z * plane, min((z + 2) * plane, g.num_nodes)) for z in zs])
+    assert res["ok"], res
+    assert res["entries"] > 30e6
+
+
+def test_cfg4_full_size_193_newton_step_matches_committed_reference(cfg4_full):
+    """one Newton step of the north_star system at full size, solved to 1e-13, against tests/golden/newton_samples_cfg4_193.json"""
+    import json
+    import os
+
+    import bench
+
+    s, kw, st = cfg4_full
+    path = os.path.join(os.path.dirname(__file__), "golden", "newton_samples_cfg4_193.json")
+    if not os.path.exists(path):
+        pytest.skip("no committed Newton reference for cfg4 at 193^3")
+    gold = json.load(open(path))
+    sol, info = bench.newton_solution(st, s, bench.generic_state(s), kw["tstep"], reltol=1e-13)
+    diff = np.abs(sol[:, gold["nodes"]] - np.asarray(gold["solution"])).max()
+    assert diff <= 1e-10, (diff, info, gold["how"])
+
+
+def test_cfg3_full_size_193_newton_step_matches_committed_reference(cfg3):
+    import json
+    import os
+
+    import bench
+
+    s, st = cfg3
+    path = os.path.join(os.path.dirname(__file__), "golden", "newton_samples_cfg3_193.json")
+    if not os.path.exists(path):
+        pytest.skip("no committed Newton reference for cfg3 at 193^3")
+    gold = json.load(open(path))
+    sol, info = bench.newton_solution(st, s, bench.generic_state(s), math.inf, reltol=1e-13)
+    diff = np.abs(sol[:, gold["nodes"]] - np.asarray(gold["solution"])).max()
+    assert diff <= 1e-10, (diff, info, gold["how"])
 
 
 def test_cfg5_full_size_against_oracle():

@@ -58,7 +58,19 @@ def test_probe_accepts_identical_rows_and_detects_a_wrong_entry():
     st.A = sp.csr_matrix(A)
     bad = probe_rows(s, st, None, U, tstep=0.1)
     assert not bad["ok"] and bad["max_err_over_bound"] > 1.0
-    st.A = _OracleBackedState(s, U, 0.1).A
+    # an explicit zero the oracle does not hold is tolerated (value-independent device pattern), a non-zero extra entry is not
+    good = _OracleBackedState(s, U, 0.1).A
+    A = good.copy().tolil()
+    free = [c for c in range(A.shape[1]) if c not in A.rows[r0]][0]
+    A[r0, free] = 1.0
+    A = sp.csr_matrix(A)
+    A.data[A.indptr[r0] + list(A.indices[A.indptr[r0]:A.indptr[r0 + 1]]).index(free)] = 0.0
+    st.A = A
+    res0 = probe_rows(s, st, None, U, tstep=0.1)
+    assert res0["ok"] and not res0["pattern_equal"] and res0["explicit_zero_extras"] == 1
+    A.data[A.indptr[r0] + list(A.indices[A.indptr[r0]:A.indptr[r0 + 1]]).index(free)] = 1e-20
+    assert not probe_rows(s, st, None, U, tstep=0.1)["ok"]
+    st.A = good
     st.F = st.F.copy()
     st.F[1, 5] += 1e-6
     assert not probe_rows(s, st, None, U, tstep=0.1)["ok"]
