@@ -11,7 +11,8 @@ hdr = rows[0]
 iK, iM, iV, iU, iID = (hdr.index(k) for k in ("Kernel Name", "Metric Name", "Metric Value", "Metric Unit", "ID"))
 L = collections.OrderedDict()
 for r in rows[1:]:
-    d = L.setdefault(r[iID], {"k": r[iK].split("(")[0].replace("<unnamed>::", "").replace("void ", "")})
+    name = r[iK].replace("<unnamed>::", "").replace("(anonymous namespace)::", "").replace("void ", "").replace("(int)", "").replace("(bool)", "")
+    d = L.setdefault(r[iID], {"k": name.split("(")[0]})
     v = float(r[iV].replace(",", ""))
     if "duration" in r[iM]:
         d["ns"] = v * {"ns": 1, "us": 1e3, "ms": 1e6}.get(r[iU], 1)
@@ -26,4 +27,4 @@ for d in L.values():
 tot = sum(v[1] for v in agg.values())
 print(f"{len(L)} launches, {tot / 1e3:.1f} us of kernel time (serialised under ncu)")
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-    print(f"{k[0]:34s} {k[1]:6s} n={v[0]:4d}  total {v[1] / 1e3:8.1f} us ({100 * v[1] / tot:4.1f} %)  avg {v[1] / v[0] / 1e3:7.1f} us  DRAM {v[2] / max(v[1], 1):7.1f} GB/s")
+    print(f"{k[0]:50s} {k[1]:6s} n={v[0]:4d}  total {v[1] / 1e3:8.1f} us ({100 * v[1] / tot:4.1f} %)  avg {v[1] / v[0] / 1e3:7.1f} us  DRAM {v[2] / max(v[1], 1):7.1f} GB/s")

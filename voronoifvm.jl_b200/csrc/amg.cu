@@ -31,6 +31,34 @@
 
 namespace {
 
+#define FUSE_THREADS 512
+#define FUSE_SMALL_N 2048
+enum { FOP_SMOOTH_FIRST = 1, FOP_SPMV, FOP_SMOOTH, FOP_RESTRICT, FOP_WRES, FOP_WADD, FOP_PROLONG };
+
+struct LevelDev {
+    int64_t N, Nvec, nnz_sell, Nc;
+    int nslices;
+    const int32_t *sell_ptr, *colidx;
+    const double *offval, *diagval, *binv;
+    const int32_t *agg, *agg_ptr, *agg_nodes;
+    double *x, *t, *b, *b2, *x2;
+    // several ranks: this level's exchange lists (neighbour slots as on level 0)
+    int64_t send_ptr[VFVM_PEER_MAX + 1], recv_ptr[VFVM_PEER_MAX + 1];
+    const int32_t* send_idx;
+};
+struct FuseOp {
+    int code, lvl, bsel, small;  // bsel: 0 = the level's b, 1 = its b2; small: executed by block 0 alone
+};
+struct FuseArgs {
+    const LevelDev* lev;
+    const FuseOp* prog;
+    int nops, distributed;
+    double omega, alpha;
+    unsigned long long *bar_ctr, *bar_gen;
+    PeerArgs P;
+    signed char idxF[100], idxD[100];
+};
+
 struct Level {
     int64_t N = 0;     // nodes of this level (level 0: the owned nodes)
     int64_t Nvec = 0;  // nodes a vector of this level holds (level 0: including the halo, whose entries stay zero here)
@@ -91,6 +119,14 @@ struct Amg {
     }
     bool struct_valid = false, distributed = false;
     int64_t pattern_nnz = -1, pattern_N = -1;
+    // fused coarse cycle (k_fused_cycle): levels >= fuse_level run in one persistent kernel
+    int fuse_level = 1;  // 0 = off
+    bool fuse_valid = false;
+    DevBuf<LevelDev> lev_dev;
+    DevBuf<FuseOp> prog_dev[2];  // entry with the level's b / with its b2 (second visit of a W-cycle)
+    int prog_len[2] = {0, 0};
+    DevBuf<unsigned long long> bar;  // [0] barrier counter, [1] generation
+    int fuse_grid = 0;
     double omega = 0.8, alpha = 1.75, theta = 0.08;  // alpha: measured on cfg3 (CG iterations 153 / 101 / 79 / 71 / 69 for alpha = 1 / 1.25 / 1.5 / 1.75 / 2)
     int coarse_sweeps = 4, max_levels = 20, sweeps = 1;
     int wdepth = 0;  // levels 1..wdepth are visited twice per visit of their parent (W-cycle on the top of the hierarchy), 0 = V-cycle  // sweeps: pre- and post-smoothing steps per level
@@ -455,6 +491,221 @@ __global__ void k_prolong(int64_t N, double alpha, const int32_t* __restrict__ a
     for (int i = 0; i < NS; i++) x[K * NS + i] += alpha * xc[(int64_t)I * NS + i];
 }
 
+
+// ------------------------------------------------------------------------------------------------ fused coarse cycle
+// Everything below the finest level runs in ONE persistent kernel: the recursive cycle is unrolled by the host into a short program
+// of level operations (smooth / SpMV / restrict / prolong / W-cycle bookkeeping), every block executes the program in lock step and
+// a grid-wide barrier in global memory separates dependent operations (a sense-free counter barrier: ~1-2 us against ~2.5 us per
+// kernel of a replayed graph and 4-5 us eager).  Levels that fit one block (N <= FUSE_SMALL_N) are processed by block 0 alone with
+// __syncthreads between the operations, so the deepest levels of the hierarchy -- pure latency -- cost ~0.1 us per step.
+// With several ranks the halo exchange of a level SpMV happens inside the kernel through the peer mailboxes (peer.cuh): push the
+// boundary values, barrier, raise the flags, wait for the neighbours' flags, multiply.  The sequence counter is advanced in a
+// register by every block alike and stored back once at the end of the kernel.
+// A W-cycle on the coarse levels therefore costs no launches at all, which is what makes it affordable on every rank count.
+__device__ __forceinline__ void grid_barrier(unsigned long long* ctr, unsigned long long target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(ctr, 1ull);
+        while (*(volatile unsigned long long*)ctr < target) __nanosleep(32);
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+template <int NS, bool DIAGMASK>
+__device__ __forceinline__ void fuse_spmv(const FuseArgs& a, const LevelDev& l, const double* __restrict__ x, double* __restrict__ y, int warp, int nwarps, const double* hbox) {
+    const int lane = threadIdx.x & 31;
+    const int64_t nnz = l.nnz_sell;
+    for (int g = warp; g < l.nslices; g += nwarps) {
+        const int64_t rraw = (int64_t)g * 32 + lane;
+        const bool valid = rraw < l.N;
+        const int64_t r = valid ? rraw : l.N - 1;
+        const int base = l.sell_ptr[g];
+        const int w = (l.sell_ptr[g + 1] - base) >> 5;
+        double acc[NS];
+#pragma unroll
+        for (int i = 0; i < NS; i++) acc[i] = 0.0;
+        constexpr int BATCH = NS == 1 ? 4 : 2;
+        for (int j0 = 0; j0 < w; j0 += BATCH) {
+            int Lc[BATCH];
+#pragma unroll
+            for (int b = 0; b < BATCH; b++) Lc[b] = (j0 + b < w) ? l.colidx[(int64_t)base + (int64_t)(j0 + b) * 32 + lane] : (int)r;
+            double xl[BATCH][NS];
+#pragma unroll
+            for (int b = 0; b < BATCH; b++) {
+                if (hbox && Lc[b] >= l.N) {  // halo column: read from the mailbox (level lists -> mailbox position)
+                    const int64_t c = Lc[b] - l.N;
+                    int q = 0;
+                    while (c >= l.recv_ptr[q + 1]) q++;
+                    const int64_t pos = a.P.recv_ptr0[q] + (c - l.recv_ptr[q]);
+#pragma unroll
+                    for (int jj = 0; jj < NS; jj++) xl[b][jj] = peer_ld_data(hbox + pos * NS + jj);
+                } else {
+#pragma unroll
+                    for (int jj = 0; jj < NS; jj++) xl[b][jj] = x[(int64_t)Lc[b] * NS + jj];
+                }
+            }
+#pragma unroll
+            for (int b = 0; b < BATCH; b++) {
+                if (j0 + b >= w) break;
+                const int64_t e = (int64_t)base + (int64_t)(j0 + b) * 32 + lane;
+                if constexpr (DIAGMASK) {
+#pragma unroll
+                    for (int i = 0; i < NS; i++) acc[i] += l.offval[(int64_t)i * nnz + e] * xl[b][i];
+                } else {
+#pragma unroll
+                    for (int i = 0; i < NS; i++)
+#pragma unroll
+                        for (int jj = 0; jj < NS; jj++) {
+                            const int p = a.idxF[i * NS + jj];
+                            if (p >= 0) acc[i] += l.offval[(int64_t)p * nnz + e] * xl[b][jj];
+                        }
+                }
+            }
+        }
+        if (valid) {
+            double xr[NS];
+#pragma unroll
+            for (int jj = 0; jj < NS; jj++) xr[jj] = x[r * NS + jj];
+#pragma unroll
+            for (int i = 0; i < NS; i++) {
+                double sacc = acc[i];
+                if constexpr (DIAGMASK) {
+                    sacc += l.diagval[(int64_t)i * l.N + r] * xr[i];
+                } else {
+#pragma unroll
+                    for (int jj = 0; jj < NS; jj++) {
+                        const int p = a.idxD[i * NS + jj];
+                        if (p >= 0) sacc += l.diagval[(int64_t)p * l.N + r] * xr[jj];
+                    }
+                }
+                y[r * NS + i] = sacc;
+            }
+        }
+    }
+}
+
+template <int NS, bool DIAGMASK>
+__global__ void __launch_bounds__(FUSE_THREADS) k_fused_cycle(const FuseArgs a) {
+    const unsigned long long gen = *(volatile unsigned long long*)a.bar_gen;
+    unsigned long long nbar = 0;
+    unsigned long long seq = a.distributed ? *(volatile unsigned long long*)a.P.seq_ctr : 0ull;
+    const int nblk = gridDim.x;
+    for (int k = 0; k < a.nops; k++) {
+        const FuseOp op = a.prog[k];
+        const LevelDev& l = a.lev[op.lvl];
+        const bool mine = !op.small || blockIdx.x == 0;
+        // index space of this operation: the whole grid, or block 0 alone
+        const int64_t tid = op.small ? threadIdx.x : (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        const int64_t nth = op.small ? blockDim.x : (int64_t)nblk * blockDim.x;
+        const int warp = (int)(tid >> 5), nwarps = (int)(nth >> 5);
+        const double* __restrict__ bvec = op.bsel ? l.b2 : l.b;
+        const double* hbox = nullptr;
+        if (op.code == FOP_SPMV && a.distributed) {
+            // halo exchange of x_l through the mailboxes, inside the kernel
+            seq++;
+            const int par = (int)(seq & 1ull);
+            if (mine) {
+                const int64_t total = l.send_ptr[a.P.nn] * NS;
+                for (int64_t i = tid; i < total; i += nth) {
+                    const int64_t q = i / NS;
+                    const int s = (int)(i - q * NS);
+                    int r = 0;
+                    while (q >= l.send_ptr[r + 1]) r++;
+                    a.P.halo_dst[r][par * a.P.halo_dst_stride[r] + (q - l.send_ptr[r]) * NS + s] = l.x[(int64_t)l.send_idx[q] * NS + s];
+                }
+                __threadfence_system();
+            }
+            if (op.small) {
+                if (mine) __syncthreads();
+            } else {
+                nbar++;
+                grid_barrier(a.bar_ctr, gen + nbar * nblk);
+            }
+            if (blockIdx.x == 0 && threadIdx.x < a.P.nn) peer_st_flag(a.P.hflag_dst[threadIdx.x] + par * a.P.nranks, seq);
+            if (mine) {
+                if (threadIdx.x < a.P.nn) peer_wait(a.P.hflag_local + par * a.P.nranks + threadIdx.x, seq, a.P.err, a.P.timeout_ns);
+                __syncthreads();
+            }
+            hbox = a.P.halo_local + (int64_t)par * a.P.halo_local_stride;
+        }
+        if (mine) {
+            switch (op.code) {
+                case FOP_SMOOTH_FIRST:
+                case FOP_SMOOTH: {
+                    const bool first = op.code == FOP_SMOOTH_FIRST;
+                    for (int64_t r = tid; r < l.N; r += nth) {
+                        double res[NS];
+#pragma unroll
+                        for (int j = 0; j < NS; j++) res[j] = first ? bvec[r * NS + j] : bvec[r * NS + j] - l.t[r * NS + j];
+#pragma unroll
+                        for (int i = 0; i < NS; i++) {
+                            double sacc = 0.0;
+#pragma unroll
+                            for (int j = 0; j < NS; j++) sacc += l.binv[(int64_t)(i * NS + j) * l.N + r] * res[j];
+                            l.x[r * NS + i] = (first ? 0.0 : l.x[r * NS + i]) + a.omega * sacc;
+                        }
+                    }
+                    break;
+                }
+                case FOP_SPMV: fuse_spmv<NS, DIAGMASK>(a, l, l.x, l.t, warp, nwarps, hbox); break;
+                case FOP_RESTRICT: {
+                    const LevelDev& c = a.lev[op.lvl + 1];
+                    for (int64_t I = tid; I < c.N; I += nth) {
+                        double sacc[NS];
+#pragma unroll
+                        for (int i = 0; i < NS; i++) sacc[i] = 0.0;
+                        for (int q = l.agg_ptr[I]; q < l.agg_ptr[I + 1]; q++) {
+                            const int64_t K = l.agg_nodes[q];
+#pragma unroll
+                            for (int i = 0; i < NS; i++) sacc[i] += bvec[K * NS + i] - l.t[K * NS + i];
+                        }
+#pragma unroll
+                        for (int i = 0; i < NS; i++) c.b[I * NS + i] = sacc[i];
+                    }
+                    break;
+                }
+                case FOP_WRES:
+                    for (int64_t i = tid; i < l.N * NS; i += nth) {
+                        l.b2[i] = l.b[i] - l.t[i];
+                        l.x2[i] = l.x[i];
+                    }
+                    break;
+                case FOP_WADD:
+                    for (int64_t i = tid; i < l.N * NS; i += nth) l.x[i] += l.x2[i];
+                    break;
+                case FOP_PROLONG: {
+                    const LevelDev& c = a.lev[op.lvl + 1];
+                    for (int64_t K = tid; K < l.N; K += nth) {
+                        const int I = l.agg[K];
+                        if (I < 0) continue;
+#pragma unroll
+                        for (int i = 0; i < NS; i++) l.x[K * NS + i] += a.alpha * c.x[(int64_t)I * NS + i];
+                    }
+                    break;
+                }
+                default: break;
+            }
+        }
+        // separation from the next operation: block-local if both run on block 0 alone, grid-wide otherwise
+        if (k + 1 < a.nops) {
+            if (op.small && a.prog[k + 1].small) {
+                if (mine) __syncthreads();
+            } else {
+                nbar++;
+                grid_barrier(a.bar_ctr, gen + nbar * nblk);
+            }
+        }
+    }
+    nbar++;
+    grid_barrier(a.bar_ctr, gen + nbar * nblk);  // every block has read `gen` (and the sequence counter) by now
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        *a.bar_gen = gen + nbar * nblk;
+        if (a.distributed) *a.P.seq_ctr = seq;
+    }
+}
+
 #define NS_SWITCH(n, ...)                                                                  \
     switch (n) {                                                                           \
         case 1: { constexpr int NS = 1; __VA_ARGS__; } break;                              \
@@ -696,6 +947,7 @@ void build_coarse_halo(vfvm_handle* h, Amg& A, size_t fi, Level& f, Level& c) {
 
 void build_hierarchy(vfvm_handle* h, Amg& A) {
     A.drop_graphs();
+    A.fuse_valid = false;
     for (Level* l : A.L) delete l;
     A.L.clear();
     A.distributed = h->nranks > 1 && !h->nb_ranks.empty() && !getenv("VFVM_AMG_LOCAL");
@@ -796,9 +1048,140 @@ void smooth(vfvm_handle* h, Amg& A, size_t i, const double* b, bool first, doubl
     h->launches++;
 }
 
+// ---- fused coarse cycle: host side ----------------------------------------------------------------------------------------------
+void emit_program(const Amg& A, size_t i, int bsel, std::vector<FuseOp>& P) {
+    auto small = [&](size_t lv) { return A.L[lv]->N <= FUSE_SMALL_N ? 1 : 0; };
+    auto op = [&](int code, size_t lv, int bs) { P.push_back(FuseOp{code, (int)lv, bs, small(lv)}); };
+    if (i + 1 == A.L.size()) {  // coarsest level: a few sweeps
+        for (int k = 0; k < A.coarse_sweeps; k++) {
+            if (k > 0) op(FOP_SPMV, i, 0);
+            op(k == 0 ? FOP_SMOOTH_FIRST : FOP_SMOOTH, i, bsel);
+        }
+        return;
+    }
+    op(FOP_SMOOTH_FIRST, i, bsel);
+    for (int k = 1; k < A.sweeps; k++) {
+        op(FOP_SPMV, i, 0);
+        op(FOP_SMOOTH, i, bsel);
+    }
+    op(FOP_SPMV, i, 0);
+    op(FOP_RESTRICT, i, bsel);
+    emit_program(A, i + 1, 0, P);
+    if ((int)(i + 1) <= A.wdepth && i + 2 < A.L.size()) {
+        op(FOP_SPMV, i + 1, 0);
+        op(FOP_WRES, i + 1, 0);
+        emit_program(A, i + 1, 1, P);
+        op(FOP_WADD, i + 1, 0);
+    }
+    op(FOP_PROLONG, i, 0);
+    for (int k = 1; k < A.sweeps; k++) {
+        op(FOP_SPMV, i, 0);
+        op(FOP_SMOOTH, i, bsel);
+    }
+    op(FOP_SPMV, i, 0);
+    op(FOP_SMOOTH, i, bsel);
+}
+
+void build_fused(vfvm_handle* h, Amg& A) {
+    A.fuse_valid = false;
+    static const bool off = getenv("VFVM_AMG_NO_FUSE") != nullptr;
+    if (const char* e = getenv("VFVM_AMG_FUSE_LEVEL")) A.fuse_level = std::max(0, atoi(e));
+    if (off || A.fuse_level <= 0 || (size_t)A.fuse_level >= A.L.size()) return;
+    if (A.distributed && !h->peer_ok) return;  // NCCL transport: the exchanges are host-enqueued collectives, the levels stay separate kernels
+    const int nn = (int)h->nb_ranks.size();
+    std::vector<LevelDev> lv(A.L.size());
+    for (size_t i = 0; i < A.L.size(); i++) {
+        const Level& l = *A.L[i];
+        LevelDev& d = lv[i];
+        memset(&d, 0, sizeof(d));
+        d.N = l.N;
+        d.Nvec = l.Nvec;
+        d.nnz_sell = l.nnz_sell;
+        d.Nc = l.Nc;
+        d.nslices = l.nslices;
+        d.sell_ptr = l.sell_ptr;
+        d.colidx = l.colidx;
+        d.offval = l.offval;
+        d.diagval = l.diagval;
+        d.binv = l.binv.p;
+        d.agg = l.agg.p;
+        d.agg_ptr = l.agg_ptr.p;
+        d.agg_nodes = l.agg_nodes.p;
+        d.x = l.x.p;
+        d.t = l.t.p;
+        d.b = l.b.p;
+        d.b2 = l.b2.p;
+        d.x2 = l.x2.p;
+        if (A.distributed && i > 0) {
+            for (int r = 0; r <= nn; r++) {
+                d.send_ptr[r] = l.halo.send_ptr[r];
+                d.recv_ptr[r] = l.halo.recv_ptr[r];
+            }
+            d.send_idx = l.halo.send_idx.p;
+        }
+    }
+    A.lev_dev.upload(lv.data(), lv.size(), h->stream);
+    for (int bs = 0; bs < 2; bs++) {
+        std::vector<FuseOp> P;
+        emit_program(A, (size_t)A.fuse_level, bs, P);
+        A.prog_len[bs] = (int)P.size();
+        A.prog_dev[bs].upload(P.data(), P.size(), h->stream);
+    }
+    if (!A.bar.p) {
+        A.bar.alloc(2);
+        CK(cudaMemsetAsync(A.bar.p, 0, 2 * sizeof(unsigned long long), h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    A.fuse_valid = true;
+}
+
+template <int NS, bool DIAGMASK>
+void launch_fused_k(vfvm_handle* h, Amg& A, const FuseArgs& fa) {
+    auto kern = k_fused_cycle<NS, DIAGMASK>;
+    static int occ = 0;
+    if (occ == 0) {
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, FUSE_THREADS, 0));
+        if (occ < 1) throw std::string("fused AMG cycle kernel cannot be launched");
+    }
+    int nsm = 148;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device);
+    // one resident wave (the blocks meet at barriers); no more blocks than the entry level has slices per warp
+    const int grid = std::max(1, std::min(nsm * occ, cdiv(A.L[A.fuse_level]->nslices, FUSE_THREADS / 32)));
+    kern<<<grid, FUSE_THREADS, 0, h->stream>>>(fa);
+    h->launches++;
+}
+
+void launch_fused(vfvm_handle* h, Amg& A, int bsel) {
+    FuseArgs fa;
+    memset(&fa, 0, sizeof(fa));
+    fa.lev = A.lev_dev.p;
+    fa.prog = A.prog_dev[bsel].p;
+    fa.nops = A.prog_len[bsel];
+    fa.distributed = A.distributed ? 1 : 0;
+    fa.omega = A.omega;
+    fa.alpha = A.alpha;
+    fa.bar_ctr = A.bar.p;
+    fa.bar_gen = A.bar.p + 1;
+    if (A.distributed) fa.P = vfvm_peer_args_halo(h);
+    SpmvArgs sa = vfvm_spmv_args(h);
+    memcpy(fa.idxF, sa.idxF, sizeof(fa.idxF));
+    memcpy(fa.idxD, sa.idxD, sizeof(fa.idxD));
+    bool diagmask = (h->cF == h->n && h->cD == h->n);
+    for (int i = 0; i < h->n && diagmask; i++) diagmask = (h->idxF[i * h->n + i] == i && h->idxD[i * h->n + i] == i);
+    if (diagmask) {
+        NS_SWITCH(h->n, (launch_fused_k<NS, true>(h, A, fa)));
+    } else {
+        NS_SWITCH(h->n, (launch_fused_k<NS, false>(h, A, fa)));
+    }
+}
+
 void cycle(vfvm_handle* h, Amg& A, size_t i, const double* b, double* out) {
     cudaStream_t s = h->stream;
     Level& l = *A.L[i];
+    if (A.fuse_valid && i >= 1 && (int)i == A.fuse_level && !out && (b == l.b.p || b == l.b2.p)) {  // this level and everything below: one persistent kernel
+        launch_fused(h, A, b == l.b.p ? 0 : 1);
+        return;
+    }
     if (i + 1 == A.L.size()) {  // coarsest level: a few sweeps
         for (int k = 0; k < A.coarse_sweeps; k++) smooth(h, A, i, b, k == 0, k + 1 == A.coarse_sweeps ? out : nullptr);
         return;
@@ -856,7 +1239,9 @@ void vfvm_amg_setup(vfvm_handle* h) {
     if (!(sig == A.captured)) {  // a new Jacobian in the same buffers keeps the captured cycles; new options or buffers do not
         A.drop_graphs();
         A.captured = sig;
+        A.fuse_valid = false;
     }
+    if (!A.fuse_valid) build_fused(h, A);
 }
 
 // options of the AMG preconditioner: omega (smoother damping), alpha (weight of the coarse correction), theta (strength threshold),
