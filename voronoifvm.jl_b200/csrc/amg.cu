@@ -32,7 +32,7 @@
 namespace {
 
 #define FUSE_THREADS 512
-#define FUSE_SMALL_N 2048
+#define FUSE_SMALL_N 8192
 enum { FOP_SMOOTH_FIRST = 1, FOP_SPMV, FOP_SMOOTH, FOP_RESTRICT, FOP_WRES, FOP_WADD, FOP_PROLONG };
 
 struct LevelDev {
@@ -120,7 +120,8 @@ struct Amg {
     bool struct_valid = false, distributed = false;
     int64_t pattern_nnz = -1, pattern_N = -1;
     // fused coarse cycle (k_fused_cycle): levels >= fuse_level run in one persistent kernel
-    int fuse_level = 1;  // 0 = off
+    int fuse_level = 1;  // first level of the fused kernel (chosen by build_fused), 0 = off
+    int64_t fuse_max_n = 131072;  // levels with more nodes than this keep their own (bandwidth-tuned) kernels
     bool fuse_valid = false;
     DevBuf<LevelDev> lev_dev;
     DevBuf<FuseOp> prog_dev[2];  // entry with the level's b / with its b2 (second visit of a W-cycle)
@@ -505,10 +506,11 @@ __global__ void k_prolong(int64_t N, double alpha, const int32_t* __restrict__ a
 __device__ __forceinline__ void grid_barrier(unsigned long long* ctr, unsigned long long target) {
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(ctr, 1ull);
-        while (*(volatile unsigned long long*)ctr < target) __nanosleep(32);
-        __threadfence();
+        unsigned long long v;
+        asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(ctr) : "memory");
+        do {
+            asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(ctr) : "memory");
+        } while (v < target);
     }
     __syncthreads();
 }
@@ -1085,6 +1087,14 @@ void emit_program(const Amg& A, size_t i, int bsel, std::vector<FuseOp>& P) {
 void build_fused(vfvm_handle* h, Amg& A) {
     A.fuse_valid = false;
     static const bool off = getenv("VFVM_AMG_NO_FUSE") != nullptr;
+    if (const char* e = getenv("VFVM_AMG_FUSE_MAX_N")) A.fuse_max_n = std::max(1ll, atoll(e));
+    // the fused kernel takes over where launch latency, not bandwidth, bounds a level: the first level with at most fuse_max_n nodes
+    A.fuse_level = 0;
+    for (size_t i = 1; i < A.L.size(); i++)
+        if (A.L[i]->N <= A.fuse_max_n) {
+            A.fuse_level = (int)i;
+            break;
+        }
     if (const char* e = getenv("VFVM_AMG_FUSE_LEVEL")) A.fuse_level = std::max(0, atoi(e));
     if (off || A.fuse_level <= 0 || (size_t)A.fuse_level >= A.L.size()) return;
     if (A.distributed && !h->peer_ok) return;  // NCCL transport: the exchanges are host-enqueued collectives, the levels stay separate kernels
@@ -1145,8 +1155,10 @@ void launch_fused_k(vfvm_handle* h, Amg& A, const FuseArgs& fa) {
     }
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device);
-    // one resident wave (the blocks meet at barriers); no more blocks than the entry level has slices per warp
-    const int grid = std::max(1, std::min(nsm * occ, cdiv(A.L[A.fuse_level]->nslices, FUSE_THREADS / 32)));
+    // one block per SM at most (the blocks meet at barriers: ~1 us among 148 blocks, several among 600); no more blocks than the entry
+    // level has slices per warp
+    (void)occ;
+    const int grid = std::max(1, std::min(nsm, cdiv(A.L[A.fuse_level]->nslices, FUSE_THREADS / 32)));
     kern<<<grid, FUSE_THREADS, 0, h->stream>>>(fa);
     h->launches++;
 }

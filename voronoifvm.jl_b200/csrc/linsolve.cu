@@ -11,6 +11,7 @@
 // are combined by ncclAllReduce on the same stream and the SpMV input gets a halo refresh first (comm.cu).
 #include <algorithm>
 
+#include "bulk.cuh"
 #include "vfvm_internal.h"
 
 #define LS_THREADS 256
@@ -136,6 +137,171 @@ __global__ void __launch_bounds__(LS_THREADS) k_spmv(const SpmvArgs a, const Pee
                         }
                 }
             }
+        }
+        if (valid) {
+            double xr[NS];
+#pragma unroll
+            for (int jj = 0; jj < NS; jj++) xr[jj] = a.x[r * NS + jj];
+#pragma unroll
+            for (int i = 0; i < NS; i++) {
+                double s = acc[i];
+                if constexpr (DIAGMASK) {
+                    s += a.diagval[(int64_t)i * a.Nown + r] * xr[i];
+                } else {
+#pragma unroll
+                    for (int jj = 0; jj < NS; jj++) {
+                        const int p = a.idxD[i * NS + jj];
+                        if (p >= 0) s += a.diagval[(int64_t)p * a.Nown + r] * xr[jj];
+                    }
+                }
+                a.y[r * NS + i] = s;
+                if (a.w) {
+                    d_yw += s * a.w[r * NS + i];
+                    d_yy += s * s;
+                }
+            }
+        }
+    }
+    if (a.w) {
+        const double s1 = block_sum(d_yw, red);
+        const double s2 = block_sum(d_yy, red);
+        if (threadIdx.x == 0) {
+            a.part[blockIdx.x] = s1;
+            a.part[gridDim.x + blockIdx.x] = s2;
+        }
+    }
+}
+
+
+// The same product with the index and value planes streamed through shared memory by asynchronous bulk copies (1-D TMA).
+// Motivation (ncu launch list of a cfg4 Newton step, profiles/r2_*): with n x n coupled species the register-staged kernel above holds
+// BATCH x (n + planes) doubles per lane, runs at 16 warps per SM and reaches 2.7 TB/s -- each batch waits for its column indices and
+// then for its gathers and values, and nothing else is in flight meanwhile.  Here every warp owns a ring of BULK_STAGES stages in
+// shared memory; lane 0 arms the stage's mbarrier and issues one bulk copy per plane for a chunk of BULK_CH entries per row
+// (32 rows x BULK_CH entries: 128 B-aligned contiguous pieces of every plane, because a slice is stored entry-major), so
+// BULK_STAGES chunks per warp are in flight at any time without occupying registers, across slice boundaries.  The lanes read the
+// chunk from shared memory (consecutive lanes, no bank conflicts), gather x and accumulate exactly as above -- the summation order
+// per row is unchanged, so the result is bitwise the same.
+#define BULK_CH 4
+#define BULK_STAGES 3
+#define BULK_THREADS 128
+template <int NS, bool DIAGMASK, bool PEER>
+__global__ void __launch_bounds__(BULK_THREADS) k_spmv_bulk(const SpmvArgs a, const PeerArgs P, const int cF) {
+    extern __shared__ __align__(128) unsigned char bulk_smem[];
+    __shared__ double red[32];
+    __shared__ __align__(8) uint64_t bars[(BULK_THREADS / 32) * BULK_STAGES];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int wpb = blockDim.x >> 5, nwarps = gridDim.x * wpb;
+    const int64_t nnz = a.nnz_sell;
+    const int stage_bytes = BULK_CH * 32 * 4 + cF * BULK_CH * 32 * 8;
+    unsigned char* wbase = bulk_smem + (size_t)wib * BULK_STAGES * stage_bytes;
+    uint64_t* wbar = bars + wib * BULK_STAGES;
+    if (lane == 0)
+        for (int s = 0; s < BULK_STAGES; s++) mbar_init(wbar + s, 1);
+    mbar_fence_init();
+    __syncthreads();
+    double d_yw = 0.0, d_yy = 0.0;
+    bool halo_ready = false;  // warp-uniform
+    unsigned long long seq = 0;
+    const double* __restrict__ hbox = nullptr;
+    if constexpr (PEER) {
+        seq = peer_seq(P);
+        hbox = peer_halo_local(P, seq);
+        peer_push<NS>(P, seq, a.x);
+    }
+    const int g0 = blockIdx.x * wpb + wib;
+    // producer cursor (lane 0): next chunk to request
+    int pg = g0, pj0 = 0, pbase = 0, pw = 0;
+    auto producer_seek = [&]() {  // skip slices without entries
+        while (pg < a.nslices) {
+            pbase = a.sell_ptr[pg];
+            pw = (a.sell_ptr[pg + 1] - pbase) >> 5;
+            if (pw > 0) break;
+            pg += nwarps;
+        }
+    };
+    auto issue = [&](int s) {
+        if (pg >= a.nslices) return;
+        const int nent = min(BULK_CH, pw - pj0) * 32;
+        const int64_t e0 = (int64_t)pbase + (int64_t)pj0 * 32;
+        unsigned char* st = wbase + (size_t)s * stage_bytes;
+        mbar_expect_tx(wbar + s, (uint32_t)(nent * 4 + cF * nent * 8));
+        bulk_g2s(st, a.colidx + e0, (uint32_t)(nent * 4), wbar + s);
+        for (int p = 0; p < cF; p++) bulk_g2s(st + BULK_CH * 32 * 4 + (size_t)p * BULK_CH * 32 * 8, a.offval + (int64_t)p * nnz + e0, (uint32_t)(nent * 8), wbar + s);
+        pj0 += BULK_CH;
+        if (pj0 >= pw) {
+            pg += nwarps;
+            pj0 = 0;
+            producer_seek();
+        }
+    };
+    if (lane == 0) {
+        producer_seek();
+        for (int s = 0; s < BULK_STAGES; s++) issue(s);
+    }
+    int stage = 0;
+    uint32_t phases = 0;  // bit s: parity the consumer waits for on stage s
+    for (int g = g0; g < a.nslices; g += nwarps) {
+        const int64_t rraw = (int64_t)g * 32 + lane;
+        const bool valid = rraw < a.Nown;
+        const int64_t r = valid ? rraw : a.Nown - 1;
+        const int base = a.sell_ptr[g];
+        const int w = (a.sell_ptr[g + 1] - base) >> 5;
+        double acc[NS];
+#pragma unroll
+        for (int i = 0; i < NS; i++) acc[i] = 0.0;
+        for (int j0 = 0; j0 < w; j0 += BULK_CH) {
+            mbar_wait(wbar + stage, (phases >> stage) & 1u);
+            const unsigned char* st = wbase + (size_t)stage * stage_bytes;
+            const int32_t* __restrict__ s_col = (const int32_t*)st;
+            const double* __restrict__ s_val = (const double*)(st + BULK_CH * 32 * 4);
+            int Lc[BULK_CH];
+#pragma unroll
+            for (int b = 0; b < BULK_CH; b++) Lc[b] = (j0 + b < w) ? s_col[b * 32 + lane] : (int)r;
+            double xl[BULK_CH][NS];
+            if constexpr (PEER) {
+                bool need = false;
+#pragma unroll
+                for (int b = 0; b < BULK_CH; b++) need |= Lc[b] >= a.Nown;
+                if (!halo_ready && __any_sync(0xffffffffu, need)) {
+                    if (lane < P.nn) peer_wait(peer_hflag_local(P, seq) + lane, seq, P.err, P.timeout_ns);
+                    __syncwarp();
+                    halo_ready = true;
+                }
+#pragma unroll
+                for (int b = 0; b < BULK_CH; b++)
+#pragma unroll
+                    for (int jj = 0; jj < NS; jj++)
+                        xl[b][jj] = Lc[b] >= a.Nown ? peer_ld_data(hbox + peer_halo_pos(P, Lc[b] - a.Nown) * NS + jj) : a.x[(int64_t)Lc[b] * NS + jj];
+            } else {
+#pragma unroll
+                for (int b = 0; b < BULK_CH; b++)
+#pragma unroll
+                    for (int jj = 0; jj < NS; jj++) xl[b][jj] = a.x[(int64_t)Lc[b] * NS + jj];
+            }
+#pragma unroll
+            for (int b = 0; b < BULK_CH; b++) {
+                if (j0 + b >= w) break;
+                if constexpr (DIAGMASK) {
+#pragma unroll
+                    for (int i = 0; i < NS; i++) acc[i] += s_val[i * BULK_CH * 32 + b * 32 + lane] * xl[b][i];
+                } else {
+#pragma unroll
+                    for (int i = 0; i < NS; i++)
+#pragma unroll
+                        for (int jj = 0; jj < NS; jj++) {
+                            const int p = a.idxF[i * NS + jj];
+                            if (p >= 0) acc[i] += s_val[p * BULK_CH * 32 + b * 32 + lane] * xl[b][jj];
+                        }
+                }
+            }
+            __syncwarp();  // every lane has read the stage
+            if (lane == 0) {
+                fence_proxy_async_smem();
+                issue(stage);
+            }
+            phases ^= 1u << stage;
+            stage = stage + 1 == BULK_STAGES ? 0 : stage + 1;
         }
         if (valid) {
             double xr[NS];
@@ -579,8 +745,52 @@ void finalize(vfvm_handle* h, const double* part, int nparts, int nvals, int op)
     }
 }
 
+// which matrices take the bulk-copy kernel: VFVM_SPMV_BULK = 0 (never), 1 (default: coupled species, the finest level only), 2 (every
+// species count, the finest level only)
+static int spmv_bulk_mode() {
+    static const int mode = getenv("VFVM_SPMV_BULK") ? atoi(getenv("VFVM_SPMV_BULK")) : 1;
+    return mode;
+}
+
+template <int NS, bool DIAGMASK, bool PEER>
+bool launch_spmv_bulk(vfvm_handle* h, SpmvArgs& a, int op, const LevelHalo* lh) {
+    const int mode = spmv_bulk_mode();
+    if (mode == 0 || lh || a.sell_ptr != h->sell_ptr.p || a.nslices < 4096) return false;  // coarse levels are latency bound: nothing to stream
+    if (mode == 1 && NS == 1) return false;
+    const int cF = DIAGMASK ? NS : h->cF;
+    const size_t smem = (size_t)(BULK_THREADS / 32) * BULK_STAGES * (BULK_CH * 32 * 4 + (size_t)cF * BULK_CH * 32 * 8);
+    if (smem > 100 * 1024) return false;  // many planes: fewer than two blocks per SM would fit, the register-staged kernel is the better one
+    auto kern = k_spmv_bulk<NS, DIAGMASK, PEER>;
+    static int occ = 0;
+    static size_t occ_smem = 0;
+    if (occ == 0 || occ_smem != smem) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BULK_THREADS, smem));
+        occ_smem = smem;
+        if (occ < 1) {
+            occ = 0;
+            return false;
+        }
+    }
+    int nsm = 148;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device);
+    const int grid = std::max(1, std::min(cdiv(a.nslices, BULK_THREADS / 32), nsm * occ));
+    if (a.w) {
+        if (h->work[10].n < (size_t)2 * grid) h->work[10].alloc((size_t)2 * grid);
+        a.part = h->work[10].p;
+    }
+    PeerArgs P;
+    if constexpr (PEER) P = vfvm_peer_args_halo(h);
+    else memset(&P, 0, sizeof(P));
+    kern<<<grid, BULK_THREADS, smem, h->stream>>>(a, P, cF);
+    h->launches++;
+    if (a.w) finalize(h, a.part, grid, 2, op);
+    return true;
+}
+
 template <int NS, bool DIAGMASK, bool PEER>
 void launch_spmv_k(vfvm_handle* h, SpmvArgs& a, int op, const LevelHalo* lh = nullptr) {
+    if (launch_spmv_bulk<NS, DIAGMASK, PEER>(h, a, op, lh)) return;
     auto kern = k_spmv<NS, DIAGMASK, PEER>;
     static int occ = 0;
     if (occ == 0) {
