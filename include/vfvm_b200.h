@@ -59,7 +59,9 @@ typedef struct vfvm_handle vfvm_handle;
 #define VFVM_SLOT_STORAGE 2
 #define VFVM_SLOT_SOURCE 3
 #define VFVM_SLOT_BREACTION 4
-#define VFVM_NUM_SLOTS 5
+#define VFVM_SLOT_EDGEREACTION 5 /* edgereaction(f,u,edge,data), src/vfvm_assembly.jl:202-239 */
+#define VFVM_SLOT_BSTORAGE 6     /* bstorage(f,u,bnode,data), src/vfvm_assembly.jl:409-439 */
+#define VFVM_NUM_SLOTS 7
 
 /*
  * ---- registered physics library ----------------------------------------------------------------------
@@ -100,6 +102,17 @@ typedef struct vfvm_handle vfvm_handle;
 
 /* breaction(f,u,bnode,data): the part that is not a boundary_dirichlet!/neumann!/robin! call */
 #define VFVM_BREACTION_LINEAR 1 /* if bnode.region == r: f = R u            params: r, R[n*n] row-major (Example215:33-42)           */
+
+#define VFVM_BREACTION_CATALYSIS 2 /* Example115 breaction! :128-135: if bnode.region == r: f_A = S R_AC, f_B = S R_BC, f_C = -R_BC - R_AC with
+                                     R_XC = kp_XC u_X (1 - u_C) - km_XC u_C   params: r, S, kpAC, kmAC, kpBC, kmBC, iA, iB, iC (0-based) */
+
+/* edgereaction(f,u,edge,data): a reaction term given per edge, assembled with the edge form factor into BOTH end nodes
+ * (src/vfvm_assembly.jl:202-239) */
+#define VFVM_EDGEREACTION_DIAMOND 1 /* f_i = c_i h^2 / (2 dim), h = meas(edge): a constant volume density per half diamond (DevEx002:83-87) params: c[n] */
+#define VFVM_EDGEREACTION_JOULE 2   /* f_iT = -kappa (u_iphi,K - u_iphi,L)^2                (Example206:83-86)  params: kappa, iphi, iT (0-based) */
+
+/* bstorage(f,u,bnode,data) */
+#define VFVM_BSTORAGE_LINEAR 1 /* if bnode.region == r: f_i = c_i u_i      params: r, c[n]   (Example115:138-143, Example311:78-83) */
 
 /* boundary condition entries = calls of the callback-level helpers src/vfvm_physics.jl:487-564 */
 #define VFVM_BC_DIRICHLET 1 /* boundary_dirichlet!(y,u,bnode,ispec,ireg,val) :487-494 */
@@ -162,6 +175,9 @@ int vfvm_get_bfacefactors(vfvm_handle* h, double* bfacenodefactors /* dim x NB *
 
 /* ---- system: enable_species! (src/vfvm_system.jl:433-480), physics!, legacy BC tables (:854-933) ------ */
 int vfvm_set_system(vfvm_handle* h, int nspecies, const uint8_t* region_species /* n x nregions or NULL = all */);
+/* enable_boundary_species!(sys, ispec, bregions) (src/vfvm_system.jl:492-515): species that live on boundary regions only; n x nbregions,
+ * column-major, NULL = none.  Call after vfvm_set_system and before vfvm_build_pattern. */
+int vfvm_set_boundary_species(vfvm_handle* h, int nbregions, const uint8_t* bregion_species);
 int vfvm_set_physics(vfvm_handle* h, int slot, int physics_id, const double* params, int nparams);
 int vfvm_set_nodal_source(vfvm_handle* h, const double* table /* n x N, host */);
 int vfvm_set_legacy_bc(vfvm_handle* h, int nbregions, const double* boundary_factors /* n x nbregions */,

@@ -37,7 +37,8 @@ export LinearDiffusion, PowerDiffusion, CrossDiffusion2, UnipolarSGFlux, SedanFl
 export PowerReaction, SinhReaction, AffineReaction, BilinearReaction2, RegionAffineReaction, BipolarReaction
 export LinearStorage, PowerStorage, BipolarStorage
 export ConstSource, GaussSource, XSinYExpZSource, Step1DSource, AffineXSource, NodalSource
-export LinearBoundaryReaction, BCondition, dirichlet!, neumann!, robin!
+export LinearBoundaryReaction, CatalysisBoundaryReaction, BCondition, dirichlet!, neumann!, robin!
+export DiamondEdgeReaction, JouleHeatEdgeReaction, LinearBoundaryStorage
 export AMGPrecon, BlockJacobiPrecon, JacobiPrecon, ILUZeroPrecon, DeviceKrylov
 
 const LIB = get(ENV, "VFVM_B200_LIB", joinpath(@__DIR__, "..", "voronoifvm.jl_b200", "libvfvmb200.so"))
@@ -49,7 +50,7 @@ const VFVM_ERR_LINSOLVE = -5
 const VFVM_ERR_UNREGISTERED = -6
 const VFVM_HOST = 0
 const VFVM_DEVICE = 1
-const SLOT_FLUX, SLOT_REACTION, SLOT_STORAGE, SLOT_SOURCE, SLOT_BREACTION = 0, 1, 2, 3, 4
+const SLOT_FLUX, SLOT_REACTION, SLOT_STORAGE, SLOT_SOURCE, SLOT_BREACTION, SLOT_EDGEREACTION, SLOT_BSTORAGE = 0, 1, 2, 3, 4, 5, 6
 const VEC_SOLUTION, VEC_OLDSOL, VEC_RESIDUAL, VEC_UPDATE = 0, 1, 2, 3
 const KRYLOV_BICGSTAB, KRYLOV_CG, KRYLOV_GMRES = 0, 1, 2
 const PRECON_NONE, PRECON_JACOBI, PRECON_BLOCKJACOBI, PRECON_ILU0, PRECON_ILU0_MC, PRECON_AMG = 0, 1, 2, 3, 4, 5
@@ -88,12 +89,16 @@ abstract type RegisteredReaction <: RegisteredPhysics end
 abstract type RegisteredStorage <: RegisteredPhysics end
 abstract type RegisteredSource <: RegisteredPhysics end
 abstract type RegisteredBReaction <: RegisteredPhysics end
+abstract type RegisteredEdgeReaction <: RegisteredPhysics end
+abstract type RegisteredBStorage <: RegisteredPhysics end
 
 physics_slot(::RegisteredFlux) = SLOT_FLUX
 physics_slot(::RegisteredReaction) = SLOT_REACTION
 physics_slot(::RegisteredStorage) = SLOT_STORAGE
 physics_slot(::RegisteredSource) = SLOT_SOURCE
 physics_slot(::RegisteredBReaction) = SLOT_BREACTION
+physics_slot(::RegisteredEdgeReaction) = SLOT_EDGEREACTION
+physics_slot(::RegisteredBStorage) = SLOT_BSTORAGE
 
 expand(x::Number, n) = fill(Float64(x), n)
 function expand(x::AbstractVector, n)
@@ -456,6 +461,78 @@ function (b::LinearBoundaryReaction)(f, u, bnode, data)
     return nothing
 end
 
+"Example115 breaction! :125-135 on boundary region `region` (species A, B in the bulk, C on the surface)"
+Base.@kwdef struct CatalysisBoundaryReaction <: RegisteredBReaction
+    region::Int
+    S::Float64 = 0.01
+    kp_AC::Float64 = 100.0
+    km_AC::Float64 = 1.0
+    kp_BC::Float64 = 0.1
+    km_BC::Float64 = 1.0
+    iA::Int = 1
+    iB::Int = 2
+    iC::Int = 3
+end
+physics_id(::CatalysisBoundaryReaction) = 2
+physics_params(b::CatalysisBoundaryReaction, n) = [b.region, b.S, b.kp_AC, b.km_AC, b.kp_BC, b.km_BC, b.iA - 1, b.iB - 1, b.iC - 1]
+function (b::CatalysisBoundaryReaction)(f, u, bnode, data)
+    if bnode.region == b.region
+        rac = b.kp_AC * u[b.iA] * (1 - u[b.iC]) - b.km_AC * u[b.iC]
+        rbc = b.kp_BC * u[b.iB] * (1 - u[b.iC]) - b.km_BC * u[b.iC]
+        f[b.iA] = b.S * rac
+        f[b.iB] = b.S * rbc
+        f[b.iC] = -rbc - rac
+    end
+    return nothing
+end
+
+# edgereaction(f,u,edge,data)
+"f_i = c_i h^2 / (2 dim), h = meas(edge)   DevEx002_EdgeReaction.jl:83-87"
+struct DiamondEdgeReaction{T} <: RegisteredEdgeReaction
+    c::T
+end
+physics_id(::DiamondEdgeReaction) = 1
+physics_params(r::DiamondEdgeReaction, n) = expand(r.c, n)
+function (r::DiamondEdgeReaction)(f, u, edge, data)
+    c = expand(r.c, length(f))
+    h = meas(edge)
+    dim = size(edge.coord, 1)
+    for i in eachindex(f)
+        f[i] = c[i] * h^2 / (2 * dim)
+    end
+    return nothing
+end
+
+"f_iT = -kappa (u_iphi,K - u_iphi,L)^2   Example206_JouleHeat.jl:83-86"
+struct JouleHeatEdgeReaction <: RegisteredEdgeReaction
+    kappa::Float64
+    iphi::Int
+    iT::Int
+end
+physics_id(::JouleHeatEdgeReaction) = 2
+physics_params(r::JouleHeatEdgeReaction, n) = [r.kappa, r.iphi - 1, r.iT - 1]
+function (r::JouleHeatEdgeReaction)(f, u, edge, data)
+    f[r.iT] = -r.kappa * (u[r.iphi, 1] - u[r.iphi, 2]) * (u[r.iphi, 1] - u[r.iphi, 2])
+    return nothing
+end
+
+# bstorage(f,u,bnode,data)
+"if bnode.region == region: f_i = c_i u_i   Example115:138-143, Example311:78-83"
+struct LinearBoundaryStorage <: RegisteredBStorage
+    region::Int
+    c::Vector{Float64}
+end
+physics_id(::LinearBoundaryStorage) = 1
+physics_params(s::LinearBoundaryStorage, n) = vcat(Float64(s.region), s.c)
+function (s::LinearBoundaryStorage)(f, u, bnode, data)
+    if bnode.region == s.region
+        for i in eachindex(f)
+            s.c[i] != 0 && (f[i] = s.c[i] * u[i])
+        end
+    end
+    return nothing
+end
+
 "C mirror of `vfvm_bc_entry` (include/vfvm_b200.h): one boundary_dirichlet!/neumann!/robin! call, src/vfvm_physics.jl:487-564"
 struct BCEntry
     kind::Int32
@@ -475,11 +552,11 @@ A `bcondition` callback made of `boundary_dirichlet!` / `boundary_neumann!` / `b
 boundary reaction.  On the CPU path it performs exactly those calls; on the device its entries go to `vfvm_set_bc_entries`.
 """
 struct BCondition <: RegisteredBReaction
-    reaction::Union{Nothing, LinearBoundaryReaction}
+    reaction::Union{Nothing, LinearBoundaryReaction, CatalysisBoundaryReaction}
     entries::Vector{BCEntry}
 end
 BCondition() = BCondition(nothing, BCEntry[])
-BCondition(r::LinearBoundaryReaction) = BCondition(r, BCEntry[])
+BCondition(r::Union{LinearBoundaryReaction, CatalysisBoundaryReaction}) = BCondition(r, BCEntry[])
 physics_id(b::BCondition) = b.reaction === nothing ? 0 : physics_id(b.reaction)
 physics_params(b::BCondition, n) = b.reaction === nothing ? Float64[] : physics_params(b.reaction, n)
 function push_entry!(b::BCondition, kind, species, region, value, factor, rmp)
@@ -602,10 +679,11 @@ end
 "uploads ids, parameter blocks, boundary entries and the legacy boundary tables of `system` (enable_species!, boundary_dirichlet!, ...)"
 function push_physics!(A::B200Matrix, system)
     h, n, ph = A.h, A.nspecies, system.physics
-    for name in (:edgereaction, :bflux, :bsource, :bstorage, :boutflow, :generic_operator)
+    for name in (:bflux, :bsource, :boutflow, :generic_operator)
         getproperty(ph, name) === VoronoiFVM.nofunc || throw(UnregisteredPhysicsError("physics callback `$name` is outside the device scope"))
     end
-    for (slot, cb) in ((SLOT_FLUX, ph.flux), (SLOT_REACTION, ph.reaction), (SLOT_STORAGE, ph.storage), (SLOT_SOURCE, ph.source), (SLOT_BREACTION, ph.breaction))
+    for (slot, cb) in ((SLOT_FLUX, ph.flux), (SLOT_REACTION, ph.reaction), (SLOT_STORAGE, ph.storage), (SLOT_SOURCE, ph.source), (SLOT_BREACTION, ph.breaction),
+                       (SLOT_EDGEREACTION, ph.edgereaction), (SLOT_BSTORAGE, ph.bstorage))
         r = registered(cb, slot)
         id = r === nothing ? 0 : physics_id(r)
         params = r === nothing ? Float64[] : Vector{Float64}(physics_params(r, n))
@@ -652,6 +730,10 @@ function VoronoiFVM.SystemState(backend::B200, system::VoronoiFVM.AbstractSystem
     check(h, ccall((:vfvm_build_geometry, LIB), Cint, (Ptr{Cvoid},), h))
     region_species = UInt8[system.region_species[i, r] > 0 ? 1 : 0 for i in 1:nspec, r in 1:num_cellregions(grid)]
     check(h, ccall((:vfvm_set_system, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{UInt8}), h, nspec, region_species))
+    bregion_species = UInt8[system.bregion_species[i, r] > 0 ? 1 : 0 for i in 1:nspec, r in 1:num_bfaceregions(grid)]   # enable_boundary_species!
+    if any(!=(0), bregion_species)
+        check(h, ccall((:vfvm_set_boundary_species, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{UInt8}), h, size(bregion_species, 2), bregion_species))
+    end
     A = B200Matrix(h, nspec * nnodes, nspec, nnodes, UInt64(0), nothing)
     finalizer(destroy!, A)
     push_physics!(A, system)

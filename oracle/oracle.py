@@ -78,6 +78,10 @@ class OracleSystem:
         rs = np.ascontiguousarray(desc.region_species.T, dtype=np.uint8).ravel()  # column-major n x nreg
         rc = L.vo_set_system(self.h, self.n, _p(rs, C.c_uint8))
         assert rc == 0, rc
+        bs = getattr(desc, "bregion_species", None)
+        if bs is not None and np.any(bs):
+            b = np.ascontiguousarray(np.asarray(bs).T, dtype=np.uint8).ravel()  # column-major n x nbreg
+            assert L.vo_set_boundary_species(self.h, int(np.asarray(bs).shape[1]), _p(b, C.c_uint8)) == 0
         self.push_physics()
 
     def push_physics(self):

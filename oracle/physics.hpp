@@ -283,6 +283,43 @@ inline bool eval_source(const PhysSlot& s, int n, double* f, const NodeCtx& node
     return false;
 }
 
+// ---------------------------------------------------------------- edgereaction(f,u,edge,data)
+template <class T>
+inline bool eval_edgereaction(const PhysSlot& s, int n, T* f, const T* uK, const T* uL, const EdgeCtx& edge) {
+    const double* p = s.p.data();
+    switch (s.id) {
+        case VFVM_NONE: return true;
+        case VFVM_EDGEREACTION_DIAMOND: {  // examples/DevEx002_EdgeReaction.jl:83-87: y = c h^2 / (2 dim), h = meas(edge)
+            double h2 = 0.0;
+            for (int d = 0; d < edge.dim; d++) h2 += (edge.xK[d] - edge.xL[d]) * (edge.xK[d] - edge.xL[d]);
+            const double h = std::sqrt(h2);
+            for (int i = 0; i < n; i++) f[i] = T(p[i] * (h * h) / (2 * edge.dim));
+            return true;
+        }
+        case VFVM_EDGEREACTION_JOULE: {  // examples/Example206_JouleHeat.jl:83-86
+            const int iphi = (int)p[1], iT = (int)p[2];
+            f[iT] = -p[0] * (uK[iphi] - uL[iphi]) * (uK[iphi] - uL[iphi]);
+            return true;
+        }
+    }
+    return false;
+}
+
+// ---------------------------------------------------------------- bstorage(f,u,bnode,data)
+template <class T>
+inline bool eval_bstorage(const PhysSlot& s, int n, T* f, const T* u, const BNodeCtx& b) {
+    const double* p = s.p.data();
+    switch (s.id) {
+        case VFVM_NONE: return true;
+        case VFVM_BSTORAGE_LINEAR:  // examples/Example115_HeterogeneousCatalysis1D.jl:138-143
+            if (b.region == (int)p[0])
+                for (int i = 0; i < n; i++)
+                    if (p[1 + i] != 0.0) f[i] = p[1 + i] * u[i];
+            return true;
+    }
+    return false;
+}
+
 // ---------------------------------------------------------------- breaction(f,u,bnode,data) + BC helper calls
 template <class T>
 inline bool eval_breaction(const Physics& ph, int n, T* f, const T* u, BNodeCtx& b) {
@@ -299,6 +336,18 @@ inline bool eval_breaction(const Physics& ph, int n, T* f, const T* u, BNodeCtx&
                         if (p[1 + i * n + j] != 0.0) acc = acc + p[1 + i * n + j] * u[j];
                     f[i] = acc;
                 }
+            }
+            break;
+        }
+        case VFVM_BREACTION_CATALYSIS: {  // examples/Example115_HeterogeneousCatalysis1D.jl:125-135
+            if (b.region == (int)p[0]) {
+                const double S = p[1], kpAC = p[2], kmAC = p[3], kpBC = p[4], kmBC = p[5];
+                const int iA = (int)p[6], iB = (int)p[7], iC = (int)p[8];
+                T rac = kpAC * u[iA] * (1.0 - u[iC]) - kmAC * u[iC];
+                T rbc = kpBC * u[iB] * (1.0 - u[iC]) - kmBC * u[iC];
+                f[iA] = S * rac;
+                f[iB] = S * rbc;
+                f[iC] = -rbc - rac;
             }
             break;
         }

@@ -359,6 +359,8 @@ struct System {
     std::vector<double> bfacenodefactors, bfaceedgefactors;
     int n = 0;                                // nspecies
     std::vector<uint8_t> region_species;      // n x ncellregions
+    std::vector<uint8_t> bregion_species;     // n x nbregions_bs (enable_boundary_species!, src/vfvm_system.jl:492-515), may be empty
+    int nbregions_bs = 0;
     std::vector<uint8_t> node_dof;            // n x N
     bool species_homogeneous = true;
     Physics ph;
@@ -435,6 +437,16 @@ static void complete_species(System& s) {
         for (int i = 0; i < n; i++)
             if (s.region_species[(size_t)ireg * n + i])
                 for (int l = 0; l < nn; l++) s.node_dof[(size_t)g.cellnodes[(size_t)c * nn + l] * n + i] = 1;
+    }
+    if (!s.bregion_species.empty()) {  // src/vfvm_system.jl:502-513
+        const int nbn = g.dim;
+        for (int b = 0; b < g.NB; b++) {
+            const int br = g.bfaceregions[b] - 1;
+            if (br >= s.nbregions_bs) continue;
+            for (int i = 0; i < n; i++)
+                if (s.bregion_species[(size_t)br * n + i])
+                    for (int l = 0; l < nbn; l++) s.node_dof[(size_t)g.bfacenodes[(size_t)b * nbn + l] * n + i] = 1;
+        }
     }
     s.species_homogeneous = true;
     for (auto v : s.node_dof)
@@ -538,12 +550,31 @@ static void assemble_edges(System& s, int e0, int e1, const double* U, double* F
                     addnz(s, idofL, jdofL, -f[i].d[j + n], edge.fac);
                 }
             }
+            if (s.ph.slot[VFVM_SLOT_EDGEREACTION].id != VFVM_NONE) {  // src/vfvm_assembly.jl:202-239
+                for (int i = 0; i < n; i++) f[i] = D(0.0);
+                eval_edgereaction(s.ph.slot[VFVM_SLOT_EDGEREACTION], n, f, uK, uL, edge);
+                for (int i = 0; i < n; i++) {
+                    if (!rs[i]) continue;
+                    int idofK = K * n + i, idofL = L * n + i;
+                    double val = edge.fac * f[i].v;  // :207-211: the same sign at both ends
+                    F[idofK] += val;
+                    F[idofL] += val;
+                    for (int j = 0; j < n; j++) {
+                        if (!rs[j]) continue;
+                        int jdofK = K * n + j, jdofL = L * n + j;  // :213-230, signs as the reference has them
+                        addnz(s, idofK, jdofK, +f[i].d[j], edge.fac);
+                        addnz(s, idofL, jdofK, -f[i].d[j], edge.fac);
+                        addnz(s, idofK, jdofL, -f[i].d[j + n], edge.fac);
+                        addnz(s, idofL, jdofL, +f[i].d[j + n], edge.fac);
+                    }
+                }
+            }
         }
     }
 }
 
 template <int NS>
-static void assemble_bnodes(System& s, const double* U, double* F, double time, double lambda) {
+static void assemble_bnodes(System& s, const double* U, const double* UOld, double* F, double time, double tstepinv, double lambda) {
     const Grid& g = s.g;
     const int n = NS, nbn = g.dim;
     bool has_legacy_bc = false;  // src/vfvm_assembly.jl:329
@@ -597,6 +628,26 @@ static void assemble_bnodes(System& s, const double* U, double* F, double time, 
                     addnz(s, idof, K * n + j, res[i].d[j], b.fac);  // :401
                 }
             }
+            if (s.ph.slot[VFVM_SLOT_BSTORAGE].id != VFVM_NONE) {  // src/vfvm_assembly.jl:409-439
+                D st[NS];
+                double uo[NS], sto[NS];
+                for (int i = 0; i < n; i++) {
+                    st[i] = D(0.0);
+                    sto[i] = 0.0;
+                    uo[i] = UOld[(size_t)K * n + i];
+                }
+                eval_bstorage(s.ph.slot[VFVM_SLOT_BSTORAGE], n, st, UK, b);
+                eval_bstorage(s.ph.slot[VFVM_SLOT_BSTORAGE], n, sto, uo, b);
+                for (int i = 0; i < n; i++) {
+                    if (!s.node_dof[(size_t)K * n + i]) continue;
+                    int idof = K * n + i;
+                    F[idof] += b.fac * (st[i].v - sto[i]) * tstepinv;
+                    for (int j = 0; j < n; j++) {
+                        if (!s.node_dof[(size_t)K * n + j]) continue;
+                        addnz(s, idof, K * n + j, st[i].d[j], b.fac * tstepinv);
+                    }
+                }
+            }
         }
     }
 }
@@ -644,7 +695,7 @@ static int eval_and_assemble(System& s, const double* U, const double* UOld, dou
             for (int p = color; p < nparts; p += 2) assemble_edges<NS>(s, s.part_edges[p], s.part_edges[p + 1], U, F, time, lambda);
         }
     }
-    assemble_bnodes<NS>(s, U, F, time, lambda);  // boundary loop is a single partition, src/vfvm_system.jl:751-754
+    assemble_bnodes<NS>(s, U, UOld, F, time, tstepinv, lambda);  // boundary loop is a single partition, src/vfvm_system.jl:751-754
     if (!s.species_homogeneous) {                // src/vfvm_system.jl:1012-1026
         for (int K = 0; K < g.N; K++)
             for (int i = 0; i < n; i++)
@@ -783,6 +834,14 @@ int vo_set_system(void* h, int nspecies, const uint8_t* region_species) {
     s.boundary_values.assign((size_t)nspecies * s.g.nbfaceregions, 0.0);
     s.A.init(nspecies * s.g.N);
     s.part_nodes.clear();
+    return 0;
+}
+int vo_set_boundary_species(void* h, int nbregions, const uint8_t* bregion_species) {
+    System& s = *(System*)h;
+    s.nbregions_bs = bregion_species ? nbregions : 0;
+    if (bregion_species) s.bregion_species.assign(bregion_species, bregion_species + (size_t)s.n * nbregions);
+    else s.bregion_species.clear();
+    complete_species(s);
     return 0;
 }
 int vo_set_physics(void* h, int slot, int id, const double* params, int np) {

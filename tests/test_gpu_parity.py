@@ -616,3 +616,76 @@ def test_masked_coupled_flux_two_species():
     U = _rand_u(s)
     U[~s.node_dof()] = 0.0
     _compare_assembly(s, U, _rand_u(s, seed=11) * s.node_dof(), tstep=0.05)
+
+
+# ---- boundary species, bstorage, edgereaction ---------------------------------------------------------------------
+@pytest.mark.parametrize("switchbc", [False, True])
+def test_example115_boundary_species_bstorage_device(switchbc):
+    """examples/Example115_HeterogeneousCatalysis1D.jl: surface species C (enable_boundary_species!) with bstorage and the nonlinear
+    catalysis breaction; assembly against the oracle (pattern bit-exact, values 1e-12) and the known answer
+    tsol[iC, inodeCat, end] == 0.87544440641274 after 100 implicit Euler steps on the device"""
+    from test_oracle_golden import example115_system
+
+    sys, inode = example115_system(switchbc)
+    U = _rand_u(sys)
+    U[~sys.node_dof()] = 0.0
+    Uold = _rand_u(sys, seed=4) * sys.node_dof()
+    _compare_assembly(sys, U, Uold, tstep=0.01)
+    control = v.fixed_timesteps(v.SolverControl(), 0.01)
+    tsol = v.solve(sys, inival=0.0, times=[0.0, 1.0], control=control)
+    assert tsol.u[-1][2, inode] == pytest.approx(0.87544440641274, rel=1e-10)
+    assert np.all(tsol.u[-1][2, np.arange(11) != inode] == 0.0)
+
+
+def test_boundary_species_2d_parity():
+    """a surface species on one boundary region of a 2D grid, coupled to two bulk species: pattern bit-exact, values 1e-12, Newton 1e-10"""
+    X = np.linspace(0, 1, 9)
+    g = v.simplexgrid(X, X)
+    sys = v.System(g, flux=ph.LinearDiffusion([1.0, 1.0e-1, 0.0]), storage=ph.LinearStorage([1.0, 1.0, 0.0]), source=ph.GaussSource(1, 20.0, (0.5, 0.5)),
+                   breaction=ph.CatalysisBoundaryReaction(1, S=0.05, kp_AC=10.0, km_AC=1.0, kp_BC=0.5, km_BC=1.0), bstorage=ph.LinearBoundaryStorage(1, [0.0, 0.0, 1.0]))
+    v.enable_species(sys, 1, [1])
+    v.enable_species(sys, 2, [1])
+    v.enable_boundary_species(sys, 3, [1])
+    v.boundary_dirichlet(sys, 2, 3, 0.0)
+    U = _rand_u(sys)
+    U[~sys.node_dof()] = 0.0
+    Uold = _rand_u(sys, seed=5) * sys.node_dof()
+    _compare_assembly(sys, U, Uold, tstep=0.05)
+    ref = O.OracleSystem(sys).solve_step(v.unknowns(sys, 0.1) * sys.node_dof(), tstep=0.05)
+    sol = v.solve(sys, inival=v.unknowns(sys, 0.1) * sys.node_dof(), tstep=0.05)
+    assert np.max(np.abs(sol - ref)) < TOL_NEWTON
+
+
+def test_devex002_edge_reaction_device():
+    """examples/DevEx002_EdgeReaction.jl (3D case): node reaction and edge reaction (times the half diamond volume) give the same solution;
+    the edge-reaction assembly agrees with the oracle"""
+    X = np.linspace(0, 1, 7)
+    g = v.simplexgrid(X, X, X)
+    bc = ph.BCondition()
+    for r in range(1, 7):
+        bc.dirichlet(species=1, region=r, value=0.0)
+    s_node = v.System(g, flux=ph.LinearDiffusion(), reaction=ph.AffineReaction([[0.0]], [-1.0]), storage=ph.LinearStorage(1.0), bcondition=bc, species=[1], is_linear=True)
+    s_edge = v.System(g, flux=ph.LinearDiffusion(), edgereaction=ph.DiamondEdgeReaction(-1.0), storage=ph.LinearStorage(1.0), bcondition=bc, species=[1], is_linear=True)
+    _compare_assembly(s_edge, _rand_u(s_edge))
+    u_node = v.solve(s_node, inival=0.0)
+    u_edge = v.solve(s_edge, inival=0.0)
+    assert np.abs(u_node).max() > 1e-3
+    assert np.abs(u_node - u_edge).max() <= 1e-10 * np.abs(u_node).max()
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_joule_heat_edge_reaction_parity(dim):
+    """Example206 physics (potential + temperature, Joule heat as an edge reaction that depends on the solution) on a tensor grid:
+    residual and Jacobian (with the reference's own sign convention, src/vfvm_assembly.jl:213-230) against the oracle, Newton 1e-10"""
+    g = _grid(dim, 9 if dim == 2 else 6)
+    kappa = math.exp(-0.5)
+    bc = ph.BCondition()
+    bc.dirichlet(species=1, region=2 if dim == 2 else 5, value=-1.0).dirichlet(species=1, region=4 if dim == 2 else 6, value=1.0)
+    for r in range(1, 2 * dim + 1):
+        bc.robin(species=2, region=r, factor=0.5, value=0.5)
+    sys = v.System(g, flux=ph.LinearDiffusion([kappa, 1.0]), edgereaction=ph.JouleHeatEdgeReaction(kappa, 1, 2), storage=ph.LinearStorage([0.0, 1.0]), bcondition=bc, species=[1, 2])
+    _compare_assembly(sys, _rand_u(sys))
+    _compare_assembly(sys, _rand_u(sys), _rand_u(sys, seed=3), tstep=0.1)
+    ref = O.OracleSystem(sys).solve_step(v.unknowns(sys, 0.0))
+    sol = v.solve(sys, inival=0.0)
+    assert np.max(np.abs(sol - ref)) < TOL_NEWTON

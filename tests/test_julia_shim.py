@@ -120,10 +120,10 @@ def test_every_registered_physics_id_has_a_julia_struct():
     hdr = open(HEADER).read()
     shim = open(SHIM).read()
     ids = {}
-    for m in re.finditer(r"#define VFVM_(FLUX|REACTION|STORAGE|SOURCE|BREACTION)_(\w+) (\d+)", hdr):
+    for m in re.finditer(r"#define VFVM_(FLUX|REACTION|STORAGE|SOURCE|BREACTION|EDGEREACTION|BSTORAGE)_(\w+) (\d+)", hdr):
         ids[(m.group(1), int(m.group(3)))] = m.group(2)
     have = {}
-    for m in re.finditer(r"struct (\w+)(?:\{[^}]*\})? <: Registered(Flux|Reaction|Storage|Source|BReaction)", shim):
+    for m in re.finditer(r"struct (\w+)(?:\{[^}]*\})? <: Registered(Flux|Reaction|Storage|Source|BReaction|EdgeReaction|BStorage)\b", shim):
         name, kind = m.group(1), m.group(2).upper()
         pid = re.search(rf"physics_id\(::{name}\) = (\d+)", shim)
         if pid:

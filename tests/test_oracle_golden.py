@@ -314,3 +314,44 @@ def test_example201_laplace2d_nodeflux():
     assert nfl.shape == (2, 1, g.num_nodes)
     assert np.linalg.norm(sol) + np.linalg.norm(nfl) == pytest.approx(9.63318042491699, rel=1e-13)
     assert np.allclose(nfl[1, 0], -1.0, atol=1e-13) and np.allclose(nfl[0, 0], 0.0, atol=1e-13)  # exact for the linear solution u = y
+
+
+def example115_system(switchbc=False, n=10):
+    """examples/Example115_HeterogeneousCatalysis1D.jl:79-177: bulk species A, B, surface species C on the catalytic boundary point"""
+    X = np.arange(0, n + 1) / float(n)
+    icat, ibulk = (2, 1) if switchbc else (1, 2)
+    sys = v.System(v.simplexgrid(X), flux=ph.LinearDiffusion([1.0, 1.0e-2, 0.0]), storage=ph.LinearStorage([1.0, 1.0, 0.0]), source=ph.GaussSource(1, 100.0, (0.5,)),
+                   breaction=ph.CatalysisBoundaryReaction(icat, S=0.01, kp_AC=100.0, km_AC=1.0, kp_BC=0.1, km_BC=1.0), bstorage=ph.LinearBoundaryStorage(icat, [0.0, 0.0, 1.0]))
+    v.enable_species(sys, 1, [1])
+    v.enable_species(sys, 2, [1])
+    v.enable_boundary_species(sys, 3, [icat])
+    v.boundary_dirichlet(sys, 2, ibulk, 0.0)
+    return sys, (n if switchbc else 0)
+
+
+@pytest.mark.parametrize("switchbc", [False, True])
+def test_example115_heterogeneous_catalysis_boundary_species(switchbc):
+    """examples/Example115_HeterogeneousCatalysis1D.jl:224-237: tsol[iC, inodeCat, end] == 0.87544440641274 (rtol 1e-12): boundary species
+    (enable_boundary_species!), bstorage, a nonlinear breaction coupling bulk and surface species, 100 implicit Euler steps"""
+    sys, inode = example115_system(switchbc)
+    assert sys.node_dof()[2].sum() == 1 and sys.node_dof()[2, inode]
+    tstep = 0.01
+    times, sols = O.OracleSystem(sys).solve_transient(v.unknowns(sys, 0.0), (0, 1), dt=tstep, dt_min=tstep, dt_max=tstep, du_opt=1.0e300)
+    assert sols[-1][2, inode] == pytest.approx(0.87544440641274, rel=1e-11)
+    assert np.all(sols[-1][2, np.arange(11) != inode] == 0.0)  # the surface species stays zero where it is not defined
+
+
+def test_devex002_edge_reaction_equals_node_reaction_3d():
+    """examples/DevEx002_EdgeReaction.jl:62-87, 135-147: a constant reaction given per node (times the control volume) or per edge (times
+    the half diamond volume h^2 / (2 dim)) yields the same solution; 3D tensor grid, homogeneous Dirichlet on z faces"""
+    X = np.linspace(0, 1, 5)
+    g = v.simplexgrid(X, X, X)
+    bc = ph.BCondition()
+    for r in range(1, 7):
+        bc.dirichlet(species=1, region=r, value=0.0)
+    s_node = v.System(g, flux=ph.LinearDiffusion(), reaction=ph.AffineReaction([[0.0]], [-1.0]), storage=ph.LinearStorage(1.0), bcondition=bc, species=[1], is_linear=True)
+    s_edge = v.System(g, flux=ph.LinearDiffusion(), edgereaction=ph.DiamondEdgeReaction(-1.0), storage=ph.LinearStorage(1.0), bcondition=bc, species=[1], is_linear=True)
+    u_node = O.OracleSystem(s_node).solve_step(v.unknowns(s_node, 0.0))
+    u_edge = O.OracleSystem(s_edge).solve_step(v.unknowns(s_edge, 0.0))
+    assert np.abs(u_node).max() > 1e-3
+    assert np.abs(u_node - u_edge).max() <= 1e-12 * np.abs(u_node).max()

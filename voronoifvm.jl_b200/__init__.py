@@ -7,7 +7,7 @@ missing, creating a SystemState fails loudly.
 from .grid import Grid, simplexgrid, cartesian, circular_symmetric, spherical_symmetric, cellmask  # noqa: F401
 from . import physics  # noqa: F401
 from .physics import Physics, BCondition, UnregisteredPhysicsError  # noqa: F401
-from .system import (System, enable_species, boundary_dirichlet, boundary_neumann, boundary_robin, unknowns, num_dof,  # noqa: F401
+from .system import (System, enable_species, enable_boundary_species, boundary_dirichlet, boundary_neumann, boundary_robin, unknowns, num_dof,  # noqa: F401
                      DIRICHLET)
 from .system import physics as set_physics  # noqa: F401
 from .state import SystemState  # noqa: F401,E402

@@ -45,6 +45,7 @@ SIGNATURES = {
     "vfvm_get_edgefactors": [_H, _I64, _I32, _D],
     "vfvm_get_bfacefactors": [_H, _D],
     "vfvm_set_system": [_H, C.c_int, _U8],
+    "vfvm_set_boundary_species": [_H, C.c_int, _U8],
     "vfvm_set_physics": [_H, C.c_int, C.c_int, _D, C.c_int],
     "vfvm_set_nodal_source": [_H, _D],
     "vfvm_set_legacy_bc": [_H, C.c_int, _D, _D],

@@ -32,7 +32,7 @@
 namespace {
 
 #define FUSE_THREADS 512
-#define FUSE_SMALL_N 8192
+#define FUSE_SMALL_N 512
 enum { FOP_SMOOTH_FIRST = 1, FOP_SPMV, FOP_SMOOTH, FOP_RESTRICT, FOP_WRES, FOP_WADD, FOP_PROLONG };
 
 struct LevelDev {
@@ -365,10 +365,13 @@ __global__ void k_slice_width(int nslc, int64_t Nc, const int32_t* __restrict__ 
     for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
     if (lane == 0) width32[g] = 32 * m;
 }
-__global__ void k_fill_rowid(int nslc, const int32_t* __restrict__ sell_ptr, int32_t* __restrict__ colidx) {  // padding entries point to their own row
+// padding entries point to their own row; the lanes of the last slice beyond the last row point to the last row (an index >= N
+// would make the SpMV gather read past the end of the level vector)
+__global__ void k_fill_rowid(int nslc, int64_t N, const int32_t* __restrict__ sell_ptr, int32_t* __restrict__ colidx) {
     const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (g >= nslc) return;
-    for (int e = sell_ptr[g] + lane; e < sell_ptr[g + 1]; e += 32) colidx[e] = g * 32 + lane;
+    const int32_t self = (int32_t)min((int64_t)g * 32 + lane, N - 1);
+    for (int e = sell_ptr[g] + lane; e < sell_ptr[g + 1]; e += 32) colidx[e] = self;
 }
 __global__ void k_place_uniques(int64_t nuniq, int64_t Nc, const unsigned long long* __restrict__ ukey, const int32_t* __restrict__ sell_ptr, int32_t* __restrict__ colidx,
                                 int32_t* __restrict__ gal_dst) {
@@ -859,7 +862,7 @@ void coarsen_pattern(vfvm_handle* h, Level& f, Level& c) {
     c.colidx_b.alloc(std::max<int64_t>(1, c.nnz_sell));
     c.w_b.alloc(std::max<int64_t>(1, c.nnz_sell));
     CK(cudaMemsetAsync(c.w_b.p, 0, std::max<int64_t>(1, c.nnz_sell) * sizeof(double), s));
-    if (c.nslices) k_fill_rowid<<<cdiv(c.nslices, 8), 256, 0, s>>>(c.nslices, c.sell_ptr_b.p, c.colidx_b.p);
+    if (c.nslices) k_fill_rowid<<<cdiv(c.nslices, 8), 256, 0, s>>>(c.nslices, Nrows, c.sell_ptr_b.p, c.colidx_b.p);
     if (nuniq) {
         k_place_uniques<<<cdiv(nuniq, 256), 256, 0, s>>>(nuniq, Nc, ukey.p, c.sell_ptr_b.p, c.colidx_b.p, f.gal_dst.p);
         k_gal_weight<<<cdiv(nuniq, 256), 256, 0, s>>>(nuniq, f.gal_ptr.p, f.gal_src.p, f.gal_dst.p, f.w, c.w_b.p);

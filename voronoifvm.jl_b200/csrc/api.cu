@@ -192,11 +192,35 @@ extern "C" int vfvm_set_system(vfvm_handle* h, int nspecies, const uint8_t* regi
         }
     if (h->nbfaceregions > VFVM_MAX_BREGIONS) return vfvm_fail(h, VFVM_ERR_UNSUPPORTED, "more than 16 boundary regions");
     h->n = nspecies;
+    h->bregion_species.clear();
+    h->nbregions_bs = 0;
     PhysicsDev& ph = h->phys;
     memset(&ph, 0, sizeof(ph));
     ph.nbregions = h->nbfaceregions;
     h->phys_dirty = true;
     h->have_system = true;
+    h->have_pattern = false;
+    return VFVM_OK;
+}
+
+extern "C" int vfvm_set_boundary_species(vfvm_handle* h, int nbregions, const uint8_t* bregion_species) {
+    NEED(h, h->have_system, "vfvm_set_system has not been called");
+    if (nbregions < 0 || nbregions > VFVM_MAX_BREGIONS) return vfvm_fail(h, VFVM_ERR_ARG, "more than 16 boundary regions");
+    h->bregion_species.clear();
+    h->nbregions_bs = 0;
+    bool any = false;
+    if (bregion_species)
+        for (int i = 0; i < h->n * nbregions; i++) any |= bregion_species[i] != 0;
+    if (any) {
+        for (int r = 0; r < nbregions; r++)
+            for (int i = 0; i < h->n; i++)
+                if (bregion_species[r * h->n + i])
+                    for (int c = 0; c < h->ncellregions; c++)
+                        if (h->region_species[(size_t)c * h->n + i]) return vfvm_fail(h, VFVM_ERR_ARG, "species is already a bulk species (src/vfvm_system.jl:496-498)");
+        h->bregion_species.assign(bregion_species, bregion_species + (size_t)h->n * nbregions);
+        h->nbregions_bs = nbregions;
+        h->masked = true;  // the boundary species is undefined in the interior: identity rows there
+    }
     h->have_pattern = false;
     return VFVM_OK;
 }
@@ -211,13 +235,16 @@ static int min_species(int slot, int id) {
         if (id == VFVM_REACTION_BIPOLAR) return 3;
     }
     if (slot == VFVM_SLOT_STORAGE && id == VFVM_STORAGE_BIPOLAR) return 3;
+    if (slot == VFVM_SLOT_BREACTION && id == VFVM_BREACTION_CATALYSIS) return 3;
+    if (slot == VFVM_SLOT_EDGEREACTION && id == VFVM_EDGEREACTION_JOULE) return 2;
     return 1;
 }
 
 extern "C" int vfvm_set_physics(vfvm_handle* h, int slot, int id, const double* params, int np) {
     NEED(h, h->have_system, "vfvm_set_system has not been called");
     if (slot < 0 || slot >= VFVM_NUM_SLOTS || np < 0 || (np > 0 && !params)) return vfvm_fail(h, VFVM_ERR_ARG, "bad slot / params");
-    static const int maxid[VFVM_NUM_SLOTS] = {VFVM_FLUX_SG_BIPOLAR, VFVM_REACTION_REGION_AFFINE, VFVM_STORAGE_BIPOLAR, VFVM_SOURCE_NODAL, VFVM_BREACTION_LINEAR};
+    static const int maxid[VFVM_NUM_SLOTS] = {VFVM_FLUX_SG_BIPOLAR, VFVM_REACTION_REGION_AFFINE, VFVM_STORAGE_BIPOLAR, VFVM_SOURCE_NODAL, VFVM_BREACTION_CATALYSIS,
+                                              VFVM_EDGEREACTION_JOULE, VFVM_BSTORAGE_LINEAR};
     if (id < 0 || id > maxid[slot])
         return vfvm_fail(h, VFVM_ERR_UNREGISTERED, "physics id is not in the registered device library; arbitrary host callbacks are not evaluated (no CPU fallback)");
     const int n = h->n;
@@ -259,6 +286,20 @@ extern "C" int vfvm_set_physics(vfvm_handle* h, int slot, int id, const double* 
         need = t[id];
     } else if (slot == VFVM_SLOT_BREACTION) {
         if (id == VFVM_BREACTION_LINEAR) need = 1 + n * n;
+        if (id == VFVM_BREACTION_CATALYSIS) {
+            need = 9;
+            if (np == 9)
+                for (int k = 6; k < 9; k++)
+                    if (params[k] < 0 || params[k] >= n) return vfvm_fail(h, VFVM_ERR_ARG, "catalysis boundary reaction: species index out of range");
+        }
+    } else if (slot == VFVM_SLOT_EDGEREACTION) {
+        if (id == VFVM_EDGEREACTION_DIAMOND) need = n;
+        if (id == VFVM_EDGEREACTION_JOULE) {
+            need = 3;
+            if (np == 3 && (params[1] < 0 || params[1] >= n || params[2] < 0 || params[2] >= n)) return vfvm_fail(h, VFVM_ERR_ARG, "Joule heat edge reaction: species index out of range");
+        }
+    } else if (slot == VFVM_SLOT_BSTORAGE) {
+        if (id == VFVM_BSTORAGE_LINEAR) need = 1 + n;
     }
     if (id == VFVM_NONE) need = np;  // params ignored
     if (need >= 0 && np != need) return vfvm_fail(h, VFVM_ERR_ARG, "parameter block has the wrong length for this physics id");

@@ -694,6 +694,86 @@ __global__ void __launch_bounds__(THREADS, MINB) k_assemble_rows_bipolar(const A
     if (nan_seen) atomicOr(a.flags, 1);
 }
 
+// ---- edgereaction(f,u,edge,data), src/vfvm_assembly.jl:202-239 ------------------------------------------------------------------------
+// A separate pass over the same SELL-32 rows after the row kernel (a feature path: the hot kernels stay untouched).  The reference adds
+// fac f to BOTH end nodes' residuals and (K,K) += J_K, (L,K) -= J_K, (K,L) -= J_L, (L,L) += J_L with K = edge.node[1]; seen from row r
+// with neighbour c: F_r += fac f, diag_r += fac df/du_r, offdiag(r,c) -= fac df/du_c.
+template <int NS>
+__global__ void k_edgereaction_rows(const AsmArgs a, const double* __restrict__ coord, int dim) {
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5, nwarps = gridDim.x * wpb;
+    const PhysicsDev& ph = *a.ph;
+    const int eid = ph.slot[VFVM_SLOT_EDGEREACTION].id;
+    const double* __restrict__ pe = ph.params + ph.slot[VFVM_SLOT_EDGEREACTION].off;
+    const int64_t nnz = a.nnz_sell;
+    bool nan_seen = false;
+    for (int g = a.slice0 + blockIdx.x * wpb + (threadIdx.x >> 5); g < a.nslices; g += nwarps) {
+        const int64_t rraw = (int64_t)g * 32 + lane;
+        const bool valid = rraw < a.Nown;
+        const int64_t r = valid ? rraw : a.Nown - 1;
+        const int base = a.sell_ptr[g];
+        const int w = (a.sell_ptr[g + 1] - base) >> 5;
+        double u_r[NS], Fr[NS], Dr[NS * NS], xr[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+        for (int i = 0; i < NS; i++) {
+            u_r[i] = a.U[r * NS + i];
+            Fr[i] = 0.0;
+        }
+#pragma unroll
+        for (int i = 0; i < NS * NS; i++) Dr[i] = 0.0;
+        for (int d = 0; d < dim; d++) xr[d] = coord[r * dim + d];
+        for (int j = 0; j < w; j++) {
+            const int64_t e = (int64_t)base + (int64_t)j * 32 + lane;
+            const int L = a.colidx[e];
+            const double fac = a.nzfac[e];
+            if (!valid || L == r) continue;  // padding
+            double h2 = 0.0;
+            for (int d = 0; d < dim; d++) {
+                const double dx = xr[d] - coord[(int64_t)L * dim + d];
+                h2 += dx * dx;
+            }
+            const bool pos = r > L;  // row node is edge.node[1]
+            typedef Dual<2 * NS> D;
+            D x[NS], y[NS], f[NS];
+#pragma unroll
+            for (int i = 0; i < NS; i++) {
+                const double uc = a.U[(int64_t)L * NS + i];
+                x[i] = D(pos ? u_r[i] : uc);
+                x[i].d[i] = 1.0;
+                y[i] = D(pos ? uc : u_r[i]);
+                y[i].d[NS + i] = 1.0;
+                f[i] = D(0.0);
+            }
+            eval_edgereaction<NS>(eid, pe, f, x, y, sqrt(h2), dim);
+#pragma unroll
+            for (int i = 0; i < NS; i++) {
+                Fr[i] += fac * f[i].v;
+#pragma unroll
+                for (int jj = 0; jj < NS; jj++) {
+                    const int p = a.idxF[i * NS + jj];
+                    if (p < 0) continue;
+                    const double drow = pos ? f[i].d[jj] : f[i].d[NS + jj], dcol = pos ? f[i].d[NS + jj] : f[i].d[jj];
+                    nan_seen |= (drow != drow) | (dcol != dcol);
+                    Dr[i * NS + jj] += fac * drow;
+                    a.offval[(int64_t)p * nnz + e] -= fac * dcol;
+                }
+            }
+        }
+        if (valid) {
+#pragma unroll
+            for (int i = 0; i < NS; i++) {
+                a.F[r * NS + i] += Fr[i];
+#pragma unroll
+                for (int jj = 0; jj < NS; jj++) {
+                    const int pD = a.idxD[i * NS + jj];
+                    if (pD >= 0 && a.idxF[i * NS + jj] >= 0) a.diagval[(int64_t)pD * a.Nown + r] += Dr[i * NS + jj];
+                }
+            }
+        }
+    }
+    if (nan_seen) atomicOr(a.flags, 1);
+}
+
 // tabulates the (u-independent) source callback once per physics change: src[i,K] = source(f, node)[i]
 template <int NS>
 __global__ void k_source_cache(int64_t N, int dim, const double* __restrict__ coord, const PhysicsDev* __restrict__ ph, double* __restrict__ out) {
@@ -716,6 +796,8 @@ struct BNodeArgs {
     const int32_t* __restrict__ bfaceregions;
     const double* __restrict__ bfnf;
     double* U;  // read (assembly) or written (init_dirichlet)
+    const double* __restrict__ UOld;
+    double tstepinv;
     double* __restrict__ F;
     double* __restrict__ diagval;
     const PhysicsDev* __restrict__ ph;
@@ -780,6 +862,31 @@ __global__ void k_assemble_bnodes(const BNodeArgs a) {
                 nan_seen |= (jv != jv);
                 const int pD = a.idxD[i * NS + j];
                 if (pD >= 0 && jv != 0.0) a.diagval[(int64_t)pD * a.Nown + K] += jv * fac;
+            }
+        }
+        if (ph.slot[VFVM_SLOT_BSTORAGE].id != VFVM_NONE) {  // src/vfvm_assembly.jl:409-439
+            DN st[NS];
+            double uo[NS], sto[NS];
+#pragma unroll
+            for (int i = 0; i < NS; i++) {
+                st[i] = DN(0.0);
+                sto[i] = 0.0;
+                uo[i] = a.UOld[(int64_t)K * NS + i];
+            }
+            eval_bstorage<NS>(ph, st, u, region);
+            eval_bstorage<NS>(ph, sto, uo, region);
+#pragma unroll
+            for (int i = 0; i < NS; i++) {
+                if (!((act >> i) & 1u)) continue;
+                Fk[i] += fac * (st[i].v - sto[i]) * a.tstepinv;
+#pragma unroll
+                for (int j = 0; j < NS; j++) {
+                    if (!((act >> j) & 1u)) continue;
+                    const double jv = st[i].d[j];
+                    nan_seen |= (jv != jv);
+                    const int pD = a.idxD[i * NS + j];
+                    if (pD >= 0 && jv != 0.0) a.diagval[(int64_t)pD * a.Nown + K] += jv * (fac * a.tstepinv);
+                }
             }
         }
     }
@@ -1061,6 +1168,8 @@ static void fill_bnode_args(vfvm_handle* h, BNodeArgs& b, const AsmArgs& a, doub
     b.bfaceregions = h->bfaceregions.p;
     b.bfnf = h->bfacenodefac.p;
     b.U = h->vec[VFVM_VEC_SOLUTION].p;
+    b.UOld = a.UOld;
+    b.tstepinv = a.tstepinv;
     b.F = h->vec[VFVM_VEC_RESIDUAL].p;
     b.diagval = h->diagval.p;
     b.ph = a.ph;
@@ -1086,6 +1195,12 @@ static void launch_rows_range(vfvm_handle* h, AsmArgs a, int s0, int s1) {
     a.slice0 = s0;
     a.nslices = s1;
     NS_DISPATCH(h->n, (launch_rows_ns<NS>(h, a)));
+    if (h->phys.slot[VFVM_SLOT_EDGEREACTION].id != VFVM_NONE) {
+        if (h->masked) throw std::string("edgereaction with species enabled per region has no device instantiation");
+        const int grid = std::max(1, std::min(cdiv(s1 - s0, ASM_WARPS), 148 * 4));
+        NS_DISPATCH(h->n, (k_edgereaction_rows<NS><<<grid, ASM_THREADS, 0, h->stream>>>(a, h->coord.p, h->dim)));
+        h->launches++;
+    }
 }
 static void launch_bnodes_range(vfvm_handle* h, BNodeArgs b, int64_t b0, int64_t b1) {
     if (b1 <= b0) return;
@@ -1196,6 +1311,7 @@ int vfvm_eval_res_jac_pipelined(vfvm_handle* h, const double* U, const double* U
     // after the last chunk (a device copy per piece on the copy-in stream would compete with the copy engines)
     const bool have_old = UOld && UOld != U;
     if (!have_old) a.UOld = a.U;
+    bn.UOld = a.UOld;
     auto node_begin = [&](int c) { return c >= K ? h->N : (int64_t)P.slice_begin[c] * 32; };  // the last piece carries the tail
     CK(cudaMemsetAsync(h->flags.p + 1, 0, sizeof(int32_t), s));
     CK(cudaEventRecord(h->ev0, s));

@@ -210,6 +210,7 @@ __global__ void __launch_bounds__(BULK_THREADS) k_spmv_bulk(const SpmvArgs a, co
         peer_push<NS>(P, seq, a.x);
     }
     const int g0 = blockIdx.x * wpb + wib;
+    const uint64_t stream_policy = l2_policy_evict_first();  // the planes are read once: keep x (gathered ~15 times per entry) in L2 instead
     // producer cursor (lane 0): next chunk to request
     int pg = g0, pj0 = 0, pbase = 0, pw = 0;
     auto producer_seek = [&]() {  // skip slices without entries
@@ -226,8 +227,9 @@ __global__ void __launch_bounds__(BULK_THREADS) k_spmv_bulk(const SpmvArgs a, co
         const int64_t e0 = (int64_t)pbase + (int64_t)pj0 * 32;
         unsigned char* st = wbase + (size_t)s * stage_bytes;
         mbar_expect_tx(wbar + s, (uint32_t)(nent * 4 + cF * nent * 8));
-        bulk_g2s(st, a.colidx + e0, (uint32_t)(nent * 4), wbar + s);
-        for (int p = 0; p < cF; p++) bulk_g2s(st + BULK_CH * 32 * 4 + (size_t)p * BULK_CH * 32 * 8, a.offval + (int64_t)p * nnz + e0, (uint32_t)(nent * 8), wbar + s);
+        bulk_g2s_hint(st, a.colidx + e0, (uint32_t)(nent * 4), wbar + s, stream_policy);
+        for (int p = 0; p < cF; p++)
+            bulk_g2s_hint(st + BULK_CH * 32 * 4 + (size_t)p * BULK_CH * 32 * 8, a.offval + (int64_t)p * nnz + e0, (uint32_t)(nent * 8), wbar + s, stream_policy);
         pj0 += BULK_CH;
         if (pj0 >= pw) {
             pg += nwarps;
@@ -1057,7 +1059,12 @@ extern "C" int vfvm_linsolve(vfvm_handle* h, double abstol, double reltol, int m
         CK(cudaMemsetAsync(h->flags.p, 0, sizeof(int32_t), st));
 
         CK(cudaEventRecord(h->ev0, st));
-        if (!(reuse_precs && h->precon_valid)) precond_setup(h);
+        // reuse_precs (factorize_every_newtonstep = false, src/vfvm_solver.jl:99) keeps an ILU factorisation across Newton steps, as the
+        // reference keeps its preconditioner.  Jacobi, node-block Jacobi and the AMG numeric phase cost less than one Krylov iteration on
+        // the device and the AMG cycle multiplies with the CURRENT finest-level Jacobian, so they are always refreshed (a stale Galerkin
+        // hierarchy under a new finest level is not a consistent preconditioner: measured stagnation on the bipolar system).
+        const bool keep = reuse_precs && h->precon_valid && (h->precon == VFVM_PRECON_ILU0 || h->precon == VFVM_PRECON_ILU0_MC);
+        if (!keep) precond_setup(h);
         CK(cudaEventRecord(h->ev1, st));
 
         const bool fusedpc = (h->precon == VFVM_PRECON_NONE || h->precon == VFVM_PRECON_JACOBI);

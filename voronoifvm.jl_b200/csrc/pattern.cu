@@ -200,6 +200,33 @@ int vfvm_physics_masks(vfvm_handle* h) {
                 if (p[1 + i] != 0.0) mask_set(m.boundary, i);
             break;
         }
+        case VFVM_BREACTION_CATALYSIS: {  // f_A(u_A, u_C), f_B(u_B, u_C), f_C(u_A, u_B, u_C)
+            const double* p = P(VFVM_SLOT_BREACTION);
+            const int iA = (int)p[6], iB = (int)p[7], iC = (int)p[8];
+            const int pairs[7][2] = {{iA, iA}, {iA, iC}, {iB, iB}, {iB, iC}, {iC, iA}, {iC, iB}, {iC, iC}};
+            for (auto& q : pairs) mask_set(m.boundary, q[0] * n + q[1]);
+            break;
+        }
+        default: return VFVM_ERR_UNREGISTERED;
+    }
+    switch (ph.slot[VFVM_SLOT_BSTORAGE].id) {
+        case VFVM_NONE: break;
+        case VFVM_BSTORAGE_LINEAR: {
+            const double* p = P(VFVM_SLOT_BSTORAGE);
+            for (int i = 0; i < n; i++)
+                if (p[1 + i] != 0.0) mask_set(m.boundary, i * n + i);
+            break;
+        }
+        default: return VFVM_ERR_UNREGISTERED;
+    }
+    switch (ph.slot[VFVM_SLOT_EDGEREACTION].id) {
+        case VFVM_NONE:
+        case VFVM_EDGEREACTION_DIAMOND: break;  // does not depend on u: no Jacobian entries
+        case VFVM_EDGEREACTION_JOULE: {
+            const double* p = P(VFVM_SLOT_EDGEREACTION);
+            if (p[0] != 0.0) mask_set(m.edgereaction, (int)p[2] * n + (int)p[1]);  // d f_iT / d u_iphi
+            break;
+        }
         default: return VFVM_ERR_UNREGISTERED;
     }
     for (int e = 0; e < ph.nbc; e++) {
@@ -223,6 +250,20 @@ static void boundary_bits(const vfvm_handle* h, int breg, uint64_t* out) {
             for (int i = 0; i < n * n; i++)
                 if (p[1 + i] != 0.0) mask_set(out, i);
     }
+    if (ph.slot[VFVM_SLOT_BREACTION].id == VFVM_BREACTION_CATALYSIS) {
+        const double* p = ph.params + ph.slot[VFVM_SLOT_BREACTION].off;
+        if ((int)p[0] == breg) {
+            const int iA = (int)p[6], iB = (int)p[7], iC = (int)p[8];
+            const int pairs[7][2] = {{iA, iA}, {iA, iC}, {iB, iB}, {iB, iC}, {iC, iA}, {iC, iB}, {iC, iC}};
+            for (auto& q : pairs) mask_set(out, q[0] * n + q[1]);
+        }
+    }
+    if (ph.slot[VFVM_SLOT_BSTORAGE].id == VFVM_BSTORAGE_LINEAR && h->seen_transient) {
+        const double* p = ph.params + ph.slot[VFVM_SLOT_BSTORAGE].off;
+        if ((int)p[0] == breg)
+            for (int i = 0; i < n; i++)
+                if (p[1 + i] != 0.0) mask_set(out, i * n + i);
+    }
     for (int e = 0; e < ph.nbc; e++) {
         const vfvm_bc_entry& b = ph.bc[e];
         if (b.region != 0 && b.region != breg) continue;
@@ -245,12 +286,12 @@ int vfvm_pattern_build(vfvm_handle* h) {
     h->cF = h->cD = 0;
     for (int b = 0; b < n * n; b++) {
         h->idxF[b] = h->idxD[b] = -1;
-        if (mask_get(h->masks.flux, b)) {
+        if (mask_get(h->masks.flux, b) || mask_get(h->masks.edgereaction, b)) {
             h->idxF[b] = h->cF;
             h->planeF[h->cF++] = b;
         }
         const bool diag = (b / n) == (b % n);
-        if (diag || mask_get(h->masks.flux, b) || mask_get(h->masks.reaction, b) || mask_get(h->masks.storage, b) || mask_get(h->masks.boundary, b)) {
+        if (diag || mask_get(h->masks.flux, b) || mask_get(h->masks.edgereaction, b) || mask_get(h->masks.reaction, b) || mask_get(h->masks.storage, b) || mask_get(h->masks.boundary, b)) {
             h->idxD[b] = h->cD;
             h->planeD[h->cD++] = b;
         }
@@ -354,9 +395,19 @@ int vfvm_pattern_build(vfvm_handle* h) {
                 for (int64_t q = cp[K]; q < cp[K + 1]; q++)
                     for (int i = 0; i < h->n; i++)
                         if (h->region_species[(size_t)(rg[q] - 1) * h->n + i]) act[K] |= (1 << i);
+            if (!h->bregion_species.empty())  // boundary species are defined at the nodes of their boundary regions (src/vfvm_system.jl:502-513)
+                for (int64_t b = 0; b < (int64_t)bfr.size(); b++) {
+                    const int br = bfr[b] - 1;
+                    if (br >= h->nbregions_bs) continue;
+                    for (int i = 0; i < h->n; i++)
+                        if (h->bregion_species[(size_t)br * h->n + i])
+                            for (int l = 0; l < dim; l++) act[bfn[b * dim + l]] |= (1 << i);
+                }
+            h->node_active_host = act;
             h->node_active.upload(act.data(), act.size(), s);
         } else {
             h->node_active.release();
+            h->node_active_host.clear();
         }
         h->bn_node_host = node;
         h->pipe.valid = false;
@@ -440,29 +491,31 @@ static void build_scalar_range(vfvm_handle* h, int64_t K0, int64_t K1, ScalarPat
     sp.rowptr.assign((size_t)(K1 - K0) * n + 1, 0);
     sp.colidx.clear();
     sp.src.clear();
+    const uint64_t offm[2] = {h->masks.flux[0] | h->masks.edgereaction[0], h->masks.flux[1] | h->masks.edgereaction[1]};
     for (int64_t K = K0; K < K1; K++) {
-        uint64_t dm[2] = {h->masks.flux[0] | h->masks.reaction[0], h->masks.flux[1] | h->masks.reaction[1]};
+        uint64_t dm[2] = {offm[0] | h->masks.reaction[0], offm[1] | h->masks.reaction[1]};  // node and edge terms
         if (h->seen_transient) {
             dm[0] |= h->masks.storage[0];
             dm[1] |= h->masks.storage[1];
         }
-        if (bnode_of[K - K0] >= 0) {
-            uint64_t bits[2];
-            memcpy(bits, &h->bnode_mask_host[(size_t)bnode_of[K - K0] * 16], 16);
-            dm[0] |= bits[0];
-            dm[1] |= bits[1];
-        }
+        uint64_t bm[2] = {0, 0};  // boundary terms of this node
+        if (bnode_of[K - K0] >= 0) memcpy(bm, &h->bnode_mask_host[(size_t)bnode_of[K - K0] * 16], 16);
+        // species defined at the node: every species, or (masked systems) the union over its cell regions and boundary regions
+        const unsigned act = h->masked ? (unsigned)h->node_active_host[(size_t)K] : 0xffffffffu;
         const int len = rp[K - K0 + 1] - rp[K - K0];
         const int64_t ebase = (int64_t)sl[(K >> 5) - g0] + (K & 31);
         for (int i = 0; i < n; i++) {
             bool diag_done = false;
-            const bool inactive = h->masked && !pair_ok(nfp, nfr, K, i, i);  // identity row
+            const bool inactive = !((act >> i) & 1u);  // identity row
             auto emit_diag = [&]() {
-                for (int j = 0; j < n; j++)
-                    if (inactive ? (i == j) : (mask_get(dm, i * n + j) && pair_ok(nfp, nfr, K, i, j))) {
+                for (int j = 0; j < n; j++) {
+                    const bool node_term = mask_get(dm, i * n + j) && pair_ok(nfp, nfr, K, i, j);
+                    const bool bnd_term = mask_get(bm, i * n + j) && ((act >> j) & 1u);  // assemble_res_jac(bnode): both species defined at the node
+                    if (inactive ? (i == j) : (node_term || bnd_term)) {
                         sp.colidx.push_back(K * n + j);
                         sp.src.push_back(-(1 + (int64_t)h->idxD[i * n + j] * Nown + K));
                     }
+                }
                 diag_done = true;
             };
             for (int q = 0; q < len; q++) {
@@ -470,7 +523,7 @@ static void build_scalar_range(vfvm_handle* h, int64_t K0, int64_t K1, ScalarPat
                 const int64_t L = ci[e - e0];
                 if (!diag_done && L > K) emit_diag();
                 for (int j = 0; j < n; j++)
-                    if (mask_get(h->masks.flux, i * n + j) && (!h->masked || (nze[e - e0] >= 0 && pair_ok(efp, efr, nze[e - e0], i, j)))) {
+                    if (mask_get(offm, i * n + j) && (!h->masked || (nze[e - e0] >= 0 && pair_ok(efp, efr, nze[e - e0], i, j)))) {
                         sp.colidx.push_back(L * n + j);
                         sp.src.push_back((int64_t)h->idxF[i * n + j] * h->nnz_sell + e);
                     }

@@ -267,6 +267,29 @@ __device__ __forceinline__ void eval_breaction(const PhysicsDev& ph, T* f, const
             }
         }
     }
+    if (s.id == VFVM_BREACTION_CATALYSIS) {  // examples/Example115_HeterogeneousCatalysis1D.jl:125-135
+        if constexpr (NS >= 3) {
+            if (bregion == (int)p[0]) {
+                const double S = p[1], kpAC = p[2], kmAC = p[3], kpBC = p[4], kmBC = p[5];
+                const int iA = (int)p[6], iB = (int)p[7], iC = (int)p[8];
+                T uA(0.0), uB(0.0), uC(0.0);
+#pragma unroll
+                for (int i = 0; i < NS; i++) {  // register arrays: select instead of indexing
+                    if (i == iA) uA = u[i];
+                    if (i == iB) uB = u[i];
+                    if (i == iC) uC = u[i];
+                }
+                const T rac = kpAC * uA * (1.0 - uC) - kmAC * uC;
+                const T rbc = kpBC * uB * (1.0 - uC) - kmBC * uC;
+#pragma unroll
+                for (int i = 0; i < NS; i++) {
+                    if (i == iA) f[i] = S * rac;
+                    if (i == iB) f[i] = S * rbc;
+                    if (i == iC) f[i] = -rbc - rac;
+                }
+            }
+        }
+    }
     for (int e = 0; e < ph.nbc; e++) {
         const vfvm_bc_entry& bc = ph.bc[e];
         const int ireg = bc.region == 0 ? bregion : bc.region;
@@ -284,5 +307,35 @@ __device__ __forceinline__ void eval_breaction(const PhysicsDev& ph, T* f, const
                 f[i] = f[i] + (bc.factor * u[i] - val);
             }
         }
+    }
+}
+
+// ---- bstorage(f,u,bnode,data): f pre-zeroed ---------------------------------------------------------------------------------------
+template <int NS, class T>
+__device__ __forceinline__ void eval_bstorage(const PhysicsDev& ph, T* f, const T* u, int bregion) {
+    const PhysSlotDev& s = ph.slot[VFVM_SLOT_BSTORAGE];
+    const double* p = ph.params + s.off;
+    if (s.id == VFVM_BSTORAGE_LINEAR && bregion == (int)p[0]) {  // examples/Example115_HeterogeneousCatalysis1D.jl:138-143
+#pragma unroll
+        for (int i = 0; i < NS; i++)
+            if (p[1 + i] != 0.0) f[i] = p[1 + i] * u[i];
+    }
+}
+
+// ---- edgereaction(f,u,edge,data): f pre-zeroed; h = meas(edge) ------------------------------------------------------------------
+template <int NS, class T>
+__device__ __forceinline__ void eval_edgereaction(int id, const double* __restrict__ p, T* f, const T* uK, const T* uL, double h, int dim) {
+    if (id == VFVM_EDGEREACTION_DIAMOND) {  // examples/DevEx002_EdgeReaction.jl:83-87
+#pragma unroll
+        for (int i = 0; i < NS; i++) f[i] = T(p[i] * (h * h) / (2 * dim));
+    } else if (id == VFVM_EDGEREACTION_JOULE) {  // examples/Example206_JouleHeat.jl:83-86
+        const int iphi = (int)p[1], iT = (int)p[2];
+        T d(0.0);
+#pragma unroll
+        for (int i = 0; i < NS; i++)
+            if (i == iphi) d = uK[i] - uL[i];
+#pragma unroll
+        for (int i = 0; i < NS; i++)
+            if (i == iT) f[i] = -p[0] * d * d;
     }
 }

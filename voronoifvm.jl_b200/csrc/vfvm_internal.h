@@ -87,6 +87,7 @@ struct Masks {
     uint64_t reaction[2];
     uint64_t storage[2];
     uint64_t boundary[2];  // union over all boundary contributions
+    uint64_t edgereaction[2];
 };
 static inline bool mask_get(const uint64_t* m, int bit) { return (m[bit >> 6] >> (bit & 63)) & 1ull; }
 static inline void mask_set(uint64_t* m, int bit) { m[bit >> 6] |= (1ull << (bit & 63)); }
@@ -143,7 +144,10 @@ struct vfvm_handle {
     // system
     int n = 0;
     std::vector<uint8_t> region_species;  // n x ncellregions: species enabled per cell region
+    std::vector<uint8_t> bregion_species;  // n x nbregions_bs: boundary species (enable_boundary_species!), may be empty
+    int nbregions_bs = 0;
     bool masked = false;                   // some species is not enabled in every cell region
+    std::vector<int32_t> node_active_host;
     DevBuf<int32_t> node_active;           // masked systems: bit i set <=> species i is defined at the node (node_dof, src/vfvm_system.jl:445-456)
     PhysicsDev phys;
     DevBuf<PhysicsDev> phys_dev;  // device copy, refreshed by vfvm_sync_physics

@@ -96,6 +96,7 @@ def local_system(system: System, info: PartitionInfo) -> System:
     ls = System(info.grid, system.physics, is_linear=system.is_linear, assembly=system.assembly_type, unknown_storage=system.unknown_storage)
     ls._increase_num_species(system.num_species)
     ls.region_species[:, :] = system.region_species
+    ls.bregion_species[:, :] = system.bregion_species
     ls.boundary_factors[:, :] = system.boundary_factors
     ls.boundary_values[:, :] = system.boundary_values
     ls._version += 1

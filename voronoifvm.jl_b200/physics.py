@@ -15,14 +15,16 @@ from __future__ import annotations
 import numpy as np
 
 # ids: keep in sync with include/vfvm_b200.h
-SLOT_FLUX, SLOT_REACTION, SLOT_STORAGE, SLOT_SOURCE, SLOT_BREACTION = range(5)
-SLOT_NAMES = ("flux", "reaction", "storage", "source", "breaction")
+SLOT_FLUX, SLOT_REACTION, SLOT_STORAGE, SLOT_SOURCE, SLOT_BREACTION, SLOT_EDGEREACTION, SLOT_BSTORAGE = range(7)
+SLOT_NAMES = ("flux", "reaction", "storage", "source", "breaction", "edgereaction", "bstorage")
 
 FLUX_DIFFUSION, FLUX_POWDIFF, FLUX_CROSSDIFF2, FLUX_SG_UNIPOLAR, FLUX_SEDAN, FLUX_SG_BIPOLAR = 1, 2, 3, 4, 5, 6
 REACTION_POW, REACTION_SINH, REACTION_AFFINE, REACTION_BILINEAR2, REACTION_BIPOLAR, REACTION_REGION_AFFINE = 1, 2, 3, 4, 5, 6
 STORAGE_LINEAR, STORAGE_POW, STORAGE_BIPOLAR = 1, 2, 3
 SOURCE_CONST, SOURCE_GAUSS, SOURCE_XSINYEXPZ, SOURCE_STEP1D, SOURCE_AFFINE_X, SOURCE_NODAL = 1, 2, 3, 4, 5, 6
-BREACTION_LINEAR = 1
+BREACTION_LINEAR, BREACTION_CATALYSIS = 1, 2
+EDGEREACTION_DIAMOND, EDGEREACTION_JOULE = 1, 2
+BSTORAGE_LINEAR = 1
 BC_DIRICHLET, BC_NEUMANN, BC_ROBIN = 1, 2, 3
 
 
@@ -341,6 +343,57 @@ class LinearBoundaryReaction(RegisteredPhysics):
         return np.concatenate([[self.region], self.R.ravel(order="C")])
 
 
+class CatalysisBoundaryReaction(RegisteredPhysics):
+    """Example115 `breaction!` :125-135 on boundary region `region`: surface species C exchanges with the bulk species A and B,
+    R_XC = kp_XC u_X (1 - u_C) - km_XC u_C;  f_A = S R_AC, f_B = S R_BC, f_C = -R_BC - R_AC"""
+
+    slot, id, min_species = SLOT_BREACTION, BREACTION_CATALYSIS, 3
+
+    def __init__(self, region, S=0.01, kp_AC=100.0, km_AC=1.0, kp_BC=0.1, km_BC=1.0, iA=1, iB=2, iC=3):
+        self.p = [region, S, kp_AC, km_AC, kp_BC, km_BC, iA - 1, iB - 1, iC - 1]
+
+    def params(self, n):
+        return np.array(self.p, dtype=np.float64)
+
+
+# ------------------------------------------------------------------------------------------- edge reaction
+class DiamondEdgeReaction(RegisteredPhysics):
+    """f_i = c_i h^2 / (2 dim), h = meas(edge): a constant volume density given per edge (DevEx002_EdgeReaction.jl:83-87)"""
+
+    slot, id = SLOT_EDGEREACTION, EDGEREACTION_DIAMOND
+
+    def __init__(self, c=-1.0):
+        self.c = c
+
+    def params(self, n):
+        return _vec(self.c, n)
+
+
+class JouleHeatEdgeReaction(RegisteredPhysics):
+    """f_iT = -kappa (u_iphi,K - u_iphi,L)^2   (Example206_JouleHeat.jl:83-86)"""
+
+    slot, id, min_species = SLOT_EDGEREACTION, EDGEREACTION_JOULE, 2
+
+    def __init__(self, kappa=1.0, iphi=1, iT=2):
+        self.p = [kappa, iphi - 1, iT - 1]
+
+    def params(self, n):
+        return np.array(self.p, dtype=np.float64)
+
+
+# ------------------------------------------------------------------------------------------- boundary storage
+class LinearBoundaryStorage(RegisteredPhysics):
+    """if bnode.region == region: f_i = c_i u_i   (Example115:138-143, Example311:78-83)"""
+
+    slot, id = SLOT_BSTORAGE, BSTORAGE_LINEAR
+
+    def __init__(self, region, c):
+        self.region, self.c = region, c
+
+    def params(self, n):
+        return np.concatenate([[float(self.region)], _vec(self.c, n)])
+
+
 class BCondition(RegisteredPhysics):
     """A `bcondition` callback made of boundary_dirichlet!/neumann!/robin! calls (src/vfvm_physics.jl:487-564),
     optionally after a registered boundary reaction.  `region=None` means "all boundary regions"
@@ -377,14 +430,14 @@ class BCondition(RegisteredPhysics):
         return self._add(BC_ROBIN, species, region, value, factor=factor, ramp=ramp)
 
 
-_UNSUPPORTED = ("edgereaction", "bflux", "bsource", "bstorage", "boutflow", "generic_operator", "generic_operator_sparsity")
+_UNSUPPORTED = ("bflux", "bsource", "boutflow", "generic_operator", "generic_operator_sparsity")
 
 
 class Physics:
     """Mirror of `VoronoiFVM.Physics(; flux, reaction, storage, source, breaction/bcondition, data, ...)`
     (src/vfvm_physics.jl:184-238) restricted to registered device callbacks."""
 
-    def __init__(self, flux=None, reaction=None, storage=None, source=None, breaction=None, bcondition=None, data=None, **other):
+    def __init__(self, flux=None, reaction=None, storage=None, source=None, breaction=None, bcondition=None, edgereaction=None, bstorage=None, data=None, **other):
         for k, v in other.items():
             if k in _UNSUPPORTED and v is not None:
                 raise NotImplementedError(f"physics callback `{k}` is outside the B200 hot-path scope (SURVEY.md section 8f)")
@@ -397,8 +450,8 @@ class Physics:
             if isinstance(breaction, RegisteredPhysics):
                 breaction = BCondition(reaction=breaction)
         self.data = data
-        self.slots = [flux, reaction, storage, source, breaction]
-        for name, cb, slot in zip(SLOT_NAMES, self.slots, range(5)):
+        self.slots = [flux, reaction, storage, source, breaction, edgereaction, bstorage]
+        for name, cb, slot in zip(SLOT_NAMES, self.slots, range(7)):
             if cb is None:
                 continue
             if not isinstance(cb, RegisteredPhysics):
@@ -414,3 +467,5 @@ class Physics:
     storage = property(lambda self: self.slots[2])
     source = property(lambda self: self.slots[3])
     breaction = property(lambda self: self.slots[4])
+    edgereaction = property(lambda self: self.slots[5])
+    bstorage = property(lambda self: self.slots[6])

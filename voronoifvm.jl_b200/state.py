@@ -37,6 +37,9 @@ class SystemState:
         check(h, self.L.vfvm_build_geometry(h))  # update_grid! (src/vfvm_system.jl:607-631)
         rs = np.ascontiguousarray(system.region_species.ravel(order="F"), dtype=np.uint8)
         check(h, self.L.vfvm_set_system(h, self.n, rs.ctypes.data_as(C.POINTER(C.c_uint8))))
+        if system.bregion_species.any():
+            bs = np.ascontiguousarray(system.bregion_species.ravel(order="F"), dtype=np.uint8)
+            check(h, self.L.vfvm_set_boundary_species(h, system.bregion_species.shape[1], bs.ctypes.data_as(C.POINTER(C.c_uint8))))
         self._version = -1
         self._push_physics()
         check(h, self.L.vfvm_build_pattern(h))

@@ -36,6 +36,7 @@ class System:
         self.is_linear = bool(is_linear)
         self.num_species = 0
         self.region_species = np.zeros((0, grid.num_cellregions), dtype=np.uint8, order="F")
+        self.bregion_species = np.zeros((0, grid.num_bfaceregions), dtype=np.uint8, order="F")  # enable_boundary_species!
         self.boundary_factors = np.zeros((0, grid.num_bfaceregions), order="F")
         self.boundary_values = np.zeros((0, grid.num_bfaceregions), order="F")
         self.physics = physics if physics is not None else Physics(**physics_kwargs)
@@ -54,6 +55,7 @@ class System:
             b[: a.shape[0], :] = a
             return b
         self.region_species = grow(self.region_species, np.uint8)
+        self.bregion_species = grow(self.bregion_species, np.uint8)
         self.boundary_factors = grow(self.boundary_factors, np.float64)
         self.boundary_values = grow(self.boundary_values, np.float64)
         self.num_species = nspec
@@ -72,6 +74,12 @@ class System:
             for i in range(self.num_species):
                 if self.region_species[i, ireg]:
                     mask[i, nodes] = True
+        for ibreg in range(g.num_bfaceregions):  # boundary species, src/vfvm_system.jl:502-513
+            if self.bregion_species[:, ibreg].any():
+                nodes = np.unique(g.bfacenodes[:, g.bfaceregions == ibreg + 1])
+                for i in range(self.num_species):
+                    if self.bregion_species[i, ibreg]:
+                        mask[i, nodes] = True
         return mask
 
     def has_legacy_bc(self) -> bool:
@@ -120,6 +128,17 @@ def enable_species(system: System, ispec=None, regions=None, *, species=None):
         system._increase_num_species(int(isp))
         for ireg in regions:
             system.region_species[int(isp) - 1, int(ireg) - 1] = 1
+    system._version += 1
+    return system
+
+
+def enable_boundary_species(system: System, ispec: int, bregions):
+    """`enable_boundary_species!(system, ispec, bregions)` src/vfvm_system.jl:492-515: a species that lives on boundary regions only"""
+    system._increase_num_species(int(ispec))
+    if system.region_species[int(ispec) - 1].any():
+        raise ValueError(f"Species {ispec} is already bulk species")
+    for ireg in bregions:
+        system.bregion_species[int(ispec) - 1, int(ireg) - 1] = 1
     system._version += 1
     return system
 
