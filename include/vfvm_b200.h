@@ -79,6 +79,10 @@ typedef struct vfvm_handle vfvm_handle;
 #define VFVM_FLUX_SEDAN 5       /* Example160 sedanflux! :68-77            params: eps, z, iphi, ic, eps_reg                         */
 #define VFVM_FLUX_SG_BIPOLAR 6  /* Example161 flux! :134-150               params: lambda, mun, mup, zn, zp, En, Ep, iphin, iphip, ipsi */
 
+#define VFVM_FLUX_MIXTURE 7     /* DevEx005_Mixture.jl:74-104: f = M(u)^{-1} (uK - uL) with the Maxwell-Stefan matrix M_ii = 1/DK_i + sum_{j!=i} au_j / DB_ij,
+                                   M_ij = -au_i / DB_ij, au = (uK + uL)/2, solved in the callback by inplace_linsolve! (src/vfvm_functions.jl:98-168)
+                                   params: DK[n], DB[n*n] row-major (diagonal ignored) */
+
 /* reaction(f,u,node,data) */
 #define VFVM_REACTION_POW 1       /* f_i = k_i u_i^{p_i}                    params: k[n], p[n]   (Example207:32-34)                  */
 #define VFVM_REACTION_SINH 2      /* f_i = k_i (exp(u_i) - exp(-u_i))       params: k[n]         (Example105:55-58)                  */
@@ -288,6 +292,9 @@ int vfvm_block_counts(vfvm_handle* h, int64_t* nblocks_off, int64_t* nblocks_sto
 /* parity probe for test/test010_bernoulli.jl: evaluates the device fbernoulli_pm (src/vfvm_functions.jl:78-90) and its
  * dual-number derivative at n host points: bp = B(x), bm = B(-x), dbp = B'(x) */
 int vfvm_probe_bernoulli(vfvm_handle* h, int n, const double* x, double* bp, double* bm, double* dbp);
+/* parity probe for test/test040_inplacelu.jl: the device twins of inplace_linsolve!(A, b) (non-pivoting Doolittle, src/vfvm_functions.jl:98-155)
+ * and inplace_linsolve!(A, b, ipiv) (pivoting LU, :165-168) on `nsys` systems of size n x n (n <= 10; A row-major, nsys x n x n; b, x: nsys x n) */
+int vfvm_probe_inplace_linsolve(vfvm_handle* h, int n, int nsys, int pivoting, const double* A, const double* b, double* x);
 
 #ifdef __cplusplus
 }

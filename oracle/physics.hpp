@@ -108,6 +108,53 @@ inline double ramp(double t, double tbegin, double tend, double ubegin, double u
 
 // ---------------------------------------------------------------- flux(f,u,edge,data)
 // f must be zeroed by the caller (fwrap does y .= 0, src/vfvm_physics.jl:424-430)
+// ---------------------------------------------------------------- inplace_linsolve!, src/vfvm_functions.jl:98-168
+// non-pivoting Doolittle (doolittle_ludecomp! :98-115, doolittle_lusolve! :124-142); A row-major n x n, overwritten by L+U-I, b by x
+template <class T>
+inline void inplace_linsolve_nopiv(int n, T* A, T* b) {
+    for (int i = 0; i < n; i++) {
+        for (int j = 0; j < i; j++) {
+            for (int k = 0; k < j; k++) A[i * n + j] = A[i * n + j] - A[i * n + k] * A[k * n + j];
+            A[i * n + j] = A[i * n + j] / A[j * n + j];
+        }
+        for (int j = i; j < n; j++)
+            for (int k = 0; k < i; k++) A[i * n + j] = A[i * n + j] - A[i * n + k] * A[k * n + j];
+    }
+    for (int i = 0; i < n; i++)
+        for (int k = 0; k < i; k++) b[i] = b[i] - A[i * n + k] * b[k];
+    for (int i = n - 1; i >= 0; i--) {
+        for (int k = i + 1; k < n; k++) b[i] = b[i] - A[i * n + k] * b[k];
+        b[i] = b[i] / A[i * n + i];
+    }
+}
+// LU with partial (row) pivoting on the VALUE of the entries, then the two triangular solves: what
+// ldiv!(RecursiveFactorization.lu!(A, ipiv, Val(true), Val(false)), b) computes (:165-168)
+template <class T>
+inline void inplace_linsolve_piv(int n, T* A, T* b) {
+    for (int c = 0; c < n; c++) {
+        int piv = c;
+        double best = std::fabs(value(A[c * n + c]));
+        for (int r = c + 1; r < n; r++)
+            if (std::fabs(value(A[r * n + c])) > best) {
+                best = std::fabs(value(A[r * n + c]));
+                piv = r;
+            }
+        if (piv != c) {
+            for (int j = 0; j < n; j++) std::swap(A[c * n + j], A[piv * n + j]);
+            std::swap(b[c], b[piv]);
+        }
+        for (int r = c + 1; r < n; r++) {
+            A[r * n + c] = A[r * n + c] / A[c * n + c];
+            for (int j = c + 1; j < n; j++) A[r * n + j] = A[r * n + j] - A[r * n + c] * A[c * n + j];
+            b[r] = b[r] - A[r * n + c] * b[c];
+        }
+    }
+    for (int i = n - 1; i >= 0; i--) {
+        for (int k = i + 1; k < n; k++) b[i] = b[i] - A[i * n + k] * b[k];
+        b[i] = b[i] / A[i * n + i];
+    }
+}
+
 template <class T>
 inline bool eval_flux(const PhysSlot& s, int n, T* f, const T* uK, const T* uL, const EdgeCtx& e) {
     const double* p = s.p.data();
@@ -119,6 +166,23 @@ inline bool eval_flux(const PhysSlot& s, int n, T* f, const T* uK, const T* uL, 
         case VFVM_FLUX_POWDIFF: {
             double m = p[n];
             for (int i = 0; i < n; i++) f[i] = p[i] * (powr(uK[i], m) - powr(uL[i], m));
+            return true;
+        }
+        case VFVM_FLUX_MIXTURE: {  // examples/DevEx005_Mixture.jl:74-104
+            std::vector<T> M((size_t)n * n, T(0.0)), au(n), du(n);
+            for (int i = 0; i < n; i++) {
+                M[(size_t)i * n + i] = T(1.0 / p[i]);
+                du[i] = uK[i] - uL[i];
+                au[i] = 0.5 * (uK[i] + uL[i]);
+            }
+            for (int i = 0; i < n; i++)
+                for (int j = 0; j < n; j++)
+                    if (i != j) {
+                        M[(size_t)i * n + i] = M[(size_t)i * n + i] + au[j] / p[n + i * n + j];
+                        M[(size_t)i * n + j] = -au[i] / p[n + i * n + j];
+                    }
+            inplace_linsolve_piv(n, M.data(), du.data());
+            for (int i = 0; i < n; i++) f[i] = du[i];
             return true;
         }
         case VFVM_FLUX_CROSSDIFF2:

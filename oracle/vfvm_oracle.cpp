@@ -1228,3 +1228,16 @@ extern "C" int vo_krylov_solve(void* hv, int method, int precon, const double* b
     if (seconds_out) *seconds_out = omp_get_wtime() - t_start;
     return 0;
 }
+
+// test/test040_inplacelu.jl probe: solves nsys systems with the oracle's restatement of inplace_linsolve!
+extern "C" int vo_probe_inplace_linsolve(int n, int nsys, int pivoting, const double* A, const double* b, double* x) {
+    std::vector<double> M((size_t)n * n), r(n);
+    for (int s = 0; s < nsys; s++) {
+        std::copy(A + (size_t)s * n * n, A + (size_t)(s + 1) * n * n, M.begin());
+        std::copy(b + (size_t)s * n, b + (size_t)(s + 1) * n, r.begin());
+        if (pivoting) inplace_linsolve_piv(n, M.data(), r.data());
+        else inplace_linsolve_nopiv(n, M.data(), r.data());
+        std::copy(r.begin(), r.end(), x + (size_t)s * n);
+    }
+    return 0;
+}

@@ -355,3 +355,40 @@ def test_devex002_edge_reaction_equals_node_reaction_3d():
     u_edge = O.OracleSystem(s_edge).solve_step(v.unknowns(s_edge, 0.0))
     assert np.abs(u_node).max() > 1e-3
     assert np.abs(u_node - u_edge).max() <= 1e-12 * np.abs(u_node).max()
+
+
+def devex005_system(dim, n=11, nspec=5):
+    """examples/DevEx005_Mixture.jl:197-262: five-species Maxwell-Stefan mixture, a dense nspec x nspec solve inside the flux callback"""
+    X = np.arange(0, n) / float(n - 1)
+    g = v.simplexgrid(*([X] * dim))
+    DB = np.full((nspec, nspec), 0.1)
+    diribc = [1, 2] if dim == 1 else [4, 2]
+    bc = ph.BCondition()
+    for sp in range(1, nspec + 1):
+        bc.dirichlet(species=sp, region=diribc[0], value=float(sp % 2))
+        bc.dirichlet(species=sp, region=diribc[1], value=float(1 - sp % 2))
+    return v.System(g, flux=ph.MixtureFlux(np.ones(nspec), DB), storage=ph.LinearStorage(1.0), bcondition=bc, species=list(range(1, nspec + 1)))
+
+
+@pytest.mark.parametrize("dim,expected", [(1, 4.788926530387466), (2, 15.883072449873742), (3, 52.67819183426213)])
+def test_devex005_mixture_inplace_linsolve(dim, expected):
+    """examples/DevEx005_Mixture.jl:293-309: norm(u) for dim = 1, 2, 3 (atol 1e-5) with damp_initial = 0.5, tol_mono = 1e-10, tol_round = 1e-15,
+    max_round = 3, maxiters = 500"""
+    sys = devex005_system(dim)
+    u = O.OracleSystem(sys).solve_step(v.unknowns(sys, 0.0), damp_initial=0.5, tol_mono=1.0e-10, tol_round=1.0e-15, max_round=3, maxiters=500)
+    assert np.linalg.norm(u) == pytest.approx(expected, abs=1.0e-5)
+
+
+def test_inplace_linsolve_oracle_test040():
+    """test/test040_inplacelu.jl:16-38: A = -rand + 100 I, x = 1, b = A x; sqrt(sum (x_solved - 1)^2) / N < 100 eps for N = 2..10, both variants"""
+    import ctypes as C
+
+    L = O.lib()
+    rng = np.random.default_rng(40)
+    for n in range(2, 11):
+        A = -rng.uniform(size=(50, n, n)) + 100.0 * np.eye(n)
+        b = A.sum(axis=2)
+        for piv in (0, 1):
+            x = np.zeros((50, n))
+            assert L.vo_probe_inplace_linsolve(n, 50, piv, A.ctypes.data_as(C.POINTER(C.c_double)), b.ctypes.data_as(C.POINTER(C.c_double)), x.ctypes.data_as(C.POINTER(C.c_double))) == 0
+            assert np.all(np.sqrt(((x - 1.0) ** 2).sum(axis=1)) / n < 100 * np.finfo(float).eps)

@@ -90,6 +90,7 @@ SIGNATURES = {
     "vfvm_device_bytes": [_H, _I64],
     "vfvm_plane_counts": [_H, _p(C.c_int), _p(C.c_int)],
     "vfvm_block_counts": [_H, _I64, _I64],
+    "vfvm_probe_inplace_linsolve": [_H, C.c_int, C.c_int, C.c_int, _D, _D, _D],
     "vfvm_probe_bernoulli": [_H, C.c_int, _D, _D, _D, _D],
 }
 OTHER = {"vfvm_destroy": ([_H], None), "vfvm_last_error": ([_H], C.c_char_p), "vfvm_abi_version": ([], C.c_int)}

@@ -229,6 +229,7 @@ static int min_species(int slot, int id) {
     if (slot == VFVM_SLOT_FLUX) {
         if (id == VFVM_FLUX_CROSSDIFF2 || id == VFVM_FLUX_SG_UNIPOLAR || id == VFVM_FLUX_SEDAN) return 2;
         if (id == VFVM_FLUX_SG_BIPOLAR) return 3;
+        if (id == VFVM_FLUX_MIXTURE) return 2;
     }
     if (slot == VFVM_SLOT_REACTION) {
         if (id == VFVM_REACTION_BILINEAR2) return 2;
@@ -243,7 +244,7 @@ static int min_species(int slot, int id) {
 extern "C" int vfvm_set_physics(vfvm_handle* h, int slot, int id, const double* params, int np) {
     NEED(h, h->have_system, "vfvm_set_system has not been called");
     if (slot < 0 || slot >= VFVM_NUM_SLOTS || np < 0 || (np > 0 && !params)) return vfvm_fail(h, VFVM_ERR_ARG, "bad slot / params");
-    static const int maxid[VFVM_NUM_SLOTS] = {VFVM_FLUX_SG_BIPOLAR, VFVM_REACTION_REGION_AFFINE, VFVM_STORAGE_BIPOLAR, VFVM_SOURCE_NODAL, VFVM_BREACTION_CATALYSIS,
+    static const int maxid[VFVM_NUM_SLOTS] = {VFVM_FLUX_MIXTURE, VFVM_REACTION_REGION_AFFINE, VFVM_STORAGE_BIPOLAR, VFVM_SOURCE_NODAL, VFVM_BREACTION_CATALYSIS,
                                               VFVM_EDGEREACTION_JOULE, VFVM_BSTORAGE_LINEAR};
     if (id < 0 || id > maxid[slot])
         return vfvm_fail(h, VFVM_ERR_UNREGISTERED, "physics id is not in the registered device library; arbitrary host callbacks are not evaluated (no CPU fallback)");
@@ -252,8 +253,9 @@ extern "C" int vfvm_set_physics(vfvm_handle* h, int slot, int id, const double* 
     // exact-size checks and device restrictions
     int need = -1;
     if (slot == VFVM_SLOT_FLUX) {
-        const int t[] = {0, n, n + 1, 3, 3, 5, 10};
+        const int t[] = {0, n, n + 1, 3, 3, 5, 10, n + n * n};
         need = t[id];
+        if (id == VFVM_FLUX_MIXTURE && !(n == 2 || n == 3 || n == 5)) return vfvm_fail(h, VFVM_ERR_UNSUPPORTED, "mixture flux: device instantiations for 2, 3 and 5 species");
         if ((id == VFVM_FLUX_CROSSDIFF2 || id == VFVM_FLUX_SG_UNIPOLAR || id == VFVM_FLUX_SEDAN) && n != 2)
             return vfvm_fail(h, VFVM_ERR_UNSUPPORTED, "this flux has a device instantiation for exactly 2 species");
         if (id == VFVM_FLUX_SG_BIPOLAR && (n != 3 || np != 10 || params[7] != 0 || params[8] != 1 || params[9] != 2))

@@ -1086,6 +1086,7 @@ static void launch_rows_ns(vfvm_handle* h, const AsmArgs& a) {
         case VFVM_FLUX_SG_UNIPOLAR: launch_rows<NS, VFVM_FLUX_SG_UNIPOLAR>(h, a); break;
         case VFVM_FLUX_SEDAN: launch_rows<NS, VFVM_FLUX_SEDAN>(h, a); break;
         case VFVM_FLUX_SG_BIPOLAR: launch_rows<NS, VFVM_FLUX_SG_BIPOLAR>(h, a); break;
+        case VFVM_FLUX_MIXTURE: launch_rows<NS, VFVM_FLUX_MIXTURE>(h, a); break;
         default: throw std::string("unregistered flux id");
     }
 }
@@ -1456,6 +1457,48 @@ extern "C" int vfvm_probe_bernoulli(vfvm_handle* h, int n, const double* x, doub
         d1.download(bp, h->stream);
         d2.download(bm, h->stream);
         d3.download(dbp, h->stream);
+        CK(cudaGetLastError());
+    })
+    return VFVM_OK;
+}
+
+// ---- parity probe of the device inplace_linsolve! (test/test040_inplacelu.jl) ----------------------------------------------------------
+template <int N>
+__global__ void k_probe_linsolve(int nsys, int pivoting, const double* __restrict__ A, const double* __restrict__ b, double* __restrict__ x) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nsys) return;
+    double M[N * N], r[N];
+    for (int i = 0; i < N * N; i++) M[i] = A[(size_t)s * N * N + i];
+    for (int i = 0; i < N; i++) r[i] = b[(size_t)s * N + i];
+    if (pivoting) inplace_linsolve_piv<N>(M, r);
+    else inplace_linsolve_nopiv<N>(M, r);
+    for (int i = 0; i < N; i++) x[(size_t)s * N + i] = r[i];
+}
+
+extern "C" int vfvm_probe_inplace_linsolve(vfvm_handle* h, int n, int nsys, int pivoting, const double* A, const double* b, double* x) {
+    if (!h || n < 1 || n > 10 || nsys < 0 || !A || !b || !x) return VFVM_ERR_ARG;
+    VFVM_TRY(h, {
+        CK(cudaSetDevice(h->device));
+        DevBuf<double> dA, db, dx;
+        dA.upload(A, (size_t)nsys * n * n, h->stream);
+        db.upload(b, (size_t)nsys * n, h->stream);
+        dx.alloc((size_t)std::max(1, nsys) * n);
+        const int grid = std::max(1, cdiv(nsys, 64));
+        switch (n) {
+            case 1: k_probe_linsolve<1><<<grid, 64, 0, h->stream>>>(nsys, pivoting, dA.p, db.p, dx.p); break;
+            case 2: k_probe_linsolve<2><<<grid, 64, 0, h->stream>>>(nsys, pivoting, dA.p, db.p, dx.p); break;
+            case 3: k_probe_linsolve<3><<<grid, 64, 0, h->stream>>>(nsys, pivoting, dA.p, db.p, dx.p); break;
+            case 4: k_probe_linsolve<4><<<grid, 64, 0, h->stream>>>(nsys, pivoting, dA.p, db.p, dx.p); break;
+            case 5: k_probe_linsolve<5><<<grid, 64, 0, h->stream>>>(nsys, pivoting, dA.p, db.p, dx.p); break;
+            case 6: k_probe_linsolve<6><<<grid, 64, 0, h->stream>>>(nsys, pivoting, dA.p, db.p, dx.p); break;
+            case 7: k_probe_linsolve<7><<<grid, 64, 0, h->stream>>>(nsys, pivoting, dA.p, db.p, dx.p); break;
+            case 8: k_probe_linsolve<8><<<grid, 64, 0, h->stream>>>(nsys, pivoting, dA.p, db.p, dx.p); break;
+            case 9: k_probe_linsolve<9><<<grid, 64, 0, h->stream>>>(nsys, pivoting, dA.p, db.p, dx.p); break;
+            default: k_probe_linsolve<10><<<grid, 64, 0, h->stream>>>(nsys, pivoting, dA.p, db.p, dx.p); break;
+        }
+        h->launches++;
+        if (nsys) CK(cudaMemcpyAsync(x, dx.p, sizeof(double) * nsys * n, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
         CK(cudaGetLastError());
     })
     return VFVM_OK;

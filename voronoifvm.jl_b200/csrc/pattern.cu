@@ -117,7 +117,8 @@ int vfvm_physics_masks(vfvm_handle* h) {
                 for (int i = 0; i < n; i++)
                     if (p[i] != 0.0) mask_set(m.flux, i * n + i);
                 break;
-            case VFVM_FLUX_CROSSDIFF2: full(m.flux); break;
+            case VFVM_FLUX_CROSSDIFF2:
+            case VFVM_FLUX_MIXTURE: full(m.flux); break;
             case VFVM_FLUX_SG_UNIPOLAR:
             case VFVM_FLUX_SEDAN: {
                 const bool sedan = ph.slot[VFVM_SLOT_FLUX].id == VFVM_FLUX_SEDAN;

@@ -51,6 +51,60 @@ __device__ __forceinline__ double ramp_fn(double t, double tbegin, double tend, 
     return uend;
 }
 
+// ---- inplace_linsolve!, src/vfvm_functions.jl:98-168: small dense systems solved inside a callback (DevEx005 mixture flux) ----------------
+// non-pivoting Doolittle (doolittle_ludecomp! :98-115 + doolittle_lusolve! :124-142); A row-major, overwritten by L+U-I, b by the solution
+template <int N, class T>
+__device__ __forceinline__ void inplace_linsolve_nopiv(T* A, T* b) {
+    for (int i = 0; i < N; i++) {
+        for (int j = 0; j < i; j++) {
+            for (int k = 0; k < j; k++) A[i * N + j] = A[i * N + j] - A[i * N + k] * A[k * N + j];
+            A[i * N + j] = A[i * N + j] / A[j * N + j];
+        }
+        for (int j = i; j < N; j++)
+            for (int k = 0; k < i; k++) A[i * N + j] = A[i * N + j] - A[i * N + k] * A[k * N + j];
+    }
+    for (int i = 0; i < N; i++)
+        for (int k = 0; k < i; k++) b[i] = b[i] - A[i * N + k] * b[k];
+    for (int i = N - 1; i >= 0; i--) {
+        for (int k = i + 1; k < N; k++) b[i] = b[i] - A[i * N + k] * b[k];
+        b[i] = b[i] / A[i * N + i];
+    }
+}
+// LU with partial (row) pivoting on the value of the entries + triangular solves: inplace_linsolve!(A, b, ipiv) (:165-168)
+template <int N, class T>
+__device__ __forceinline__ void inplace_linsolve_piv(T* A, T* b) {
+    for (int c = 0; c < N; c++) {
+        int piv = c;
+        double best = fabs(dvalue(A[c * N + c]));
+        for (int r = c + 1; r < N; r++) {
+            const double v = fabs(dvalue(A[r * N + c]));
+            if (v > best) {
+                best = v;
+                piv = r;
+            }
+        }
+        if (piv != c) {
+            for (int j = 0; j < N; j++) {
+                const T t = A[c * N + j];
+                A[c * N + j] = A[piv * N + j];
+                A[piv * N + j] = t;
+            }
+            const T t = b[c];
+            b[c] = b[piv];
+            b[piv] = t;
+        }
+        for (int r = c + 1; r < N; r++) {
+            A[r * N + c] = A[r * N + c] / A[c * N + c];
+            for (int j = c + 1; j < N; j++) A[r * N + j] = A[r * N + j] - A[r * N + c] * A[c * N + j];
+            b[r] = b[r] - A[r * N + c] * b[c];
+        }
+    }
+    for (int i = N - 1; i >= 0; i--) {
+        for (int k = i + 1; k < N; k++) b[i] = b[i] - A[i * N + k] * b[k];
+        b[i] = b[i] / A[i * N + i];
+    }
+}
+
 // ---- flux(f,u,edge,data): f must be pre-zeroed ------------------------------------------------------
 template <int FLUX, int NS, class T>
 __device__ __forceinline__ void eval_flux(const double* __restrict__ p, T* f, const T* uK, const T* uL) {
@@ -98,13 +152,30 @@ __device__ __forceinline__ void eval_flux(const double* __restrict__ p, T* f, co
         T np2 = dexp(zp * (uL[1] - uL[2] + Ep));
         f[0] = (-zn * mun) * (bm * nn2 - bp * nn1);
         f[1] = (-zp * mup) * (bp * np2 - bm * np1);
+    } else if constexpr (FLUX == VFVM_FLUX_MIXTURE) {  // examples/DevEx005_Mixture.jl:74-104
+        T M[NS * NS], au[NS], du[NS];
+        for (int i = 0; i < NS; i++) {
+            for (int j = 0; j < NS; j++) M[i * NS + j] = T(0.0);
+            M[i * NS + i] = T(1.0 / p[i]);
+            du[i] = uK[i] - uL[i];
+            au[i] = 0.5 * (uK[i] + uL[i]);
+        }
+        for (int i = 0; i < NS; i++)
+            for (int j = 0; j < NS; j++)
+                if (i != j) {
+                    M[i * NS + i] = M[i * NS + i] + au[j] / p[NS + i * NS + j];
+                    M[i * NS + j] = -au[i] / p[NS + i * NS + j];
+                }
+        inplace_linsolve_piv<NS>(M, du);
+        for (int i = 0; i < NS; i++) f[i] = du[i];
     }
 }
 
 // which (NS, FLUX) pairs have a device instantiation
 __host__ __device__ constexpr bool flux_supported(int flux, int ns) {
     return flux == VFVM_NONE || flux == VFVM_FLUX_DIFFUSION || flux == VFVM_FLUX_POWDIFF || (flux == VFVM_FLUX_CROSSDIFF2 && ns == 2) ||
-           (flux == VFVM_FLUX_SG_UNIPOLAR && ns == 2) || (flux == VFVM_FLUX_SEDAN && ns == 2) || (flux == VFVM_FLUX_SG_BIPOLAR && ns == 3);
+           (flux == VFVM_FLUX_SG_UNIPOLAR && ns == 2) || (flux == VFVM_FLUX_SEDAN && ns == 2) || (flux == VFVM_FLUX_SG_BIPOLAR && ns == 3) ||
+           (flux == VFVM_FLUX_MIXTURE && (ns == 2 || ns == 3 || ns == 5));
 }
 
 // ---- reaction(f,u,node,data) -------------------------------------------------------------------------

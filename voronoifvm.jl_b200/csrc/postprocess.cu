@@ -212,6 +212,7 @@ void launch_edges_ns(vfvm_handle* h, int region, const double* U, const FnArgs& 
         case VFVM_FLUX_SG_UNIPOLAR: launch_edges<NS, VFVM_FLUX_SG_UNIPOLAR>(h, region, U, fn, rsm, part); break;
         case VFVM_FLUX_SEDAN: launch_edges<NS, VFVM_FLUX_SEDAN>(h, region, U, fn, rsm, part); break;
         case VFVM_FLUX_SG_BIPOLAR: launch_edges<NS, VFVM_FLUX_SG_BIPOLAR>(h, region, U, fn, rsm, part); break;
+        case VFVM_FLUX_MIXTURE: launch_edges<NS, VFVM_FLUX_MIXTURE>(h, region, U, fn, rsm, part); break;
         default: throw std::string("unregistered flux id");
     }
 }
@@ -233,6 +234,7 @@ void launch_edge_flux_ns(vfvm_handle* h, const double* U, const FnArgs& fn, doub
         case VFVM_FLUX_SG_UNIPOLAR: launch_edge_flux<NS, VFVM_FLUX_SG_UNIPOLAR>(h, U, fn, out); break;
         case VFVM_FLUX_SEDAN: launch_edge_flux<NS, VFVM_FLUX_SEDAN>(h, U, fn, out); break;
         case VFVM_FLUX_SG_BIPOLAR: launch_edge_flux<NS, VFVM_FLUX_SG_BIPOLAR>(h, U, fn, out); break;
+        case VFVM_FLUX_MIXTURE: launch_edge_flux<NS, VFVM_FLUX_MIXTURE>(h, U, fn, out); break;
         default: throw std::string("unregistered flux id");
     }
 }

@@ -18,7 +18,7 @@ import numpy as np
 SLOT_FLUX, SLOT_REACTION, SLOT_STORAGE, SLOT_SOURCE, SLOT_BREACTION, SLOT_EDGEREACTION, SLOT_BSTORAGE = range(7)
 SLOT_NAMES = ("flux", "reaction", "storage", "source", "breaction", "edgereaction", "bstorage")
 
-FLUX_DIFFUSION, FLUX_POWDIFF, FLUX_CROSSDIFF2, FLUX_SG_UNIPOLAR, FLUX_SEDAN, FLUX_SG_BIPOLAR = 1, 2, 3, 4, 5, 6
+FLUX_DIFFUSION, FLUX_POWDIFF, FLUX_CROSSDIFF2, FLUX_SG_UNIPOLAR, FLUX_SEDAN, FLUX_SG_BIPOLAR, FLUX_MIXTURE = 1, 2, 3, 4, 5, 6, 7
 REACTION_POW, REACTION_SINH, REACTION_AFFINE, REACTION_BILINEAR2, REACTION_BIPOLAR, REACTION_REGION_AFFINE = 1, 2, 3, 4, 5, 6
 STORAGE_LINEAR, STORAGE_POW, STORAGE_BIPOLAR = 1, 2, 3
 SOURCE_CONST, SOURCE_GAUSS, SOURCE_XSINYEXPZ, SOURCE_STEP1D, SOURCE_AFFINE_X, SOURCE_NODAL = 1, 2, 3, 4, 5, 6
@@ -124,6 +124,23 @@ class BipolarSGFlux(RegisteredPhysics):
 
     def params(self, n):
         return np.array(self.p, dtype=np.float64)
+
+
+class MixtureFlux(RegisteredPhysics):
+    """Maxwell-Stefan mixture flux of DevEx005_Mixture.jl:74-104: f = M(u)^{-1} (u_K - u_L), M_ii = 1/DK_i + sum_{j != i} au_j / DB_ij,
+    M_ij = -au_i / DB_ij, au = (u_K + u_L) / 2; the n x n system is solved inside the callback (`inplace_linsolve!`)"""
+
+    slot, id, min_species = SLOT_FLUX, FLUX_MIXTURE, 2
+
+    def __init__(self, DKnudsen, DBinary):
+        self.DK = np.asarray(DKnudsen, dtype=np.float64).ravel()
+        self.DB = np.asarray(DBinary, dtype=np.float64)
+
+    def params(self, n):
+        assert self.DK.size == n and self.DB.shape == (n, n)
+        DB = self.DB.copy()
+        np.fill_diagonal(DB, 1.0)  # never read
+        return np.concatenate([self.DK, DB.ravel(order="C")])
 
 
 # ------------------------------------------------------------------------------------------- reaction
