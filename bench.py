@@ -491,6 +491,7 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: the line below is the only output
     import torch
 
     rank = int(os.environ.get("RANK", "0"))

@@ -110,6 +110,8 @@ typedef struct vfvm_handle vfvm_handle;
 #define VFVM_BREACTION_CATALYSIS 2 /* Example115 breaction! :128-135: if bnode.region == r: f_A = S R_AC, f_B = S R_BC, f_C = -R_BC - R_AC with
                                      R_XC = kp_XC u_X (1 - u_C) - km_XC u_C   params: r, S, kpAC, kmAC, kpBC, kmBC, iA, iB, iC (0-based) */
 
+#define VFVM_BREACTION_POW 3 /* if bnode.region == r: f_i = k_i u_i^{p_i}   params: r, k[n], p[n]   (Example226_BoundaryIntegral.jl:42-47: u^2) */
+
 /* edgereaction(f,u,edge,data): a reaction term given per edge, assembled with the edge form factor into BOTH end nodes
  * (src/vfvm_assembly.jl:202-239) */
 #define VFVM_EDGEREACTION_DIAMOND 1 /* f_i = c_i h^2 / (2 dim), h = meas(edge): a constant volume density per half diamond (DevEx002:83-87) params: c[n] */
@@ -249,6 +251,10 @@ int vfvm_vector_diffnorm(vfvm_handle* h, int which_a, int which_b, double* norm_
  * (w1pseminorm, :300-312), -2 = the edge average (u_K + u_L) / 2 (test/test120_norms.jl:35-38).  Collective with several ranks. */
 int vfvm_integrate(vfvm_handle* h, int slot, int id, const double* params, int np, int which, double* out);
 int vfvm_edgeintegrate(vfvm_handle* h, int id, const double* params, int np, int which, double* out);
+/* integrate(system, F, U; boundary = true) (src/vfvm_postprocess.jl:29-46): out is n x nbfaceregions (host); slot selects the evaluator of the
+ * registered function (VFVM_SLOT_BREACTION, VFVM_SLOT_REACTION, VFVM_SLOT_STORAGE, VFVM_SLOT_BSTORAGE), id = VFVM_NONE integrates the vector itself;
+ * a species contributes at the boundary nodes where it is defined (isnodespecies).  Collective with several ranks. */
+int vfvm_integrate_boundary(vfvm_handle* h, int slot, int id, const double* params, int np, int which, double* out);
 /* mass_matrix(state), src/vfvm_diffeq_interface.jl:60-101: Jacobian of the registered storage at U = 0 times the node factors;
  * out (host): one n x n block per owned node, out[(K*n + i)*n + j] = M[(K,i),(K,j)].  eval_rhs! / eval_jacobian! of the ODE
  * interface (:27-52) are vfvm_eval_res_jac with tstep = Inf and a sign flip on the host side. */

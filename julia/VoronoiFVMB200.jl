@@ -33,11 +33,11 @@ import VoronoiFVM: eval_and_assemble, _solve_linear!, solve_step!, SystemState, 
     boundary_dirichlet!, boundary_neumann!, boundary_robin!, ramp
 
 export B200, B200Matrix, UnregisteredPhysicsError
-export LinearDiffusion, PowerDiffusion, CrossDiffusion2, UnipolarSGFlux, SedanFlux, BipolarSGFlux
+export LinearDiffusion, PowerDiffusion, CrossDiffusion2, UnipolarSGFlux, SedanFlux, BipolarSGFlux, MixtureFlux
 export PowerReaction, SinhReaction, AffineReaction, BilinearReaction2, RegionAffineReaction, BipolarReaction
 export LinearStorage, PowerStorage, BipolarStorage
 export ConstSource, GaussSource, XSinYExpZSource, Step1DSource, AffineXSource, NodalSource
-export LinearBoundaryReaction, CatalysisBoundaryReaction, BCondition, dirichlet!, neumann!, robin!
+export LinearBoundaryReaction, CatalysisBoundaryReaction, PowerBoundaryReaction, BCondition, dirichlet!, neumann!, robin!
 export DiamondEdgeReaction, JouleHeatEdgeReaction, LinearBoundaryStorage
 export AMGPrecon, BlockJacobiPrecon, JacobiPrecon, ILUZeroPrecon, DeviceKrylov
 
@@ -206,6 +206,44 @@ function (p::BipolarSGFlux)(f, u, edge, data)
     f[1] = -p.zn * p.mun * (bm * nL - bp * nK)
     pK, pL = bipolar_density(p.zp, u[2, 1], u[3, 1], p.Ep), bipolar_density(p.zp, u[2, 2], u[3, 2], p.Ep)
     f[2] = -p.zp * p.mup * (bp * pL - bm * pK)
+    return nothing
+end
+
+"Maxwell-Stefan mixture flux of DevEx005_Mixture.jl:74-104; the nspec x nspec system is solved in the callback by `inplace_linsolve!`"
+struct MixtureFlux <: RegisteredFlux
+    DKnudsen::Vector{Float64}
+    DBinary::Matrix{Float64}
+end
+physics_id(::MixtureFlux) = 7
+function physics_params(p::MixtureFlux, n)
+    DB = copy(p.DBinary)
+    for i in 1:n
+        DB[i, i] = 1.0   # never read
+    end
+    return vcat(p.DKnudsen, vec(permutedims(DB)))
+end
+function (p::MixtureFlux)(f, u, edge, data)
+    n = length(p.DKnudsen)
+    T = eltype(u)
+    M = zeros(T, n, n)
+    du = zeros(T, n)
+    au = zeros(T, n)
+    ipiv = zeros(Int, n)
+    for i in 1:n
+        M[i, i] = 1.0 / p.DKnudsen[i]
+        du[i] = u[i, 1] - u[i, 2]
+        au[i] = 0.5 * (u[i, 1] + u[i, 2])
+    end
+    for i in 1:n, j in 1:n
+        if i != j
+            M[i, i] += au[j] / p.DBinary[i, j]
+            M[i, j] = -au[i] / p.DBinary[i, j]
+        end
+    end
+    VoronoiFVM.inplace_linsolve!(M, du, ipiv)
+    for i in 1:n
+        f[i] = du[i]
+    end
     return nothing
 end
 
@@ -461,6 +499,23 @@ function (b::LinearBoundaryReaction)(f, u, bnode, data)
     return nothing
 end
 
+"if bnode.region == region: f_i = k_i u_i^{p_i}   Example226_BoundaryIntegral.jl:42-47"
+struct PowerBoundaryReaction <: RegisteredBReaction
+    region::Int
+    k::Vector{Float64}
+    p::Vector{Float64}
+end
+physics_id(::PowerBoundaryReaction) = 3
+physics_params(b::PowerBoundaryReaction, n) = vcat(Float64(b.region), b.k, b.p)
+function (b::PowerBoundaryReaction)(f, u, bnode, data)
+    if bnode.region == b.region
+        for i in eachindex(f)
+            b.k[i] != 0 && (f[i] = b.k[i] * u[i]^b.p[i])
+        end
+    end
+    return nothing
+end
+
 "Example115 breaction! :125-135 on boundary region `region` (species A, B in the bulk, C on the surface)"
 Base.@kwdef struct CatalysisBoundaryReaction <: RegisteredBReaction
     region::Int
@@ -552,11 +607,11 @@ A `bcondition` callback made of `boundary_dirichlet!` / `boundary_neumann!` / `b
 boundary reaction.  On the CPU path it performs exactly those calls; on the device its entries go to `vfvm_set_bc_entries`.
 """
 struct BCondition <: RegisteredBReaction
-    reaction::Union{Nothing, LinearBoundaryReaction, CatalysisBoundaryReaction}
+    reaction::Union{Nothing, LinearBoundaryReaction, CatalysisBoundaryReaction, PowerBoundaryReaction}
     entries::Vector{BCEntry}
 end
 BCondition() = BCondition(nothing, BCEntry[])
-BCondition(r::Union{LinearBoundaryReaction, CatalysisBoundaryReaction}) = BCondition(r, BCEntry[])
+BCondition(r::Union{LinearBoundaryReaction, CatalysisBoundaryReaction, PowerBoundaryReaction}) = BCondition(r, BCEntry[])
 physics_id(b::BCondition) = b.reaction === nothing ? 0 : physics_id(b.reaction)
 physics_params(b::BCondition, n) = b.reaction === nothing ? Float64[] : physics_params(b.reaction, n)
 function push_entry!(b::BCondition, kind, species, region, value, factor, rmp)

@@ -188,6 +188,14 @@ class OracleSystem:
         assert self.L.vo_integrate(self.h, slot, pid, _p(prm, C.c_double), prm.size, _p(u, C.c_double), _p(out, C.c_double)) == 0
         return out.reshape((self.n, self.g.num_cellregions), order="F")
 
+    def integrate_boundary(self, U, slot=4, pid=0, params=()):
+        """integrate(system, F, U; boundary=true) src/vfvm_postprocess.jl:29-46 -> n x nbfaceregions"""
+        u = np.ascontiguousarray(np.asarray(U, dtype=np.float64).T).ravel()
+        prm = np.ascontiguousarray(params, dtype=np.float64)
+        out = np.zeros(self.n * self.g.num_bfaceregions)
+        assert self.L.vo_integrate_boundary(self.h, slot, pid, _p(prm, C.c_double), prm.size, _p(u, C.c_double), _p(out, C.c_double)) == 0
+        return out.reshape((self.n, self.g.num_bfaceregions), order="F")
+
     def edgeintegrate(self, U, pid, params=()):
         """edgeintegrate(system, F, U) src/vfvm_postprocess.jl:109-146 for a registered flux (pid -1: the W^{1,p} integrand)"""
         u = np.ascontiguousarray(np.asarray(U, dtype=np.float64).T).ravel()

@@ -403,6 +403,11 @@ inline bool eval_breaction(const Physics& ph, int n, T* f, const T* u, BNodeCtx&
             }
             break;
         }
+        case VFVM_BREACTION_POW:  // examples/Example226_BoundaryIntegral.jl:42-47
+            if (b.region == (int)p[0])
+                for (int i = 0; i < n; i++)
+                    if (p[1 + i] != 0.0) f[i] = p[1 + i] * powr(u[i], p[1 + n + i]);
+            break;
         case VFVM_BREACTION_CATALYSIS: {  // examples/Example115_HeterogeneousCatalysis1D.jl:125-135
             if (b.region == (int)p[0]) {
                 const double S = p[1], kpAC = p[2], kmAC = p[3], kpBC = p[4], kmBC = p[5];

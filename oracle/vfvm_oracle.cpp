@@ -927,6 +927,49 @@ int vo_integrate(void* h, int slot, int id, const double* params, int np, const 
         }
     return 0;
 }
+// integrate(system, F, U; boundary = true), src/vfvm_postprocess.jl:29-46.  out: n x nbfaceregions, column-major.
+int vo_integrate_boundary(void* h, int slot, int id, const double* params, int np, const double* U, double* out) {
+    System& s = *(System*)h;
+    const Grid& g = s.g;
+    const int n = s.n, nbn = g.dim;
+    Physics tmp;  // the function alone: no boundary-condition helper calls
+    if (slot >= 0 && slot < VFVM_NUM_SLOTS) {
+        tmp.slot[slot].id = id;
+        tmp.slot[slot].p.assign(params, params + np);
+    }
+    std::fill(out, out + (size_t)n * g.nbfaceregions, 0.0);
+    std::vector<double> res(n), u(n);
+    BNodeCtx b;
+    b.dim = g.dim;
+    NodeCtx node;
+    node.dim = g.dim;
+    for (int ibf = 0; ibf < g.NB; ibf++)
+        for (int ibn = 0; ibn < nbn; ibn++) {
+            b.ibface = ibf;
+            b.ibnode = ibn;
+            b.region = g.bfaceregions[ibf];
+            b.index = g.bfacenodes[(size_t)ibf * nbn + ibn];
+            b.fac = s.bfacenodefactors[(size_t)ibf * nbn + ibn];
+            b.x = &g.coord[(size_t)b.index * g.dim];
+            b.dirichlet_value = nullptr;
+            node.index = b.index;
+            node.region = b.region;
+            node.x = b.x;
+            const int K = b.index;
+            for (int i = 0; i < n; i++) {
+                u[i] = U[(size_t)K * n + i];
+                res[i] = 0.0;
+            }
+            if (id == 0) res = u;
+            else if (slot == VFVM_SLOT_BREACTION) eval_breaction(tmp, n, res.data(), u.data(), b);
+            else if (slot == VFVM_SLOT_BSTORAGE) eval_bstorage(tmp.slot[slot], n, res.data(), u.data(), b);
+            else if (slot == VFVM_SLOT_STORAGE) eval_storage(tmp.slot[slot], n, res.data(), u.data(), node);
+            else eval_reaction(tmp.slot[slot], n, res.data(), u.data(), node);
+            for (int i = 0; i < n; i++)
+                if (s.node_dof[(size_t)K * n + i]) out[(size_t)(b.region - 1) * n + i] += b.fac * res[i];  // :42, assemble_res(bnode)
+        }
+    return 0;
+}
 // id: a registered flux id, or -1 = the W^{1,p} seminorm integrand dim ((u_K - u_L) / h)^p with p = params[0] (:300-312)
 int vo_edgeintegrate(void* h, int id, const double* params, int np, const double* U, double* out) {
     System& s = *(System*)h;

@@ -689,3 +689,39 @@ def test_joule_heat_edge_reaction_parity(dim):
     ref = O.OracleSystem(sys).solve_step(v.unknowns(sys, 0.0))
     sol = v.solve(sys, inival=0.0)
     assert np.max(np.abs(sol - ref)) < TOL_NEWTON
+
+
+# ---- small dense LU inside a callback (inplace_linsolve!), DevEx005 mixture flux ----------------------------------------
+def test_inplace_linsolve_device_probe():
+    """test/test040_inplacelu.jl:16-38 on the device: A = -rand + 100 I, x = 1, b = A x, error < 100 eps for N = 2..10 (non-pivoting Doolittle and
+    pivoting LU); both agree with the oracle's restatement to rounding"""
+    import ctypes as C
+
+    sys = v.System(_grid(1, 5), flux=ph.LinearDiffusion(), species=[1])
+    st = v.SystemState(sys)
+    rng = np.random.default_rng(40)
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    try:
+        for n in range(2, 11):
+            A = np.ascontiguousarray(-rng.uniform(size=(64, n, n)) + 100.0 * np.eye(n))
+            b = np.ascontiguousarray(A.sum(axis=2))
+            for piv in (0, 1):
+                x, xo = np.zeros((64, n)), np.zeros((64, n))
+                v._lib.check(st.h, st.L.vfvm_probe_inplace_linsolve(st.h, n, 64, piv, dp(A), dp(b), dp(x)))
+                assert np.all(np.sqrt(((x - 1.0) ** 2).sum(axis=1)) / n < 100 * np.finfo(float).eps)
+                assert O.lib().vo_probe_inplace_linsolve(n, 64, piv, dp(A), dp(b), dp(xo)) == 0
+                assert np.max(np.abs(x - xo)) < 1e-14
+    finally:
+        st.close()
+
+
+@pytest.mark.parametrize("dim,expected", [(1, 4.788926530387466), (2, 15.883072449873742), (3, 52.67819183426213)])
+def test_devex005_mixture_device(dim, expected):
+    """examples/DevEx005_Mixture.jl: five-species Maxwell-Stefan flux with a 5 x 5 pivoting LU inside the flux callback, evaluated in Dual<10>
+    on the device: assembly against the oracle (1e-12) and the reference's known answers norm(u) (atol 1e-5)"""
+    from test_oracle_golden import devex005_system
+
+    sys = devex005_system(dim)
+    _compare_assembly(sys, _rand_u(sys))
+    u = v.solve(sys, inival=0.0, damp_initial=0.5, tol_mono=1.0e-10, tol_round=1.0e-15, max_round=3, maxiters=500)
+    assert np.linalg.norm(u) == pytest.approx(expected, abs=1.0e-5)

@@ -169,3 +169,30 @@ def test_example201_nodeflux_device():
         assert nf2.shape == (2, 2, g.num_nodes) and np.all(np.isfinite(nf2))
     finally:
         st2.close()
+
+
+@pytest.mark.parametrize("dim", [1, 2, 3])
+def test_boundary_integrals_device(dim):
+    """integrate(system, F, U; boundary = true) on the device: known measures of the boundary regions, and agreement with the oracle for the
+    registered boundary / node functions on a system with a boundary species"""
+    X = np.linspace(0, 1, 9)
+    g = v.simplexgrid(*([X] * dim))
+    sys = v.System(g, flux=ph.LinearDiffusion([1.0, 1.0, 0.0]), breaction=ph.CatalysisBoundaryReaction(2, S=0.05), bstorage=ph.LinearBoundaryStorage(2, [0.0, 0.0, 1.0]))
+    v.enable_species(sys, 1, [1])
+    v.enable_species(sys, 2, [1])
+    v.enable_boundary_species(sys, 3, [2])
+    U = np.asfortranarray(np.random.default_rng(9).uniform(0.1, 1.0, (3, g.num_nodes))) * sys.node_dof()
+    o = O.OracleSystem(sys)
+    st = v.SystemState(sys)
+    try:
+        one = np.asfortranarray(np.ones((3, g.num_nodes)) * sys.node_dof())
+        B = v.integrate(sys, one, state=st, boundary=True)
+        np.testing.assert_allclose(B[0], 1.0, rtol=1e-12)  # |Gamma_r| = 1 for every region of the unit square / cube
+        assert B[2, 1] == pytest.approx(1.0, rel=1e-12) and np.all(np.delete(B[2], 1) == 0.0)  # the surface species lives on region 2 only
+        for F in (None, sys.physics.breaction, sys.physics.bstorage, ph.PowerBoundaryReaction(2, [1.0, 0.5, 2.0], 2.0), ph.PowerReaction(1.0, 2.0)):
+            dev = v.integrate(sys, U, state=st, boundary=True) if F is None else v.integrate(sys, F, U, state=st, boundary=True)
+            ref = o.integrate_boundary(U) if F is None else o.integrate_boundary(U, F.slot, F.id, F.params(3))
+            assert dev.shape == ref.shape == (3, 2 * dim)
+            assert np.all(np.abs(dev - ref) <= 1e-12 * np.abs(ref) + 1e-14), (F, dev, ref)
+    finally:
+        st.close()

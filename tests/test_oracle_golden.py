@@ -392,3 +392,24 @@ def test_inplace_linsolve_oracle_test040():
             x = np.zeros((50, n))
             assert L.vo_probe_inplace_linsolve(n, 50, piv, A.ctypes.data_as(C.POINTER(C.c_double)), b.ctypes.data_as(C.POINTER(C.c_double)), x.ctypes.data_as(C.POINTER(C.c_double))) == 0
             assert np.all(np.sqrt(((x - 1.0) ** 2).sum(axis=1)) / n < 100 * np.finfo(float).eps)
+
+
+@pytest.mark.parametrize("dim", [1, 2, 3])
+def test_boundary_integrals_known_answers(dim):
+    """integrate(system, F, U; boundary = true), src/vfvm_postprocess.jl:29-46: int_Gamma_r 1 ds = |Gamma_r| (1 on every face of the unit cube /
+    square, 1 per end point in 1D), int c = c |Gamma_r|, and the Example226 integrand u^2 on one region only"""
+    X = np.linspace(0, 1, 9)
+    g = v.simplexgrid(*([X] * dim))
+    sys = v.System(g, flux=ph.LinearDiffusion(), species=[1, 2])
+    o = O.OracleSystem(sys)
+    U = np.asfortranarray(np.vstack([np.full(g.num_nodes, 2.0), g.coord[0]]))
+    B = o.integrate_boundary(U)
+    nb = 2 * dim
+    assert B.shape == (2, nb)
+    np.testing.assert_allclose(B[0], 2.0, rtol=1e-13)  # every boundary region has measure 1
+    xmean = {1: [0.0, 1.0], 2: [0.5, 1.0, 0.5, 0.0], 3: [0.5, 1.0, 0.5, 0.0, 0.5, 0.5]}[dim]  # regions: 1 south/left, 2 east/right, 3 north, 4 west, 5 bottom, 6 top
+    np.testing.assert_allclose(B[1], xmean, rtol=1e-13, atol=1e-15)
+    f = ph.PowerBoundaryReaction(2, 1.0, 2.0)
+    B2 = o.integrate_boundary(U, f.slot, f.id, f.params(2))
+    assert B2[0, 1] == pytest.approx(4.0, rel=1e-13) and B2[1, 1] == pytest.approx(1.0, rel=1e-13)
+    assert np.all(np.delete(B2, 1, axis=1) == 0.0)

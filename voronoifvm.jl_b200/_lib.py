@@ -63,6 +63,7 @@ SIGNATURES = {
     "vfvm_edgeflux": [_H, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p],
     "vfvm_amg_set_options": [_H, C.c_void_p, C.c_int],
     "vfvm_integrate": [_H, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p],
+    "vfvm_integrate_boundary": [_H, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p],
     "vfvm_edgeintegrate": [_H, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p],
     "vfvm_peer_export": [_H, C.c_char_p],
     "vfvm_peer_connect": [_H, C.c_char_p],

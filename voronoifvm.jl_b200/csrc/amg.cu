@@ -1089,7 +1089,9 @@ void emit_program(const Amg& A, size_t i, int bsel, std::vector<FuseOp>& P) {
 
 void build_fused(vfvm_handle* h, Amg& A) {
     A.fuse_valid = false;
-    static const bool off = getenv("VFVM_AMG_NO_FUSE") != nullptr;
+    // measured (profiles/r2_*): on one and two B200s the persistent kernel is not faster than the replayed graph of per-level kernels -- every
+    // phase still pays its dependent load chain plus a grid barrier -- so it is opt-in (VFVM_AMG_FUSE=1)
+    static const bool off = getenv("VFVM_AMG_FUSE") == nullptr || getenv("VFVM_AMG_NO_FUSE") != nullptr;
     if (const char* e = getenv("VFVM_AMG_FUSE_MAX_N")) A.fuse_max_n = std::max(1ll, atoll(e));
     // the fused kernel takes over where launch latency, not bandwidth, bounds a level: the first level with at most fuse_max_n nodes
     A.fuse_level = 0;

@@ -244,7 +244,7 @@ static int min_species(int slot, int id) {
 extern "C" int vfvm_set_physics(vfvm_handle* h, int slot, int id, const double* params, int np) {
     NEED(h, h->have_system, "vfvm_set_system has not been called");
     if (slot < 0 || slot >= VFVM_NUM_SLOTS || np < 0 || (np > 0 && !params)) return vfvm_fail(h, VFVM_ERR_ARG, "bad slot / params");
-    static const int maxid[VFVM_NUM_SLOTS] = {VFVM_FLUX_MIXTURE, VFVM_REACTION_REGION_AFFINE, VFVM_STORAGE_BIPOLAR, VFVM_SOURCE_NODAL, VFVM_BREACTION_CATALYSIS,
+    static const int maxid[VFVM_NUM_SLOTS] = {VFVM_FLUX_MIXTURE, VFVM_REACTION_REGION_AFFINE, VFVM_STORAGE_BIPOLAR, VFVM_SOURCE_NODAL, VFVM_BREACTION_POW,
                                               VFVM_EDGEREACTION_JOULE, VFVM_BSTORAGE_LINEAR};
     if (id < 0 || id > maxid[slot])
         return vfvm_fail(h, VFVM_ERR_UNREGISTERED, "physics id is not in the registered device library; arbitrary host callbacks are not evaluated (no CPU fallback)");
@@ -288,6 +288,7 @@ extern "C" int vfvm_set_physics(vfvm_handle* h, int slot, int id, const double* 
         need = t[id];
     } else if (slot == VFVM_SLOT_BREACTION) {
         if (id == VFVM_BREACTION_LINEAR) need = 1 + n * n;
+        if (id == VFVM_BREACTION_POW) need = 1 + 2 * n;
         if (id == VFVM_BREACTION_CATALYSIS) {
             need = 9;
             if (np == 9)

@@ -201,6 +201,12 @@ int vfvm_physics_masks(vfvm_handle* h) {
                 if (p[1 + i] != 0.0) mask_set(m.boundary, i);
             break;
         }
+        case VFVM_BREACTION_POW: {
+            const double* p = P(VFVM_SLOT_BREACTION);
+            for (int i = 0; i < n; i++)
+                if (p[1 + i] != 0.0) mask_set(m.boundary, i * n + i);
+            break;
+        }
         case VFVM_BREACTION_CATALYSIS: {  // f_A(u_A, u_C), f_B(u_B, u_C), f_C(u_A, u_B, u_C)
             const double* p = P(VFVM_SLOT_BREACTION);
             const int iA = (int)p[6], iB = (int)p[7], iC = (int)p[8];
@@ -250,6 +256,12 @@ static void boundary_bits(const vfvm_handle* h, int breg, uint64_t* out) {
         if ((int)p[0] == breg)
             for (int i = 0; i < n * n; i++)
                 if (p[1 + i] != 0.0) mask_set(out, i);
+    }
+    if (ph.slot[VFVM_SLOT_BREACTION].id == VFVM_BREACTION_POW) {
+        const double* p = ph.params + ph.slot[VFVM_SLOT_BREACTION].off;
+        if ((int)p[0] == breg)
+            for (int i = 0; i < n; i++)
+                if (p[1 + i] != 0.0) mask_set(out, i * n + i);
     }
     if (ph.slot[VFVM_SLOT_BREACTION].id == VFVM_BREACTION_CATALYSIS) {
         const double* p = ph.params + ph.slot[VFVM_SLOT_BREACTION].off;

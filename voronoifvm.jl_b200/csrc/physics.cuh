@@ -319,12 +319,10 @@ __device__ __forceinline__ void eval_source(int id, const double* __restrict__ p
 
 // ---- breaction(f,u,bnode,data) + boundary_dirichlet!/neumann!/robin! calls --------------------------
 // dirichlet_value (may be null) receives the values set by boundary_dirichlet! (src/vfvm_physics.jl:492)
+// the registered boundary reaction function alone (no boundary_dirichlet!/neumann!/robin! helper calls)
 template <int NS, class T>
-__device__ __forceinline__ void eval_breaction(const PhysicsDev& ph, T* f, const T* u, int bregion, double time, double Dirichlet,
-                                               double* dirichlet_value) {
-    const PhysSlotDev& s = ph.slot[VFVM_SLOT_BREACTION];
-    const double* p = ph.params + s.off;
-    if (s.id == VFVM_BREACTION_LINEAR) {
+__device__ __forceinline__ void eval_breaction_fn(int id, const double* __restrict__ p, T* f, const T* u, int bregion) {
+    if (id == VFVM_BREACTION_LINEAR) {
         if (bregion == (int)p[0]) {
 #pragma unroll
             for (int i = 0; i < NS; i++) {
@@ -337,8 +335,13 @@ __device__ __forceinline__ void eval_breaction(const PhysicsDev& ph, T* f, const
                 f[i] = acc;
             }
         }
-    }
-    if (s.id == VFVM_BREACTION_CATALYSIS) {  // examples/Example115_HeterogeneousCatalysis1D.jl:125-135
+    } else if (id == VFVM_BREACTION_POW) {  // examples/Example226_BoundaryIntegral.jl:42-47
+        if (bregion == (int)p[0]) {
+#pragma unroll
+            for (int i = 0; i < NS; i++)
+                if (p[1 + i] != 0.0) f[i] = p[1 + i] * dpowr(u[i], p[1 + NS + i]);
+        }
+    } else if (id == VFVM_BREACTION_CATALYSIS) {  // examples/Example115_HeterogeneousCatalysis1D.jl:125-135
         if constexpr (NS >= 3) {
             if (bregion == (int)p[0]) {
                 const double S = p[1], kpAC = p[2], kmAC = p[3], kpBC = p[4], kmBC = p[5];
@@ -361,6 +364,13 @@ __device__ __forceinline__ void eval_breaction(const PhysicsDev& ph, T* f, const
             }
         }
     }
+}
+
+template <int NS, class T>
+__device__ __forceinline__ void eval_breaction(const PhysicsDev& ph, T* f, const T* u, int bregion, double time, double Dirichlet,
+                                               double* dirichlet_value) {
+    const PhysSlotDev& s = ph.slot[VFVM_SLOT_BREACTION];
+    eval_breaction_fn<NS>(s.id, ph.params + s.off, f, u, bregion);
     for (int e = 0; e < ph.nbc; e++) {
         const vfvm_bc_entry& bc = ph.bc[e];
         const int ireg = bc.region == 0 ? bregion : bc.region;
@@ -383,14 +393,17 @@ __device__ __forceinline__ void eval_breaction(const PhysicsDev& ph, T* f, const
 
 // ---- bstorage(f,u,bnode,data): f pre-zeroed ---------------------------------------------------------------------------------------
 template <int NS, class T>
-__device__ __forceinline__ void eval_bstorage(const PhysicsDev& ph, T* f, const T* u, int bregion) {
-    const PhysSlotDev& s = ph.slot[VFVM_SLOT_BSTORAGE];
-    const double* p = ph.params + s.off;
-    if (s.id == VFVM_BSTORAGE_LINEAR && bregion == (int)p[0]) {  // examples/Example115_HeterogeneousCatalysis1D.jl:138-143
+__device__ __forceinline__ void eval_bstorage_fn(int id, const double* __restrict__ p, T* f, const T* u, int bregion) {
+    if (id == VFVM_BSTORAGE_LINEAR && bregion == (int)p[0]) {  // examples/Example115_HeterogeneousCatalysis1D.jl:138-143
 #pragma unroll
         for (int i = 0; i < NS; i++)
             if (p[1 + i] != 0.0) f[i] = p[1 + i] * u[i];
     }
+}
+template <int NS, class T>
+__device__ __forceinline__ void eval_bstorage(const PhysicsDev& ph, T* f, const T* u, int bregion) {
+    const PhysSlotDev& s = ph.slot[VFVM_SLOT_BSTORAGE];
+    eval_bstorage_fn<NS>(s.id, ph.params + s.off, f, u, bregion);
 }
 
 // ---- edgereaction(f,u,edge,data): f pre-zeroed; h = meas(edge) ------------------------------------------------------------------

@@ -67,6 +67,55 @@ __global__ void k_integrate_nodes(int64_t Nown, int region, const int64_t* __res
     }
 }
 
+// integrate(system, F, U; boundary = true), src/vfvm_postprocess.jl:29-46: one thread per boundary node over its (bface, local node)
+// items of boundary region `bregion`; the registered node / boundary functions depend on the item only through its region
+template <int NS>
+__global__ void k_integrate_bnodes(int64_t nbnodes, int bregion, int dim, const int32_t* __restrict__ bn_node, const int32_t* __restrict__ bn_ptr,
+                                   const int32_t* __restrict__ bn_bface, const int32_t* __restrict__ bn_local, const int32_t* __restrict__ bfaceregions,
+                                   const double* __restrict__ bfnf, const double* __restrict__ U, const FnArgs fn, const int32_t* __restrict__ node_active,
+                                   double* __restrict__ part) {
+    __shared__ double red[32];
+    double acc[NS];
+#pragma unroll
+    for (int i = 0; i < NS; i++) acc[i] = 0.0;
+    for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < nbnodes; b += (int64_t)gridDim.x * blockDim.x) {
+        double fac = 0.0;
+        for (int q = bn_ptr[b]; q < bn_ptr[b + 1]; q++) {
+            const int ibf = bn_bface[q];
+            if (bfaceregions[ibf] == bregion) fac += bfnf[(int64_t)ibf * dim + bn_local[q]];
+        }
+        if (fac == 0.0) continue;
+        const int K = bn_node[b];
+        double u[NS], f[NS];
+#pragma unroll
+        for (int i = 0; i < NS; i++) {
+            u[i] = U[(int64_t)K * NS + i];
+            f[i] = 0.0;
+        }
+        if (fn.id == VFVM_NONE) {
+#pragma unroll
+            for (int i = 0; i < NS; i++) f[i] = u[i];
+        } else if (fn.slot == VFVM_SLOT_BREACTION) {
+            eval_breaction_fn<NS>(fn.id, fn.p, f, u, bregion);
+        } else if (fn.slot == VFVM_SLOT_BSTORAGE) {
+            eval_bstorage_fn<NS>(fn.id, fn.p, f, u, bregion);
+        } else if (fn.slot == VFVM_SLOT_STORAGE) {
+            eval_storage<NS>(fn.id, fn.p, f, u);
+        } else {
+            eval_reaction<NS>(fn.id, fn.p, f, u, bregion);
+        }
+        const unsigned act = node_active ? (unsigned)node_active[K] : 0xffffffffu;
+#pragma unroll
+        for (int i = 0; i < NS; i++)
+            if ((act >> i) & 1u) acc[i] += fac * f[i];
+    }
+#pragma unroll
+    for (int i = 0; i < NS; i++) {
+        const double s = pp_block_sum(acc[i], red);
+        if (threadIdx.x == 0) part[(int64_t)i * gridDim.x + blockIdx.x] = s;
+    }
+}
+
 // FLUX == -1: dim ((u_K - u_L) / h)^p;  FLUX == -2: (u_K + u_L) / 2
 template <int NS, int FLUX>
 __global__ void k_integrate_edges(int64_t E, int64_t Nown, int region, int dim, const int32_t* __restrict__ edgenodes, const int64_t* __restrict__ colptr,
@@ -280,6 +329,38 @@ extern "C" int vfvm_integrate(vfvm_handle* h, int slot, int id, const double* pa
     VFVM_TRY(h, {
         CK(cudaSetDevice(h->device));
         return integrate_impl(h, false, slot, id, params, np, which, out);
+    })
+}
+
+extern "C" int vfvm_integrate_boundary(vfvm_handle* h, int slot, int id, const double* params, int np, int which, double* out) {
+    if (!h || !h->have_pattern || !out || which < 0 || which > 3 || np < 0 || np > VFVM_MAX_PARAMS)
+        return vfvm_fail(h, VFVM_ERR_ARG, "vfvm_integrate_boundary: pattern first (the boundary-node lists are built there); vector id 0..3");
+    if (!(slot == VFVM_SLOT_BREACTION || slot == VFVM_SLOT_REACTION || slot == VFVM_SLOT_STORAGE || slot == VFVM_SLOT_BSTORAGE))
+        return vfvm_fail(h, VFVM_ERR_ARG, "boundary integrals take a registered boundary reaction / boundary storage / reaction / storage function");
+    VFVM_TRY(h, {
+        CK(cudaSetDevice(h->device));
+        FnArgs fn;
+        memset(&fn, 0, sizeof(fn));
+        fn.slot = slot;
+        fn.id = id;
+        fn.np = np;
+        for (int i = 0; i < np; i++) fn.p[i] = params[i];
+        const int n = h->n, nreg = std::max(1, h->phys.nbregions);
+        DevBuf<double> part, res;
+        part.alloc((size_t)n * PP_GRID);
+        res.alloc((size_t)n * nreg);
+        CK(cudaMemsetAsync(res.p, 0, sizeof(double) * n * nreg, h->stream));
+        for (int r = 1; r <= nreg && h->nbnodes; r++) {
+            PP_NS(n, (k_integrate_bnodes<NS><<<PP_GRID, PP_THREADS, 0, h->stream>>>(h->nbnodes, r, h->dim, h->bn_node.p, h->bn_ptr.p, h->bn_bface.p, h->bn_local.p, h->bfaceregions.p,
+                                                                                    h->bfacenodefac.p, h->vec[which].p, fn, h->masked ? h->node_active.p : nullptr, part.p)));
+            k_pp_finalize<<<1, 1024, 0, h->stream>>>(part.p, PP_GRID, n, res.p + (size_t)(r - 1) * n);
+            h->launches += 2;
+        }
+        for (int off = 0; off < n * nreg; off += VFVM_PEER_RED_W) vfvm_comm_allreduce_sum(h, res.p + off, std::min(VFVM_PEER_RED_W, n * nreg - off));
+        CK(cudaMemcpyAsync(out, res.p, sizeof(double) * n * nreg, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        CK(cudaGetLastError());
+        return vfvm_peer_check(h);
     })
 }
 

@@ -22,7 +22,7 @@ FLUX_DIFFUSION, FLUX_POWDIFF, FLUX_CROSSDIFF2, FLUX_SG_UNIPOLAR, FLUX_SEDAN, FLU
 REACTION_POW, REACTION_SINH, REACTION_AFFINE, REACTION_BILINEAR2, REACTION_BIPOLAR, REACTION_REGION_AFFINE = 1, 2, 3, 4, 5, 6
 STORAGE_LINEAR, STORAGE_POW, STORAGE_BIPOLAR = 1, 2, 3
 SOURCE_CONST, SOURCE_GAUSS, SOURCE_XSINYEXPZ, SOURCE_STEP1D, SOURCE_AFFINE_X, SOURCE_NODAL = 1, 2, 3, 4, 5, 6
-BREACTION_LINEAR, BREACTION_CATALYSIS = 1, 2
+BREACTION_LINEAR, BREACTION_CATALYSIS, BREACTION_POW = 1, 2, 3
 EDGEREACTION_DIAMOND, EDGEREACTION_JOULE = 1, 2
 BSTORAGE_LINEAR = 1
 BC_DIRICHLET, BC_NEUMANN, BC_ROBIN = 1, 2, 3
@@ -358,6 +358,18 @@ class LinearBoundaryReaction(RegisteredPhysics):
     def params(self, n):
         assert self.R.shape == (n, n)
         return np.concatenate([[self.region], self.R.ravel(order="C")])
+
+
+class PowerBoundaryReaction(RegisteredPhysics):
+    """if bnode.region == region: f_i = k_i u_i^p_i   (Example226_BoundaryIntegral.jl:42-47: u^2)"""
+
+    slot, id = SLOT_BREACTION, BREACTION_POW
+
+    def __init__(self, region, k=1.0, p=2.0):
+        self.region, self.k, self.p = region, k, p
+
+    def params(self, n):
+        return np.concatenate([[float(self.region)], _vec(self.k, n), _vec(self.p, n)])
 
 
 class CatalysisBoundaryReaction(RegisteredPhysics):

@@ -13,7 +13,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import check
-from .physics import RegisteredPhysics, UnregisteredPhysicsError, SLOT_FLUX, SLOT_REACTION, SLOT_STORAGE
+from .physics import RegisteredPhysics, UnregisteredPhysicsError, BCondition, SLOT_BREACTION, SLOT_BSTORAGE, SLOT_FLUX, SLOT_REACTION, SLOT_STORAGE
 from .state import SystemState
 from .system import System
 
@@ -24,12 +24,13 @@ def _with_state(system, state):
     return SystemState(system), True
 
 
-def _call(state: SystemState, U, fn):
+def _call(state: SystemState, U, fn, nregions=None):
     state.sync()
     state.set_vector(_lib.VEC_UPDATE, np.asfortranarray(np.asarray(U, dtype=np.float64)))  # scratch vector of the Newton loop
-    out = np.zeros(state.n * state.system.grid.num_cellregions)
+    nreg = state.system.grid.num_cellregions if nregions is None else nregions
+    out = np.zeros(state.n * nreg)
     check(state.h, fn(out))
-    return out.reshape((state.n, state.system.grid.num_cellregions), order="F")
+    return out.reshape((state.n, nreg), order="F")
 
 
 def integrate(system: System, F, U=None, state: SystemState | None = None, boundary=False):
@@ -37,8 +38,20 @@ def integrate(system: System, F, U=None, state: SystemState | None = None, bound
     `integrate(system, U)` integrates the solution itself (src/vfvm_postprocess.jl:94-98)"""
     if U is None:
         F, U = None, F
-    if boundary:
-        raise NotImplementedError("boundary integrals are not on the device path yet")
+    if boundary:  # src/vfvm_postprocess.jl:29-46 -> (nspecies, nbfaceregions)
+        if isinstance(F, BCondition):
+            F = F.reaction  # the boundary reaction function itself; boundary_dirichlet!/... helper calls are not integrands
+        if F is not None and not (isinstance(F, RegisteredPhysics) and F.slot in (SLOT_BREACTION, SLOT_BSTORAGE, SLOT_REACTION, SLOT_STORAGE)):
+            raise UnregisteredPhysicsError("integrate(boundary=True): F must be a registered boundary reaction / boundary storage / reaction / storage object")
+        st, own = _with_state(system, state)
+        try:
+            n = system.num_species
+            slot, pid, prm = (SLOT_BREACTION, 0, np.zeros(0)) if F is None else (F.slot, F.id, np.ascontiguousarray(F.params(n), dtype=np.float64))
+            return _call(st, U, lambda out: st.L.vfvm_integrate_boundary(st.h, slot, pid, prm.ctypes.data if prm.size else None, prm.size, _lib.VEC_UPDATE, out.ctypes.data),
+                         nregions=system.grid.num_bfaceregions)
+        finally:
+            if own:
+                st.close()
     if F is not None and not (isinstance(F, RegisteredPhysics) and F.slot in (SLOT_REACTION, SLOT_STORAGE)):
         raise UnregisteredPhysicsError("integrate: F must be a registered reaction or storage object")
     st, own = _with_state(system, state)
