@@ -68,7 +68,9 @@ def test_probe_accepts_identical_rows_and_detects_a_wrong_entry():
     st.A = A
     res0 = probe_rows(s, st, None, U, tstep=0.1)
     assert res0["ok"] and not res0["pattern_equal"] and res0["explicit_zero_extras"] == 1
-    A.data[A.indptr[r0] + list(A.indices[A.indptr[r0]:A.indptr[r0 + 1]]).index(free)] = 1e-20
+    A.data[A.indptr[r0] + list(A.indices[A.indptr[r0]:A.indptr[r0 + 1]]).index(free)] = 1e-20  # rounding-level: tolerated
+    assert probe_rows(s, st, None, U, tstep=0.1)["ok"]
+    A.data[A.indptr[r0] + list(A.indices[A.indptr[r0]:A.indptr[r0 + 1]]).index(free)] = 1e-9
     assert not probe_rows(s, st, None, U, tstep=0.1)["ok"]
     st.A = good
     st.F = st.F.copy()

@@ -104,9 +104,9 @@ struct Amg {
     struct Signature {
         double omega = 0, alpha = 0;
         int sweeps = 0, coarse_sweeps = 0, wdepth = 0;
-        const void *off0 = nullptr, *diag0 = nullptr;
+        const void *off0 = nullptr, *diag0 = nullptr, *off32 = nullptr;
         bool operator==(const Signature& o) const {
-            return omega == o.omega && alpha == o.alpha && sweeps == o.sweeps && coarse_sweeps == o.coarse_sweeps && wdepth == o.wdepth && off0 == o.off0 && diag0 == o.diag0;
+            return off32 == o.off32 && omega == o.omega && alpha == o.alpha && sweeps == o.sweeps && coarse_sweeps == o.coarse_sweeps && wdepth == o.wdepth && off0 == o.off0 && diag0 == o.diag0;
         }
     } captured;
     vfvm_handle* owner = nullptr;
@@ -120,6 +120,7 @@ struct Amg {
     bool struct_valid = false, distributed = false;
     int64_t pattern_nnz = -1, pattern_N = -1;
     // fused coarse cycle (k_fused_cycle): levels >= fuse_level run in one persistent kernel
+    bool fp32 = true;  // the SpMVs of the cycle on the finest level read an fp32 copy of the off-diagonal planes (VFVM_AMG_FP32=0: fp64)
     int fuse_level = 1;  // first level of the fused kernel (chosen by build_fused), 0 = off
     int64_t fuse_max_n = 131072;  // levels with more nodes than this keep their own (bandwidth-tuned) kernels
     bool fuse_valid = false;
@@ -1014,8 +1015,24 @@ void build_hierarchy(vfvm_handle* h, Amg& A) {
     }
 }
 
+__global__ void k_to_float(int64_t n, const double* __restrict__ in, float* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = (float)in[i];
+}
+
 void numeric_setup(vfvm_handle* h, Amg& A) {
     cudaStream_t s = h->stream;
+    // Preconditioner-internal precision: the two finest-level SpMVs of a cycle are its bandwidth; their off-diagonal planes are read from an
+    // fp32 copy (the diagonal blocks, the vectors and the accumulation stay fp64, and so does the outer Krylov method with the fp64 matrix --
+    // the solution converges to the same tolerance, only the preconditioner is perturbed at the 1e-7 level)
+    if (const char* e = getenv("VFVM_AMG_FP32")) A.fp32 = atoi(e) != 0;
+    if (A.fp32 && h->cF > 0) {
+        const int64_t nv = (int64_t)h->cF * h->nnz_sell;
+        h->offval32.alloc((size_t)nv);
+        k_to_float<<<148 * 8, 256, 0, s>>>(nv, h->offval.p, h->offval32.p);
+        h->launches++;
+    } else {
+        h->offval32.release();
+    }
     PlaneMap pm;
     pm.cF = h->cF;
     for (int p = 0; p < 100; p++) pm.toD[p] = p < h->cF ? h->idxD[h->planeF[p]] : 0;
@@ -1037,11 +1054,13 @@ void numeric_setup(vfvm_handle* h, Amg& A) {
 void level_spmv(vfvm_handle* h, Amg& A, size_t i) {
     Level& l = *A.L[i];
     if (A.distributed && i == 0) {
-        vfvm_spmv_impl(h, l.x.p, l.t.p);
+        vfvm_spmv_impl(h, l.x.p, l.t.p, A.fp32);
         return;
     }
-    if (A.distributed) vfvm_spmv_level_halo(h, level_args(h, l), l.halo, l.x.p, l.t.p);
-    else if (l.N) vfvm_spmv_level(h, level_args(h, l), l.x.p, l.t.p);
+    SpmvArgs a = level_args(h, l);
+    if (i == 0 && A.fp32) a.offval32 = h->offval32.p;
+    if (A.distributed) vfvm_spmv_level_halo(h, a, l.halo, l.x.p, l.t.p);
+    else if (l.N) vfvm_spmv_level(h, a, l.x.p, l.t.p);
 }
 
 void smooth(vfvm_handle* h, Amg& A, size_t i, const double* b, bool first, double* out) {
@@ -1253,6 +1272,7 @@ void vfvm_amg_setup(vfvm_handle* h) {
     sig.wdepth = A.wdepth;
     sig.off0 = h->offval.p;
     sig.diag0 = h->diagval.p;
+    sig.off32 = h->offval32.p;
     if (!(sig == A.captured)) {  // a new Jacobian in the same buffers keeps the captured cycles; new options or buffers do not
         A.drop_graphs();
         A.captured = sig;

@@ -47,6 +47,7 @@ extern "C" int vfvm_create(int device, vfvm_handle** out) {
                               &h->rowptr, &h->colidx, &h->sell_ptr, &h->nz_edge, &h->tile_row, &h->bn_node, &h->bn_ptr, &h->bn_bface, &h->bn_local, &h->upos, &h->ilu_rank, &h->ilu_lrows, &h->ilu_urows, &h->send_idx};
     for (auto* b : i32) b->tally = &h->bytes;
     h->nf_colptr.tally = h->ef_colptr.tally = &h->bytes;
+    h->offval32.tally = &h->bytes;
     *out = h;
     return VFVM_OK;
 }

@@ -61,9 +61,12 @@ __device__ __forceinline__ double block_max(double v, double* sh) {
 // PEER (several ranks, peer.cuh): the kernel first pushes this rank's boundary values of x into the neighbours' mailboxes and
 // raises its flag there; columns >= Nown are read from the local mailbox, and only a warp that reaches such a column waits
 // for the neighbours' flags -- halo exchange and SpMV are one kernel, the transfer hides behind the interior rows.
-template <int NS, bool DIAGMASK, bool PEER>
+template <int NS, bool DIAGMASK, bool PEER, class VT = double>
 __global__ void __launch_bounds__(LS_THREADS) k_spmv(const SpmvArgs a, const PeerArgs P) {
     __shared__ double red[32];
+    const VT* __restrict__ vals;  // fp64 planes, or their fp32 copy (preconditioner-internal products)
+    if constexpr (sizeof(VT) == 4) vals = (const VT*)a.offval32;
+    else vals = (const VT*)a.offval;
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5, nwarps = gridDim.x * wpb;
     const int64_t nnz = a.nnz_sell;
@@ -94,7 +97,7 @@ __global__ void __launch_bounds__(LS_THREADS) k_spmv(const SpmvArgs a, const Pee
                 const bool ok = j0 + b < w;
                 const int64_t e = (int64_t)base + (int64_t)(j0 + b) * 32 + lane;
                 Lc[b] = ok ? a.colidx[e] : (int)r;
-                v1[b] = (NS == 1 && DIAGMASK && ok) ? a.offval[e] : 0.0;
+                v1[b] = (NS == 1 && DIAGMASK && ok) ? (double)vals[e] : 0.0;
             }
             double xl[BATCH][NS];
             if constexpr (PEER) {
@@ -125,7 +128,7 @@ __global__ void __launch_bounds__(LS_THREADS) k_spmv(const SpmvArgs a, const Pee
                 } else if constexpr (DIAGMASK) {  // species-decoupled planes: plane i <-> (i,i)
                     const int64_t e = (int64_t)base + (int64_t)(j0 + b) * 32 + lane;
 #pragma unroll
-                    for (int i = 0; i < NS; i++) acc[i] += a.offval[(int64_t)i * nnz + e] * xl[b][i];
+                    for (int i = 0; i < NS; i++) acc[i] += (double)vals[(int64_t)i * nnz + e] * xl[b][i];
                 } else {
                     const int64_t e = (int64_t)base + (int64_t)(j0 + b) * 32 + lane;
 #pragma unroll
@@ -133,7 +136,7 @@ __global__ void __launch_bounds__(LS_THREADS) k_spmv(const SpmvArgs a, const Pee
 #pragma unroll
                         for (int jj = 0; jj < NS; jj++) {
                             const int p = a.idxF[i * NS + jj];
-                            if (p >= 0) acc[i] += a.offval[(int64_t)p * nnz + e] * xl[b][jj];
+                            if (p >= 0) acc[i] += (double)vals[(int64_t)p * nnz + e] * xl[b][jj];
                         }
                 }
             }
@@ -185,15 +188,19 @@ __global__ void __launch_bounds__(LS_THREADS) k_spmv(const SpmvArgs a, const Pee
 #define BULK_CH 4
 #define BULK_STAGES 3
 #define BULK_THREADS 128
-template <int NS, bool DIAGMASK, bool PEER>
+template <int NS, bool DIAGMASK, bool PEER, class VT = double>
 __global__ void __launch_bounds__(BULK_THREADS) k_spmv_bulk(const SpmvArgs a, const PeerArgs P, const int cF) {
+    constexpr int VB = (int)sizeof(VT);
+    const VT* __restrict__ vals;
+    if constexpr (VB == 4) vals = (const VT*)a.offval32;
+    else vals = (const VT*)a.offval;
     extern __shared__ __align__(128) unsigned char bulk_smem[];
     __shared__ double red[32];
     __shared__ __align__(8) uint64_t bars[(BULK_THREADS / 32) * BULK_STAGES];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int wpb = blockDim.x >> 5, nwarps = gridDim.x * wpb;
     const int64_t nnz = a.nnz_sell;
-    const int stage_bytes = BULK_CH * 32 * 4 + cF * BULK_CH * 32 * 8;
+    const int stage_bytes = BULK_CH * 32 * 4 + cF * BULK_CH * 32 * VB;
     unsigned char* wbase = bulk_smem + (size_t)wib * BULK_STAGES * stage_bytes;
     uint64_t* wbar = bars + wib * BULK_STAGES;
     if (lane == 0)
@@ -226,10 +233,10 @@ __global__ void __launch_bounds__(BULK_THREADS) k_spmv_bulk(const SpmvArgs a, co
         const int nent = min(BULK_CH, pw - pj0) * 32;
         const int64_t e0 = (int64_t)pbase + (int64_t)pj0 * 32;
         unsigned char* st = wbase + (size_t)s * stage_bytes;
-        mbar_expect_tx(wbar + s, (uint32_t)(nent * 4 + cF * nent * 8));
+        mbar_expect_tx(wbar + s, (uint32_t)(nent * 4 + cF * nent * VB));
         bulk_g2s_hint(st, a.colidx + e0, (uint32_t)(nent * 4), wbar + s, stream_policy);
         for (int p = 0; p < cF; p++)
-            bulk_g2s_hint(st + BULK_CH * 32 * 4 + (size_t)p * BULK_CH * 32 * 8, a.offval + (int64_t)p * nnz + e0, (uint32_t)(nent * 8), wbar + s, stream_policy);
+            bulk_g2s_hint(st + BULK_CH * 32 * 4 + (size_t)p * BULK_CH * 32 * VB, vals + (int64_t)p * nnz + e0, (uint32_t)(nent * VB), wbar + s, stream_policy);
         pj0 += BULK_CH;
         if (pj0 >= pw) {
             pg += nwarps;
@@ -256,7 +263,7 @@ __global__ void __launch_bounds__(BULK_THREADS) k_spmv_bulk(const SpmvArgs a, co
             mbar_wait(wbar + stage, (phases >> stage) & 1u);
             const unsigned char* st = wbase + (size_t)stage * stage_bytes;
             const int32_t* __restrict__ s_col = (const int32_t*)st;
-            const double* __restrict__ s_val = (const double*)(st + BULK_CH * 32 * 4);
+            const VT* __restrict__ s_val = (const VT*)(st + BULK_CH * 32 * 4);
             int Lc[BULK_CH];
 #pragma unroll
             for (int b = 0; b < BULK_CH; b++) Lc[b] = (j0 + b < w) ? s_col[b * 32 + lane] : (int)r;
@@ -286,14 +293,14 @@ __global__ void __launch_bounds__(BULK_THREADS) k_spmv_bulk(const SpmvArgs a, co
                 if (j0 + b >= w) break;
                 if constexpr (DIAGMASK) {
 #pragma unroll
-                    for (int i = 0; i < NS; i++) acc[i] += s_val[i * BULK_CH * 32 + b * 32 + lane] * xl[b][i];
+                    for (int i = 0; i < NS; i++) acc[i] += (double)s_val[i * BULK_CH * 32 + b * 32 + lane] * xl[b][i];
                 } else {
 #pragma unroll
                     for (int i = 0; i < NS; i++)
 #pragma unroll
                         for (int jj = 0; jj < NS; jj++) {
                             const int p = a.idxF[i * NS + jj];
-                            if (p >= 0) acc[i] += s_val[p * BULK_CH * 32 + b * 32 + lane] * xl[b][jj];
+                            if (p >= 0) acc[i] += (double)s_val[p * BULK_CH * 32 + b * 32 + lane] * xl[b][jj];
                         }
                 }
             }
@@ -754,15 +761,15 @@ static int spmv_bulk_mode() {
     return mode;
 }
 
-template <int NS, bool DIAGMASK, bool PEER>
+template <int NS, bool DIAGMASK, bool PEER, class VT>
 bool launch_spmv_bulk(vfvm_handle* h, SpmvArgs& a, int op, const LevelHalo* lh) {
     const int mode = spmv_bulk_mode();
-    if (mode == 0 || lh || a.sell_ptr != h->sell_ptr.p || a.nslices < 4096) return false;  // coarse levels are latency bound: nothing to stream
+    if (mode == 0 || a.nslices < 4096) return false;  // small levels are latency bound: nothing to stream
     if (mode == 1 && NS == 1) return false;
     const int cF = DIAGMASK ? NS : h->cF;
-    const size_t smem = (size_t)(BULK_THREADS / 32) * BULK_STAGES * (BULK_CH * 32 * 4 + (size_t)cF * BULK_CH * 32 * 8);
+    const size_t smem = (size_t)(BULK_THREADS / 32) * BULK_STAGES * (BULK_CH * 32 * 4 + (size_t)cF * BULK_CH * 32 * sizeof(VT));
     if (smem > 100 * 1024) return false;  // many planes: fewer than two blocks per SM would fit, the register-staged kernel is the better one
-    auto kern = k_spmv_bulk<NS, DIAGMASK, PEER>;
+    auto kern = k_spmv_bulk<NS, DIAGMASK, PEER, VT>;
     static int occ = 0;
     static size_t occ_smem = 0;
     if (occ == 0 || occ_smem != smem) {
@@ -782,7 +789,7 @@ bool launch_spmv_bulk(vfvm_handle* h, SpmvArgs& a, int op, const LevelHalo* lh) 
         a.part = h->work[10].p;
     }
     PeerArgs P;
-    if constexpr (PEER) P = vfvm_peer_args_halo(h);
+    if constexpr (PEER) P = lh ? vfvm_peer_args_halo_level(h, *lh) : vfvm_peer_args_halo(h);
     else memset(&P, 0, sizeof(P));
     kern<<<grid, BULK_THREADS, smem, h->stream>>>(a, P, cF);
     h->launches++;
@@ -790,10 +797,19 @@ bool launch_spmv_bulk(vfvm_handle* h, SpmvArgs& a, int op, const LevelHalo* lh) 
     return true;
 }
 
+template <int NS, bool DIAGMASK, bool PEER, class VT>
+void launch_spmv_kv(vfvm_handle* h, SpmvArgs& a, int op, const LevelHalo* lh);
+
 template <int NS, bool DIAGMASK, bool PEER>
 void launch_spmv_k(vfvm_handle* h, SpmvArgs& a, int op, const LevelHalo* lh = nullptr) {
-    if (launch_spmv_bulk<NS, DIAGMASK, PEER>(h, a, op, lh)) return;
-    auto kern = k_spmv<NS, DIAGMASK, PEER>;
+    if (a.offval32) launch_spmv_kv<NS, DIAGMASK, PEER, float>(h, a, op, lh);
+    else launch_spmv_kv<NS, DIAGMASK, PEER, double>(h, a, op, lh);
+}
+
+template <int NS, bool DIAGMASK, bool PEER, class VT>
+void launch_spmv_kv(vfvm_handle* h, SpmvArgs& a, int op, const LevelHalo* lh) {
+    if (launch_spmv_bulk<NS, DIAGMASK, PEER, VT>(h, a, op, lh)) return;
+    auto kern = k_spmv<NS, DIAGMASK, PEER, VT>;
     static int occ = 0;
     if (occ == 0) {
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, LS_THREADS, 0));
@@ -987,7 +1003,19 @@ struct IterationGraph {
 
 }  // namespace
 
-void vfvm_spmv_impl(vfvm_handle* h, const double* x, double* y) { spmv(h, const_cast<double*>(x), y, nullptr); }
+void vfvm_spmv_impl(vfvm_handle* h, const double* x, double* y, bool planes32) {
+    if (!planes32 || !h->offval32.p) {
+        spmv(h, const_cast<double*>(x), y, nullptr);
+        return;
+    }
+    if (h->nranks > 1 && !h->peer_ok) vfvm_halo_exchange_ptr(h, const_cast<double*>(x));
+    SpmvArgs a = make_spmv_args(h);
+    a.x = x;
+    a.y = y;
+    a.w = nullptr;
+    a.offval32 = h->offval32.p;
+    NS_DISPATCH(h->n, launch_spmv<NS>(h, a, OP_NONE));
+}
 
 // y = A x for any matrix in the DBSR / SELL-32 layout described by `a` (AMG levels): rank-local, no halo exchange, no dots
 void vfvm_spmv_level(vfvm_handle* h, SpmvArgs a, const double* x, double* y) {

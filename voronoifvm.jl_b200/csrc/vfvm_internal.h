@@ -180,6 +180,7 @@ struct vfvm_handle {
     std::vector<uint8_t> bnode_mask_host;  // per boundary node: extra diag bits (for the exported scalar pattern)
 
     // values
+    DevBuf<float> offval32;  // fp32 copy of offval for the SpMVs inside the AMG cycle (amg.cu: Amg::fp32), refreshed by the numeric setup
     DevBuf<double> offval;   // cF planes x nnz_off
     DevBuf<double> diagval;  // cD planes x Nown
     DevBuf<double> vec[4];   // SOLUTION, OLDSOL, RESIDUAL, UPDATE: n x N (N incl. halo)
@@ -253,6 +254,7 @@ struct SpmvArgs {
     const int32_t* __restrict__ sell_ptr;
     const int32_t* __restrict__ colidx;
     const double* __restrict__ offval;
+    const float* __restrict__ offval32;  // optional fp32 copy of the off-diagonal planes (preconditioner-internal products only)
     const double* __restrict__ diagval;
     const double* __restrict__ x;
     double* __restrict__ y;
@@ -272,7 +274,7 @@ bool vfvm_pipeline_applies(vfvm_handle* h);
 int vfvm_eval_res_jac_pipelined(vfvm_handle* h, const double* U, const double* UOld, double* F, double time, double tstep, double lambda);
 int vfvm_init_dirichlet_impl(vfvm_handle* h, double time, double lambda);
 int vfvm_physics_masks(vfvm_handle* h);
-void vfvm_spmv_impl(vfvm_handle* h, const double* x, double* y);
+void vfvm_spmv_impl(vfvm_handle* h, const double* x, double* y, bool planes32 = false);
 void vfvm_sync_physics(vfvm_handle* h);
 void vfvm_source_cache(vfvm_handle* h);
 void vfvm_zero_inactive(vfvm_handle* h, double* vec);
