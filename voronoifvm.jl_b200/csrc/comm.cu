@@ -27,6 +27,7 @@ struct NcclApi {
     int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     int (*CommDestroy)(ncclComm_t) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
@@ -58,6 +59,7 @@ bool load_nccl(std::string& err) {
     SYM(CommInitRank, "ncclCommInitRank")
     SYM(CommDestroy, "ncclCommDestroy")
     SYM(AllReduce, "ncclAllReduce")
+    SYM(AllGather, "ncclAllGather")
     SYM(Send, "ncclSend")
     SYM(Recv, "ncclRecv")
     SYM(GroupStart, "ncclGroupStart")
@@ -443,6 +445,18 @@ int vfvm_comm_allreduce_sum(vfvm_handle* h, double* dev, int count) {
     }
     int rc = g_nccl.AllReduce(dev, dev, (size_t)count, ncclFloat64, ncclSum, (ncclComm_t)h->nccl, h->stream);
     if (rc != ncclSuccess) throw std::string("ncclAllReduce: ") + g_nccl.GetErrorString(rc);
+    return VFVM_OK;
+}
+// every rank contributes `count` doubles at recv + rank * count (in place: send == recv + rank * count is allowed); NCCL over NVLink.
+// Used by the replicated coarse levels of the AMG hierarchy (amg.cu): one all-gather of the coarse right-hand side per cycle instead of a
+// halo exchange per coarse-level SpMV.
+int vfvm_comm_allgather(vfvm_handle* h, const double* send, double* recv, int64_t count) {
+    if (h->nranks <= 1) {
+        if (send != recv) CK(cudaMemcpyAsync(recv, send, (size_t)count * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        return VFVM_OK;
+    }
+    int rc = g_nccl.AllGather(send, recv, (size_t)count, ncclFloat64, (ncclComm_t)h->nccl, h->stream);
+    if (rc != ncclSuccess) throw std::string("ncclAllGather: ") + g_nccl.GetErrorString(rc);
     return VFVM_OK;
 }
 int vfvm_comm_allreduce_max(vfvm_handle* h, double* dev, int count) {

@@ -289,6 +289,7 @@ PeerArgs vfvm_peer_args_halo_level(vfvm_handle* h, const LevelHalo& c);
 void vfvm_spmv_level_halo(vfvm_handle* h, SpmvArgs a, LevelHalo& lh, double* x, double* y);
 int vfvm_halo_exchange_ptr(vfvm_handle* h, double* x);
 int vfvm_comm_allreduce_sum(vfvm_handle* h, double* dev, int count);
+int vfvm_comm_allgather(vfvm_handle* h, const double* send, double* recv, int64_t count);
 int vfvm_peer_check(vfvm_handle* h);  // after peer kernels: VFVM_ERR_COMM if a wait on a peer timed out
 PeerArgs vfvm_peer_args_halo(vfvm_handle* h);    // arguments of a halo exchange (the sequence number lives on the device)
 PeerArgs vfvm_peer_args_reduce(vfvm_handle* h);  // arguments of a reduction
