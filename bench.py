@@ -491,7 +491,12 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
-    os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: the line below is the only output
+    # the JSON line is the only thing on stdout: native libraries write their banners to fd 1 (NCCL prints its version there at
+    # NCCL_DEBUG=VERSION/WARN), so fd 1 is pointed at stderr for the run and the line goes to a duplicate of the original stdout
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    os.environ.setdefault("NCCL_DEBUG", "WARN")
     import torch
 
     rank = int(os.environ.get("RANK", "0"))
@@ -531,7 +536,8 @@ def main():
             line["newton_vs_cpu_port"] = {"ratio": cpu["newton_step"]["ms"] / r["newton_step"]["ms"], "same_config": True,
                                           "note": "CPU port Newton step (oracle assembly + oracle Krylov, all host threads) / device Newton step, same grid, same tolerance"
                                                   + ("" if cpu["newton_step"].get("converged") else "; the CPU solve hit its iteration cap before 1e-10 (lower bound of its time)")}
-        print(json.dumps(line))
+        json_out.write(json.dumps(line) + "\n")
+        json_out.flush()
     if world > 1:
         dist.destroy_process_group()
 

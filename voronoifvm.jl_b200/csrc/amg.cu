@@ -81,9 +81,11 @@ struct Level {
     DevBuf<int32_t> gal_ptr, gal_src, gal_dst;  // coarse entry u <- fine entries gal_src[gal_ptr[u] .. gal_ptr[u+1]); dst >= 0: SELL position, < 0: diagonal of node -dst-1
     // work vectors (n x Nvec); b2 / x2: second visit of a W-cycle
     DevBuf<double> x, b, t, b2, x2;
+    DevBuf<double> xs;  // lean levels: the pre-smoothed iterate (k_lean)
     // several ranks: halo of this level (level 0 uses the handle's lists)
     LevelHalo halo;
     std::vector<int32_t> send_idx_host;
+    bool dist = false;  // rank-local rows of a distributed level: its SpMVs refresh the halo of their input (false: the level is complete on this rank)
 };
 
 // one captured V-/W-cycle per (input, output) vector pair: Krylov methods call the preconditioner with the same few pairs in every
@@ -104,9 +106,10 @@ struct Amg {
     struct Signature {
         double omega = 0, alpha = 0;
         int sweeps = 0, coarse_sweeps = 0, wdepth = 0;
+        long long lean = -1;
         const void *off0 = nullptr, *diag0 = nullptr, *off32 = nullptr;
         bool operator==(const Signature& o) const {
-            return off32 == o.off32 && omega == o.omega && alpha == o.alpha && sweeps == o.sweeps && coarse_sweeps == o.coarse_sweeps && wdepth == o.wdepth && off0 == o.off0 && diag0 == o.diag0;
+            return lean == o.lean && off32 == o.off32 && omega == o.omega && alpha == o.alpha && sweeps == o.sweeps && coarse_sweeps == o.coarse_sweeps && wdepth == o.wdepth && off0 == o.off0 && diag0 == o.diag0;
         }
     } captured;
     vfvm_handle* owner = nullptr;
@@ -119,6 +122,19 @@ struct Amg {
     }
     bool struct_valid = false, distributed = false;
     int64_t pattern_nnz = -1, pattern_N = -1;
+    // Replicated coarse levels (several ranks).  A halo exchange costs ~15 us whatever its size, and a distributed cycle pays two of them
+    // per level; below `repl_max_n` nodes (summed over the ranks) a level is pure latency, so from the first such level on every rank
+    // holds the WHOLE level matrix and the whole sub-hierarchy under it: one all-gather of the restricted right-hand side per cycle
+    // replaces all exchanges of those levels.  L[repl_level] is the replicated level (global numbering: rank r's nodes at r * repl_S,
+    // its stored entries at r * repl_M); `local_part` is the same level as the distributed coarsening produced it (rank-local rows +
+    // halo columns) and is only the target of the Galerkin product, whose values are all-gathered plane by plane in the numeric phase.
+    int repl_level = 0;
+    Level* local_part = nullptr;
+    int64_t repl_S = 0, repl_M = 0, repl_max_n = 200000;
+    // lean levels: complete (not distributed) levels with at most lean_max_n nodes run their visits in three launches instead of six
+    // (k_lean), the coarsest level its sweeps in coarse_sweeps - 1 launches; VFVM_AMG_LEAN=0 keeps the separate kernels
+    bool lean = true;
+    int64_t lean_max_n = 131072;
     // fused coarse cycle (k_fused_cycle): levels >= fuse_level run in one persistent kernel
     bool fp32 = true;  // the SpMVs of the cycle on the finest level read an fp32 copy of the off-diagonal planes (VFVM_AMG_FP32=0: fp64)
     int fuse_level = 1;  // first level of the fused kernel (chosen by build_fused), 0 = off
@@ -135,6 +151,7 @@ struct Amg {
     ~Amg() {
         drop_graphs();
         for (Level* l : L) delete l;
+        delete local_part;
     }
 };
 
@@ -496,6 +513,125 @@ __global__ void k_prolong(int64_t N, double alpha, const int32_t* __restrict__ a
     for (int i = 0; i < NS; i++) x[K * NS + i] += alpha * xc[(int64_t)I * NS + i];
 }
 
+
+// ------------------------------------------------------------------------------------------------ lean level kernels
+// The coarse levels are latency bound: every kernel of a visit costs its launch plus a chain of three or four dependent L2 round trips,
+// whatever it computes.  k_lean therefore folds the vector operations around a level SpMV into the SpMV itself: the multiplied vector is
+// produced on the fly per column --
+//   V_SMOOTH0: v_L = omega B_L^-1 b_L          (the first smoothing step from a zero guess),
+//   V_PROLONG: v_L = x_L + alpha x_c[agg(L)]   (the coarse correction),
+//   V_X:       v_L = x_L
+// -- and the epilogue either stores v and t = A v (E_STORE_VT: what the restriction needs) or applies the smoothing step
+// out = v + omega B^-1 (b - A v) (E_SMOOTH).  A visit of a level is then  (V_SMOOTH0, E_STORE_VT) -> restrict -> ... -> (V_PROLONG,
+// E_SMOOTH): three launches instead of six; the sweeps of the coarsest level are (V_SMOOTH0, E_SMOOTH), (V_X, E_SMOOTH), ...  The
+// operations and their order per row are those of k_smooth / k_spmv / k_prolong, only the intermediate vectors never travel.
+enum { V_X = 0, V_SMOOTH0 = 1, V_PROLONG = 2 };
+enum { E_STORE_VT = 0, E_SMOOTH = 1 };
+struct LeanArgs {
+    int64_t N, nnz;
+    int nslices;
+    const int32_t *sell_ptr, *colidx;
+    const double *offval, *diagval, *binv;
+    const double *b, *vin, *xc;
+    const int32_t* agg;
+    double *vout, *tout;
+    double omega, alpha;
+    signed char idxF[100], idxD[100];
+};
+template <int NS, int VMODE>
+__device__ __forceinline__ void lean_value(const LeanArgs& a, int64_t L, double (&v)[NS]) {
+    if constexpr (VMODE == V_X) {
+#pragma unroll
+        for (int j = 0; j < NS; j++) v[j] = a.vin[L * NS + j];
+    } else if constexpr (VMODE == V_SMOOTH0) {
+        double bl[NS];
+#pragma unroll
+        for (int j = 0; j < NS; j++) bl[j] = a.b[L * NS + j];
+#pragma unroll
+        for (int i = 0; i < NS; i++) {
+            double s = 0.0;
+#pragma unroll
+            for (int j = 0; j < NS; j++) s += a.binv[(int64_t)(i * NS + j) * a.N + L] * bl[j];
+            v[i] = 0.0 + a.omega * s;
+        }
+    } else {
+        const int I = a.agg[L];
+#pragma unroll
+        for (int j = 0; j < NS; j++) {
+            double x = a.vin[L * NS + j];
+            if (I >= 0) x += a.alpha * a.xc[(int64_t)I * NS + j];
+            v[j] = x;
+        }
+    }
+}
+template <int NS, bool DIAGMASK, int VMODE, int EPI>
+__global__ void __launch_bounds__(128) k_lean(const LeanArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (g >= a.nslices) return;
+    const int64_t rraw = (int64_t)g * 32 + lane;
+    const bool valid = rraw < a.N;
+    const int64_t r = valid ? rraw : a.N - 1;
+    const int base = a.sell_ptr[g];
+    const int w = (a.sell_ptr[g + 1] - base) >> 5;
+    double acc[NS];
+#pragma unroll
+    for (int i = 0; i < NS; i++) acc[i] = 0.0;
+#pragma unroll 2
+    for (int j = 0; j < w; j++) {
+        const int64_t e = (int64_t)base + (int64_t)j * 32 + lane;
+        const int64_t L = a.colidx[e];
+        double v[NS];
+        lean_value<NS, VMODE>(a, L, v);
+        if constexpr (DIAGMASK) {
+#pragma unroll
+            for (int i = 0; i < NS; i++) acc[i] += a.offval[(int64_t)i * a.nnz + e] * v[i];
+        } else {
+#pragma unroll
+            for (int i = 0; i < NS; i++)
+#pragma unroll
+                for (int jj = 0; jj < NS; jj++) {
+                    const int p = a.idxF[i * NS + jj];
+                    if (p >= 0) acc[i] += a.offval[(int64_t)p * a.nnz + e] * v[jj];
+                }
+        }
+    }
+    if (!valid) return;
+    double vr[NS], t[NS];
+    lean_value<NS, VMODE>(a, r, vr);
+#pragma unroll
+    for (int i = 0; i < NS; i++) {
+        double sacc = acc[i];
+        if constexpr (DIAGMASK) {
+            sacc += a.diagval[(int64_t)i * a.N + r] * vr[i];
+        } else {
+#pragma unroll
+            for (int jj = 0; jj < NS; jj++) {
+                const int p = a.idxD[i * NS + jj];
+                if (p >= 0) sacc += a.diagval[(int64_t)p * a.N + r] * vr[jj];
+            }
+        }
+        t[i] = sacc;
+    }
+    if constexpr (EPI == E_STORE_VT) {
+#pragma unroll
+        for (int i = 0; i < NS; i++) {
+            a.vout[r * NS + i] = vr[i];
+            a.tout[r * NS + i] = t[i];
+        }
+    } else {
+        double res[NS];
+#pragma unroll
+        for (int j = 0; j < NS; j++) res[j] = a.b[r * NS + j] - t[j];
+#pragma unroll
+        for (int i = 0; i < NS; i++) {
+            double s = 0.0;
+#pragma unroll
+            for (int j = 0; j < NS; j++) s += a.binv[(int64_t)(i * NS + j) * a.N + r] * res[j];
+            a.vout[r * NS + i] = vr[i] + a.omega * s;
+        }
+    }
+}
 
 // ------------------------------------------------------------------------------------------------ fused coarse cycle
 // Everything below the finest level runs in ONE persistent kernel: the recursive cycle is unrolled by the host into a short program
@@ -896,6 +1032,127 @@ void exchange(vfvm_handle* h, Amg& A, size_t i, double* x) {  // halo refresh of
     else vfvm_halo_exchange_level(h, A.L[i]->halo, x);
 }
 
+double global_max(vfvm_handle* h, double v) {
+    if (h->nranks <= 1) return v;
+    DevBuf<double> d;
+    d.alloc(1);
+    CK(cudaMemcpyAsync(d.p, &v, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    vfvm_comm_allreduce_max(h, d.p, 1);
+    return fetch(d.p, h->stream);
+}
+
+// ---- replicated coarse levels (see Amg::repl_level) -------------------------------------------------------------------------------
+__global__ void k_iota_vec(int64_t N, int ns, double* __restrict__ out) {  // local node id as the first component of a level vector
+    const int64_t K = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (K < N) out[K * ns] = (double)K;
+}
+// my segment of the replicated pattern: local entries with their columns in global numbering; the rest of the segment belongs to the
+// rank's last (padding) slice, whose rows point to themselves with weight zero
+__global__ void k_repl_fill(int64_t nnz_loc, int64_t M, int64_t seg0, int64_t padrow0, const int32_t* __restrict__ colidx, const int32_t* __restrict__ colmap,
+                            const double* __restrict__ w, int32_t* __restrict__ colidx_g, double* __restrict__ w_g) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= M) return;
+    if (e < nnz_loc) {
+        colidx_g[seg0 + e] = colmap[colidx[e]];
+        w_g[seg0 + e] = w[e];
+    } else {
+        colidx_g[seg0 + e] = (int32_t)(padrow0 + (e & 31));
+        w_g[seg0 + e] = 0.0;
+    }
+}
+
+// Builds the replicated level G from the distributed level c (rank-local rows, halo columns).  Collective.
+// Layout: every rank gets S rows (a multiple of 32 with at least one whole padding slice) and M stored entries; rank r's slices keep
+// their local SELL order at entry offset r * M, and its last padding slice absorbs the unused part of the segment, so that slice g of the
+// global matrix still ends where slice g + 1 begins.  Padding rows are identity rows (diagonal 1, right-hand side 0).  With equal
+// segment sizes every plane is all-gathered in place.
+void replicate_level(vfvm_handle* h, Amg& A, Level& c, Level& G) {
+    cudaStream_t s = h->stream;
+    const int n = h->n, R = h->nranks, rank = h->rank, nn = (int)h->nb_ranks.size();
+    const int64_t Nloc = c.N, nnz_loc = c.nnz_sell;
+    const int64_t S = ((int64_t)global_max(h, (double)Nloc) + 31) / 32 * 32 + 32;
+    const int64_t M = std::max<int64_t>(32, ((int64_t)global_max(h, (double)nnz_loc) + 31) / 32 * 32);
+    A.repl_S = S;
+    A.repl_M = M;
+    // global ids of my columns: owned = rank * S + id; halo = owner's rank * S + the owner's local id (one halo exchange of the ids)
+    std::vector<int32_t> colmap((size_t)std::max<int64_t>(1, c.Nvec), 0);
+    for (int64_t K = 0; K < Nloc; K++) colmap[K] = (int32_t)(rank * S + K);
+    {
+        DevBuf<double> T;
+        T.alloc((size_t)n * std::max<int64_t>(1, c.Nvec));
+        CK(cudaMemsetAsync(T.p, 0, T.n * sizeof(double), s));
+        if (Nloc) k_iota_vec<<<cdiv(Nloc, 256), 256, 0, s>>>(Nloc, n, T.p);
+        vfvm_halo_exchange_level(h, c.halo, T.p);
+        std::vector<double> Th = T.to_host(s);
+        for (int r = 0; r < nn; r++)
+            for (int64_t q = c.halo.recv_ptr[r]; q < c.halo.recv_ptr[r + 1]; q++)
+                colmap[Nloc + q] = (int32_t)((int64_t)h->nb_ranks[r] * S + (int64_t)Th[(size_t)(Nloc + q) * n]);
+    }
+    G.N = G.Nvec = (int64_t)R * S;
+    G.nslices = (int)(G.N / 32);
+    G.nnz_sell = (int64_t)R * M;
+    G.dist = false;
+    G.sell_ptr_b.alloc(G.nslices + 1);
+    G.colidx_b.alloc(G.nnz_sell);
+    G.w_b.alloc(G.nnz_sell);
+    G.offval_b.alloc((size_t)std::max(1, h->cF) * G.nnz_sell);
+    G.diagval_b.alloc((size_t)std::max(1, h->cD) * G.N);
+    CK(cudaMemsetAsync(G.offval_b.p, 0, G.offval_b.n * sizeof(double), s));  // padding entries and segment tails stay exact zeros
+    CK(cudaMemsetAsync(G.diagval_b.p, 0, G.diagval_b.n * sizeof(double), s));
+    DevBuf<int32_t> cm;
+    cm.upload(colmap.data(), colmap.size(), s);
+    k_repl_fill<<<cdiv(M, 256), 256, 0, s>>>(nnz_loc, M, (int64_t)rank * M, (int64_t)rank * S + S - 32, c.colidx, cm.p, c.w, G.colidx_b.p, G.w_b.p);
+    h->launches += 2;
+    vfvm_comm_allgather_bytes(h, G.colidx_b.p, (size_t)M * sizeof(int32_t));
+    vfvm_comm_allgather_bytes(h, G.w_b.p, (size_t)M * sizeof(double));
+    // slice pointers: local ones shifted by the segment offset; slices past the local ones are empty except the last, which ends at the
+    // next rank's segment
+    const int spr = (int)(S / 32);
+    std::vector<int32_t> sp_loc = c.sell_ptr_b.to_host(s);
+    std::vector<int32_t> seg((size_t)spr);
+    for (int g = 0; g < spr; g++) seg[g] = g < c.nslices ? sp_loc[g] : (int32_t)nnz_loc;
+    DevBuf<int32_t> segs;
+    segs.alloc((size_t)R * spr);
+    CK(cudaMemcpyAsync(segs.p + (size_t)rank * spr, seg.data(), (size_t)spr * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    vfvm_comm_allgather_bytes(h, segs.p, (size_t)spr * sizeof(int32_t));
+    std::vector<int32_t> all = segs.to_host(s);
+    std::vector<int32_t> spg((size_t)G.nslices + 1);
+    for (int r = 0; r < R; r++)
+        for (int g = 0; g < spr; g++) spg[(size_t)r * spr + g] = (int32_t)((int64_t)r * M + all[(size_t)r * spr + g]);
+    spg[(size_t)G.nslices] = (int32_t)((int64_t)R * M);
+    G.sell_ptr_b.upload(spg.data(), spg.size(), s);
+    // identity diagonal of my padding rows (the other ranks' arrive with the all-gather of the numeric phase)
+    std::vector<double> ones((size_t)(S - Nloc), 1.0);
+    for (int i = 0; i < n; i++) {
+        const int p = h->idxD[i * n + i];
+        if (p >= 0) CK(cudaMemcpyAsync(G.diagval_b.p + (size_t)p * G.N + (size_t)rank * S + Nloc, ones.data(), ones.size() * sizeof(double), cudaMemcpyHostToDevice, s));
+    }
+    CK(cudaStreamSynchronize(s));
+    G.sell_ptr = G.sell_ptr_b.p;
+    G.colidx = G.colidx_b.p;
+    G.offval = G.offval_b.p;
+    G.diagval = G.diagval_b.p;
+    G.w = G.w_b.p;
+    vfvm_gather_box_create(h, S * n);
+    h->amg_nccl_in_cycle = !h->gbox_ok;
+}
+
+// numeric phase: my rows of the replicated level come from the Galerkin product into the local part; every plane is then all-gathered in
+// place (equal segment sizes).  NCCL: the volume is the whole level matrix (cfg4 at 193^3: 9 planes x 1.7 M entries), bandwidth bound.
+void replicate_values(vfvm_handle* h, Amg& A) {
+    cudaStream_t s = h->stream;
+    Level &c = *A.local_part, &G = *A.L[A.repl_level];
+    const int64_t S = A.repl_S, M = A.repl_M, rank = h->rank;
+    for (int p = 0; p < h->cF && c.nnz_sell; p++)
+        CK(cudaMemcpyAsync(G.offval_b.p + (size_t)p * G.nnz_sell + (size_t)rank * M, c.offval_b.p + (size_t)p * c.nnz_sell, (size_t)c.nnz_sell * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    for (int p = 0; p < h->cD && c.N; p++)
+        CK(cudaMemcpyAsync(G.diagval_b.p + (size_t)p * G.N + (size_t)rank * S, c.diagval_b.p + (size_t)p * c.N, (size_t)c.N * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    vfvm_comm_group_start();
+    for (int p = 0; p < h->cF; p++) vfvm_comm_allgather_bytes(h, G.offval_b.p + (size_t)p * G.nnz_sell, (size_t)M * sizeof(double));
+    for (int p = 0; p < h->cD; p++) vfvm_comm_allgather_bytes(h, G.diagval_b.p + (size_t)p * G.N, (size_t)S * sizeof(double));
+    vfvm_comm_group_end();
+}
+
 // Halo of the next level (several ranks).  Every rank sends the aggregate ids of its boundary nodes to the neighbours (one halo
 // exchange on level f); the distinct ids per neighbour, ascending, are the coarse halo nodes, and the owner builds the matching
 // send list from the same ids -- both sides see the same multiset in the same order, so no second exchange is needed.
@@ -956,7 +1213,12 @@ void build_hierarchy(vfvm_handle* h, Amg& A) {
     A.fuse_valid = false;
     for (Level* l : A.L) delete l;
     A.L.clear();
+    delete A.local_part;
+    A.local_part = nullptr;
+    A.repl_level = 0;
+    h->amg_nccl_in_cycle = false;
     A.distributed = h->nranks > 1 && !h->nb_ranks.empty() && !getenv("VFVM_AMG_LOCAL");
+    if (const char* e = getenv("VFVM_AMG_REPL_MAX_N")) A.repl_max_n = atoll(e);
     Level* l0 = new Level();
     l0->N = h->Nown;
     l0->Nvec = h->N;
@@ -967,13 +1229,16 @@ void build_hierarchy(vfvm_handle* h, Amg& A) {
     l0->offval = h->offval.p;
     l0->diagval = h->diagval.p;
     l0->w = h->nzfac.p;
+    l0->dist = A.distributed;
     A.L.push_back(l0);
+    // below the replicated level every rank holds the same complete levels and takes the same decisions without communication
+    auto gsum = [&](double v) { return A.repl_level ? v : global_sum(h, v); };
     while ((int)A.L.size() < A.max_levels) {
         Level& f = *A.L.back();
         // every decision about the depth is taken on rank-summed numbers: all ranks must build the same number of levels
-        const double Nglob = global_sum(h, (double)f.N);
-        if (Nglob <= 64.0 * h->nranks) break;
-        if (global_sum(h, f.N < 16 ? 1.0 : 0.0) > 0.0) break;  // some rank has (almost) run out of nodes: this level is the coarsest everywhere
+        const double Nglob = gsum((double)f.N);
+        if (Nglob <= 64.0 * (A.repl_level ? 1 : h->nranks)) break;
+        if (gsum(f.N < 16 ? 1.0 : 0.0) > 0.0) break;  // some rank has (almost) run out of nodes: this level is the coarsest everywhere
         const int64_t Nc = f.N > 0 ? aggregate(h, A, f, A.L.size() == 1) : 0;
         if (f.N == 0) {
             f.agg.alloc(std::max<int64_t>(1, f.Nvec));
@@ -981,15 +1246,25 @@ void build_hierarchy(vfvm_handle* h, Amg& A) {
             CK(cudaMemsetAsync(f.agg_ptr.p, 0, sizeof(int32_t), h->stream));
             f.Nc = 0;
         }
-        const double Ncglob = global_sum(h, (double)Nc);
+        const double Ncglob = gsum((double)Nc);
         if (Ncglob < 1.0 || Ncglob > 0.8 * Nglob) {  // no real coarsening any more: this level is the coarsest
             f.Nc = 0;
             break;
         }
         Level* c = new Level();
-        if (A.distributed) build_coarse_halo(h, A, A.L.size() - 1, f, *c);
+        const bool dist_level = A.distributed && !A.repl_level;
+        if (dist_level) build_coarse_halo(h, A, A.L.size() - 1, f, *c);
         coarsen_pattern(h, f, *c);
-        A.L.push_back(c);
+        c->dist = dist_level;
+        if (dist_level && A.repl_max_n > 0 && Ncglob <= (double)A.repl_max_n) {  // small enough: replicate this level and everything below
+            Level* G = new Level();
+            replicate_level(h, A, *c, *G);
+            A.local_part = c;
+            A.repl_level = (int)A.L.size();
+            A.L.push_back(G);
+        } else {
+            A.L.push_back(c);
+        }
     }
     A.L.back()->Nc = 0;
     const int n = h->n;
@@ -999,10 +1274,16 @@ void build_hierarchy(vfvm_handle* h, Amg& A) {
         l.x.alloc((size_t)n * std::max<int64_t>(1, l.Nvec));
         l.t.alloc((size_t)n * std::max<int64_t>(1, l.Nvec));
         CK(cudaMemsetAsync(l.x.p, 0, l.x.n * sizeof(double), h->stream));
+        CK(cudaMemsetAsync(l.t.p, 0, l.t.n * sizeof(double), h->stream));
         if (i > 0) {
             l.b.alloc((size_t)n * std::max<int64_t>(1, l.Nvec));
             l.b2.alloc((size_t)n * std::max<int64_t>(1, l.Nvec));
             l.x2.alloc((size_t)n * std::max<int64_t>(1, l.Nvec));
+            l.xs.alloc((size_t)n * std::max<int64_t>(1, l.Nvec));
+            CK(cudaMemsetAsync(l.xs.p, 0, l.xs.n * sizeof(double), h->stream));
+            CK(cudaMemsetAsync(l.b.p, 0, l.b.n * sizeof(double), h->stream));  // (padding rows of a replicated level keep a zero right-hand side)
+            CK(cudaMemsetAsync(l.b2.p, 0, l.b2.n * sizeof(double), h->stream));
+            CK(cudaMemsetAsync(l.x2.p, 0, l.x2.n * sizeof(double), h->stream));
         }
     }
     A.struct_valid = true;
@@ -1010,7 +1291,10 @@ void build_hierarchy(vfvm_handle* h, Amg& A) {
     A.pattern_N = h->Nown;
     if (getenv("VFVM_AMG_VERBOSE")) {
         fprintf(stderr, "[vfvm amg] rank %d %s levels (nodes+halo(stored blocks)):", h->rank, A.distributed ? "distributed" : "local");
-        for (Level* l : A.L) fprintf(stderr, " %lld+%lld(%lld)", (long long)l->N, (long long)(l->Nvec - l->N), (long long)l->nnz_sell);
+        for (size_t i = 0; i < A.L.size(); i++) {
+            Level* l = A.L[i];
+            fprintf(stderr, " %s%lld+%lld(%lld)", A.repl_level && (int)i == A.repl_level ? "| replicated: " : "", (long long)l->N, (long long)(l->Nvec - l->N), (long long)l->nnz_sell);
+        }
         fprintf(stderr, "\n");
     }
 }
@@ -1039,11 +1323,13 @@ void numeric_setup(vfvm_handle* h, Amg& A) {
     A.L[0]->offval = h->offval.p;  // (the handle may have reallocated its planes)
     A.L[0]->diagval = h->diagval.p;
     for (size_t i = 0; i + 1 < A.L.size(); i++) {
-        Level &f = *A.L[i], &c = *A.L[i + 1];
+        const bool to_repl = A.repl_level && (int)(i + 1) == A.repl_level;  // the product lands in the rank-local part, then travels
+        Level &f = *A.L[i], &c = to_repl ? *A.local_part : *A.L[i + 1];
         if (c.N) k_gal_diag<<<cdiv(c.N, 128), 128, 0, s>>>(c.N, h->cD, f.agg_ptr.p, f.agg_nodes.p, f.diagval, f.N, c.diagval_b.p);
         if (f.nuniq)
             k_gal_off<<<cdiv(f.nuniq, 128), 128, 0, s>>>(f.nuniq, pm, f.gal_ptr.p, f.gal_src.p, f.gal_dst.p, f.offval, f.nnz_sell, c.offval_b.p, c.nnz_sell, c.diagval_b.p, c.N);
         h->launches += 2;
+        if (to_repl) replicate_values(h, A);
     }
     for (Level* l : A.L)
         if (l->N) vfvm_blockinv_level(h, level_args(h, *l), l->N, l->diagval, l->binv.p);
@@ -1059,7 +1345,7 @@ void level_spmv(vfvm_handle* h, Amg& A, size_t i) {
     }
     SpmvArgs a = level_args(h, l);
     if (i == 0 && A.fp32) a.offval32 = h->offval32.p;
-    if (A.distributed) vfvm_spmv_level_halo(h, a, l.halo, l.x.p, l.t.p);
+    if (l.dist) vfvm_spmv_level_halo(h, a, l.halo, l.x.p, l.t.p);
     else if (l.N) vfvm_spmv_level(h, a, l.x.p, l.t.p);
 }
 
@@ -1122,6 +1408,7 @@ void build_fused(vfvm_handle* h, Amg& A) {
     if (const char* e = getenv("VFVM_AMG_FUSE_LEVEL")) A.fuse_level = std::max(0, atoi(e));
     if (off || A.fuse_level <= 0 || (size_t)A.fuse_level >= A.L.size()) return;
     if (A.distributed && !h->peer_ok) return;  // NCCL transport: the exchanges are host-enqueued collectives, the levels stay separate kernels
+    if (A.repl_level) return;  // replicated coarse levels: the restriction into them ends in an all-gather, the levels stay separate kernels
     const int nn = (int)h->nb_ranks.size();
     std::vector<LevelDev> lv(A.L.size());
     for (size_t i = 0; i < A.L.size(); i++) {
@@ -1211,22 +1498,77 @@ void launch_fused(vfvm_handle* h, Amg& A, int bsel) {
     }
 }
 
-void cycle(vfvm_handle* h, Amg& A, size_t i, const double* b, double* out) {
+// ---- lean levels: host side ------------------------------------------------------------------------------------------------------
+bool is_lean(const Amg& A, size_t i) { return A.lean && i >= 1 && A.sweeps == 1 && !A.L[i]->dist && A.L[i]->N > 0 && A.L[i]->N <= A.lean_max_n; }
+
+template <int NS, bool DIAGMASK>
+void launch_lean_k(vfvm_handle* h, const LeanArgs& a, int vmode, int epi) {
+    const int grid = cdiv(a.nslices, 4);
+    cudaStream_t s = h->stream;
+    if (vmode == V_SMOOTH0 && epi == E_STORE_VT) k_lean<NS, DIAGMASK, V_SMOOTH0, E_STORE_VT><<<grid, 128, 0, s>>>(a);
+    else if (vmode == V_PROLONG && epi == E_SMOOTH) k_lean<NS, DIAGMASK, V_PROLONG, E_SMOOTH><<<grid, 128, 0, s>>>(a);
+    else if (vmode == V_SMOOTH0 && epi == E_SMOOTH) k_lean<NS, DIAGMASK, V_SMOOTH0, E_SMOOTH><<<grid, 128, 0, s>>>(a);
+    else if (vmode == V_X && epi == E_SMOOTH) k_lean<NS, DIAGMASK, V_X, E_SMOOTH><<<grid, 128, 0, s>>>(a);
+    else throw std::string("k_lean: combination without instantiation");
+    h->launches++;
+}
+void launch_lean(vfvm_handle* h, Amg& A, size_t i, int vmode, int epi, const double* b, const double* vin, const double* xc, double* vout, double* tout) {
+    const Level& l = *A.L[i];
+    LeanArgs a;
+    memset(&a, 0, sizeof(a));
+    a.N = l.N;
+    a.nnz = l.nnz_sell;
+    a.nslices = l.nslices;
+    a.sell_ptr = l.sell_ptr;
+    a.colidx = l.colidx;
+    a.offval = l.offval;
+    a.diagval = l.diagval;
+    a.binv = l.binv.p;
+    a.b = b;
+    a.vin = vin;
+    a.xc = xc;
+    a.agg = l.agg.p;
+    a.vout = vout;
+    a.tout = tout;
+    a.omega = A.omega;
+    a.alpha = A.alpha;
+    SpmvArgs sa = vfvm_spmv_args(h);
+    memcpy(a.idxF, sa.idxF, sizeof(a.idxF));
+    memcpy(a.idxD, sa.idxD, sizeof(a.idxD));
+    bool diagmask = (h->cF == h->n && h->cD == h->n);
+    for (int k = 0; k < h->n && diagmask; k++) diagmask = (h->idxF[k * h->n + k] == k && h->idxD[k * h->n + k] == k);
+    if (diagmask) {
+        NS_SWITCH(h->n, (launch_lean_k<NS, true>(h, a, vmode, epi)));
+    } else {
+        NS_SWITCH(h->n, (launch_lean_k<NS, false>(h, a, vmode, epi)));
+    }
+}
+
+void cycle(vfvm_handle* h, Amg& A, size_t i, const double* b, double* out);
+
+// one visit of a lean level; the result ends in l.x like that of the separate kernels
+void cycle_lean(vfvm_handle* h, Amg& A, size_t i, const double* b) {
     cudaStream_t s = h->stream;
     Level& l = *A.L[i];
-    if (A.fuse_valid && i >= 1 && (int)i == A.fuse_level && !out && (b == l.b.p || b == l.b2.p)) {  // this level and everything below: one persistent kernel
-        launch_fused(h, A, b == l.b.p ? 0 : 1);
-        return;
-    }
-    if (i + 1 == A.L.size()) {  // coarsest level: a few sweeps
-        for (int k = 0; k < A.coarse_sweeps; k++) smooth(h, A, i, b, k == 0, k + 1 == A.coarse_sweeps ? out : nullptr);
+    if (i + 1 == A.L.size()) {  // coarsest level: sweeps 1 and 2 in one launch, one launch per further sweep, the last one writes l.x
+        if (A.coarse_sweeps == 1) {
+            NS_SWITCH(h->n, (k_smooth<NS><<<cdiv(l.N, 128), 128, 0, s>>>(l.N, A.omega, l.binv.p, b, nullptr, l.x.p, nullptr)));
+            h->launches++;
+            return;
+        }
+        const int m = A.coarse_sweeps - 1;
+        const double* prev = nullptr;
+        for (int j = 0; j < m; j++) {
+            double* dst = ((m - 1 - j) & 1) ? l.xs.p : l.x.p;
+            launch_lean(h, A, i, j == 0 ? V_SMOOTH0 : V_X, E_SMOOTH, b, prev, nullptr, dst, nullptr);
+            prev = dst;
+        }
         return;
     }
     Level& c = *A.L[i + 1];
-    smooth(h, A, i, b, true, nullptr);
-    for (int k = 1; k < A.sweeps; k++) smooth(h, A, i, b, false, nullptr);
-    level_spmv(h, A, i);
+    launch_lean(h, A, i, V_SMOOTH0, E_STORE_VT, b, nullptr, nullptr, l.xs.p, l.t.p);
     if (c.N) NS_SWITCH(h->n, (k_restrict<NS><<<cdiv(c.N, 128), 128, 0, s>>>(c.N, l.agg_ptr.p, l.agg_nodes.p, b, l.t.p, c.b.p)));
+    h->launches++;
     cycle(h, A, i + 1, c.b.p, nullptr);
     if ((int)(i + 1) <= A.wdepth && i + 2 < A.L.size()) {  // second visit: correct x_c by a cycle on its residual
         const int64_t nd = c.N * h->n;
@@ -1236,7 +1578,43 @@ void cycle(vfvm_handle* h, Amg& A, size_t i, const double* b, double* out) {
         if (nd) k_w_add<<<cdiv(nd, 256), 256, 0, s>>>(nd, c.x2.p, c.x.p);
         h->launches += 2;
     }
-    if (l.N) NS_SWITCH(h->n, (k_prolong<NS><<<cdiv(l.N, 256), 256, 0, s>>>(l.N, A.alpha, l.agg.p, c.x.p, l.x.p)));
+    launch_lean(h, A, i, V_PROLONG, E_SMOOTH, b, l.xs.p, c.x.p, l.x.p, nullptr);
+}
+
+void cycle(vfvm_handle* h, Amg& A, size_t i, const double* b, double* out) {
+    cudaStream_t s = h->stream;
+    Level& l = *A.L[i];
+    if (A.fuse_valid && i >= 1 && (int)i == A.fuse_level && !out && (b == l.b.p || b == l.b2.p)) {  // this level and everything below: one persistent kernel
+        launch_fused(h, A, b == l.b.p ? 0 : 1);
+        return;
+    }
+    if (!out && is_lean(A, i)) {
+        cycle_lean(h, A, i, b);
+        return;
+    }
+    if (i + 1 == A.L.size()) {  // coarsest level: a few sweeps
+        for (int k = 0; k < A.coarse_sweeps; k++) smooth(h, A, i, b, k == 0, k + 1 == A.coarse_sweeps ? out : nullptr);
+        return;
+    }
+    Level& c = *A.L[i + 1];
+    // transfer into a replicated level: my aggregates are segment `rank` of its vectors; the right-hand side is completed by one all-gather
+    const bool to_repl = A.repl_level && (int)(i + 1) == A.repl_level;
+    const int64_t cN = to_repl ? l.Nc : c.N, coff = to_repl ? (int64_t)h->rank * A.repl_S * h->n : 0;
+    smooth(h, A, i, b, true, nullptr);
+    for (int k = 1; k < A.sweeps; k++) smooth(h, A, i, b, false, nullptr);
+    level_spmv(h, A, i);
+    if (cN) NS_SWITCH(h->n, (k_restrict<NS><<<cdiv(cN, 128), 128, 0, s>>>(cN, l.agg_ptr.p, l.agg_nodes.p, b, l.t.p, c.b.p + coff)));
+    if (to_repl) vfvm_allgather_segments(h, c.b.p, A.repl_S * h->n);
+    cycle(h, A, i + 1, c.b.p, nullptr);
+    if ((int)(i + 1) <= A.wdepth && i + 2 < A.L.size()) {  // second visit: correct x_c by a cycle on its residual
+        const int64_t nd = c.N * h->n;
+        level_spmv(h, A, i + 1);
+        if (nd) k_w_residual<<<cdiv(nd, 256), 256, 0, s>>>(nd, c.b.p, c.t.p, c.x.p, c.b2.p, c.x2.p);
+        cycle(h, A, i + 1, c.b2.p, nullptr);
+        if (nd) k_w_add<<<cdiv(nd, 256), 256, 0, s>>>(nd, c.x2.p, c.x.p);
+        h->launches += 2;
+    }
+    if (l.N) NS_SWITCH(h->n, (k_prolong<NS><<<cdiv(l.N, 256), 256, 0, s>>>(l.N, A.alpha, l.agg.p, c.x.p + coff, l.x.p)));
     h->launches += 2;
     for (int k = 1; k < A.sweeps; k++) smooth(h, A, i, b, false, nullptr);
     smooth(h, A, i, b, false, out);
@@ -1257,6 +1635,8 @@ void vfvm_amg_setup(vfvm_handle* h) {
         if (const char* e = getenv("VFVM_AMG_COARSE_SWEEPS")) A.coarse_sweeps = std::max(1, atoi(e));
         if (const char* e = getenv("VFVM_AMG_SWEEPS")) A.sweeps = std::max(1, atoi(e));
         if (const char* e = getenv("VFVM_AMG_WDEPTH")) A.wdepth = std::max(0, atoi(e));
+        if (const char* e = getenv("VFVM_AMG_LEAN")) A.lean = atoi(e) != 0;
+        if (const char* e = getenv("VFVM_AMG_LEAN_MAX_N")) A.lean_max_n = std::max(1ll, atoll(e));
         const int ml_old = A.max_levels;
         if (const char* e = getenv("VFVM_AMG_MAX_LEVELS")) A.max_levels = std::max(1, atoi(e));
         if (A.max_levels != ml_old) A.struct_valid = false;
@@ -1273,6 +1653,7 @@ void vfvm_amg_setup(vfvm_handle* h) {
     sig.off0 = h->offval.p;
     sig.diag0 = h->diagval.p;
     sig.off32 = h->offval32.p;
+    sig.lean = A.lean ? (long long)A.lean_max_n : 0;
     if (!(sig == A.captured)) {  // a new Jacobian in the same buffers keeps the captured cycles; new options or buffers do not
         A.drop_graphs();
         A.captured = sig;

@@ -18,7 +18,7 @@ typedef struct {
     char internal[128];
 } ncclUniqueId;
 enum { ncclSuccess = 0 };
-enum { ncclFloat64 = 8 };  // ncclDataType_t: ncclDouble
+enum { ncclInt8 = 0, ncclFloat64 = 8 };  // ncclDataType_t: ncclChar, ncclDouble
 enum { ncclSum = 0, ncclMax = 2 };
 
 struct NcclApi {
@@ -123,6 +123,45 @@ __global__ void k_peer_allreduce(const PeerArgs P, double* __restrict__ vals, in
             acc = ismax ? fmax(acc, v) : acc + v;
         }
         vals[t] = acc;
+    }
+}
+
+
+// all-gather of vec = [nranks][cap] in place through the gather boxes: push my segment into every peer's box, raise my flag there, wait
+// for the peers' flags, copy their segments out of my box.  One kernel; the grid is one resident wave (the block that finishes the push
+// last raises the flags).  16-byte stores over NVLink (cap is even).
+__global__ void k_peer_allgather(const GatherArgs G, double* __restrict__ vec) {
+    const unsigned long long seq = *(volatile unsigned long long*)G.seq_ctr + 1ull;
+    const int par = (int)(seq & 1ull);
+    const int R = G.nranks;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+    const int64_t cap2 = G.cap >> 1;
+    const double2* __restrict__ mine = (const double2*)(vec + (int64_t)G.rank * G.cap);
+    for (int q = 0; q < R; q++) {
+        if (q == G.rank) continue;
+        double2* dst = (double2*)(G.dst[q] + ((int64_t)par * R + G.rank) * G.cap);
+        for (int64_t i = tid; i < cap2; i += nth) dst[i] = mine[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        const unsigned int prev = atomicAdd(G.count, 1u);
+        if (prev == gridDim.x - 1) {
+            *G.count = 0;
+            *G.seq_ctr = seq;
+            __threadfence_system();
+            for (int q = 0; q < R; q++)
+                if (q != G.rank) peer_st_flag(G.flag_dst[q] + par * R + G.rank, seq);
+        }
+    }
+    if ((int)threadIdx.x < R && (int)threadIdx.x != G.rank) peer_wait(G.flag_local + par * R + threadIdx.x, seq, G.err, G.timeout_ns);
+    __syncthreads();
+    for (int q = 0; q < R; q++) {
+        if (q == G.rank) continue;
+        const double* __restrict__ src = G.box_local + ((int64_t)par * R + q) * G.cap;
+        double* __restrict__ out = vec + (int64_t)q * G.cap;
+        for (int64_t i = tid; i < G.cap; i += nth) out[i] = peer_ld_data(src + i);
     }
 }
 
@@ -309,6 +348,7 @@ extern "C" int vfvm_comm_init(vfvm_handle* h, int rank, int nranks, const char i
 }
 
 int vfvm_comm_destroy(vfvm_handle* h) {
+    vfvm_gather_box_free(h);
     if (h->peer_box) {
         cudaStreamSynchronize(h->stream);
         for (size_t q = 0; q < h->peer_base.size(); q++)
@@ -458,6 +498,117 @@ int vfvm_comm_allgather(vfvm_handle* h, const double* send, double* recv, int64_
     int rc = g_nccl.AllGather(send, recv, (size_t)count, ncclFloat64, (ncclComm_t)h->nccl, h->stream);
     if (rc != ncclSuccess) throw std::string("ncclAllGather: ") + g_nccl.GetErrorString(rc);
     return VFVM_OK;
+}
+void vfvm_comm_group_start() {
+    if (g_nccl.GroupStart) g_nccl.GroupStart();
+}
+void vfvm_comm_group_end() {
+    if (g_nccl.GroupEnd) {
+        int rc = g_nccl.GroupEnd();
+        if (rc != ncclSuccess) throw std::string("ncclGroupEnd: ") + g_nccl.GetErrorString(rc);
+    }
+}
+// in-place all-gather of raw bytes: rank r's piece lives at buf + r * bytes_per_rank (NCCL's in-place convention)
+int vfvm_comm_allgather_bytes(vfvm_handle* h, void* buf, size_t bytes_per_rank) {
+    if (h->nranks <= 1 || bytes_per_rank == 0) return VFVM_OK;
+    int rc = g_nccl.AllGather((const char*)buf + (size_t)h->rank * bytes_per_rank, buf, bytes_per_rank, ncclInt8, (ncclComm_t)h->nccl, h->stream);
+    if (rc != ncclSuccess) throw std::string("ncclAllGather: ") + g_nccl.GetErrorString(rc);
+    return VFVM_OK;
+}
+
+// ---- gather box (replicated AMG levels) -------------------------------------------------------------------------------------
+// A second IPC allocation per rank: u64 flags [2][R] at offset 0, double data [2][R][cap] at offset 256.  The IPC handles travel through
+// NCCL itself (an all-gather of 64 bytes per rank), so the host API needs no extra rendezvous.  Collective: every rank calls it with the
+// same capacity.  Without mapped peers (NCCL transport) nothing is allocated and vfvm_allgather_segments uses ncclAllGather.
+void vfvm_gather_box_free(vfvm_handle* h) {
+    if (h->gbox) {
+        cudaStreamSynchronize(h->stream);
+        for (size_t q = 0; q < h->gbox_base.size(); q++)
+            if ((int)q != h->rank && h->gbox_base[q]) cudaIpcCloseMemHandle(h->gbox_base[q]);
+        cudaFree(h->gbox);
+    }
+    h->gbox = nullptr;
+    h->gbox_base.clear();
+    h->gbox_cap = 0;
+    h->gbox_ok = false;
+}
+int vfvm_gather_box_create(vfvm_handle* h, int64_t cap) {
+    if (h->nranks <= 1 || !h->peer_ok || getenv("VFVM_NO_GATHER_BOX")) return VFVM_OK;
+    if (h->gbox_ok && h->gbox_cap >= cap) return VFVM_OK;
+    vfvm_gather_box_free(h);
+    const int R = h->nranks;
+    const size_t bytes = 256 + sizeof(double) * 2 * (size_t)R * (size_t)cap;
+    CK(cudaMalloc((void**)&h->gbox, bytes));
+    CK(cudaMemset(h->gbox, 0, bytes));
+    cudaIpcMemHandle_t ih;
+    CK(cudaIpcGetMemHandle(&ih, h->gbox));
+    DevBuf<char> hb;
+    hb.alloc((size_t)R * 64);
+    CK(cudaMemcpyAsync(hb.p + (size_t)h->rank * 64, &ih, 64, cudaMemcpyHostToDevice, h->stream));
+    vfvm_comm_allgather_bytes(h, hb.p, 64);
+    std::vector<char> all = hb.to_host(h->stream);
+    h->gbox_base.assign(R, nullptr);
+    h->gbox_base[h->rank] = h->gbox;
+    bool ok = true;
+    for (int q = 0; q < R && ok; q++) {
+        if (q == h->rank) continue;
+        cudaIpcMemHandle_t qh;
+        memcpy(&qh, all.data() + (size_t)q * 64, 64);
+        void* p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, qh, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            ok = false;
+        } else {
+            h->gbox_base[q] = (char*)p;
+        }
+    }
+    // every rank must take the same path: agree on the outcome
+    DevBuf<double> flag;
+    flag.alloc(1);
+    const double mine = ok ? 0.0 : 1.0;
+    CK(cudaMemcpyAsync(flag.p, &mine, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    vfvm_comm_allreduce_max(h, flag.p, 1);
+    double any = 0.0;
+    CK(cudaMemcpyAsync(&any, flag.p, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (any != 0.0) {
+        vfvm_gather_box_free(h);
+        return VFVM_OK;  // NCCL all-gather instead
+    }
+    h->gbox_seq.alloc(1);
+    h->gbox_count.alloc(1);
+    CK(cudaMemsetAsync(h->gbox_seq.p, 0, sizeof(unsigned long long), h->stream));
+    CK(cudaMemsetAsync(h->gbox_count.p, 0, sizeof(unsigned int), h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->gbox_cap = cap;
+    h->gbox_ok = true;
+    return VFVM_OK;
+}
+int vfvm_allgather_segments(vfvm_handle* h, double* vec, int64_t cap) {
+    if (h->nranks <= 1) return VFVM_OK;
+    if (h->gbox_ok && cap <= h->gbox_cap && (cap & 1) == 0) {
+        GatherArgs G;
+        memset(&G, 0, sizeof(G));
+        G.nranks = h->nranks;
+        G.rank = h->rank;
+        G.cap = cap;
+        G.seq_ctr = h->gbox_seq.p;
+        G.count = h->gbox_count.p;
+        for (int q = 0; q < h->nranks; q++) {
+            G.dst[q] = (double*)(h->gbox_base[q] + 256);
+            G.flag_dst[q] = (unsigned long long*)h->gbox_base[q];
+        }
+        G.box_local = (const double*)(h->gbox + 256);
+        G.flag_local = (const unsigned long long*)h->gbox;
+        G.err = h->flags.p;
+        G.timeout_ns = h->peer_timeout_ns;
+        const int grid = std::max(1, std::min(cdiv(cap * (h->nranks - 1), 2 * 256), 148));  // one resident wave
+        k_peer_allgather<<<grid, 256, 0, h->stream>>>(G, vec);
+        h->launches++;
+        return VFVM_OK;
+    }
+    return vfvm_comm_allgather(h, vec + (int64_t)h->rank * cap, vec, cap);
 }
 int vfvm_comm_allreduce_max(vfvm_handle* h, double* dev, int count) {
     if (h->nranks <= 1) return VFVM_OK;

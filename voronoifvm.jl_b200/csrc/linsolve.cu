@@ -959,7 +959,8 @@ struct IterationGraph {
     IterationGraph(vfvm_handle* hh, const double* b_, const double* x_, const double* part_) : h(hh), b(b_), x(x_), part(part_) {
         static const bool off = getenv("VFVM_NO_KRYLOV_GRAPH") != nullptr;
         // ILU applications launch one kernel per dependency level from host-side level lists: eager; NCCL transport: eager
-        enabled = !off && (h->nranks <= 1 || h->peer_ok) && h->precon != VFVM_PRECON_ILU0 && h->precon != VFVM_PRECON_ILU0_MC;
+        enabled = !off && (h->nranks <= 1 || h->peer_ok) && h->precon != VFVM_PRECON_ILU0 && h->precon != VFVM_PRECON_ILU0_MC &&
+                  !(h->precon == VFVM_PRECON_AMG && h->amg_nccl_in_cycle);
     }
     template <class Body>
     void run(int it, Body& body) {

@@ -50,6 +50,22 @@ struct PeerArgs {
     long long timeout_ns;                    // bound of a wait on a peer (a lost peer becomes VFVM_ERR_COMM instead of a hung GPU)
 };
 
+// Kernel argument of an all-gather through the gather boxes (replicated AMG levels): every rank stores its segment into every peer's
+// box [parity][rank][cap] and raises flag [parity][rank] there; the consumer waits on its local flags and copies the peers' segments
+// out of its local box.  Same sequence-counter scheme as above.
+struct GatherArgs {
+    int nranks, rank;
+    int64_t cap;                              // doubles per segment
+    unsigned long long* seq_ctr;
+    unsigned int* count;                      // grid-wide completion counter of the push phase
+    double* dst[VFVM_PEER_MAX];               // rank q's box data, parity 0, segment 0 (peer-mapped)
+    unsigned long long* flag_dst[VFVM_PEER_MAX];
+    const double* box_local;
+    const unsigned long long* flag_local;     // [parity][rank]
+    int32_t* err;
+    long long timeout_ns;
+};
+
 #ifdef __CUDACC__
 __device__ __forceinline__ unsigned long long peer_ld_flag(const unsigned long long* p) {
     unsigned long long v;

@@ -218,6 +218,13 @@ struct vfvm_handle {
     DevBuf<unsigned long long> peer_seq;      // device-resident sequence counters: [0] halo exchanges, [1] reductions
     long long peer_timeout_ns = 30000000000ll;  // bound of a wait on a peer (VFVM_PEER_TIMEOUT_MS)
     DevBuf<unsigned int> peer_counter;
+    // all-gather box of the replicated AMG levels (comm.cu: vfvm_gather_box_create): a second IPC allocation, mapped by every rank
+    char* gbox = nullptr;
+    std::vector<char*> gbox_base;             // every rank's box as mapped here ([rank] = gbox)
+    int64_t gbox_cap = 0;                     // doubles per rank segment
+    bool gbox_ok = false;
+    DevBuf<unsigned long long> gbox_seq;      // device-resident sequence counter of the all-gathers
+    DevBuf<unsigned int> gbox_count;
     void* amg = nullptr;  // aggregation AMG hierarchy (amg.cu)
     // one Krylov iteration captured as a CUDA graph (linsolve.cu): valid while its signature (method, buffers, graph_epoch) holds
     void* iter_graph = nullptr;  // cudaGraphExec_t
@@ -225,6 +232,7 @@ struct vfvm_handle {
     int64_t iter_graph_launches = 0;
     uint64_t graph_epoch = 0;  // bumped by everything that changes what a captured iteration bakes in (solver options, AMG hierarchy / options)
     bool in_capture = false;   // the handle's stream is being captured: preconditioners must enqueue plain kernels
+    bool amg_nccl_in_cycle = false;  // the AMG cycle contains a host-enqueued NCCL collective (replicated levels without a gather box): iterations stay eager
 };
 
 #define VFVM_TRY(h, ...)                                        \
@@ -289,7 +297,16 @@ PeerArgs vfvm_peer_args_halo_level(vfvm_handle* h, const LevelHalo& c);
 void vfvm_spmv_level_halo(vfvm_handle* h, SpmvArgs a, LevelHalo& lh, double* x, double* y);
 int vfvm_halo_exchange_ptr(vfvm_handle* h, double* x);
 int vfvm_comm_allreduce_sum(vfvm_handle* h, double* dev, int count);
+int vfvm_comm_allreduce_max(vfvm_handle* h, double* dev, int count);
 int vfvm_comm_allgather(vfvm_handle* h, const double* send, double* recv, int64_t count);
+int vfvm_comm_allgather_bytes(vfvm_handle* h, void* buf, size_t bytes_per_rank);  // in place: rank r's piece at buf + r * bytes_per_rank
+void vfvm_comm_group_start();
+void vfvm_comm_group_end();
+// all-gather of vec = [nranks][cap] doubles in place (rank r owns segment r): one kernel over the gather box when the peers are mapped,
+// ncclAllGather otherwise
+int vfvm_gather_box_create(vfvm_handle* h, int64_t cap_doubles);
+void vfvm_gather_box_free(vfvm_handle* h);
+int vfvm_allgather_segments(vfvm_handle* h, double* vec, int64_t cap);
 int vfvm_peer_check(vfvm_handle* h);  // after peer kernels: VFVM_ERR_COMM if a wait on a peer timed out
 PeerArgs vfvm_peer_args_halo(vfvm_handle* h);    // arguments of a halo exchange (the sequence number lives on the device)
 PeerArgs vfvm_peer_args_reduce(vfvm_handle* h);  // arguments of a reduction
