@@ -459,9 +459,10 @@ def _newton_parity(st, system, pinfo, workload, nx, ctx, iters, resn):
         diff = float(np.max(np.abs(sol[:, nodes] - ref)))
         cnt = int(nodes.size)
     else:
-        lo, hi = int(pinfo.node_ranges[pinfo.rank]), int(pinfo.node_ranges[pinfo.rank + 1])
-        mine = (nodes >= lo) & (nodes < hi)
-        diff = float(np.max(np.abs(sol[:, nodes[mine] - lo] - ref[:, mine]))) if mine.any() else 0.0
+        g2l = np.full(system.grid.num_nodes, -1, dtype=np.int64)
+        g2l[pinfo.owned_global] = np.arange(pinfo.n_owned)
+        mine = g2l[nodes] >= 0
+        diff = float(np.max(np.abs(sol[:, g2l[nodes[mine]]] - ref[:, mine]))) if mine.any() else 0.0
         cnt = int(mine.sum())
     if ctx["world"] > 1:
         alld = [None] * ctx["world"]

@@ -119,3 +119,70 @@ def test_partition_covers_all_nodes_four_ranks():
             send_global = info.local_nodes[info.send_idx[info.send_ptr[i]:info.send_ptr[i + 1]]]
             assert np.array_equal(recv_global, send_global)
     assert np.all(seen == 1)
+
+
+def _scrambled_system(seed=5):
+    """a 2D tensor grid whose nodes are numbered at random: contiguous node ranges have no locality at all"""
+    import vfvm_b200 as v
+    from vfvm_b200 import physics as ph
+    from vfvm_b200.grid import Grid
+
+    X = np.linspace(0, 1, 21)
+    g = v.simplexgrid(X, X)
+    perm = np.random.default_rng(seed).permutation(g.num_nodes)  # new id -> old id
+    inv = np.empty_like(perm)
+    inv[perm] = np.arange(perm.size)
+    g2 = Grid(g.dim, g.coord[:, perm], inv[g.cellnodes].astype(np.int32), g.cellregions, inv[g.bfacenodes].astype(np.int32), g.bfaceregions, g.coordsys)
+    s = v.System(g2, flux=ph.PowerDiffusion([1.0, 0.5], 2), reaction=ph.AffineReaction([[1.0, -1.0], [-1.0, 1.0]]), storage=ph.LinearStorage(1.0), species=[1, 2])
+    v.boundary_dirichlet(s, 1, 3, 0.0)
+    v.boundary_dirichlet(s, 2, 4, 1.0)
+    return s
+
+
+def test_rcb_partition_of_a_scrambled_numbering():
+    """recursive coordinate bisection (the Metis stand-in): balanced parts, a halo of boundary-layer size where contiguous ranges
+    would make almost every node a halo node, symmetric exchange lists, and owned rows of the local operator == global rows"""
+    sys.path.insert(0, ROOT)
+    from vfvm_b200 import partition as P
+    from oracle import oracle as O
+
+    s = _scrambled_system()
+    g, n, N = s.grid, s.num_species, s.grid.num_nodes
+    part = P.rcb_parts(g.coord, 3)
+    assert np.bincount(part).max() - np.bincount(part).min() <= 1
+    assert P.choose_parts(g, 4, "auto")[0] == "rcb"
+    X = np.linspace(0, 1, 9)
+    import vfvm_b200 as v
+    assert P.choose_parts(v.simplexgrid(X, X, X), 2, "auto")[0] == "ranges"  # x-fastest tensor grid: slabs are the better cut
+    infos = [P.partition_grid(g, r, 4, "rcb") for r in range(4)]
+    ranged = [P.partition_grid(g, r, 4, "ranges") for r in range(4)]
+    assert sum(i.num_halo for i in infos) * 3 < sum(i.num_halo for i in ranged)
+    seen = np.zeros(N, int)
+    for info in infos:
+        seen[info.owned_global] += 1
+        assert np.array_equal(info.owned_global, info.local_nodes[:info.n_owned])
+        for i, q in enumerate(info.neighbor_ranks):
+            other = infos[int(q)]
+            j = list(other.neighbor_ranks).index(info.rank)
+            recv_global = other.local_nodes[other.n_owned + other.recv_ptr[j]:other.n_owned + other.recv_ptr[j + 1]]
+            send_global = info.local_nodes[info.send_idx[info.send_ptr[i]:info.send_ptr[i + 1]]]
+            assert np.array_equal(recv_global, send_global)
+    assert np.all(seen == 1)
+    rng = np.random.default_rng(3)
+    Ug = np.asfortranarray(rng.uniform(0.1, 1.0, (n, N)))
+    Fg, Ag = O.OracleSystem(s).assemble(Ug, Ug, tstep=0.1)
+    Ag = Ag.tocsr()
+    info = infos[2]
+    ls = P.local_system(s, info)
+    Ul = np.asfortranarray(Ug[:, info.local_nodes])
+    Fl, Al = O.OracleSystem(ls).assemble(Ul, Ul, tstep=0.1)
+    Al = Al.tocsr()
+    gl = np.asarray(info.local_nodes)
+    for K in range(info.n_owned):
+        for i in range(n):
+            rl, rg = Al.getrow(K * n + i), Ag.getrow(gl[K] * n + i)
+            cols_g = gl[rl.indices // n] * n + rl.indices % n
+            o = np.argsort(cols_g)
+            assert np.array_equal(cols_g[o], rg.indices), "row pattern differs"
+            np.testing.assert_allclose(rl.data[o], rg.data, rtol=1e-12, atol=1e-300)
+    np.testing.assert_allclose(Fl[:, :info.n_owned], Fg[:, gl[:info.n_owned]], rtol=1e-11, atol=1e-13)
