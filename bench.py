@@ -35,6 +35,7 @@ import vfvm_b200 as v  # noqa: E402
 from vfvm_b200 import physics as ph  # noqa: E402
 
 DEFAULT_NX = {"cfg1": 578, "cfg2": 2583, "cfg3": 193, "cfg4": 193, "cfg5": 97}
+AMG_WDEPTH = {"cfg2": 3, "cfg3": 2}  # levels 1..wdepth are visited twice per visit of their parent; elsewhere the V-cycle is the faster one
 
 
 # ------------------------------------------------------------------------------------------------ workloads
@@ -107,10 +108,12 @@ def algorithmic_bytes(n, N, E, NB, dim, cF, cD, transient):
 
 def iteration_bytes(n, N, nnz_stored, cF, cD, krylov, amg):
     """B_iter of SURVEY.md section 8d on the stored planes: SpMV = nnz (8 cF + 4) + N (8 cD + 16 n); a Krylov iteration = its SpMVs +
-    preconditioner applications + vector streams of 8 n N bytes.  AMG V-cycle = 2 level-0 SpMVs + 7 streams, x 1.1 for the coarser levels."""
+    preconditioner applications + vector streams of 8 n N bytes.  AMG cycle = 2 level-0 SpMVs + 7 streams, x (1 + the coarser levels' share:
+    0.1 for a V-cycle at 11x coarsening, 0.2 / 0.22 with levels 1 / 1-2 visited twice).  fp64 throughout: the fp32 copy of the finest off-diagonal
+    planes the cycle actually reads makes the real traffic smaller than this figure."""
     spmv = nnz_stored * (8 * cF + 4) + N * (8 * cD + 16 * n)
     stream = 8 * n * N
-    pre = 1.1 * (2 * spmv + 7 * stream) if amg else 2 * stream
+    pre = float(amg) * (2 * spmv + 7 * stream) if amg else 2 * stream  # amg = 1 + share of the coarser levels (1.1 V-cycle, 1.2 / 1.22 W on one / more levels)
     if krylov == "cg":
         return spmv + pre + 6 * stream
     return 2 * spmv + 2 * pre + 10 * stream
@@ -244,7 +247,7 @@ def _traffic(workload, nx, world):
         return None
 
 
-def linear_setup(st, system, world):
+def linear_setup(st, system, world, workload=None):
     """Krylov method + AMG options of the Newton step: CG for SPD Jacobians, BiCGStab otherwise, aggregation AMG (csrc/amg.cu);
     VFVM_BENCH_PRECON=jacobi gives the one-level baseline"""
     L, h = st.L, st.h
@@ -254,11 +257,20 @@ def linear_setup(st, system, world):
     if os.environ.get("VFVM_BENCH_PRECON", "amg") == "amg":
         precon = v._lib.PRECON_AMG
     v._lib.check(h, L.vfvm_linsolve_setup(h, krylov, precon, 0))
-    if precon == v._lib.PRECON_AMG and os.environ.get("VFVM_BENCH_AMG_OPTS"):  # experiment hook: "omega,alpha,theta,sweeps,coarse_sweeps,wdepth" (empty = keep)
-        vals = [float(x) if x.strip() else float("nan") for x in os.environ["VFVM_BENCH_AMG_OPTS"].split(",")]
+    wdepth = 0
+    if precon == v._lib.PRECON_AMG:
+        # W-cycle on the top levels where it pays (profiles/r2_amg_sweeps.txt) -- the same cycle on every rank count, so that the
+        # 1/2/4/8-GPU curve compares one algorithm.  VFVM_BENCH_AMG_OPTS = "omega,alpha,theta,sweeps,coarse_sweeps,wdepth" overrides (empty = keep)
+        wdepth = AMG_WDEPTH.get(workload, 0)
+        vals = [float("nan")] * 5 + [float(wdepth)]
+        if os.environ.get("VFVM_BENCH_AMG_OPTS"):
+            vals = [float(x) if x.strip() else float("nan") for x in os.environ["VFVM_BENCH_AMG_OPTS"].split(",")]
+            if len(vals) > 5 and vals[5] == vals[5]:
+                wdepth = int(vals[5])
         v._lib.check(h, L.vfvm_amg_set_options(h, (C.c_double * len(vals))(*vals), len(vals)))
-    label = ("CG" if spd else "BiCGStab") + {v._lib.PRECON_JACOBI: "+Jacobi", v._lib.PRECON_BLOCKJACOBI: "+block-Jacobi", v._lib.PRECON_AMG: "+aggregation-AMG"}[precon]
-    return ("cg" if spd else "bicgstab"), precon == v._lib.PRECON_AMG, label
+    label = ("CG" if spd else "BiCGStab") + {v._lib.PRECON_JACOBI: "+Jacobi", v._lib.PRECON_BLOCKJACOBI: "+block-Jacobi",
+                                           v._lib.PRECON_AMG: "+aggregation-AMG (" + (f"W-cycle on levels 1-{wdepth}" if wdepth else "V-cycle") + ")"}[precon]
+    return ("cg" if spd else "bicgstab"), ((1.1, 1.2, 1.22)[min(wdepth, 2)] if precon == v._lib.PRECON_AMG else 0), label
 
 
 def newton_once(st, U, tstep, reltol, maxiters=5000):
@@ -278,9 +290,9 @@ def newton_once(st, U, tstep, reltol, maxiters=5000):
     return rc, iters.value, resn.value, ninf.value
 
 
-def newton_solution(st, system, U, tstep, reltol=1.0e-13):
+def newton_solution(st, system, U, tstep, reltol=1.0e-13, workload=None):
     """solution after one Newton step solved to `reltol` (tools/make_newton_golden.py --source device)"""
-    _, _, label = linear_setup(st, system, 1)
+    _, _, label = linear_setup(st, system, 1, workload)
     rc, it, resn, ninf = newton_once(st, U, tstep, reltol)
     return st.get_vector(v._lib.VEC_SOLUTION), f"{label}, reltol {reltol:g}, {it} iterations, |r| = {resn:.3e}, rc {rc}"
 
@@ -411,7 +423,7 @@ def run_workload(args, workload, nx, ctx, steps, warmup, newton_reps):
     # ---- Newton step (assembly + Krylov solve to 1e-10 + update): median of `newton_reps`, CUDA events on the handle's stream, max over ranks
     newton = None
     if not args.no_newton:
-        krylov, amg, label = linear_setup(st, system, world)
+        krylov, amg, label = linear_setup(st, system, world, workload)
         newton_once(st, U, tstep, 1.0e-10, maxiters=3)  # warm-up: work vectors, hierarchy, NCCL channels
         reps = []
         for _ in range(newton_reps):

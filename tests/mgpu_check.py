@@ -86,11 +86,13 @@ def check(name, s, tstep, urange, rank, world, local, amg_parity=True):
     # every rank learns every rank's outcome before anybody asserts: a rank that fails alone would leave the others waiting in a collective
     damg = [None] * world
     dist.all_gather_object(damg, float(np.max(np.abs(sol_amg[:, own] - sol[:, own]))))
-    if max(damg) >= 1e-10:
+    # two Krylov solves that each stop at a relative residual of 1e-13 agree to cond(A) x 1e-13 x |b|: 1.6e-10 on the masked system (|r| = 2e-12 in
+    # both, condition ~ 1e2); the bound against the ORACLE below stays 1e-10
+    if max(damg) >= 5e-10:
         print(f"mgpu_check[{name}] rank {rank}: AMG-preconditioned solve differs from the direct-like solve: per-rank max diff {damg}; direct-like: {len(h1)} Newton steps, "
               f"{h1.nlin} Krylov iterations, last |r| {h1.linres:.3e}, updates {h1.updatenorm}; AMG: {len(h2)} Newton steps, {h2.nlin} Krylov iterations, last |r| {h2.linres:.3e}, "
               f"updates {h2.updatenorm}", flush=True)
-    assert max(damg) < 1e-10, f"{name}: AMG-preconditioned solve differs"
+    assert max(damg) < 5e-10, f"{name}: AMG-preconditioned solve differs"
     gathered = [None] * world
     dist.all_gather_object(gathered, (info.local_nodes[own], F[:, own], sol[:, own], pr["entries"]))
     if rank == 0:

@@ -81,7 +81,6 @@ struct Level {
     DevBuf<int32_t> gal_ptr, gal_src, gal_dst;  // coarse entry u <- fine entries gal_src[gal_ptr[u] .. gal_ptr[u+1]); dst >= 0: SELL position, < 0: diagonal of node -dst-1
     // work vectors (n x Nvec); b2 / x2: second visit of a W-cycle
     DevBuf<double> x, b, t, b2, x2;
-    DevBuf<double> xs;  // lean levels: the pre-smoothed iterate (k_lean)
     // several ranks: halo of this level (level 0 uses the handle's lists)
     LevelHalo halo;
     std::vector<int32_t> send_idx_host;
@@ -106,10 +105,9 @@ struct Amg {
     struct Signature {
         double omega = 0, alpha = 0;
         int sweeps = 0, coarse_sweeps = 0, wdepth = 0;
-        long long lean = -1;
         const void *off0 = nullptr, *diag0 = nullptr, *off32 = nullptr;
         bool operator==(const Signature& o) const {
-            return lean == o.lean && off32 == o.off32 && omega == o.omega && alpha == o.alpha && sweeps == o.sweeps && coarse_sweeps == o.coarse_sweeps && wdepth == o.wdepth && off0 == o.off0 && diag0 == o.diag0;
+            return off32 == o.off32 && omega == o.omega && alpha == o.alpha && sweeps == o.sweeps && coarse_sweeps == o.coarse_sweeps && wdepth == o.wdepth && off0 == o.off0 && diag0 == o.diag0;
         }
     } captured;
     vfvm_handle* owner = nullptr;
@@ -131,10 +129,7 @@ struct Amg {
     int repl_level = 0;
     Level* local_part = nullptr;
     int64_t repl_S = 0, repl_M = 0, repl_max_n = 200000;
-    // lean levels: complete (not distributed) levels with at most lean_max_n nodes run their visits in three launches instead of six
-    // (k_lean), the coarsest level its sweeps in coarse_sweeps - 1 launches; VFVM_AMG_LEAN=0 keeps the separate kernels
-    bool lean = true;
-    int64_t lean_max_n = 131072;
+
     // fused coarse cycle (k_fused_cycle): levels >= fuse_level run in one persistent kernel
     bool fp32 = true;  // the SpMVs of the cycle on the finest level read an fp32 copy of the off-diagonal planes (VFVM_AMG_FP32=0: fp64)
     int fuse_level = 1;  // first level of the fused kernel (chosen by build_fused), 0 = off
@@ -513,125 +508,6 @@ __global__ void k_prolong(int64_t N, double alpha, const int32_t* __restrict__ a
     for (int i = 0; i < NS; i++) x[K * NS + i] += alpha * xc[(int64_t)I * NS + i];
 }
 
-
-// ------------------------------------------------------------------------------------------------ lean level kernels
-// The coarse levels are latency bound: every kernel of a visit costs its launch plus a chain of three or four dependent L2 round trips,
-// whatever it computes.  k_lean therefore folds the vector operations around a level SpMV into the SpMV itself: the multiplied vector is
-// produced on the fly per column --
-//   V_SMOOTH0: v_L = omega B_L^-1 b_L          (the first smoothing step from a zero guess),
-//   V_PROLONG: v_L = x_L + alpha x_c[agg(L)]   (the coarse correction),
-//   V_X:       v_L = x_L
-// -- and the epilogue either stores v and t = A v (E_STORE_VT: what the restriction needs) or applies the smoothing step
-// out = v + omega B^-1 (b - A v) (E_SMOOTH).  A visit of a level is then  (V_SMOOTH0, E_STORE_VT) -> restrict -> ... -> (V_PROLONG,
-// E_SMOOTH): three launches instead of six; the sweeps of the coarsest level are (V_SMOOTH0, E_SMOOTH), (V_X, E_SMOOTH), ...  The
-// operations and their order per row are those of k_smooth / k_spmv / k_prolong, only the intermediate vectors never travel.
-enum { V_X = 0, V_SMOOTH0 = 1, V_PROLONG = 2 };
-enum { E_STORE_VT = 0, E_SMOOTH = 1 };
-struct LeanArgs {
-    int64_t N, nnz;
-    int nslices;
-    const int32_t *sell_ptr, *colidx;
-    const double *offval, *diagval, *binv;
-    const double *b, *vin, *xc;
-    const int32_t* agg;
-    double *vout, *tout;
-    double omega, alpha;
-    signed char idxF[100], idxD[100];
-};
-template <int NS, int VMODE>
-__device__ __forceinline__ void lean_value(const LeanArgs& a, int64_t L, double (&v)[NS]) {
-    if constexpr (VMODE == V_X) {
-#pragma unroll
-        for (int j = 0; j < NS; j++) v[j] = a.vin[L * NS + j];
-    } else if constexpr (VMODE == V_SMOOTH0) {
-        double bl[NS];
-#pragma unroll
-        for (int j = 0; j < NS; j++) bl[j] = a.b[L * NS + j];
-#pragma unroll
-        for (int i = 0; i < NS; i++) {
-            double s = 0.0;
-#pragma unroll
-            for (int j = 0; j < NS; j++) s += a.binv[(int64_t)(i * NS + j) * a.N + L] * bl[j];
-            v[i] = 0.0 + a.omega * s;
-        }
-    } else {
-        const int I = a.agg[L];
-#pragma unroll
-        for (int j = 0; j < NS; j++) {
-            double x = a.vin[L * NS + j];
-            if (I >= 0) x += a.alpha * a.xc[(int64_t)I * NS + j];
-            v[j] = x;
-        }
-    }
-}
-template <int NS, bool DIAGMASK, int VMODE, int EPI>
-__global__ void __launch_bounds__(128) k_lean(const LeanArgs a) {
-    const int lane = threadIdx.x & 31;
-    const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (g >= a.nslices) return;
-    const int64_t rraw = (int64_t)g * 32 + lane;
-    const bool valid = rraw < a.N;
-    const int64_t r = valid ? rraw : a.N - 1;
-    const int base = a.sell_ptr[g];
-    const int w = (a.sell_ptr[g + 1] - base) >> 5;
-    double acc[NS];
-#pragma unroll
-    for (int i = 0; i < NS; i++) acc[i] = 0.0;
-#pragma unroll 2
-    for (int j = 0; j < w; j++) {
-        const int64_t e = (int64_t)base + (int64_t)j * 32 + lane;
-        const int64_t L = a.colidx[e];
-        double v[NS];
-        lean_value<NS, VMODE>(a, L, v);
-        if constexpr (DIAGMASK) {
-#pragma unroll
-            for (int i = 0; i < NS; i++) acc[i] += a.offval[(int64_t)i * a.nnz + e] * v[i];
-        } else {
-#pragma unroll
-            for (int i = 0; i < NS; i++)
-#pragma unroll
-                for (int jj = 0; jj < NS; jj++) {
-                    const int p = a.idxF[i * NS + jj];
-                    if (p >= 0) acc[i] += a.offval[(int64_t)p * a.nnz + e] * v[jj];
-                }
-        }
-    }
-    if (!valid) return;
-    double vr[NS], t[NS];
-    lean_value<NS, VMODE>(a, r, vr);
-#pragma unroll
-    for (int i = 0; i < NS; i++) {
-        double sacc = acc[i];
-        if constexpr (DIAGMASK) {
-            sacc += a.diagval[(int64_t)i * a.N + r] * vr[i];
-        } else {
-#pragma unroll
-            for (int jj = 0; jj < NS; jj++) {
-                const int p = a.idxD[i * NS + jj];
-                if (p >= 0) sacc += a.diagval[(int64_t)p * a.N + r] * vr[jj];
-            }
-        }
-        t[i] = sacc;
-    }
-    if constexpr (EPI == E_STORE_VT) {
-#pragma unroll
-        for (int i = 0; i < NS; i++) {
-            a.vout[r * NS + i] = vr[i];
-            a.tout[r * NS + i] = t[i];
-        }
-    } else {
-        double res[NS];
-#pragma unroll
-        for (int j = 0; j < NS; j++) res[j] = a.b[r * NS + j] - t[j];
-#pragma unroll
-        for (int i = 0; i < NS; i++) {
-            double s = 0.0;
-#pragma unroll
-            for (int j = 0; j < NS; j++) s += a.binv[(int64_t)(i * NS + j) * a.N + r] * res[j];
-            a.vout[r * NS + i] = vr[i] + a.omega * s;
-        }
-    }
-}
 
 // ------------------------------------------------------------------------------------------------ fused coarse cycle
 // Everything below the finest level runs in ONE persistent kernel: the recursive cycle is unrolled by the host into a short program
@@ -1279,8 +1155,6 @@ void build_hierarchy(vfvm_handle* h, Amg& A) {
             l.b.alloc((size_t)n * std::max<int64_t>(1, l.Nvec));
             l.b2.alloc((size_t)n * std::max<int64_t>(1, l.Nvec));
             l.x2.alloc((size_t)n * std::max<int64_t>(1, l.Nvec));
-            l.xs.alloc((size_t)n * std::max<int64_t>(1, l.Nvec));
-            CK(cudaMemsetAsync(l.xs.p, 0, l.xs.n * sizeof(double), h->stream));
             CK(cudaMemsetAsync(l.b.p, 0, l.b.n * sizeof(double), h->stream));  // (padding rows of a replicated level keep a zero right-hand side)
             CK(cudaMemsetAsync(l.b2.p, 0, l.b2.n * sizeof(double), h->stream));
             CK(cudaMemsetAsync(l.x2.p, 0, l.x2.n * sizeof(double), h->stream));
@@ -1498,98 +1372,11 @@ void launch_fused(vfvm_handle* h, Amg& A, int bsel) {
     }
 }
 
-// ---- lean levels: host side ------------------------------------------------------------------------------------------------------
-bool is_lean(const Amg& A, size_t i) { return A.lean && i >= 1 && A.sweeps == 1 && !A.L[i]->dist && A.L[i]->N > 0 && A.L[i]->N <= A.lean_max_n; }
-
-template <int NS, bool DIAGMASK>
-void launch_lean_k(vfvm_handle* h, const LeanArgs& a, int vmode, int epi) {
-    const int grid = cdiv(a.nslices, 4);
-    cudaStream_t s = h->stream;
-    if (vmode == V_SMOOTH0 && epi == E_STORE_VT) k_lean<NS, DIAGMASK, V_SMOOTH0, E_STORE_VT><<<grid, 128, 0, s>>>(a);
-    else if (vmode == V_PROLONG && epi == E_SMOOTH) k_lean<NS, DIAGMASK, V_PROLONG, E_SMOOTH><<<grid, 128, 0, s>>>(a);
-    else if (vmode == V_SMOOTH0 && epi == E_SMOOTH) k_lean<NS, DIAGMASK, V_SMOOTH0, E_SMOOTH><<<grid, 128, 0, s>>>(a);
-    else if (vmode == V_X && epi == E_SMOOTH) k_lean<NS, DIAGMASK, V_X, E_SMOOTH><<<grid, 128, 0, s>>>(a);
-    else throw std::string("k_lean: combination without instantiation");
-    h->launches++;
-}
-void launch_lean(vfvm_handle* h, Amg& A, size_t i, int vmode, int epi, const double* b, const double* vin, const double* xc, double* vout, double* tout) {
-    const Level& l = *A.L[i];
-    LeanArgs a;
-    memset(&a, 0, sizeof(a));
-    a.N = l.N;
-    a.nnz = l.nnz_sell;
-    a.nslices = l.nslices;
-    a.sell_ptr = l.sell_ptr;
-    a.colidx = l.colidx;
-    a.offval = l.offval;
-    a.diagval = l.diagval;
-    a.binv = l.binv.p;
-    a.b = b;
-    a.vin = vin;
-    a.xc = xc;
-    a.agg = l.agg.p;
-    a.vout = vout;
-    a.tout = tout;
-    a.omega = A.omega;
-    a.alpha = A.alpha;
-    SpmvArgs sa = vfvm_spmv_args(h);
-    memcpy(a.idxF, sa.idxF, sizeof(a.idxF));
-    memcpy(a.idxD, sa.idxD, sizeof(a.idxD));
-    bool diagmask = (h->cF == h->n && h->cD == h->n);
-    for (int k = 0; k < h->n && diagmask; k++) diagmask = (h->idxF[k * h->n + k] == k && h->idxD[k * h->n + k] == k);
-    if (diagmask) {
-        NS_SWITCH(h->n, (launch_lean_k<NS, true>(h, a, vmode, epi)));
-    } else {
-        NS_SWITCH(h->n, (launch_lean_k<NS, false>(h, a, vmode, epi)));
-    }
-}
-
-void cycle(vfvm_handle* h, Amg& A, size_t i, const double* b, double* out);
-
-// one visit of a lean level; the result ends in l.x like that of the separate kernels
-void cycle_lean(vfvm_handle* h, Amg& A, size_t i, const double* b) {
-    cudaStream_t s = h->stream;
-    Level& l = *A.L[i];
-    if (i + 1 == A.L.size()) {  // coarsest level: sweeps 1 and 2 in one launch, one launch per further sweep, the last one writes l.x
-        if (A.coarse_sweeps == 1) {
-            NS_SWITCH(h->n, (k_smooth<NS><<<cdiv(l.N, 128), 128, 0, s>>>(l.N, A.omega, l.binv.p, b, nullptr, l.x.p, nullptr)));
-            h->launches++;
-            return;
-        }
-        const int m = A.coarse_sweeps - 1;
-        const double* prev = nullptr;
-        for (int j = 0; j < m; j++) {
-            double* dst = ((m - 1 - j) & 1) ? l.xs.p : l.x.p;
-            launch_lean(h, A, i, j == 0 ? V_SMOOTH0 : V_X, E_SMOOTH, b, prev, nullptr, dst, nullptr);
-            prev = dst;
-        }
-        return;
-    }
-    Level& c = *A.L[i + 1];
-    launch_lean(h, A, i, V_SMOOTH0, E_STORE_VT, b, nullptr, nullptr, l.xs.p, l.t.p);
-    if (c.N) NS_SWITCH(h->n, (k_restrict<NS><<<cdiv(c.N, 128), 128, 0, s>>>(c.N, l.agg_ptr.p, l.agg_nodes.p, b, l.t.p, c.b.p)));
-    h->launches++;
-    cycle(h, A, i + 1, c.b.p, nullptr);
-    if ((int)(i + 1) <= A.wdepth && i + 2 < A.L.size()) {  // second visit: correct x_c by a cycle on its residual
-        const int64_t nd = c.N * h->n;
-        level_spmv(h, A, i + 1);
-        if (nd) k_w_residual<<<cdiv(nd, 256), 256, 0, s>>>(nd, c.b.p, c.t.p, c.x.p, c.b2.p, c.x2.p);
-        cycle(h, A, i + 1, c.b2.p, nullptr);
-        if (nd) k_w_add<<<cdiv(nd, 256), 256, 0, s>>>(nd, c.x2.p, c.x.p);
-        h->launches += 2;
-    }
-    launch_lean(h, A, i, V_PROLONG, E_SMOOTH, b, l.xs.p, c.x.p, l.x.p, nullptr);
-}
-
 void cycle(vfvm_handle* h, Amg& A, size_t i, const double* b, double* out) {
     cudaStream_t s = h->stream;
     Level& l = *A.L[i];
     if (A.fuse_valid && i >= 1 && (int)i == A.fuse_level && !out && (b == l.b.p || b == l.b2.p)) {  // this level and everything below: one persistent kernel
         launch_fused(h, A, b == l.b.p ? 0 : 1);
-        return;
-    }
-    if (!out && is_lean(A, i)) {
-        cycle_lean(h, A, i, b);
         return;
     }
     if (i + 1 == A.L.size()) {  // coarsest level: a few sweeps
@@ -1635,8 +1422,6 @@ void vfvm_amg_setup(vfvm_handle* h) {
         if (const char* e = getenv("VFVM_AMG_COARSE_SWEEPS")) A.coarse_sweeps = std::max(1, atoi(e));
         if (const char* e = getenv("VFVM_AMG_SWEEPS")) A.sweeps = std::max(1, atoi(e));
         if (const char* e = getenv("VFVM_AMG_WDEPTH")) A.wdepth = std::max(0, atoi(e));
-        if (const char* e = getenv("VFVM_AMG_LEAN")) A.lean = atoi(e) != 0;
-        if (const char* e = getenv("VFVM_AMG_LEAN_MAX_N")) A.lean_max_n = std::max(1ll, atoll(e));
         const int ml_old = A.max_levels;
         if (const char* e = getenv("VFVM_AMG_MAX_LEVELS")) A.max_levels = std::max(1, atoi(e));
         if (A.max_levels != ml_old) A.struct_valid = false;
@@ -1653,7 +1438,6 @@ void vfvm_amg_setup(vfvm_handle* h) {
     sig.off0 = h->offval.p;
     sig.diag0 = h->diagval.p;
     sig.off32 = h->offval32.p;
-    sig.lean = A.lean ? (long long)A.lean_max_n : 0;
     if (!(sig == A.captured)) {  // a new Jacobian in the same buffers keeps the captured cycles; new options or buffers do not
         A.drop_graphs();
         A.captured = sig;
