@@ -618,6 +618,40 @@ def test_masked_coupled_flux_two_species():
     _compare_assembly(s, U, _rand_u(s, seed=11) * s.node_dof(), tstep=0.05)
 
 
+def test_enable_species_after_state_creation():
+    """enable_species! on a system whose SystemState already exists: the device twin takes the new region masks at the next sync (new
+    pattern, all physics pushed again) and assembles what a fresh state assembles; transient callbacks receive the solution arrays"""
+    g = _grid(2, 13)
+    v.cellmask(g, [0.0, 0.0], [0.5, 1.0], 2)
+    s = v.System(g, flux=ph.LinearDiffusion([1.0, 0.5]), reaction=ph.AffineReaction([[1.0, -0.2], [-0.1, 2.0]]), storage=ph.LinearStorage([1.0, 2.0]))
+    v.enable_species(s, 1, [1, 2])
+    v.enable_species(s, 2, [2])
+    v.boundary_dirichlet(s, 1, 2, 1.0)
+    st = v.SystemState(s)
+    try:
+        U = _rand_u(s)
+        st.eval_res_jac(U * s.node_dof(), None, tstep=0.05)
+        v.enable_species(s, 2, [1])  # species 2 everywhere now
+        st.sync()
+        U2 = _rand_u(s, seed=3)
+        F = st.eval_res_jac(U2, None, tstep=0.05)
+        A = st.matrix("csc")
+        Fo, Ao = O.OracleSystem(s).assemble(U2, None, tstep=0.05)
+        assert np.array_equal(A.indptr, Ao.indptr) and np.array_equal(A.indices, Ao.indices)
+        np.testing.assert_allclose(A.data, Ao.data, rtol=1e-12, atol=1e-13)
+        np.testing.assert_allclose(F, Fo, rtol=1e-12, atol=1e-13)
+        seen = []
+        tsol = v.solve_state(st, inival=0.5, times=[0.0, 0.1], Δt=0.05, Δt_min=0.05, Δt_max=0.05,
+                             pre=lambda sol, t: seen.append(("pre", None if sol is None else sol.shape, t)),
+                             post=lambda sol, oldsol, t, dt: seen.append(("post", sol.shape, oldsol.shape, float(np.abs(sol - oldsol).max()) > 0.0)),
+                             sample=lambda sol, t: seen.append(("sample", sol.shape, t)))
+        assert ("pre", (2, g.num_nodes), 0.05) in seen and any(e[0] == "sample" and e[1] == (2, g.num_nodes) for e in seen)
+        assert ("post", (2, g.num_nodes), (2, g.num_nodes), True) in seen
+        assert len(tsol.t) >= 2
+    finally:
+        st.close()
+
+
 # ---- SURVEY 8f rank 3: boundary species, bstorage, edgereaction ---------------------------------------------------------------------
 @pytest.mark.parametrize("switchbc", [False, True])
 def test_example115_boundary_species_bstorage_device(switchbc):

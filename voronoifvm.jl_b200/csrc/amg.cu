@@ -128,7 +128,11 @@ struct Amg {
     // halo columns) and is only the target of the Galerkin product, whose values are all-gathered plane by plane in the numeric phase.
     int repl_level = 0;
     Level* local_part = nullptr;
-    int64_t repl_S = 0, repl_M = 0, repl_max_n = 200000;
+    // The price is that every rank runs the replicated levels in full, so the rule is on WORK, not on nodes: a level is replicated when its
+    // stored values (entries x planes, summed over the ranks) stay below repl_max_vals -- cfg3: from level 2 (63 k nodes, 1.6 M values), the
+    // three-species system cfg4: from level 3 (7 k nodes, 1.6 M values; its level 2 holds 14 M values and costs more replicated on 8 GPUs
+    // than its exchanges do: measured 3.5 against 2.6 ms per BiCGStab iteration, profiles/r2_amg_sweeps.txt).
+    int64_t repl_S = 0, repl_M = 0, repl_max_n = 200000, repl_max_vals = 4000000;
 
     // fused coarse cycle (k_fused_cycle): levels >= fuse_level run in one persistent kernel
     bool fp32 = true;  // the SpMVs of the cycle on the finest level read an fp32 copy of the off-diagonal planes (VFVM_AMG_FP32=0: fp64)
@@ -1095,6 +1099,7 @@ void build_hierarchy(vfvm_handle* h, Amg& A) {
     h->amg_nccl_in_cycle = false;
     A.distributed = h->nranks > 1 && !h->nb_ranks.empty() && !getenv("VFVM_AMG_LOCAL");
     if (const char* e = getenv("VFVM_AMG_REPL_MAX_N")) A.repl_max_n = atoll(e);
+    if (const char* e = getenv("VFVM_AMG_REPL_MAX_VALS")) A.repl_max_vals = atoll(e);
     Level* l0 = new Level();
     l0->N = h->Nown;
     l0->Nvec = h->N;
@@ -1132,7 +1137,8 @@ void build_hierarchy(vfvm_handle* h, Amg& A) {
         if (dist_level) build_coarse_halo(h, A, A.L.size() - 1, f, *c);
         coarsen_pattern(h, f, *c);
         c->dist = dist_level;
-        if (dist_level && A.repl_max_n > 0 && Ncglob <= (double)A.repl_max_n) {  // small enough: replicate this level and everything below
+        const double vals_glob = dist_level ? gsum((double)c->nnz_sell * std::max(1, h->cF)) : 0.0;
+        if (dist_level && A.repl_max_n > 0 && Ncglob <= (double)A.repl_max_n && vals_glob <= (double)A.repl_max_vals) {  // small enough: replicate this level and everything below
             Level* G = new Level();
             replicate_level(h, A, *c, *G);
             A.local_part = c;

@@ -106,6 +106,18 @@ class DeviceDirectLike(_Krylov):
         self.reltol, self.abstol, self.maxiters = reltol, abstol, maxiters
 
 
+def _no_pre(sol, t):
+    return None
+
+
+def _no_post(sol, oldsol, t, dt):
+    return None
+
+
+def _no_sample(sol, t):
+    return None
+
+
 @dataclasses.dataclass
 class SolverControl:
     verbose: bool | str = False
@@ -141,9 +153,9 @@ class SolverControl:
     handle_exceptions: bool = False
     store_all: bool = True
     log: bool = False
-    pre: Callable = lambda sol, t: None
-    post: Callable = lambda sol, oldsol, t, dt: None
-    sample: Callable = lambda sol, t: None
+    pre: Callable = _no_pre
+    post: Callable = _no_post
+    sample: Callable = _no_sample
 
 
 def fixed_timesteps(control: SolverControl, dt: float, grow: float = 1.0) -> SolverControl:
@@ -328,7 +340,8 @@ def solve_transient(state: SystemState, inival, lambdas, control: SolverControl,
     if transient:
         tsol = TransientSolution(lambdas[0], np.array(inival, order="F", copy=True))
     else:
-        control.pre(None, float(lambdas[0]))
+        if control.pre is not _no_pre:
+            control.pre(np.array(inival, order="F", copy=True), float(lambdas[0]))
         hist = solve_step(state, True, control, time, math.inf, float(lambdas[0]), istep_factorize)
         sol = state.get_vector(_lib.VEC_SOLUTION)
         control.post(sol, inival, lambdas[0], 0)
@@ -347,7 +360,8 @@ def solve_transient(state: SystemState, inival, lambdas, control: SolverControl,
                 solved, forced, errored = True, False, False
                 try:
                     lam = lam0 + dl
-                    control.pre(None, lam)
+                    if control.pre is not _no_pre:  # the callbacks see the arrays the reference hands them (src/vfvm_solver.jl:380, :478, :519);
+                        control.pre(state.get_vector(_lib.VEC_OLDSOL), lam)  # they are downloaded only when a callback is set
                     if transient:
                         hist = solve_step(state, True, control, lam, dl, 0.0, istep)
                     else:
@@ -381,12 +395,14 @@ def solve_transient(state: SystemState, inival, lambdas, control: SolverControl,
                         istep_factorize = 0
             if solved:
                 istep += 1
-                sol = state.get_vector(_lib.VEC_SOLUTION) if control.store_all else None
+                want_post = control.post is not _no_post
+                sol = state.get_vector(_lib.VEC_SOLUTION) if (control.store_all or want_post) else None
                 if control.log:
                     tsol.history.append(hist)
                 if control.store_all:
                     tsol.append(lam, sol)
-                control.post(sol, None, lam, dl)
+                if want_post:
+                    control.post(sol, state.get_vector(_lib.VEC_OLDSOL), lam, dl)
                 check(h, L.vfvm_copy_vector(h, _lib.VEC_OLDSOL, _lib.VEC_SOLUTION))  # oldsolution .= solution (:480)
                 steps_to_go = math.ceil((lend - lam) / dl)
                 lpredict = lend - lam
@@ -400,9 +416,11 @@ def solve_transient(state: SystemState, inival, lambdas, control: SolverControl,
                         dl = lend - lam
             else:
                 break
+        last = state.get_vector(_lib.VEC_SOLUTION) if (not control.store_all or control.sample is not _no_sample) else None
         if not control.store_all:
-            tsol.append(lam0, state.get_vector(_lib.VEC_SOLUTION))
-        control.sample(None, lam0)
+            tsol.append(lam0, last)
+        if control.sample is not _no_sample:
+            control.sample(last, lam0)
         if not solved:
             break
     return tsol

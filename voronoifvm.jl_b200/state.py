@@ -35,11 +35,7 @@ class SystemState:
             check(h, self.L.vfvm_set_owned_nodes(h, owned_nodes))
             self.Nown = owned_nodes
         check(h, self.L.vfvm_build_geometry(h))  # update_grid! (src/vfvm_system.jl:607-631)
-        rs = np.ascontiguousarray(system.region_species.ravel(order="F"), dtype=np.uint8)
-        check(h, self.L.vfvm_set_system(h, self.n, rs.ctypes.data_as(C.POINTER(C.c_uint8))))
-        if system.bregion_species.any():
-            bs = np.ascontiguousarray(system.bregion_species.ravel(order="F"), dtype=np.uint8)
-            check(h, self.L.vfvm_set_boundary_species(h, system.bregion_species.shape[1], bs.ctypes.data_as(C.POINTER(C.c_uint8))))
+        self._push_species()
         self._version = -1
         self._push_physics()
         check(h, self.L.vfvm_build_pattern(h))
@@ -47,12 +43,24 @@ class SystemState:
         self.history = None
 
     # ------------------------------------------------------------------------------------------------
+    def _push_species(self):
+        """species enabled per cell / boundary region (enable_species!, enable_boundary_species!): resets the device twin's physics and pattern"""
+        sysm, h = self.system, self.h
+        rs = np.ascontiguousarray(sysm.region_species.ravel(order="F"), dtype=np.uint8)
+        check(h, self.L.vfvm_set_system(h, self.n, rs.ctypes.data_as(C.POINTER(C.c_uint8))))
+        if sysm.bregion_species.any():
+            bs = np.ascontiguousarray(sysm.bregion_species.ravel(order="F"), dtype=np.uint8)
+            check(h, self.L.vfvm_set_boundary_species(h, sysm.bregion_species.shape[1], bs.ctypes.data_as(C.POINTER(C.c_uint8))))
+        self._species_pushed = (sysm.region_species.copy(), sysm.bregion_species.copy())
+
     def _push_physics(self):
         sysm, h, L = self.system, self.h, self.L
         if sysm._version == self._version:
             return
         if sysm.num_species != self.n:
             raise RuntimeError("the number of species changed after the SystemState was created")
+        if not (np.array_equal(sysm.region_species, self._species_pushed[0]) and np.array_equal(sysm.bregion_species, self._species_pushed[1])):
+            self._push_species()  # enable_species! after the state was created: new masks, then all physics again, then a new pattern (sync)
         for slot, pid, params in sysm.physics_slots():
             params = np.ascontiguousarray(params, dtype=np.float64)
             check(h, L.vfvm_set_physics(h, slot, pid, dptr(params) if params.size else None, params.size))
