@@ -1,6 +1,7 @@
 """CPU-side checks (no GPU): the C-ABI library loads and exports every symbol include/vfvm_b200.h declares; the host
 mirror rejects unregistered callbacks; grid generator invariants; the product package never touches the oracle."""
 import ctypes as C
+import math
 import os
 import re
 
@@ -149,3 +150,45 @@ def test_amg_builder_options_vector():
     assert b.precon == v._lib.PRECON_AMG and len(b.options) == 6
     assert b.options[1] == 2.0 and b.options[5] == 2.0 and all(o != o for o in (b.options[0], b.options[2], b.options[3], b.options[4]))
     assert v.SmoothedAggregationPreconBuilder is v.AMGPreconBuilder
+
+
+def test_sparse_unknown_storage_host_mirror():
+    """unknown_storage = :sparse (src/vfvm_system.jl:813-825, src/vfvm_sparsesolution.jl): only dofs of species defined at a node are
+    stored, column by column; undefined dofs read as NaN and ignore assignments; dense() / from_dense() are the device conversions"""
+    import vfvm_b200 as v
+    from vfvm_b200 import physics as ph
+    from vfvm_b200.sparsesolution import SparseSolutionArray
+
+    X = np.linspace(0, 1, 5)
+    g = v.simplexgrid(X, X)
+    v.cellmask(g, [0.0, 0.0], [0.5, 1.0], 2)
+    s = v.System(g, flux=ph.LinearDiffusion([1.0, 1.0, 1.0]), unknown_storage="sparse")
+    v.enable_species(s, 1, [1, 2])
+    v.enable_species(s, 2, [2])
+    v.enable_boundary_species(s, 3, [2])
+    mask = s.node_dof()
+    u = v.unknowns(s, inival=0.5)
+    assert isinstance(u, SparseSolutionArray) and u.shape == (3, g.num_nodes)
+    assert len(u) == v.num_dof(s) == int(mask.sum()) < 3 * g.num_nodes
+    K_in = int(np.nonzero(mask[1])[0][0])
+    K_out = int(np.nonzero(~mask[1])[0][0])
+    assert u[1, K_in] == 0.5 and math.isnan(u[1, K_out]) and u.dof(1, K_out) == -1
+    u[1, K_out] = 7.0  # ignored
+    u[1, K_in] = 2.0
+    d = u.dense()
+    assert d.flags.f_contiguous and d[1, K_in] == 2.0 and d[1, K_out] == 0.0 and np.all(d[~mask] == 0.0)
+    # CSC layout of node_dof: species ascending inside a node
+    for K in (K_in, K_out):
+        sp = u.rowval[u.colptr[K]:u.colptr[K + 1]]
+        assert np.array_equal(sp, np.nonzero(mask[:, K])[0])
+    rng = np.random.default_rng(0)
+    D = np.asfortranarray(rng.uniform(size=mask.shape)) * mask
+    w = SparseSolutionArray.from_dense(mask, D)
+    assert np.array_equal(w.dense(), D)
+    assert np.array_equal((w + w).dense(), 2 * D) and np.array_equal((w - w).dofs(), np.zeros(len(w)))
+    c = w.copy()
+    c[0, 0] = -1.0
+    assert w[0, 0] != -1.0 and w.similar().shape == w.shape
+    # dense systems keep the dense array
+    s2 = v.System(g, flux=ph.LinearDiffusion(), species=[1])
+    assert isinstance(v.unknowns(s2), np.ndarray) and v.num_dof(s2) == g.num_nodes

@@ -652,6 +652,28 @@ def test_enable_species_after_state_creation():
         st.close()
 
 
+def test_sparse_unknown_storage_solve():
+    """unknown_storage = :sparse changes the host container only (test/ of the reference runs every example with both storages and
+    expects the same numbers): solve() hands back a SparseSolutionArray with the dense solve's values at the defined dofs"""
+    from vfvm_b200.sparsesolution import SparseSolutionArray
+
+    sols = {}
+    for storage in ("dense", "sparse"):
+        g = _grid(2, 13)
+        v.cellmask(g, [0.0, 0.0], [0.5, 1.0], 2)
+        s = v.System(g, flux=ph.LinearDiffusion([1.0, 0.5]), reaction=ph.AffineReaction([[1.0, -0.2], [-0.1, 2.0]]), unknown_storage=storage)
+        v.enable_species(s, 1, [1, 2])
+        v.enable_species(s, 2, [2])
+        v.boundary_dirichlet(s, 1, 2, 1.0)
+        v.boundary_dirichlet(s, 2, 4, 0.5)
+        sols[storage] = (v.solve(s, inival=v.unknowns(s, inival=0.1)), s.node_dof())
+    sp, mask = sols["sparse"]
+    assert isinstance(sp, SparseSolutionArray) and isinstance(sols["dense"][0], np.ndarray)
+    assert len(sp) == int(mask.sum())
+    assert np.array_equal(sp.dense()[mask], sols["dense"][0][mask])
+    assert sp.history is not None
+
+
 # ---- SURVEY 8f rank 3: boundary species, bstorage, edgereaction ---------------------------------------------------------------------
 @pytest.mark.parametrize("switchbc", [False, True])
 def test_example115_boundary_species_bstorage_device(switchbc):

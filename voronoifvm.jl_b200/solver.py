@@ -318,8 +318,12 @@ def solve_step(state: SystemState, oldsol_on_device: bool, control: SolverContro
 
 
 def _as_inival(system: System, inival):
+    """dense (n, N) initial value for the device twin; a SparseSolutionArray is scattered (undefined dofs are zero on the device)"""
     if np.isscalar(inival):
-        return unknowns(system, inival)
+        u = unknowns(system, inival)
+        return u.dense() if hasattr(u, "dense") else u
+    if hasattr(inival, "dense"):
+        return inival.dense()
     a = np.asfortranarray(inival, dtype=np.float64)
     if a.shape != (system.num_species, system.grid.num_nodes):
         raise ValueError(f"wrong shape of inival: {a.shape}")
@@ -441,8 +445,13 @@ def solve_state(state: SystemState, inival=0, control: SolverControl | None = No
     if embed is not None:
         return solve_transient(state, inival, list(embed), control, transient=False, time=time)
     state.set_vector(_lib.VEC_OLDSOL, inival)
-    solve_step(state, True, control, time, tstep, 0.0, 0)
-    return state.get_vector(_lib.VEC_SOLUTION)
+    hist = solve_step(state, True, control, time, tstep, 0.0, 0)
+    sol = state.get_vector(_lib.VEC_SOLUTION)
+    if state.system.unknown_storage == "sparse":  # the reference hands back the storage type of the system (src/vfvm_solver.jl:607-616)
+        from .sparsesolution import SparseSolutionArray
+
+        return SparseSolutionArray.from_dense(state.system.node_dof(), sol, history=hist)
+    return sol
 
 
 def solve(system: System, state: SystemState | None = None, **kwargs):

@@ -171,11 +171,22 @@ def boundary_robin(system: System, ispec, ibc, alpha, v):
 
 
 def num_dof(system: System) -> int:
+    """`num_dof(system)`: n N for dense storage (src/vfvm_system.jl:790), the number of defined dofs for sparse storage (:806)"""
+    if system.unknown_storage == "sparse":
+        return int(system.node_dof().sum())
     return system.num_species * system.grid.num_nodes
 
 
-def unknowns(system: System, inival=None) -> np.ndarray:
-    """`unknowns(system; inival)` src/vfvm_system.jl:1086-1191 (dense storage)"""
+def unknowns(system: System, inival=None):
+    """`unknowns(system; inival)` src/vfvm_system.jl:1086-1191: a dense (n, N) array, or a `SparseSolutionArray` that stores only the
+    dofs of species defined at a node when the system was created with `unknown_storage="sparse"`"""
+    if system.unknown_storage == "sparse":
+        from .sparsesolution import SparseSolutionArray
+
+        u = SparseSolutionArray(system.node_dof())
+        if inival is not None:
+            u.nzval[:] = inival
+        return u
     u = np.zeros((system.num_species, system.grid.num_nodes), order="F")
     if inival is not None:
         u[...] = inival
