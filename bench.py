@@ -36,7 +36,7 @@ from vfvm_b200 import physics as ph  # noqa: E402
 
 DEFAULT_NX = {"cfg1": 578, "cfg2": 2583, "cfg3": 193, "cfg4": 193, "cfg5": 97}
 AMG_WDEPTH = {"cfg2": 3, "cfg3": 2}  # levels 1..wdepth are visited twice per visit of their parent; elsewhere the V-cycle is the faster one
-W_CYCLE_MIN_NODES_PER_RANK = 1500000
+W_CYCLE_MIN_NODES_PER_RANK = 2500000
 
 
 # ------------------------------------------------------------------------------------------------ workloads
@@ -263,7 +263,7 @@ def linear_setup(st, system, world, workload=None):
         # W-cycle on the top levels where it pays (profiles/r2_amg_sweeps.txt); the cycle in use is named in `krylov`.
         # VFVM_BENCH_AMG_OPTS = "omega,alpha,theta,sweeps,coarse_sweeps,wdepth" overrides (empty = keep)
         # The second visits are pure latency (small coarse-level kernels): they pay while an iteration is bandwidth bound, i.e. while a rank holds
-        # enough of the finest level -- measured on cfg3: 1 GPU 78 -> 53 ms, 2 GPUs 59 -> 49 ms, but 8 GPUs (0.9 M nodes per rank) ~40 -> 57 ms
+        # enough of the finest level -- measured on cfg3: 1 GPU (7.2 M nodes) 78 -> 53 ms, 2 GPUs (3.6 M per rank) 59 -> 49 ms, but 8 GPUs (0.9 M per rank) 45.5 -> 57 ms
         wdepth = AMG_WDEPTH.get(workload, 0) if st.Nown >= W_CYCLE_MIN_NODES_PER_RANK else 0
         vals = [float("nan")] * 5 + [float(wdepth)]
         if os.environ.get("VFVM_BENCH_AMG_OPTS"):

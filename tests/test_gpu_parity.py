@@ -641,7 +641,7 @@ def test_enable_species_after_state_creation():
         np.testing.assert_allclose(A.data, Ao.data, rtol=1e-12, atol=1e-13)
         np.testing.assert_allclose(F, Fo, rtol=1e-12, atol=1e-13)
         seen = []
-        tsol = v.solve_state(st, inival=0.5, times=[0.0, 0.1], Δt=0.05, Δt_min=0.05, Δt_max=0.05,
+        tsol = v.solve_state(st, inival=0.5, times=[0.0, 0.1], Δt=0.05, Δt_min=0.05, Δt_max=0.05, Δu_opt=1.0e5,
                              pre=lambda sol, t: seen.append(("pre", None if sol is None else sol.shape, t)),
                              post=lambda sol, oldsol, t, dt: seen.append(("post", sol.shape, oldsol.shape, float(np.abs(sol - oldsol).max()) > 0.0)),
                              sample=lambda sol, t: seen.append(("sample", sol.shape, t)))
