@@ -670,7 +670,10 @@ def test_sparse_unknown_storage_solve():
     sp, mask = sols["sparse"]
     assert isinstance(sp, SparseSolutionArray) and isinstance(sols["dense"][0], np.ndarray)
     assert len(sp) == int(mask.sum())
-    assert np.array_equal(sp.dense()[mask], sols["dense"][0][mask])
+    # (the two solves start from different values at the undefined dofs -- 0.1 in the dense array, nothing in the sparse one -- so their Krylov
+    # right-hand sides differ there and the defined dofs agree to solver accuracy, not bitwise)
+    np.testing.assert_allclose(sp.dense()[mask], sols["dense"][0][mask], rtol=0, atol=1e-11)
+    assert np.all(sp.dense()[~mask] == 0.0)
     assert sp.history is not None
 
 
