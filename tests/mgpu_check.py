@@ -75,7 +75,16 @@ def check(name, s, tstep, urange, rank, world, local, amg_parity=True):
     Sl = np.asfortranarray(Sg[:, info.local_nodes])
     own = slice(0, info.n_owned)
     # ---- residual rows + Jacobian rows (probe planes of every rank against the oracle, entry by entry)
+    # host-vector call: the plain path (upload, assemble, download) and the pipelined one (halo piece first, then chunks of owned rows on three
+    # streams; forced here, these systems are below its size threshold) must give the same bits; the Jacobian the pipelined call leaves is probed below
+    os.environ["VFVM_NO_PIPELINE"] = "1"
+    F_plain = st.eval_res_jac(Ul, tstep=tstep)
+    del os.environ["VFVM_NO_PIPELINE"]
+    os.environ.update(VFVM_PIPE_MIN_BYTES="0", VFVM_PIPE_CHUNKS="5")
     F = st.eval_res_jac(Ul, tstep=tstep)
+    for k in ("VFVM_PIPE_MIN_BYTES", "VFVM_PIPE_CHUNKS"):
+        del os.environ[k]
+    pipe_same = bool(np.array_equal(F[:, :info.n_owned], F_plain[:, :info.n_owned]))
     pr = probe_rows(s, st, info, Ug, Ug, tstep=tstep)
     assert pr["ok"], (name, rank, pr)
     # ---- one implicit Euler step (Newton to convergence), default direct-like solver across ranks, then BiCGStab + distributed AMG
@@ -84,6 +93,9 @@ def check(name, s, tstep, urange, rank, world, local, amg_parity=True):
     sol_amg = v.solve_state(st, inival=Sl, tstep=tstep, method_linear=v.KrylovJL_BICGSTAB(precs=v.AMGPreconBuilder()), reltol_linear=1e-13, abstol_linear=0.0, maxiters_linear=2000)
     h2 = st.history
     # every rank learns every rank's outcome before anybody asserts: a rank that fails alone would leave the others waiting in a collective
+    same = [None] * world
+    dist.all_gather_object(same, pipe_same)
+    assert all(same), f"{name}: pipelined host-vector assembly differs from the plain path on ranks {[r for r, ok in enumerate(same) if not ok]}"
     damg = [None] * world
     dist.all_gather_object(damg, float(np.max(np.abs(sol_amg[:, own] - sol[:, own]))))
     # two Krylov solves that each stop at a relative residual of 1e-13 agree to cond(A) x 1e-13 x |b|: 1.6e-10 on the masked system (|r| = 2e-12 in

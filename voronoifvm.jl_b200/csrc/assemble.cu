@@ -1240,14 +1240,27 @@ int vfvm_assemble_impl(vfvm_handle* h, double time, double tstep, double lambda,
 // are assembled as soon as the last piece of U their columns reach has arrived (for a banded numbering: piece c+1), and
 // the residual of chunk c returns to the host on a second copy stream while later chunks are still being uploaded and
 // assembled.  PCIe is full duplex, so the call approaches max(H2D, D2H) instead of H2D + assembly + D2H.
-__global__ void k_slice_colmax(int nslices, const int32_t* __restrict__ sell_ptr, const int32_t* __restrict__ colidx, int32_t* __restrict__ out) {
+// per slice: the largest OWNED column its rows reach (>= the rows themselves), and whether any column is a halo node (>= Nown)
+__global__ void k_slice_colmax(int nslices, int64_t Nown, const int32_t* __restrict__ sell_ptr, const int32_t* __restrict__ colidx, int32_t* __restrict__ out,
+                               int32_t* __restrict__ out_halo) {
     const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (g >= nslices) return;
-    int m = g * 32 + lane;  // the row itself
-    for (int e = sell_ptr[g] + lane; e < sell_ptr[g + 1]; e += 32) m = max(m, colidx[e]);
+    int m = (int)min((int64_t)g * 32 + lane, Nown - 1);  // the row itself
+    int hl = 0;
+    for (int e = sell_ptr[g] + lane; e < sell_ptr[g + 1]; e += 32) {
+        const int c = colidx[e];
+        if (c >= Nown) hl = 1;
+        else m = max(m, c);
+    }
 #pragma unroll
-    for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if (lane == 0) out[g] = m;
+    for (int o = 16; o; o >>= 1) {
+        m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+        hl |= __shfl_xor_sync(0xffffffffu, hl, o);
+    }
+    if (lane == 0) {
+        out[g] = m;
+        out_halo[g] = hl;
+    }
 }
 
 static int pipe_chunks(const vfvm_handle* h) {  // pieces of >= 4 MB keep the copies at full PCIe rate
@@ -1263,16 +1276,21 @@ static void build_pipe_plan(vfvm_handle* h) {
     P.K = K;
     P.slice_begin.assign(K + 1, 0);
     for (int c = 0; c <= K; c++) P.slice_begin[c] = (int)((int64_t)h->ngroups * c / K);
-    DevBuf<int32_t> cm;
+    DevBuf<int32_t> cm, ch;
     cm.alloc(h->ngroups);
-    k_slice_colmax<<<cdiv(h->ngroups, 8), 256, 0, h->stream>>>(h->ngroups, h->sell_ptr.p, h->colidx.p, cm.p);
+    ch.alloc(h->ngroups);
+    k_slice_colmax<<<cdiv(h->ngroups, 8), 256, 0, h->stream>>>(h->ngroups, h->Nown, h->sell_ptr.p, h->colidx.p, cm.p, ch.p);
     h->launches++;
-    std::vector<int32_t> colmax = cm.to_host(h->stream);
+    std::vector<int32_t> colmax = cm.to_host(h->stream), colhalo = ch.to_host(h->stream);
     P.piece_hi.assign(K, 0);
+    P.needs_halo.assign(K, 0);
     P.bn_begin.assign(K + 1, 0);
     for (int c = 0; c < K; c++) {
         int32_t m = 0;
-        for (int g = P.slice_begin[c]; g < P.slice_begin[c + 1]; g++) m = std::max(m, colmax[g]);
+        for (int g = P.slice_begin[c]; g < P.slice_begin[c + 1]; g++) {
+            m = std::max(m, colmax[g]);
+            if (colhalo[g]) P.needs_halo[c] = 1;
+        }
         int p = c;
         while (p + 1 < K && (int64_t)P.slice_begin[p + 1] * 32 <= m) p++;
         P.piece_hi[c] = p;
@@ -1283,7 +1301,7 @@ static void build_pipe_plan(vfvm_handle* h) {
         CK(cudaStreamCreateWithFlags(&h->stream_in, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&h->stream_out, cudaStreamNonBlocking));
     }
-    while ((int)h->pipe_ev.size() < 2 * K + 1) {
+    while ((int)h->pipe_ev.size() < 2 * K + 2) {
         cudaEvent_t e;
         CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         h->pipe_ev.push_back(e);
@@ -1292,7 +1310,7 @@ static void build_pipe_plan(vfvm_handle* h) {
 }
 
 bool vfvm_pipeline_applies(vfvm_handle* h) {
-    if (h->nranks > 1 || getenv("VFVM_NO_PIPELINE")) return false;
+    if (getenv("VFVM_NO_PIPELINE")) return false;
     const char* env = getenv("VFVM_PIPE_MIN_BYTES");  // below this vector size one copy each way is as fast
     return (int64_t)sizeof(double) * h->n * h->N >= (env ? atoll(env) : (8ll << 20));
 }
@@ -1313,7 +1331,10 @@ int vfvm_eval_res_jac_pipelined(vfvm_handle* h, const double* U, const double* U
     const bool have_old = UOld && UOld != U;
     if (!have_old) a.UOld = a.U;
     bn.UOld = a.UOld;
-    auto node_begin = [&](int c) { return c >= K ? h->N : (int64_t)P.slice_begin[c] * 32; };  // the last piece carries the tail
+    // owned pieces [node_begin(p), node_begin(p + 1)); with several ranks the halo nodes [Nown, N) form one more piece that travels FIRST: the rows
+    // next to a partition boundary sit in the first and the last chunk, and a halo at the end of the queue would serialise the whole call
+    auto node_begin = [&](int c) { return c >= K ? h->Nown : std::min<int64_t>((int64_t)P.slice_begin[c] * 32, h->Nown); };
+    const int64_t nhalo = h->N - h->Nown;
     CK(cudaMemsetAsync(h->flags.p + 1, 0, sizeof(int32_t), s));
     CK(cudaEventRecord(h->ev0, s));
     CK(cudaEventRecord(h->pipe_ev[2 * K], s));  // the copy-in stream must not overwrite U before earlier work on the main stream is done
@@ -1321,10 +1342,18 @@ int vfvm_eval_res_jac_pipelined(vfvm_handle* h, const double* U, const double* U
     double* dU = h->vec[VFVM_VEC_SOLUTION].p;
     double* dO = h->vec[VFVM_VEC_OLDSOL].p;
     double* dF = h->vec[VFVM_VEC_RESIDUAL].p;
-    for (int p = 0; p < K; p++) {
-        const int64_t o = node_begin(p) * n, cnt = (node_begin(p + 1) - node_begin(p)) * n;
+    if (nhalo > 0) {
+        const int64_t o = h->Nown * n, cnt = nhalo * n;
         CK(cudaMemcpyAsync(dU + o, U + o, cnt * sizeof(double), cudaMemcpyHostToDevice, sin));
         if (have_old) CK(cudaMemcpyAsync(dO + o, UOld + o, cnt * sizeof(double), cudaMemcpyHostToDevice, sin));
+        CK(cudaEventRecord(h->pipe_ev[2 * K + 1], sin));
+    }
+    for (int p = 0; p < K; p++) {
+        const int64_t o = node_begin(p) * n, cnt = (node_begin(p + 1) - node_begin(p)) * n;
+        if (cnt > 0) {
+            CK(cudaMemcpyAsync(dU + o, U + o, cnt * sizeof(double), cudaMemcpyHostToDevice, sin));
+            if (have_old) CK(cudaMemcpyAsync(dO + o, UOld + o, cnt * sizeof(double), cudaMemcpyHostToDevice, sin));
+        }
         CK(cudaEventRecord(h->pipe_ev[p], sin));
     }
     // A row kernel on the full persistent grid saturates HBM and starves the copy engines (measured: the upload stalls for
@@ -1337,7 +1366,13 @@ int vfvm_eval_res_jac_pipelined(vfvm_handle* h, const double* U, const double* U
     } grid_share{h};
     h->grid_pct = gp ? std::max(1, std::min(100, atoi(gp))) : 30;
     int arrived = -1;  // last piece the main stream has waited for
+    bool halo_arrived = nhalo == 0;
     for (int c = 0; c < K; c++) {
+        if (!halo_arrived && P.needs_halo[c]) {
+            CK(cudaStreamWaitEvent(s, h->pipe_ev[2 * K + 1], 0));
+            launch_node_transform(h, a, h->Nown, h->N);
+            halo_arrived = true;
+        }
         if (P.piece_hi[c] > arrived) {
             CK(cudaStreamWaitEvent(s, h->pipe_ev[P.piece_hi[c]], 0));
             launch_node_transform(h, a, node_begin(arrived + 1), node_begin(P.piece_hi[c] + 1));

@@ -105,7 +105,8 @@ struct PipePlan {
     bool valid = false;
     int K = 0;
     std::vector<int> slice_begin;   // K+1: chunk c = slices [slice_begin[c], slice_begin[c+1])
-    std::vector<int> piece_hi;      // K: last piece of U the columns of chunk c reach
+    std::vector<int> piece_hi;      // K: last piece of U the (owned) columns of chunk c reach
+    std::vector<int> needs_halo;    // K: chunk c has halo columns (several ranks): it also waits for the halo piece
     std::vector<int64_t> bn_begin;  // K+1: boundary nodes of chunk c
 };
 
