@@ -127,6 +127,30 @@ def test_cfg2_conservation_full_size():
         st.close()
 
 
+def test_cfg2_full_size_rows_against_oracle():
+    """cfg2 (Example207 physics, 2583^2, 20.0 M edges, transient): ten bands of grid rows -- both Dirichlet sides run through every band --
+    compared with the oracle entry by entry (tests/parity_probe.py), pattern bit-exact, values under the bound of test_gpu_parity.py"""
+    from parity_probe import probe_rows
+
+    nx = 2583
+    X = np.linspace(0, 1, nx)
+    g = v.simplexgrid(X, X)
+    s = v.System(g, flux=ph.PowerDiffusion(1.0e-2, 2), reaction=ph.PowerReaction(1.0, 2.0), source=ph.GaussSource(1, 20.0, (0.5, 0.5)), storage=ph.LinearStorage(1.0))
+    v.enable_species(s, 1, [1])
+    v.boundary_dirichlet(s, 1, 2, 0.1)
+    v.boundary_dirichlet(s, 1, 4, 0.1)
+    st = v.SystemState(s)
+    try:
+        U, Uold = _smooth(g), _smooth(g, k=2.0)
+        st.eval_res_jac(U, Uold, tstep=0.01)
+        ys = [0, nx - 8, 1, 333, 861, 1290, 1291, 1777, 2222, 2570]
+        res = probe_rows(s, st, None, U, Uold, tstep=0.01, ranges=[(y * nx, min((y + 8) * nx, g.num_nodes)) for y in ys])
+        assert res["ok"] and res["pattern_equal"], res
+        assert res["rows"] >= 10 * 8 * nx - 8 * nx and res["entries"] > 1.2e6
+    finally:
+        st.close()
+
+
 def test_pipelined_host_assembly_is_bitwise_the_plain_one(cfg3, monkeypatch):
     """vfvm_eval_res_jac with host vectors overlaps the upload of U, the row chunks and the download of F; the result must be
     bit-identical to upload -> assemble -> download (same kernels, same per-row order)."""
