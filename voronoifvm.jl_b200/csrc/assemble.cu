@@ -1061,6 +1061,8 @@ static void launch_rows(vfvm_handle* h, const AsmArgs& a) {
         if (a.Q != a.U) {
             // 128-thread blocks x 3 per SM (168 registers, no spills in the neighbour loop) measured 5-8 % faster than 256 x 2
             static int ps = 0, pb = 0;
+            // Round 2 re-measured the occupancy / batch trade on cfg4 at 193^3 (profiles/r2_bipolar_variants.txt): <2,128,4> (128 registers,
+            // 244 B spills, 16 warps/SM) 1.89 ms, <1,128,5> (96 registers, 20 warps/SM) 2.15 ms, <3,128,3> 1.81 ms against 1.79 ms for this one
             if (h->single_region) launch_slices(h, k_assemble_rows_bipolar<false, 2, 128, 3>, ps, a, 128);
             else launch_slices(h, k_assemble_rows_bipolar<true, 2, 128, 3>, pb, a, 128);
             return;
