@@ -756,6 +756,29 @@ function push_physics!(A::B200Matrix, system)
     return nothing
 end
 
+# ---- unknown storage: the device always works on the dense n x N layout (dofs of undefined species are identity rows and stay zero).
+# A SparseSolutionArray (unknown_storage = :sparse, src/vfvm_sparsesolution.jl:10-172) stores only the defined dofs in the CSC layout of
+# `system.node_dof`; it is scattered on the way up and gathered on the way down.  `Matrix{Float64}(U)` would not do: reading an undefined
+# dof of a sparse solution yields NaN (:156-166).
+to_dense(U::AbstractMatrix) = Matrix{Float64}(U)
+function to_dense(U::VoronoiFVM.SparseSolutionArray)
+    A = U.u
+    d = zeros(Float64, size(A)...)
+    for K in 1:size(A, 2), k in A.colptr[K]:(A.colptr[K + 1] - 1)
+        d[A.rowval[k], K] = A.nzval[k]
+    end
+    return d
+end
+from_dense!(U::AbstractMatrix, d::Matrix{Float64}) = (U .= d; U)
+function from_dense!(U::VoronoiFVM.SparseSolutionArray, d::Matrix{Float64})
+    A = U.u
+    for K in 1:size(A, 2), k in A.colptr[K]:(A.colptr[K + 1] - 1)
+        A.nzval[k] = d[A.rowval[k], K]
+    end
+    return U
+end
+dense_size(U) = size(U)
+
 """
     SystemState(B200(), system; data = system.physics.data)
 
@@ -765,7 +788,6 @@ pattern (K3) on the device, and returns a `VoronoiFVM.SystemState` whose `matrix
 function VoronoiFVM.SystemState(backend::B200, system::VoronoiFVM.AbstractSystem; data = system.physics.data, params = zeros(system.num_parameters))
     VoronoiFVM._complete!(system)
     system.num_parameters == 0 || throw(UnregisteredPhysicsError("parameter derivatives (dudp) are outside the device scope"))
-    VoronoiFVM.isdensesystem(system) || throw(UnregisteredPhysicsError("sparse unknown storage: create the system with unknown_storage = :dense for the device"))
     grid = system.grid
     dim = dim_space(grid)
     coord = Matrix{Float64}(grid[Coordinates])
@@ -804,6 +826,7 @@ function CommonSolve.solve(system::VoronoiFVM.AbstractSystem, backend::B200; dat
 end
 
 # ---- eval_and_assemble: the reference's signature, dispatched on the matrix type (src/vfvm_assembly.jl:520-534) ---------------------
+# U, UOld, F are dense arrays or SparseSolutionArrays (both are AbstractMatrix): to_dense / from_dense! above.
 function VoronoiFVM.eval_and_assemble(
         system,
         U::AbstractMatrix{Tv},
@@ -820,12 +843,12 @@ function VoronoiFVM.eval_and_assemble(
         edge_cutoff = 0.0,
     ) where {Tv}
     push_physics!(matrix, system)
-    u, uold, f = Matrix{Float64}(U), Matrix{Float64}(UOld), Matrix{Float64}(undef, size(F)...)
+    u, uold, f = to_dense(U), to_dense(UOld), Matrix{Float64}(undef, dense_size(F)...)
     rc = ccall((:vfvm_eval_res_jac, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Cint, Cdouble, Cdouble, Cdouble),
                matrix.h, u, uold, f, VFVM_HOST, Float64(time), Float64(tstep), Float64(λ))
     rc == VFVM_ERR_NAN && error("trying to assemble NaN")   # src/vfvm_assembly.jl:10-12
     check(matrix.h, rc)
-    F .= f
+    from_dense!(F, f)
     return 0, 0, 1   # (ncalloc, nballoc, neval)
 end
 
@@ -904,7 +927,7 @@ function VoronoiFVM.solve_step!(
     t = @elapsed begin
         push_physics!(A, state.system)
         # solution .= oldsol ; _initialize!(solution, ...)                                                     (:28, :31)
-        check(h, ccall((:vfvm_set_vector, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Cint), h, VEC_OLDSOL, Matrix{Float64}(oldsol), VFVM_HOST))
+        check(h, ccall((:vfvm_set_vector, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Cint), h, VEC_OLDSOL, to_dense(oldsol), VFVM_HOST))
         check(h, ccall((:vfvm_copy_vector, LIB), Cint, (Ptr{Cvoid}, Cint, Cint), h, VEC_SOLUTION, VEC_OLDSOL))
         check(h, ccall((:vfvm_init_dirichlet, LIB), Cint, (Ptr{Cvoid}, Cdouble, Cdouble), h, Float64(time), Float64(embedparam)))
         oldnorm = 1.0
@@ -973,9 +996,9 @@ function VoronoiFVM.solve_step!(
             niter = niter + 1
         end
         converged || throw(ConvergenceError())
-        sol = Matrix{Float64}(undef, size(solution)...)
+        sol = Matrix{Float64}(undef, dense_size(solution)...)
         check(h, ccall((:vfvm_get_vector, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}, Cint), h, VEC_SOLUTION, sol, VFVM_HOST))
-        solution .= sol
+        from_dense!(solution, sol)
     end
     if control.log
         nlhistory.time = t
