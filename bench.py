@@ -194,9 +194,11 @@ def cpu_port(workload, nx, steps=3, warmup=1, newton=True, newton_budget_s=150.0
             t_asm = time.perf_counter() - t0
             spd = is_spd(system)
             method, precon = ("cg" if spd else "bicgstab"), ("jacobi" if system.num_species == 1 else "blockjacobi")
-            # bounded: the iteration cap keeps the arm inside its time budget; an unconverged solve is reported as such
-            per_it = (3.0 if spd else 6.0) * 16.0 * E * max(1, system.num_species) ** 2 / (2.0e9 * max(1, min(nth, 16)))
-            cap = int(max(50, min(20000, newton_budget_s / max(per_it, 1e-4))))
+            # bounded: the iteration cap keeps the arm inside its time budget (calibrated on a ten-iteration run of the same solve on this
+            # host); an unconverged solve is reported as such
+            _, it0, _, sec0 = o.krylov_solve(F, method, precon, reltol=1e-30, maxiters=10, nthreads=nth)
+            per_it = sec0 / max(1, it0)
+            cap = int(max(50, min(20000, newton_budget_s / max(per_it, 1e-5))))
             x, it, rel, sec = o.krylov_solve(F, method, precon, reltol=1e-10, maxiters=cap, nthreads=nth)
             res["newton_step"] = {"ms": (t_asm + sec) * 1e3, "assemble_ms": t_asm * 1e3, "linsolve_ms": sec * 1e3, "iters": it, "relres": rel, "converged": bool(rel <= 2e-10),
                                   "krylov": ("CG" if spd else "BiCGStab") + ("+Jacobi" if precon == "jacobi" else "+node-block-Jacobi") + f" (oracle CPU Krylov, {nth} threads)",
