@@ -678,6 +678,23 @@ def test_sparse_unknown_storage_solve():
 
 
 # ---- boundary species, bstorage, edgereaction ---------------------------------------------------------------------
+def test_example220_boundary_species_2d_device():
+    """examples/Example220_NonlinearPoisson2D_BoundarySpecies.jl:65-101 on the device: two bulk species, one species on boundary region 2, linear
+    exchange boundary reaction, bstorage; 100 implicit Euler steps, U_bound[5] == 0.0020781361856598"""
+    from test_oracle_golden import _example220_system
+
+    s, bnodes = _example220_system()
+    st = v.SystemState(s)
+    try:
+        U = v.unknowns(s)
+        for _ in range(100):
+            U = v.solve_state(st, inival=U, tstep=0.01, reltol=1.0e-5)
+        assert U[2, bnodes[4]] == pytest.approx(0.0020781361856598, rel=1e-8)
+        assert np.all(U[2][~s.node_dof()[2]] == 0.0)
+    finally:
+        st.close()
+
+
 @pytest.mark.parametrize("switchbc", [False, True])
 def test_example115_boundary_species_bstorage_device(switchbc):
     """examples/Example115_HeterogeneousCatalysis1D.jl: surface species C (enable_boundary_species!) with bstorage and the nonlinear

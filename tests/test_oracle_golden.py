@@ -444,3 +444,31 @@ def test_example120_three_regions_1d():
         errs.append(abs(tv / ref - 1.0))
     assert min(errs) < 1.0e-12, errs
     assert max(errs) < 5.0e-4, errs  # the other branch of the final-step rounding
+
+
+def _example220_system(n=10):
+    """examples/Example220_NonlinearPoisson2D_BoundarySpecies.jl:17-63"""
+    h = 1.0 / n
+    X = np.arange(0, 1 + h / 2, h)
+    g = v.simplexgrid(X, X)
+    k, eps = 1.0, 1.0e-2
+    R = k * np.array([[1, 0, -1], [0, 1, -1], [-1, -1, 2.0]])  # f1 = k (u1 - u3), f2 = k (u2 - u3), f3 = k (u3 - u1) + k (u3 - u2) on boundary region 2
+    sys = v.System(g, flux=ph.LinearDiffusion([eps, eps, 0.0]), source=ph.GaussSource(1, 20.0, (0.5, 0.5)), storage=ph.LinearStorage([1.0, 1.0, 0.0]),
+                   breaction=ph.LinearBoundaryReaction(2, R), bstorage=ph.LinearBoundaryStorage(2, [0.0, 0.0, 1.0]))
+    v.enable_species(sys, 1, [1])
+    v.enable_species(sys, 2, [1])
+    v.enable_boundary_species(sys, 3, [2])
+    bn = np.unique(g.bfacenodes[:, g.bfaceregions == 2])
+    return sys, bn[np.argsort(g.coord[1, bn])]  # nodes of the boundary subgrid, along y
+
+
+def test_example220_boundary_species_2d():
+    """examples/Example220_NonlinearPoisson2D_BoundarySpecies.jl:65-101: 100 implicit Euler steps (tstep = 0.01, Newton reltol 1e-5),
+    U_bound[5] == 0.0020781361856598"""
+    sys, bnodes = _example220_system()
+    o = O.OracleSystem(sys)
+    U = v.unknowns(sys)
+    for _ in range(100):
+        U = o.solve_step(U, tstep=0.01, reltol=1.0e-5)
+    assert U[2, bnodes[4]] == pytest.approx(0.0020781361856598, rel=1e-12)
+    assert np.all(U[2][~sys.node_dof()[2]] == 0.0)
