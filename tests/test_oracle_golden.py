@@ -472,3 +472,17 @@ def test_example220_boundary_species_2d():
         U = o.solve_step(U, tstep=0.01, reltol=1.0e-5)
     assert U[2, bnodes[4]] == pytest.approx(0.0020781361856598, rel=1e-12)
     assert np.all(U[2][~sys.node_dof()[2]] == 0.0)
+
+
+def test_example440_parallel_state():
+    """examples/Example440_ParallelState.jl:14-53: flux u_K^2 - u_L^2, Dirichlet 0.1 at the left end, Neumann `influx` at the right end, 100
+    influx values each solved to round-off (abstol 1e-15, reltol 1e-20) from the constant 0.1; sum of the masses == 140.79872772042577"""
+    X = np.linspace(0, 1, 10 * 2**5 + 1)
+    total = 0.0
+    for influx in np.linspace(0.0, 10.0, 100):
+        bc = ph.BCondition().dirichlet(species=1, region=1, value=0.1).neumann(species=1, region=2, value=float(influx))
+        sys = v.System(v.simplexgrid(X), flux=ph.PowerDiffusion(1.0, 2), bcondition=bc, species=[1])
+        o = O.OracleSystem(sys)
+        sol = o.solve_step(v.unknowns(sys, inival=0.1), abstol=1.0e-15, reltol=1.0e-20)
+        total += o.integrate(sol)[0, 0]
+    assert total == pytest.approx(140.79872772042577, rel=1e-13)
