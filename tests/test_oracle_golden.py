@@ -486,3 +486,39 @@ def test_example440_parallel_state():
         sol = o.solve_step(v.unknowns(sys, inival=0.1), abstol=1.0e-15, reltol=1.0e-20)
         total += o.integrate(sol)[0, 0]
     assert total == pytest.approx(140.79872772042577, rel=1e-13)
+
+
+@pytest.mark.parametrize("case", ["disk", "cylinder", "ring", "cylindershell", "sphere", "sphereshell"])
+def test_example203_coordinate_systems(case):
+    """examples/Example203_CoordinateSystems.jl:28-230: -Laplace u = 1 on the disk / cylinder / sphere of radius 5 (the discretisation is exact:
+    |u - exact|_inf < 1e-14) and -Laplace u = 0 on the ring / cylinder shell / sphere shell between radii 1 and 5 (second order:
+    |u - exact|_inf / h^2 < 0.01, 0.01, 0.04) -- the cylindrical and spherical form factors (src/vfvm_formfactors.jl:29-62, 102-161, 255-288)
+    against closed-form solutions, with the reference's own thresholds"""
+    h = 0.1
+    r1, r2 = 1.0, 5.0
+    R0, R1, Z = np.arange(0, r2 + h / 2, h), np.arange(r1, r2 + h / 2, h), np.arange(0, 1 + h / 2, h)
+    if case == "disk":
+        g, bcs, src, exact, bound = v.circular_symmetric(v.simplexgrid(R0)), [(2, 0.0)], 1.0, lambda r: 0.25 * (r2**2 - r**2), 1.0e-14
+    elif case == "cylinder":
+        g, bcs, src, exact, bound = v.circular_symmetric(v.simplexgrid(R0, Z)), [(2, 0.0)], 1.0, lambda r: 0.25 * (r2**2 - r**2), 1.0e-14
+    elif case == "sphere":
+        g, bcs, src, exact, bound = v.spherical_symmetric(v.simplexgrid(R0)), [(2, 0.0)], 1.0, lambda r: (r2**2 - r**2) / 6.0, 1.0e-14
+    elif case == "ring":
+        g, bcs, src, exact, bound = v.circular_symmetric(v.simplexgrid(R1)), [(1, 1.0), (2, 0.0)], 0.0, lambda r: (np.log(r) - np.log(r2)) / (np.log(r1) - np.log(r2)), 0.01 * h**2
+    elif case == "cylindershell":
+        g, bcs, src, exact, bound = v.circular_symmetric(v.simplexgrid(R1, Z)), [(4, 1.0), (2, 0.0)], 0.0, lambda r: (np.log(r) - np.log(r2)) / (np.log(r1) - np.log(r2)), 0.01 * h**2
+    else:
+        g, bcs, src, exact, bound = v.spherical_symmetric(v.simplexgrid(R1)), [(1, 1.0), (2, 0.0)], 0.0, lambda r: (r2 * r1 / r - r1) / (r2 - r1), 0.04 * h**2
+    sys = v.System(g, flux=ph.LinearDiffusion(1.0), source=ph.ConstSource([src]), species=[1])
+    for region, value in bcs:
+        v.boundary_dirichlet(sys, 1, region, value)
+    sol = O.OracleSystem(sys).solve_step(v.unknowns(sys))
+    assert np.abs(sol[0] - exact(g.coord[0])).max() < bound
+
+
+def test_example101_laplace1d():
+    """examples/Example101_Laplace1D.jl:95-127: u'' = 0 on (0, 1) with callback Dirichlet values 0 and 1 on the grid 0:0.2:1; sum(solution) == 3.0"""
+    bc = ph.BCondition().dirichlet(species=1, region=1, value=0.0).dirichlet(species=1, region=2, value=1.0)
+    sys = v.System(v.simplexgrid(np.arange(0, 1.0 + 0.1, 0.2)), flux=ph.LinearDiffusion(1.0), bcondition=bc, species=[1])
+    sol = O.OracleSystem(sys).solve_step(v.unknowns(sys))
+    assert sol.sum() == pytest.approx(3.0, rel=1e-14)
