@@ -678,6 +678,36 @@ def test_sparse_unknown_storage_solve():
 
 
 # ---- boundary species, bstorage, edgereaction ---------------------------------------------------------------------
+@pytest.mark.parametrize("storage", ["dense", "sparse"])
+def test_state_reuse_and_restart_test060(storage):
+    """test/test060_state.jl:16-44: a solve through a reused SystemState equals the solve that builds its own; a transient run restarted
+    from the end of a previous one equals the run over both intervals, with and without a shared state, for both unknown storages"""
+    def dense(u):
+        return u.dense() if hasattr(u, "dense") else u
+
+    bc = ph.BCondition().robin(species=1, region=1, value=0.0, factor=0.1).dirichlet(species=1, region=2, value=1.0)
+    s = v.System(v.simplexgrid(np.arange(0, 1.05, 0.1)), flux=ph.LinearDiffusion(1.0), bcondition=bc, species=[1], unknown_storage=storage)
+    sol1 = dense(v.solve(s))
+    st = v.SystemState(s)
+    try:
+        sol2 = dense(v.solve_state(st))
+        np.testing.assert_allclose(sol1, sol2, rtol=1.5e-8)
+        control = v.SolverControl()
+        v.fixed_timesteps(control, 0.025)
+        tsol1 = v.solve(s, inival=0.0, times=(0, 0.1), control=control)
+        tsol2 = v.solve(s, inival=tsol1.u[-1], times=(0.1, 0.2), control=control)
+        tsol3 = v.solve(s, inival=0.0, times=[0.0, 0.1, 0.2], control=control)
+        np.testing.assert_allclose(tsol3.u[-1], tsol2.u[-1], rtol=1.5e-8)
+        xsol1 = v.solve_state(st, inival=0.0, times=(0, 0.1), control=control)
+        xsol2 = v.solve_state(st, inival=tsol1.u[-1], times=(0.1, 0.2), control=control)
+        xsol3 = v.solve_state(st, inival=0.0, times=[0.0, 0.1, 0.2], control=control)
+        np.testing.assert_allclose(xsol3.u[-1], xsol2.u[-1], rtol=1.5e-8)
+        np.testing.assert_allclose(xsol3.u[-1], tsol3.u[-1], rtol=1.5e-8)
+        assert len(xsol1.t) == 5 and xsol3.t[-1] == pytest.approx(0.2)
+    finally:
+        st.close()
+
+
 def test_example220_boundary_species_2d_device():
     """examples/Example220_NonlinearPoisson2D_BoundarySpecies.jl:65-101 on the device: two bulk species, one species on boundary region 2, linear
     exchange boundary reaction, bstorage; 100 implicit Euler steps, U_bound[5] == 0.0020781361856598"""
