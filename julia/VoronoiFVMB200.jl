@@ -878,7 +878,9 @@ end
 function device_linsolve!(A::B200Matrix, nlhistory, control, reuse_precs)
     m, fresh, (abstol, reltol, maxiters) = linear_setup!(A, control)
     reuse = reuse_precs && !fresh
-    reuse || (nlhistory.nlu += 1)
+    # nlu counts the set-ups that really happen: the device keeps only an ILU factorisation across solves (csrc/linsolve.cu)
+    keeps = precon_id(m.precs) in (PRECON_ILU0, PRECON_ILU0_MC)
+    (reuse && keeps) || (nlhistory.nlu += 1)
     iters, resnorm = Ref{Cint}(0), Ref{Cdouble}(0.0)
     rc = ccall((:vfvm_linsolve, LIB), Cint, (Ptr{Cvoid}, Cdouble, Cdouble, Cint, Cint, Ptr{Cint}, Ptr{Cdouble}),
                A.h, abstol, reltol, maxiters, reuse ? 1 : 0, iters, resnorm)

@@ -225,7 +225,10 @@ def _solve_linear(state: SystemState, hist: NewtonSolverHistory, control: Solver
     """`_solve_linear!` src/vfvm_linsolve.jl:6-61: A * update = residual on the device"""
     fresh, abstol, reltol, maxit = _linear_setup(state, control)
     reuse = bool(reuse_precs and not fresh)
-    if not reuse:
+    # nlu counts the preconditioner set-ups that really happen: the device keeps only an ILU factorisation across solves, everything else
+    # (Jacobi, block-Jacobi, the AMG numeric phase) is rebuilt from the current Jacobian whatever `reuse` says (csrc/linsolve.cu)
+    keeps = getattr(control.method_linear, "precon", None) in (_lib.PRECON_ILU0, _lib.PRECON_ILU0_MC)
+    if not (reuse and keeps):
         hist.nlu += 1
     iters, resn = C.c_int(0), C.c_double(0.0)
     rc = state.L.vfvm_linsolve(state.h, abstol, reltol, maxit, 1 if reuse else 0, C.byref(iters), C.byref(resn))
