@@ -16,14 +16,18 @@
 //   numeric phase (every new Jacobian): A_c(I,J) = sum of the fine blocks (K,L), K in I, L in J, plane by plane, as a GATHER
 //     in the fixed sorted order (no atomics => bitwise reproducible); block inverses of the diagonal for the smoother.
 //   cycle: damped block-Jacobi pre-/post-smoothing (symmetric, so CG stays applicable), residual fused into the restriction,
-//     over-weighted coarse correction (plain aggregation under-estimates smooth corrections), four sweeps on the coarsest level.
+//     over-weighted coarse correction (plain aggregation under-estimates smooth corrections), four sweeps on the coarsest level;
+//     optionally levels 1..wdepth are visited twice (W-cycle on the top of the hierarchy); the two finest-level SpMVs read an fp32
+//     copy of the off-diagonal planes.
 // With several ranks the hierarchy is distributed: aggregates never cross a partition boundary (every rank aggregates its owned
 // nodes), but the couplings across the boundary are kept on every level.  A rank learns the aggregate of each of its halo nodes
 // from the owner (one halo exchange of the aggregate ids per level); the distinct aggregates per neighbour, in ascending order,
 // are the halo of the next level -- and the owner derives the matching send list from the same ids without a second exchange.
 // Restriction, prolongation, Galerkin product and smoothing are rank-local; every SpMV of the cycle refreshes the halo of its
-// input (level 0: fused into the SpMV kernel over the peer mailboxes; coarser levels: one push/wait/unpack kernel through the
-// same mailboxes, or NCCL).  VFVM_AMG_LOCAL=1 drops the halo couplings instead (block-Jacobi across ranks with AMG inside).
+// input (fused into the SpMV kernel over the peer mailboxes, or an NCCL exchange in front of it).  From the first level whose stored
+// values stay below a threshold every rank holds the WHOLE level and the sub-hierarchy under it (Amg::repl_level, replicate_level):
+// one all-gather of the restricted right-hand side per cycle replaces the exchanges of those levels.
+// VFVM_AMG_LOCAL=1 drops the halo couplings instead (block-Jacobi across ranks with AMG inside).
 #include <algorithm>
 #include <cub/cub.cuh>
 
