@@ -192,3 +192,24 @@ def test_sparse_unknown_storage_host_mirror():
     # dense systems keep the dense array
     s2 = v.System(g, flux=ph.LinearDiffusion(), species=[1])
     assert isinstance(v.unknowns(s2), np.ndarray) and v.num_dof(s2) == g.num_nodes
+
+
+def test_bench_byte_formulas_match_the_survey():
+    """bench.py's algorithmic bytes are SURVEY.md section 8d's formulas on the stored coupling planes: 3D tensor grid, one species -> 52.6-52.9 B
+    per edge; a CG iteration with an AMG V-cycle = 3 level-0 SpMVs + the coarser levels' share + vector streams"""
+    import bench
+
+    nx = 193
+    m = nx - 1
+    N, E, NB = nx**3, 3 * m * nx * nx + 3 * m * m * nx + m**3, 12 * m * m
+    assert E == 49877568
+    b = bench.algorithmic_bytes(1, N, E, NB, 3, 1, 1, False)
+    assert 52.5 < b / E < 53.0  # SURVEY: 52.6 B/edge for n = 1 (+ the boundary items)
+    b3 = bench.algorithmic_bytes(3, N, E, NB, 3, 9, 9, True)
+    assert 190.0 < b3 / E < 200.0  # SURVEY: 194 B/edge for n = 3, fully coupled
+    nnz = 2 * E
+    spmv = nnz * 12 + N * 24
+    it_v = bench.iteration_bytes(1, N, nnz, 1, 1, "cg", 1.1)
+    assert it_v == pytest.approx(spmv + 1.1 * (2 * spmv + 7 * 8 * N) + 6 * 8 * N)
+    assert bench.iteration_bytes(1, N, nnz, 1, 1, "cg", 1.22) > it_v > bench.iteration_bytes(1, N, nnz, 1, 1, "cg", 0)
+    assert bench.iteration_bytes(1, N, nnz, 1, 1, "bicgstab", 1.1) == pytest.approx(2 * spmv + 2 * 1.1 * (2 * spmv + 7 * 8 * N) + 10 * 8 * N)
