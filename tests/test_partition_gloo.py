@@ -26,7 +26,7 @@ def _make_system(dim):
     return s
 
 
-def _worker(rank, world, port, dim, q):
+def _worker(rank, world, port, dim, q, method="ranges"):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
@@ -38,7 +38,8 @@ def _worker(rank, world, port, dim, q):
     try:
         s = _make_system(dim)
         n, N = s.num_species, s.grid.num_nodes
-        info = P.partition_grid(s.grid, rank, world)
+        info = P.partition_grid(s.grid, rank, world, method)
+        assert info.method == method
         ls = P.local_system(s, info)
         rng = np.random.default_rng(3)
         Ug = np.asfortranarray(rng.uniform(0.1, 1.0, (n, N)))
@@ -62,16 +63,17 @@ def _worker(rank, world, port, dim, q):
         Fg, Ag = O.OracleSystem(s).assemble(Ug, Ug, tstep=0.1)
         Fl, Al = O.OracleSystem(ls).assemble(Ul, Ul, tstep=0.1)
         Ag, Al = Ag.tocsr(), Al.tocsr()
-        lo = info.node_ranges[rank]
         gl = np.asarray(info.local_nodes)
+        own = np.asarray(info.owned_global)  # == lo + arange(n_owned) for contiguous ranges, the box's nodes for rcb
+        assert np.array_equal(own, gl[:info.n_owned])
         for K in range(info.n_owned):
             for i in range(n):
-                rl, rg = Al.getrow(K * n + i), Ag.getrow((lo + K) * n + i)
+                rl, rg = Al.getrow(K * n + i), Ag.getrow(own[K] * n + i)
                 cols_g = gl[rl.indices // n] * n + rl.indices % n
                 o = np.argsort(cols_g)
                 assert np.array_equal(cols_g[o], rg.indices), "row pattern differs"
                 np.testing.assert_allclose(rl.data[o], rg.data, rtol=1e-13, atol=1e-300)
-        np.testing.assert_allclose(Fl[:, :info.n_owned], Fg[:, lo:lo + info.n_owned], rtol=1e-12, atol=1e-14)
+        np.testing.assert_allclose(Fl[:, :info.n_owned], Fg[:, own], rtol=1e-12, atol=1e-14)
         tot = torch.tensor([info.n_owned], dtype=torch.int64)
         dist.all_reduce(tot)
         assert int(tot) == N
@@ -84,14 +86,14 @@ def _worker(rank, world, port, dim, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("dim", [2, 3])
-def test_partition_two_ranks_gloo(dim):
+@pytest.mark.parametrize("dim,method", [(2, "ranges"), (3, "ranges"), (3, "rcb")])
+def test_partition_two_ranks_gloo(dim, method):
     import torch.multiprocessing as mp
 
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + os.getpid() % 2000 + dim
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, dim, q)) for r in range(2)]
+    port = 29500 + os.getpid() % 2000 + dim + (7 if method == "rcb" else 0)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, dim, q, method)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=300) for _ in procs]
