@@ -522,3 +522,62 @@ def test_example101_laplace1d():
     sys = v.System(v.simplexgrid(np.arange(0, 1.0 + 0.1, 0.2)), flux=ph.LinearDiffusion(1.0), bcondition=bc, species=[1])
     sol = O.OracleSystem(sys).solve_step(v.unknowns(sys))
     assert sol.sum() == pytest.approx(3.0, rel=1e-14)
+
+
+def test_example161_bipolar_drift_diffusion_current():
+    """examples/Example161_BipolarDriftDiffusionCurrent.jl:27-298 -- the physics of the north_star target (VFVM_FLUX_SG_BIPOLAR, VFVM_REACTION_BIPOLAR,
+    VFVM_STORAGE_BIPOLAR) against the reference's own number.  1D p-i-n structure (138 nodes, three regions with doping 10 / 0 / -10), contacts
+    driven by the scan protocol (1 V preconditioning until t = 5, ramp to -3 V within 1e-5, relaxation until t = 80), three transient solves with
+    the example's step and Newton controls, then the total current of every step of the last phase through test-function integrals
+    (src/vfvm_testfunctions.jl:71-116, 299-336): I = I_n + I_p + (I_psi - I_psi_old) / dt with I_i = sum_edges fac f_i(u_K, u_L) (T_K - T_L).
+    sum(I) == -965.3101329657035 in the reference.  The example stops Newton at abstol = reltol = 1e-5, and the sum moves by 1e-6 relative with
+    that tolerance (-965.30710 here with the example's tolerances, -965.30614 with Newton driven to 1e-10), so the pin is 1e-5 relative: 3.1e-6
+    measured.  A wrong sign, coefficient or Bernoulli branch in the restated physics moves the value by O(1)."""
+    n = 20
+    h1, h2, h3 = 0.5, 4.0, 0.5
+    ht = h1 + h2 + h3
+    coord = np.concatenate([np.linspace(0, h1, n), np.linspace(h1, h1 + h2, 4 * n)[1:], np.linspace(h1 + h2, ht, 2 * n)[1:]])  # glue(): the shared points once
+    g = v.simplexgrid(coord)
+    v.cellmask(g, [0.0], [h1], 1)
+    v.cellmask(g, [h1], [h1 + h2], 2)
+    v.cellmask(g, [h1 + h2], [ht], 3)
+    tP, tExt, tR = 5.0, 75.0, 1.0e-5
+    tEnd = tP + tR + tExt
+    Vp, VE = 1.0, -3.0
+    Cn = Cp = 10.0
+    En, Ep = 1.0, 0.0
+    scan = ((tP, tP + tR), (Vp, VE))  # scanProtocol(t): Vprecond, linear ramp, VExt
+    psi1 = 0.5 * (En + Ep) + math.asinh(Cn / (2 * math.sqrt(math.exp(-(En - Ep)))))
+    psi2 = 0.5 * (En + Ep) + math.asinh(-Cp / (2 * math.sqrt(math.exp(-(En - Ep)))))
+    bc = ph.BCondition()
+    bc.dirichlet(species=1, region=1, value=0.0).dirichlet(species=2, region=1, value=0.0).dirichlet(species=3, region=1, value=psi1)
+    bc.dirichlet(species=1, region=2, value=0.0, ramp=scan).dirichlet(species=2, region=2, value=0.0, ramp=scan)
+    bc.dirichlet(species=3, region=2, value=0.0, ramp=((tP, tP + tR), (psi2 + Vp, psi2 + VE)))
+    sys = v.System(g, flux=ph.BipolarSGFlux(lam=0.1, mun=10.0, mup=10.0), reaction=ph.BipolarReaction([Cn, 0.0, -Cp]), storage=ph.BipolarStorage(), bcondition=bc,
+                   species=[1, 2, 3])
+    o = O.OracleSystem(sys)
+    ini = v.unknowns(sys)
+    ini[2, :] = math.asinh(Cn / 2) + (math.asinh(-Cp / 2) - math.asinh(Cn / 2)) / ht * coord
+    newton = dict(abstol=1e-5, reltol=1e-5, tol_round=1e-5, max_round=3, damp_initial=0.9, damp_growth=1.61)
+    _, s1 = o.solve_transient(ini, [0.0, tP], du_opt=math.inf, **newton)
+    _, s2 = o.solve_transient(s1[-1], [tP, tP + tR], dt=1e-8, dt_min=1e-8, du_opt=math.inf, **newton)
+    t3, s3 = o.solve_transient(s2[-1], [tP + tR, tEnd], dt=1e-10, dt_min=1e-10, dt_grow=1.7, du_opt=math.inf, **newton)
+    # testfunction(factory, [1], [2]): -Laplace T = 0, T = 0 on boundary region 1, T = 1 on boundary region 2
+    ts = v.System(g, flux=ph.LinearDiffusion(1.0), storage=ph.LinearStorage(1.0), species=[1])
+    v.boundary_dirichlet(ts, 1, 1, 0.0)
+    v.boundary_dirichlet(ts, 1, 2, 1.0)
+    T = O.OracleSystem(ts).solve_step(v.unknowns(ts))[0]
+    np.testing.assert_allclose(T, coord / ht, atol=1e-13)
+    en = o.edgenodes()
+    cp, _, ef = o.edgefactors()
+    efac = np.add.reduceat(np.append(ef, 0.0), cp[:-1]) * (cp[1:] > cp[:-1])
+    fl = sys.physics.flux
+
+    def grad_t_x_flux(U):  # integrate_gradTxFlux
+        return (o.edgeflux(U, fl.id, fl.params(3)) * efac * (T[en[0]] - T[en[1]])).sum(axis=1)
+
+    total = 0.0
+    for i in range(1, len(t3)):
+        a, b = grad_t_x_flux(s3[i]), grad_t_x_flux(s3[i - 1])
+        total += a[0] + a[1] + (a[2] - b[2]) / (t3[i] - t3[i - 1])
+    assert total == pytest.approx(-965.3101329657035, rel=1e-5)
