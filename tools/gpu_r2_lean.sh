@@ -1,5 +1,6 @@
 #!/bin/bash
-# 2 GPUs: masked-system diagnosis (replication on / off), lean coarse-level kernels on one GPU (A/B in one process) and on two
+# 2 GPUs: masked-system diagnosis (replication on / off), lean coarse-level kernels on one GPU (A/B in one process) and on two.
+# (Record of a measurement: the "lean" kernels it switched with LEAN= were slower and have been removed again, profiles/r2_amg_sweeps.txt.)
 N=${1:-2}
 set -x
 cd "$(dirname "$0")/.."
