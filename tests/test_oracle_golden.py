@@ -563,10 +563,7 @@ def test_example161_bipolar_drift_diffusion_current():
     _, s2 = o.solve_transient(s1[-1], [tP, tP + tR], dt=1e-8, dt_min=1e-8, du_opt=math.inf, **newton)
     t3, s3 = o.solve_transient(s2[-1], [tP + tR, tEnd], dt=1e-10, dt_min=1e-10, dt_grow=1.7, du_opt=math.inf, **newton)
     # testfunction(factory, [1], [2]): -Laplace T = 0, T = 0 on boundary region 1, T = 1 on boundary region 2
-    ts = v.System(g, flux=ph.LinearDiffusion(1.0), storage=ph.LinearStorage(1.0), species=[1])
-    v.boundary_dirichlet(ts, 1, 1, 0.0)
-    v.boundary_dirichlet(ts, 1, 2, 1.0)
-    T = O.OracleSystem(ts).solve_step(v.unknowns(ts))[0]
+    T = _test_function(g, [1], [2])
     np.testing.assert_allclose(T, coord / ht, atol=1e-13)
     en = o.edgenodes()
     cp, _, ef = o.edgefactors()
@@ -581,3 +578,66 @@ def test_example161_bipolar_drift_diffusion_current():
         a, b = grad_t_x_flux(s3[i]), grad_t_x_flux(s3[i - 1])
         total += a[0] + a[1] + (a[2] - b[2]) / (t3[i] - t3[i - 1])
     assert total == pytest.approx(-965.3101329657035, rel=1e-5)
+
+
+def _test_function(g, bc0, bc1):
+    """testfunction(factory, bc0, bc1), src/vfvm_testfunctions.jl:38-116: -Laplace T = 0, T = 0 on the boundary regions bc0, T = 1 on bc1"""
+    ts = v.System(g, flux=ph.LinearDiffusion(1.0), storage=ph.LinearStorage(1.0), species=[1])
+    for r in bc0:
+        v.boundary_dirichlet(ts, 1, r, 0.0)
+    for r in bc1:
+        v.boundary_dirichlet(ts, 1, r, 1.0)
+    return O.OracleSystem(ts).solve_step(v.unknowns(ts))[0]
+
+
+@pytest.mark.parametrize("dim", [1, 2, 3])
+def test_example225_test_function_balances(dim):
+    """examples/Example225_TestFunctions2D.jl:97-253 (the example's own checks, rtol 1e-12): two species, u_1 -> u_2 by the reaction r = u_1 - 0.1 u_2, a constant
+    source of u_1, u_2 leaves through boundary region 2.  Stationary: source integral == reaction integral of species 1; the test-function integral
+    I = I_flux + I_react - I_src (src/vfvm_testfunctions.jl:118-134) vanishes for species 1 and equals the reaction integral for species 2.  Transient
+    (fixed steps of 0.2 until t = 5): what the source delivered == what is stored + what left through the boundary, with the outflow of every step from
+    the transient test-function integral (:192-218).  Node integrals weighted with T use the linearity of the registered functions: f(u) T = f(u T)."""
+    nn = {1: 101, 2: 21, 3: 5}[dim]
+    X = np.linspace(0.0, 1.0, nn)
+    g = v.simplexgrid(*([X] * dim))
+    bc0, bc1 = ([1], [2]) if dim == 1 else ([4], [2])
+    R = np.array([[1.0, -0.1], [-1.0, 0.1]])  # f1 = r, f2 = -r, r = u1 + reaction_coeff u2, reaction_coeff = -0.1
+    sys = v.System(g, flux=ph.LinearDiffusion([1.0, 1.0]), storage=ph.LinearStorage([1.0, 1.0]), reaction=ph.AffineReaction(R), source=ph.ConstSource([1.0, 0.0]))
+    v.enable_species(sys, 1, [1])
+    v.enable_species(sys, 2, [1])
+    v.boundary_dirichlet(sys, 2, 2, 0.0)
+    o = O.OracleSystem(sys)
+    T = _test_function(g, bc0, bc1)
+    en = o.edgenodes()
+    cp, _, ef = o.edgefactors()
+    efac = np.add.reduceat(np.append(ef, 0.0), cp[:-1]) * (cp[1:] > cp[:-1])
+    rea, fl = sys.physics.reaction, sys.physics.flux
+    src_field = np.asfortranarray(np.vstack([np.ones(g.num_nodes), np.zeros(g.num_nodes)]))
+
+    def i_flux(U):
+        return (o.edgeflux(U, fl.id, fl.params(2)) * efac * (T[en[0]] - T[en[1]])).sum(axis=1)
+
+    def i_react(U):
+        return o.integrate(np.asfortranarray(U * T), rea.slot, rea.id, rea.params(2))[:, 0]
+
+    def i_stor(U):
+        return o.integrate(np.asfortranarray(U * T))[:, 0]
+
+    i_src = o.integrate(np.asfortranarray(src_field * T))[:, 0]
+    sol = o.solve_step(v.unknowns(sys))
+    F = o.integrate(src_field)[:, 0]
+    Rint = o.integrate(sol, rea.slot, rea.id, rea.params(2))[:, 0]
+    I = i_flux(sol) + i_react(sol) - i_src
+    assert F[0] == pytest.approx(Rint[0], rel=1e-12)
+    assert abs(I[0]) < 1e-12
+    assert Rint[1] == pytest.approx(I[1], rel=1e-12)
+    t0, tend, dt = 0.0, 5.0, 0.2
+    times, sols = o.solve_transient(v.unknowns(sys), [t0, tend], dt=dt, dt_min=dt, dt_max=dt, dt_grow=1.0, du_opt=math.inf)
+    assert len(times) == 26
+    all_outflow = 0.0
+    for i in range(1, len(times)):
+        h = times[i] - times[i - 1]
+        step = i_flux(sols[i]) + i_react(sols[i]) - i_src + (i_stor(sols[i]) - i_stor(sols[i - 1])) / h  # integrate(system, T, U, Uold, dt), rate = false
+        all_outflow -= step[1] * h
+    Uend = o.integrate(sols[-1])[:, 0]
+    assert F[0] * (tend - t0) == pytest.approx(Uend[0] + Uend[1] + all_outflow, rel=1e-12)
