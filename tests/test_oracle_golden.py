@@ -641,3 +641,28 @@ def test_example225_test_function_balances(dim):
         all_outflow -= step[1] * h
     Uend = o.integrate(sols[-1])[:, 0]
     assert F[0] * (tend - t0) == pytest.approx(Uend[0] + Uend[1] + all_outflow, rel=1e-12)
+
+
+def test_example125_test_functions_1d():
+    """examples/Example125_TestFunctions1D.jl:131-236: two species exchanging by the reaction 10 (u_1 - u_2), species 1 enters with the Neumann flux 0.01 at the
+    left end, species 2 leaves at the right end; for diffusion coefficients 1, 0.1, 0.01 (each solve damped, from the previous solution) the stationary
+    test-function integral of species 1 for T = 1 on the left boundary returns the influx: I1[1] == 0.01"""
+    n = 100
+    g = v.simplexgrid(np.arange(0, n + 1) / n)
+    T = _test_function(g, [2], [1])
+    U = np.full((2, g.num_nodes), 0.1, order="F")
+    I1 = None
+    for eps in (1.0, 0.1, 0.01):
+        sys = v.System(g, flux=ph.LinearDiffusion([eps, eps]), storage=ph.LinearStorage([1.0, 1.0]), reaction=ph.AffineReaction([[10.0, -10.0], [-10.0, 10.0]]))
+        v.enable_species(sys, 1, [1])
+        v.enable_species(sys, 2, [1])
+        v.boundary_neumann(sys, 1, 1, 0.01)
+        v.boundary_dirichlet(sys, 2, 2, 0.0)
+        o = O.OracleSystem(sys)
+        U = o.solve_step(U, damp_initial=0.1)
+        en = o.edgenodes()
+        cp, _, ef = o.edgefactors()
+        efac = np.add.reduceat(np.append(ef, 0.0), cp[:-1]) * (cp[1:] > cp[:-1])
+        fl, rea = sys.physics.flux, sys.physics.reaction
+        I1 = (o.edgeflux(U, fl.id, fl.params(2)) * efac * (T[en[0]] - T[en[1]])).sum(axis=1) + o.integrate(np.asfortranarray(U * T), rea.slot, rea.id, rea.params(2))[:, 0]
+    assert I1[0] == pytest.approx(0.01, rel=1e-8)  # the reference's isapprox
