@@ -7,7 +7,6 @@ device vectors; only the n x ncellregions result comes back.
 """
 from __future__ import annotations
 
-import ctypes as C
 
 import numpy as np
 
